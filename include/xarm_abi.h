@@ -1,0 +1,142 @@
+/* xarm_abi.h - C ABI of libxarm_b200.so: the drop-in boundary for the gym-xarm environment step.
+ *
+ * The reference has no FFI of its own: its envs are Python classes that call the third-party `pybullet` C-API
+ * ~35-60 times per step.  This ABI replaces that whole call sequence with one batched call per
+ * gym method; each entry point cites the reference method it stands for.  Plain pointers and sizes only - no
+ * torch types.  Device pointers are owned by the caller (torch allocates them; addresses stay fixed so the
+ * step can be replayed as a CUDA graph).  Every function returns 0 on success or a negative XARM_E_* code and
+ * leaves a message for xarm_last_error(); nothing throws or aborts across the boundary.
+ *
+ * Threading: a handle is not thread-safe; distinct handles (one per GPU / per process) are independent.
+ * xarm_step/xarm_reset are asynchronous on the given stream; the *_host variants synchronise that stream. */
+#ifndef XARM_ABI_H
+#define XARM_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XARM_ABI_VERSION 1
+
+/* tasks: the five env classes of the hot path */
+enum {
+  XARM_TASK_REACH = 0,           /* XarmReachEnv        [REF gym_xarm/envs/xarm_reach.py:9]           */
+  XARM_TASK_PICK_AND_PLACE = 1,  /* XarmPickAndPlace    [REF gym_xarm/envs/xarm_pick_and_place.py:16] */
+  XARM_TASK_STACK_TOWER = 2,     /* XarmStackTowerEnv   [REF gym_xarm/envs/xarm_stack_tower.py:13]    */
+  XARM_TASK_PUSH_WITH_DOOR = 3,  /* XarmPushWithDoorEnv [REF gym_xarm/envs/xarm_push_with_door.py:13] */
+  XARM_TASK_HANDOVER = 4,        /* XarmHandover        [REF gym_xarm/envs/xarm_handover.py:19]       */
+  XARM_NUM_TASKS = 5
+};
+
+/* reward types: config['reward_type'] strings of the reference */
+enum {
+  XARM_REWARD_SPARSE = 0,     /* all tasks */
+  XARM_REWARD_DENSE = 1,      /* Reach: -d; PickAndPlace/Handover: staged (reads sim state); Stack/Push: -d */
+  XARM_REWARD_DENSE_O2G = 2,  /* PickAndPlace only: -d   [REF xarm_pick_and_place.py:176-177] */
+  XARM_REWARD_DENSE_DIFF = 3  /* Reach only: d_old - d   [REF xarm_reach.py:113-116] */
+};
+
+enum { XARM_GOAL_AIR = 0, XARM_GOAL_GROUND = 1 };
+
+enum {
+  XARM_OK = 0,
+  XARM_E_INVALID = -1,   /* bad argument / unsupported config (Python side raises ValueError/NotImplementedError) */
+  XARM_E_CUDA = -2,      /* CUDA runtime error (sticky errors surface at the next call) */
+  XARM_E_STATE = -3,     /* call order violated (e.g. step before bind) */
+  XARM_E_NOMEM = -4
+};
+
+/* mirrors the `config` dict of the reference constructors [REF xarm_pick_and_place.py:17,53,68,164,261,272,276;
+ * xarm_handover.py:25,60,85,380,387,391; xarm_reach.py:25] plus the batching/seeding keys this repo adds */
+typedef struct XarmConfig {
+  int32_t task;               /* XARM_TASK_* */
+  int32_t reward_type;        /* XARM_REWARD_* */
+  int32_t num_obj;            /* config['num_obj'] (PickAndPlace, Handover); fixed 3 / 1 for StackTower / PushWithDoor */
+  int32_t goal_shape;         /* config['goal_shape']: XARM_GOAL_AIR | XARM_GOAL_GROUND */
+  float init_grasp_rate;      /* config['init_grasp_rate'] */
+  float goal_ground_rate;     /* config['goal_ground_rate'] */
+  float same_side_rate;       /* config['same_side_rate'] */
+  int32_t use_stand;          /* config['use_stand'] (accepted; the stand is not simulated) */
+  int32_t max_episode_steps;  /* 0 = the registered TimeLimit (25/50/50/50/100) [REF gym_xarm/__init__.py:6-22] */
+  int32_t auto_reset;         /* 1: VecEnv semantics - a finished env is reset inside xarm_step */
+  int32_t device;             /* CUDA device ordinal */
+  int32_t reserved;
+  int64_t num_envs;           /* envs in this slab */
+  int64_t env_index_base;     /* global index of env 0 of the slab: RNG streams are keyed by the global index */
+  uint64_t seed;
+} XarmConfig;
+
+/* Caller-owned DEVICE buffers (float32 unless noted), row-major [num_envs, dim]. */
+typedef struct XarmBuffers {
+  const float* actions;    /* [N, A]  in   */
+  float* observation;      /* [N, O]  out: obs['observation'] (after auto-reset: first obs of the new episode) */
+  float* achieved_goal;    /* [N, G]  out */
+  float* desired_goal;     /* [N, G]  out */
+  float* reward;           /* [N]     out */
+  uint8_t* done;           /* [N]     out: terminated or truncated */
+  float* success;          /* [N]     out: info['is_success'] */
+  uint8_t* truncated;      /* [N]     out: info['TimeLimit.truncated'] */
+  float* terminal_observation; /* [N, O+2G] out (may be NULL): observation|achieved|desired of the step BEFORE auto-reset */
+} XarmBuffers;
+
+typedef struct XarmHandle XarmHandle;
+
+/* dims of a task: action A, observation O, goal G, state words per env S (layout in DESIGN.md "state record") */
+int xarm_task_dims(int32_t task, int32_t num_obj, int32_t* act_dim, int32_t* obs_dim, int32_t* goal_dim, int32_t* state_words);
+
+/* Env.__init__(config)  [REF xarm_pick_and_place.py:17-103; xarm_reach.py:15-77; xarm_handover.py:25-124;
+ * xarm_stack_tower.py:14-97; xarm_push_with_door.py:14-99] - allocates the SoA state slab on cfg->device. */
+int xarm_create(const XarmConfig* cfg, XarmHandle** out);
+/* Env.close()  [REF xarm_reach.py:125-126, xarm_handover.py:147-148] */
+int xarm_destroy(XarmHandle* h);
+int xarm_bind(XarmHandle* h, const XarmBuffers* bufs);
+
+/* Env.reset()  [REF xarm_pick_and_place.py:121-127,250-287; xarm_reach.py:96-102,163-173;
+ * xarm_stack_tower.py:115-119,201-219; xarm_push_with_door.py:117-121,195-212; xarm_handover.py:141-145,338-393].
+ * mask: device uint8[N] selecting envs (NULL = all).  Writes observation/achieved_goal/desired_goal. */
+int xarm_reset(XarmHandle* h, const uint8_t* mask, void* stream);
+
+/* Env.step(action)  [REF xarm_pick_and_place.py:107-119,199-248; xarm_reach.py:81-94,131-161;
+ * xarm_stack_tower.py:101-113,142-199; xarm_push_with_door.py:103-115,144-193; xarm_handover.py:128-139,244-336]
+ * for every env of the slab: _set_action (IK + motor targets + grasp friction), stepSimulation x n_substeps,
+ * _get_obs, _is_success, compute_reward, done, TimeLimit, optional auto-reset.  Replays the captured CUDA graph
+ * when xarm_graph_capture() succeeded for this stream. */
+int xarm_step(XarmHandle* h, void* stream);
+
+/* Same step with HOST buffers (the path SB3's numpy VecEnv uses): copies actions H2D, steps, copies
+ * observation|achieved|desired|reward|done|success|truncated D2H, synchronises.  NULL outputs are skipped. */
+int xarm_step_host(XarmHandle* h, const float* actions, float* observation, float* achieved_goal, float* desired_goal,
+                   float* reward, uint8_t* done, float* success, uint8_t* truncated, void* stream);
+int xarm_reset_host(XarmHandle* h, float* observation, float* achieved_goal, float* desired_goal, void* stream);
+
+/* Env.compute_reward(achieved_goal, desired_goal, info) for HER relabelling: batch form, device pointers
+ * [REF xarm_reach.py:107-116; xarm_pick_and_place.py:155-190; xarm_stack_tower.py:124-129;
+ *  xarm_push_with_door.py:126-131; xarm_handover.py:153-183].  Only the state-free reward types. */
+int xarm_compute_reward(int32_t task, int32_t reward_type, int32_t num_obj, const float* achieved_goal,
+                        const float* desired_goal, int64_t n, float* out, void* stream);
+
+/* Simulator checkpoint (the reference has none; needed for parity injection): HOST float32
+ * [num_envs, state_words] records. */
+int xarm_get_state(XarmHandle* h, float* host_out);
+int xarm_set_state(XarmHandle* h, const float* host_in);
+/* recompute observation/achieved_goal/desired_goal from the current state (_get_obs) */
+int xarm_get_obs(XarmHandle* h, void* stream);
+
+/* Capture xarm_step (step + auto-reset) into a CUDA graph on `stream`; later xarm_step calls on that stream replay it. */
+int xarm_graph_capture(XarmHandle* h, void* stream);
+
+/* Episode statistics accumulated on the device since the last call (reset on read):
+ * out[0]=episodes, out[1]=sum return, out[2]=sum length, out[3]=sum success, out[4]=diverged (NaN-guard resets). */
+int xarm_episode_stats(XarmHandle* h, double out[5], void* stream);
+
+/* kernels launched by this library since load (claim for bench.py's gpu_launches) */
+int64_t xarm_launch_count(void);
+const char* xarm_last_error(void);
+int xarm_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XARM_ABI_H */
