@@ -1,0 +1,413 @@
+// xarm_lib.cu - kernels + the C ABI of libxarm_b200.so (include/xarm_abi.h).  No torch, no CPU fallback:
+// every entry point either runs the sm_100a kernels below or returns an error.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "xarm_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------------ kernels
+// One thread per env; 128-thread blocks (a warp steps 32 envs in lock-step).
+template <class T>
+__global__ void __launch_bounds__(128) k_init(KArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.n) body_init<T>(a, i);
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) k_step(KArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  StepStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (i < a.n) body_step<T>(a, i, st);
+  // episode statistics (K8): warp-aggregate, one atomic per warp and counter
+  unsigned any = __ballot_sync(0xffffffffu, st.eps != 0.f || st.div != 0.f);
+  if (any) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      st.eps += __shfl_down_sync(0xffffffffu, st.eps, off);
+      st.ret += __shfl_down_sync(0xffffffffu, st.ret, off);
+      st.len += __shfl_down_sync(0xffffffffu, st.len, off);
+      st.suc += __shfl_down_sync(0xffffffffu, st.suc, off);
+      st.div += __shfl_down_sync(0xffffffffu, st.div, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&a.stats[0], (double)st.eps); atomicAdd(&a.stats[1], (double)st.ret); atomicAdd(&a.stats[2], (double)st.len);
+      atomicAdd(&a.stats[3], (double)st.suc);
+      if (st.div != 0.f) atomicAdd(&a.stats[4], (double)st.div);
+    }
+  }
+}
+
+// Env.reset for the envs selected by mask (or by the step kernel's need_reset flags)
+template <class T>
+__global__ void __launch_bounds__(128) k_reset(KArgs a, const uint8_t* mask, int use_flags) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  if (use_flags) { if (!a.need_reset[i]) return; }
+  else if (mask && !mask[i]) return;
+  body_reset<T>(a, i, !use_flags);
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) k_obs(KArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.n) body_obs<T>(a, i);
+}
+
+// Env.compute_reward on batches (HER relabelling)
+__global__ void k_compute_reward(int task, int reward_type, int num_obj, int G, const float* __restrict__ ag,
+                                 const float* __restrict__ dg, int64_t n, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a[9], d[9];
+  for (int k = 0; k < G; k++) { a[k] = ag[i * G + k]; d[k] = dg[i * G + k]; }
+  out[i] = reward_stateless(task, reward_type, num_obj, task_threshold(task), a, d, G);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(XARM_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } while (0)
+
+struct Ops {
+  void (*init)(const KArgs&, cudaStream_t);
+  void (*step)(const KArgs&, cudaStream_t);
+  void (*reset)(const KArgs&, const uint8_t*, int, cudaStream_t);
+  void (*obs)(const KArgs&, cudaStream_t);
+  int A, O, G, S;
+};
+
+template <class T>
+struct OpsT {
+  static dim3 grid(int64_t n) { return dim3((unsigned)((n + 127) / 128)); }
+  static void init(const KArgs& a, cudaStream_t s) { k_init<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
+  static void step(const KArgs& a, cudaStream_t s) { k_step<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
+  static void reset(const KArgs& a, const uint8_t* m, int f, cudaStream_t s) { k_reset<T><<<grid(a.n), 128, 0, s>>>(a, m, f); g_launches++; }
+  static void obs(const KArgs& a, cudaStream_t s) { k_obs<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
+  static Ops make() { Ops o = {init, step, reset, obs, T::A, T::O, T::G, state_words<T>()}; return o; }
+};
+
+static bool get_ops(int task, int num_obj, Ops* out) {
+  switch (task) {
+    case XARM_TASK_REACH: *out = OpsT<TaskT<XARM_TASK_REACH, 0>>::make(); return true;
+    case XARM_TASK_PICK_AND_PLACE:
+      if (num_obj == 1) { *out = OpsT<TaskT<XARM_TASK_PICK_AND_PLACE, 1>>::make(); return true; }
+      return false;
+    case XARM_TASK_STACK_TOWER: *out = OpsT<TaskT<XARM_TASK_STACK_TOWER, 3>>::make(); return true;
+    case XARM_TASK_PUSH_WITH_DOOR: *out = OpsT<TaskT<XARM_TASK_PUSH_WITH_DOOR, 1>>::make(); return true;
+    case XARM_TASK_HANDOVER:
+      if (num_obj == 1) { *out = OpsT<TaskT<XARM_TASK_HANDOVER, 1>>::make(); return true; }
+      return false;
+  }
+  return false;
+}
+static int norm_num_obj(int task, int num_obj) {
+  if (task == XARM_TASK_REACH) return 0;
+  if (task == XARM_TASK_STACK_TOWER) return 3;
+  if (task == XARM_TASK_PUSH_WITH_DOOR) return 1;
+  return num_obj;
+}
+
+struct XarmHandle {
+  XarmConfig cfg;
+  Ops ops;
+  KArgs k;
+  bool bound = false;
+  cudaGraphExec_t graph = nullptr;
+  cudaStream_t graph_stream = nullptr;
+  // device + pinned staging for the *_host entry points
+  float* d_io = nullptr;   // actions | obs | ag | dg | reward | success
+  uint8_t* d_flags = nullptr;  // done | truncated
+  float* h_io = nullptr;
+  uint8_t* h_flags = nullptr;
+  XarmBuffers host_bufs;
+  XarmBuffers user_bufs;
+  bool user_bound = false;
+};
+
+extern "C" {
+
+int xarm_abi_version(void) { return XARM_ABI_VERSION; }
+const char* xarm_last_error(void) { return g_err.c_str(); }
+int64_t xarm_launch_count(void) { return g_launches.load(); }
+
+int xarm_task_dims(int32_t task, int32_t num_obj, int32_t* act_dim, int32_t* obs_dim, int32_t* goal_dim, int32_t* state_words_out) {
+  Ops o;
+  if (!get_ops(task, norm_num_obj(task, num_obj), &o)) return fail(XARM_E_INVALID, "xarm_task_dims: unsupported task/num_obj");
+  if (act_dim) *act_dim = o.A;
+  if (obs_dim) *obs_dim = o.O;
+  if (goal_dim) *goal_dim = o.G;
+  if (state_words_out) *state_words_out = o.S;
+  return XARM_OK;
+}
+
+int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
+  if (!cfg || !out) return fail(XARM_E_INVALID, "xarm_create: null argument");
+  if (cfg->num_envs <= 0) return fail(XARM_E_INVALID, "xarm_create: num_envs must be positive");
+  XarmConfig c = *cfg;
+  c.num_obj = norm_num_obj(c.task, c.num_obj);
+  Ops ops;
+  if (!get_ops(c.task, c.num_obj, &ops)) return fail(XARM_E_INVALID, "xarm_create: unsupported task / num_obj (built: num_obj=1 for PickAndPlace and Handover)");
+  // reward types the reference defines per task (others raise NotImplementedError there, D6)
+  bool ok_reward = c.reward_type == XARM_REWARD_SPARSE || c.reward_type == XARM_REWARD_DENSE ||
+                   (c.task == XARM_TASK_PICK_AND_PLACE && c.reward_type == XARM_REWARD_DENSE_O2G) ||
+                   (c.task == XARM_TASK_REACH && c.reward_type == XARM_REWARD_DENSE_DIFF);
+  if (!ok_reward) return fail(XARM_E_INVALID, "xarm_create: reward_type not implemented for this task");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (c.device < 0 || c.device >= ndev) return fail(XARM_E_INVALID, "xarm_create: bad device ordinal");
+  CUDA_TRY(cudaSetDevice(c.device));
+  XarmHandle* h = new (std::nothrow) XarmHandle();
+  if (!h) return fail(XARM_E_NOMEM, "xarm_create: out of host memory");
+  h->cfg = c; h->ops = ops;
+  memset(&h->k, 0, sizeof(h->k));
+  memset(&h->host_bufs, 0, sizeof(XarmBuffers));
+  memset(&h->user_bufs, 0, sizeof(XarmBuffers));
+  const int64_t n = c.num_envs;
+  h->k.n = n; h->k.auto_reset = c.auto_reset;
+  h->k.rc.seed = c.seed; h->k.rc.env_index_base = c.env_index_base; h->k.rc.reward_type = c.reward_type;
+  h->k.rc.goal_shape = c.goal_shape; h->k.rc.max_episode_steps = c.max_episode_steps;
+  h->k.rc.init_grasp_rate = c.init_grasp_rate; h->k.rc.goal_ground_rate = c.goal_ground_rate; h->k.rc.same_side_rate = c.same_side_rate;
+  cudaError_t e1 = cudaMalloc(&h->k.state, sizeof(float) * ops.S * n);
+  cudaError_t e2 = cudaMalloc(&h->k.ep_return, sizeof(float) * n);
+  cudaError_t e3 = cudaMalloc(&h->k.need_reset, n);
+  cudaError_t e4 = cudaMalloc(&h->k.stats, sizeof(double) * 5);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+    cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats);
+    delete h; cudaGetLastError();
+    return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc failed");
+  }
+  CUDA_TRY(cudaMemset(h->k.stats, 0, sizeof(double) * 5));
+  ops.init(h->k, 0);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(0));
+  *out = h;
+  return XARM_OK;
+}
+
+int xarm_destroy(XarmHandle* h) {
+  if (!h) return XARM_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->graph) cudaGraphExecDestroy(h->graph);
+  cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats);
+  cudaFree(h->d_io); cudaFree(h->d_flags);
+  if (h->h_io) cudaFreeHost(h->h_io);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  delete h;
+  return XARM_OK;
+}
+
+int xarm_bind(XarmHandle* h, const XarmBuffers* b) {
+  if (!h || !b) return fail(XARM_E_INVALID, "xarm_bind: null argument");
+  if (!b->actions || !b->observation || !b->achieved_goal || !b->desired_goal || !b->reward || !b->done || !b->success)
+    return fail(XARM_E_INVALID, "xarm_bind: actions/observation/achieved_goal/desired_goal/reward/done/success are required");
+  h->k.b = *b; h->user_bufs = *b; h->user_bound = true;
+  h->bound = true;
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }  // addresses changed: recapture
+  return XARM_OK;
+}
+
+static int launch_step(XarmHandle* h, cudaStream_t s) {
+  h->ops.step(h->k, s);
+  if (h->cfg.auto_reset) h->ops.reset(h->k, nullptr, 1, s);
+  return XARM_OK;
+}
+
+int xarm_reset(XarmHandle* h, const uint8_t* mask, void* stream) {
+  if (!h) return fail(XARM_E_INVALID, "xarm_reset: null handle");
+  if (!h->bound) return fail(XARM_E_STATE, "xarm_reset: call xarm_bind first");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  h->ops.reset(h->k, mask, 0, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_step(XarmHandle* h, void* stream) {
+  if (!h) return fail(XARM_E_INVALID, "xarm_step: null handle");
+  if (!h->bound) return fail(XARM_E_STATE, "xarm_step: call xarm_bind first");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (h->graph && s == h->graph_stream) {
+    CUDA_TRY(cudaGraphLaunch(h->graph, s));
+    g_launches += h->cfg.auto_reset ? 2 : 1;
+  } else {
+    launch_step(h, s);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return XARM_OK;
+}
+
+int xarm_graph_capture(XarmHandle* h, void* stream) {
+  if (!h) return fail(XARM_E_INVALID, "xarm_graph_capture: null handle");
+  if (!h->bound) return fail(XARM_E_STATE, "xarm_graph_capture: call xarm_bind first");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (s == nullptr) return fail(XARM_E_INVALID, "xarm_graph_capture: needs a non-default stream");
+  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+  cudaGraph_t g = nullptr;
+  int64_t before = g_launches.load();
+  CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  launch_step(h, s);
+  cudaError_t e = cudaStreamEndCapture(s, &g);
+  g_launches = before;  // captured launches did not run
+  if (e != cudaSuccess) return fail(XARM_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&h->graph, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { h->graph = nullptr; return fail(XARM_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+  h->graph_stream = s;
+  return XARM_OK;
+}
+
+static int ensure_host_io(XarmHandle* h) {
+  if (h->d_io) return XARM_OK;
+  const int64_t n = h->cfg.num_envs;
+  const Ops& o = h->ops;
+  const size_t fl = (size_t)n * (o.A + o.O + 2 * o.G + 2);
+  CUDA_TRY(cudaMalloc(&h->d_io, fl * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&h->d_flags, 2 * n));
+  CUDA_TRY(cudaMallocHost(&h->h_io, fl * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&h->h_flags, 2 * n));
+  XarmBuffers& b = h->host_bufs;
+  float* p = h->d_io;
+  b.actions = p; p += n * o.A;
+  b.observation = p; p += n * o.O;
+  b.achieved_goal = p; p += n * o.G;
+  b.desired_goal = p; p += n * o.G;
+  b.reward = p; p += n;
+  b.success = p; p += n;
+  b.done = h->d_flags; b.truncated = h->d_flags + n;
+  b.terminal_observation = nullptr;
+  return XARM_OK;
+}
+
+// The numpy-facing path: host buffers in, host buffers out.  Uses the library's own device staging; pinned host
+// staging keeps the copies asynchronous with respect to the step kernels.
+int xarm_step_host(XarmHandle* h, const float* actions, float* observation, float* achieved_goal, float* desired_goal,
+                   float* reward, uint8_t* done, float* success, uint8_t* truncated, void* stream) {
+  if (!h || !actions) return fail(XARM_E_INVALID, "xarm_step_host: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = ensure_host_io(h);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = h->cfg.num_envs;
+  const Ops& o = h->ops;
+  KArgs k = h->k;
+  k.b = h->host_bufs;
+  float* hp = h->h_io;
+  memcpy(hp, actions, sizeof(float) * n * o.A);
+  CUDA_TRY(cudaMemcpyAsync((void*)k.b.actions, hp, sizeof(float) * n * o.A, cudaMemcpyHostToDevice, s));
+  h->ops.step(k, s);
+  if (h->cfg.auto_reset) h->ops.reset(k, nullptr, 1, s);
+  CUDA_TRY(cudaGetLastError());
+  // one D2H copy of the contiguous float outputs, one of the flags
+  const size_t out_fl = (size_t)n * (o.O + 2 * o.G + 2);
+  CUDA_TRY(cudaMemcpyAsync(hp + n * o.A, k.b.observation, out_fl * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  const float* q = hp + n * o.A;
+  if (observation) memcpy(observation, q, sizeof(float) * n * o.O);
+  q += n * o.O;
+  if (achieved_goal) memcpy(achieved_goal, q, sizeof(float) * n * o.G);
+  q += n * o.G;
+  if (desired_goal) memcpy(desired_goal, q, sizeof(float) * n * o.G);
+  q += n * o.G;
+  if (reward) memcpy(reward, q, sizeof(float) * n);
+  q += n;
+  if (success) memcpy(success, q, sizeof(float) * n);
+  if (done) memcpy(done, h->h_flags, n);
+  if (truncated) memcpy(truncated, h->h_flags + n, n);
+  return XARM_OK;
+}
+
+int xarm_reset_host(XarmHandle* h, float* observation, float* achieved_goal, float* desired_goal, void* stream) {
+  if (!h) return fail(XARM_E_INVALID, "xarm_reset_host: null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = ensure_host_io(h);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = h->cfg.num_envs;
+  const Ops& o = h->ops;
+  KArgs k = h->k;
+  k.b = h->host_bufs;
+  h->ops.reset(k, nullptr, 0, s);
+  CUDA_TRY(cudaGetLastError());
+  float* hp = h->h_io + n * o.A;
+  CUDA_TRY(cudaMemcpyAsync(hp, k.b.observation, sizeof(float) * n * (o.O + 2 * o.G), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (observation) memcpy(observation, hp, sizeof(float) * n * o.O);
+  if (achieved_goal) memcpy(achieved_goal, hp + n * o.O, sizeof(float) * n * o.G);
+  if (desired_goal) memcpy(desired_goal, hp + n * (o.O + o.G), sizeof(float) * n * o.G);
+  return XARM_OK;
+}
+
+int xarm_compute_reward(int32_t task, int32_t reward_type, int32_t num_obj, const float* ag, const float* dg, int64_t n,
+                        float* out, void* stream) {
+  Ops o;
+  num_obj = norm_num_obj(task, num_obj);
+  if (task < 0 || task >= XARM_NUM_TASKS) return fail(XARM_E_INVALID, "xarm_compute_reward: bad task");
+  int G = task == XARM_TASK_REACH ? 3 : 3 * num_obj;
+  if (G < 3 || G > 9) return fail(XARM_E_INVALID, "xarm_compute_reward: num_obj out of range");
+  bool ok = reward_type == XARM_REWARD_SPARSE ||
+            (reward_type == XARM_REWARD_DENSE && (task == XARM_TASK_REACH || task == XARM_TASK_STACK_TOWER || task == XARM_TASK_PUSH_WITH_DOOR)) ||
+            (reward_type == XARM_REWARD_DENSE_O2G && task == XARM_TASK_PICK_AND_PLACE);
+  if (!ok) return fail(XARM_E_INVALID, "xarm_compute_reward: this reward type reads simulator state (not batch-safe in the reference either)");
+  if (n <= 0) return XARM_OK;
+  if (!ag || !dg || !out) return fail(XARM_E_INVALID, "xarm_compute_reward: null pointer");
+  (void)o;
+  k_compute_reward<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(task, reward_type, num_obj, G, ag, dg, n, out);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_get_state(XarmHandle* h, float* host_out) {
+  if (!h || !host_out) return fail(XARM_E_INVALID, "xarm_get_state: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const int64_t n = h->cfg.num_envs; const int S = h->ops.S;
+  std::vector<float> tmp((size_t)n * S);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(tmp.data(), h->k.state, sizeof(float) * n * S, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; i++)
+    for (int w = 0; w < S; w++) host_out[i * S + w] = tmp[(size_t)w * n + i];
+  return XARM_OK;
+}
+
+int xarm_set_state(XarmHandle* h, const float* host_in) {
+  if (!h || !host_in) return fail(XARM_E_INVALID, "xarm_set_state: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const int64_t n = h->cfg.num_envs; const int S = h->ops.S;
+  std::vector<float> tmp((size_t)n * S);
+  for (int64_t i = 0; i < n; i++)
+    for (int w = 0; w < S; w++) tmp[(size_t)w * n + i] = host_in[i * S + w];
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(h->k.state, tmp.data(), sizeof(float) * n * S, cudaMemcpyHostToDevice));
+  return XARM_OK;
+}
+
+int xarm_get_obs(XarmHandle* h, void* stream) {
+  if (!h) return fail(XARM_E_INVALID, "xarm_get_obs: null handle");
+  if (!h->bound) return fail(XARM_E_STATE, "xarm_get_obs: call xarm_bind first");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  h->ops.obs(h->k, (cudaStream_t)stream);
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_episode_stats(XarmHandle* h, double out[5], void* stream) {
+  if (!h || !out) return fail(XARM_E_INVALID, "xarm_episode_stats: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(out, h->k.stats, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemsetAsync(h->k.stats, 0, sizeof(double) * 5, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return XARM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1083 @@
+// xarm_sim.cuh - per-env device code of the batched gym-xarm step.  One thread owns one env; all per-env
+// quantities live in registers / thread-local memory, the SoA state slab in HBM is touched once per kernel.
+//
+// What it replaces: N9 IK (arm_ik), N3 multibody dynamics (arm_dynamics: world-frame RNEA + CRBA +
+// Cholesky, mathematically the ABA Bullet runs), N4-N6 motor/limit/gear rows, N7 box-box contacts (box_box),
+// N8 the sequential-impulse PGS (solve), N10/N11 getters/setters (obs assembly, reset).
+#pragma once
+#include "xarm_tasks.cuh"
+
+#define NOINL __device__ __noinline__
+
+// ------------------------------------------------------------------------------------------------ state
+template <class MD>
+struct ArmState {
+  float q[MD::N], qd[MD::N], qt[MD::N];
+};
+struct ObjState {
+  V3 pos;
+  Q4 quat;
+  V3 v, w;
+};
+template <class T>
+struct Env {
+  ArmState<typename T::MD> arm[T::NARM];
+  ObjState obj[T::NOBJ > 0 ? T::NOBJ : 1];
+  float door_q, door_qd;
+  float goal[T::G];
+  int step_count;
+  uint32_t episode;
+  float d_old;
+  int grasp[2];
+};
+
+// SoA slab: word w of env e lives at state[w * n + e] (coalesced when consecutive threads own consecutive envs)
+template <class T>
+XD void env_load(Env<T>& e, const float* __restrict__ s, int64_t n, int64_t i) {
+  using MD = typename T::MD;
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++) {
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) e.arm[a].q[k] = s[(w++) * n + i];
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) e.arm[a].qd[k] = s[(w++) * n + i];
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) e.arm[a].qt[k] = s[(w++) * n + i];
+  }
+#pragma unroll
+  for (int o = 0; o < T::NOBJ; o++) {
+    ObjState& b = e.obj[o];
+    b.pos.x = s[(w++) * n + i]; b.pos.y = s[(w++) * n + i]; b.pos.z = s[(w++) * n + i];
+    b.quat.x = s[(w++) * n + i]; b.quat.y = s[(w++) * n + i]; b.quat.z = s[(w++) * n + i]; b.quat.w = s[(w++) * n + i];
+    b.v.x = s[(w++) * n + i]; b.v.y = s[(w++) * n + i]; b.v.z = s[(w++) * n + i];
+    b.w.x = s[(w++) * n + i]; b.w.y = s[(w++) * n + i]; b.w.z = s[(w++) * n + i];
+  }
+  if (T::HAS_DOOR) { e.door_q = s[(w++) * n + i]; e.door_qd = s[(w++) * n + i]; } else { e.door_q = 0; e.door_qd = 0; }
+#pragma unroll
+  for (int k = 0; k < T::G; k++) e.goal[k] = s[(w++) * n + i];
+  e.step_count = (int)s[(w++) * n + i];
+  e.episode = (uint32_t)s[(w++) * n + i];
+  e.d_old = s[(w++) * n + i];
+  e.grasp[0] = s[(w++) * n + i] != 0.f;
+  e.grasp[1] = s[(w++) * n + i] != 0.f;
+}
+template <class T>
+XD void env_store(const Env<T>& e, float* __restrict__ s, int64_t n, int64_t i) {
+  using MD = typename T::MD;
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++) {
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) s[(w++) * n + i] = e.arm[a].q[k];
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) s[(w++) * n + i] = e.arm[a].qd[k];
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) s[(w++) * n + i] = e.arm[a].qt[k];
+  }
+#pragma unroll
+  for (int o = 0; o < T::NOBJ; o++) {
+    const ObjState& b = e.obj[o];
+    s[(w++) * n + i] = b.pos.x; s[(w++) * n + i] = b.pos.y; s[(w++) * n + i] = b.pos.z;
+    s[(w++) * n + i] = b.quat.x; s[(w++) * n + i] = b.quat.y; s[(w++) * n + i] = b.quat.z; s[(w++) * n + i] = b.quat.w;
+    s[(w++) * n + i] = b.v.x; s[(w++) * n + i] = b.v.y; s[(w++) * n + i] = b.v.z;
+    s[(w++) * n + i] = b.w.x; s[(w++) * n + i] = b.w.y; s[(w++) * n + i] = b.w.z;
+  }
+  if (T::HAS_DOOR) { s[(w++) * n + i] = e.door_q; s[(w++) * n + i] = e.door_qd; }
+#pragma unroll
+  for (int k = 0; k < T::G; k++) s[(w++) * n + i] = e.goal[k];
+  s[(w++) * n + i] = (float)e.step_count;
+  s[(w++) * n + i] = (float)e.episode;
+  s[(w++) * n + i] = e.d_old;
+  s[(w++) * n + i] = e.grasp[0] ? 1.f : 0.f;
+  s[(w++) * n + i] = e.grasp[1] ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ RNG (Appendix E)
+XD void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(XARM_PHILOX_M0, c[0]), lo0 = XARM_PHILOX_M0 * c[0];
+    uint32_t hi1 = __umulhi(XARM_PHILOX_M1, c[2]), lo1 = XARM_PHILOX_M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += XARM_PHILOX_W0; k1 += XARM_PHILOX_W1;
+  }
+}
+struct Rng {
+  uint64_t seed, genv;
+  uint32_t episode, draw;
+  XD double uniform() {
+    uint32_t k = draw++;
+    uint32_t c[4] = {(uint32_t)genv, (uint32_t)(genv >> 32), episode, k >> 2};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t x = (k & 3) == 0 ? c[0] : ((k & 3) == 1 ? c[1] : ((k & 3) == 2 ? c[2] : c[3]));
+    return (double)x * (1.0 / 4294967296.0);
+  }
+  // gym Box.sample(): float64 arithmetic on float32-rounded bounds, then cast to float32
+  XD float box(float lo, float hi) {
+    double u = uniform();
+    return (float)((double)lo + ((double)hi - (double)lo) * u);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ kinematics / dynamics
+template <class MD>
+struct ArmDyn {
+  SV S[MD::N];                          // joint motion subspaces (world, about the origin)
+  float Minv[MD::N * (MD::N + 1) / 2];  // packed symmetric inverse joint-space inertia
+  float qdu[MD::N];                     // velocities after the unconstrained update, then the solved velocities
+  M3 Rh;                                // link7 frame (eef / hand; the Panda fingers share its orientation)
+  V3 ph, pf1, pf2;                      // origins of the link7 and finger frames
+};
+
+template <class T>
+XD void arm_base(int a, M3& R, V3& p) {
+  R = m3_identity();
+  if (T::NARM == 2 && a == 1) { R.m[0] = -1.f; R.m[4] = -1.f; }  // yaw pi [REF xarm_handover.py:53]
+  p = v3(T::base_x(a), 0.f, 0.f);
+}
+
+// FK of the first 7 joints only: eef frame, joint origins and axes (for IK and _set_action)
+template <class T>
+XD void arm_fk7(int a, const float* q, M3& Re, V3& pe, V3* org, V3* axs) {
+  using MD = typename T::MD;
+  M3 R; V3 p;
+  arm_base<T>(a, R, p);
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    const float* r0 = MD::R0(i);
+    M3 R0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) R0.m[k] = r0[k];
+    p = p + R * MD::t0(i);
+    R = R * R0;
+    axs[i] = R * MD::axis(i);
+    org[i] = p;
+    R = R * m3_axis_angle(MD::axis(i), q[i]);
+  }
+  Re = R; pe = p;
+}
+
+// calculateInverseKinematics (N9): n_ik damped-least-squares iterations on the 7 arm joints
+template <class T>
+NOINL void arm_ik(int a, const float* q_in, V3 target, float* q_out) {
+  float q[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) q[i] = q_in[i];
+  for (int it = 0; it < T::NIK; it++) {
+    M3 Re; V3 pe, org[7], axs[7];
+    arm_fk7<T>(a, q, Re, pe, org, axs);
+    float e[6];
+    e[0] = target.x - pe.x; e[1] = target.y - pe.y; e[2] = target.z - pe.z;
+    Q4 qc = m3_to_quat(Re);
+    Q4 qT = {1.f, 0.f, 0.f, 0.f}, qci = {-qc.x, -qc.y, -qc.z, qc.w};
+    Q4 dq = quat_mul(qT, qci);
+    // rotation vector of dq: Bullet takes angle = 2 acos(w) and axis = xyz / sqrt(1 - w^2); for a unit quaternion
+    // that is 2 atan2(|xyz|, w) * xyz / |xyz|, which stays accurate in float32 when the error is small
+    float vn = sqrtf(dq.x * dq.x + dq.y * dq.y + dq.z * dq.z);
+    float angle = 2.f * atan2f(vn, dq.w);
+    if (angle > 3.14159265358979f) angle -= 6.28318530717959f;
+    float an = vn > 1e-30f ? angle / vn : 0.f;
+    e[3] = an * dq.x; e[4] = an * dq.y; e[5] = an * dq.z;
+    float J[6][7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      V3 lin = cross(axs[j], pe - org[j]);
+      J[0][j] = lin.x; J[1][j] = lin.y; J[2][j] = lin.z; J[3][j] = axs[j].x; J[4][j] = axs[j].y; J[5][j] = axs[j].z;
+    }
+    // A = J^T J + 0.5 I (packed lower), b = J^T e; Cholesky solve (A is SPD)
+    float A[28], b[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+#pragma unroll
+      for (int j = 0; j <= i; j++) {
+        float s = (i == j) ? (float)XARM_IK_DAMPING : 0.f;
+#pragma unroll
+        for (int r = 0; r < 6; r++) s += J[r][i] * J[r][j];
+        A[tri(i, j)] = s;
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < 6; r++) s += J[r][i] * e[r];
+      b[i] = s;
+    }
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      float s = A[tri(j, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= A[tri(j, k)] * A[tri(j, k)];
+      float d = sqrtf(s), di = 1.f / d;
+      A[tri(j, j)] = di;  // store the reciprocal of the diagonal
+#pragma unroll
+      for (int i = j + 1; i < 7; i++) {
+        float t = A[tri(i, j)];
+#pragma unroll
+        for (int k = 0; k < j; k++) t -= A[tri(i, k)] * A[tri(j, k)];
+        A[tri(i, j)] = t * di;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      float s = b[i];
+#pragma unroll
+      for (int k = 0; k < i; k++) s -= A[tri(i, k)] * b[k];
+      b[i] = s * A[tri(i, i)];
+    }
+#pragma unroll
+    for (int i = 6; i >= 0; i--) {
+      float s = b[i];
+#pragma unroll
+      for (int k = i + 1; k < 7; k++) s -= A[tri(k, i)] * b[k];
+      b[i] = s * A[tri(i, i)];
+    }
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) mx = fmaxf(mx, fabsf(b[i]));
+    float sc = mx > (float)XARM_IK_MAX_STEP ? (float)XARM_IK_MAX_STEP / mx : 1.f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) q[i] += sc * b[i];
+    arm_fk7<T>(a, q, Re, pe, org, axs);
+    if (norm(target - pe) < (float)XARM_IK_RESIDUAL) break;
+  }
+#pragma unroll
+  for (int i = 0; i < 7; i++) q_out[i] = q[i];
+}
+
+// Full-arm pass: FK, spatial velocities, bias forces (world-frame RNEA), joint-space inertia (CRBA), its inverse
+// (Cholesky) and the unconstrained velocity update qdu = qd + h * Minv (tau - bias).  Equivalent to the ABA +
+// calcAccelerationDeltas pair Bullet runs per substep (N3); with_bias=false skips the velocity update.
+template <class T>
+NOINL void arm_dynamics(int a, const ArmState<typename T::MD>& st, bool apply_damping, ArmDyn<typename T::MD>& D) {
+  using MD = typename T::MD;
+  constexpr int N = MD::N;
+  const float h = (float)T::H;
+  M3 R[N]; V3 p[N];
+  SV v[N], f[N];
+  SI I[N];
+  M3 Rb; V3 pb;
+  arm_base<T>(a, Rb, pb);
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const int pi = MD::parent(i);
+    M3 Rp = pi < 0 ? Rb : R[pi < 0 ? 0 : pi];
+    V3 pp = pi < 0 ? pb : p[pi < 0 ? 0 : pi];
+    const float* r0 = MD::R0(i);
+    M3 R0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) R0.m[k] = r0[k];
+    M3 Rj = Rp * R0;
+    V3 tj = pp + Rp * MD::t0(i);
+    V3 ax = Rj * MD::axis(i);
+    if (!MD::prismatic(i)) {
+      R[i] = Rj * m3_axis_angle(MD::axis(i), st.q[i]);
+      p[i] = tj;
+      D.S[i].a = ax; D.S[i].l = cross(tj, ax);
+    } else {
+      R[i] = Rj;
+      p[i] = tj + st.q[i] * ax;
+      D.S[i].a = v3(0, 0, 0); D.S[i].l = ax;
+    }
+    SV vj = st.qd[i] * D.S[i];
+    SV vp = pi < 0 ? sv_zero() : v[pi < 0 ? 0 : pi];
+    v[i] = vp + vj;
+    // bias acceleration a_i = a_parent + v_i x vj is accumulated into f[] below through the parent chain
+    SV ai = motion_cross(v[i], vj);
+    if (pi >= 0) ai += f[pi < 0 ? 0 : pi];  // f[] temporarily holds the bias acceleration of each link
+    f[i] = ai;
+    V3 cw = p[i] + R[i] * MD::com(i);
+    I[i] = si_make(MD::mass(i), cw, rotate_sym(R[i], MD::inertia(i)));
+  }
+  D.Rh = R[MD::EEF]; D.ph = p[MD::EEF];
+  if (MD::HAS_BOXES) { D.pf1 = p[MD::F1]; D.pf2 = p[MD::F2 < 0 ? 0 : MD::F2]; }
+  // link forces: f_i = I a + v x* I v - gyro - external (gravity + Bullet's velocity damping per URDF link)
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    SV Iv = I[i] * v[i];
+    SV fi = I[i] * f[i] + force_cross(v[i], Iv);
+    V3 w = v[i].a;
+    S3 Gw = rotate_sym(R[i], MD::central(i));
+    V3 Gww = Gw * w;
+    if (!XARM_MB_USE_GYRO) fi.a -= cross(w, Gww);
+    float ka = (float)XARM_MB_ANGULAR_DAMPING * (1.f + norm(w));
+    fi.a += ka * Gww;  // minus the external damping torque -(G w) ka
+#pragma unroll
+    for (int pt = 0; pt < MD::NPART; pt++) {
+      if (MD::part_owner(pt) != i) continue;
+      V3 c = p[i] + R[i] * MD::part_com(pt);
+      V3 vc = v[i].l + cross(w, c);
+      float m = MD::part_mass(pt);
+      float kl = (float)XARM_MB_LINEAR_DAMPING * (1.f + norm(vc));
+      V3 F = (-m * kl) * vc;
+      F.z -= m * (float)XARM_GRAVITY;
+      fi.a -= cross(c, F);
+      fi.l -= F;
+    }
+    f[i] = fi;
+  }
+  // backward: bias torques, composite inertias, joint-space inertia matrix
+  float M[N * (N + 1) / 2], rhs[N];
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    const int pi = MD::parent(i);
+    float tau = apply_damping ? -MD::damping(i) * st.qd[i] : 0.f;
+    rhs[i] = tau - dot(D.S[i], f[i]);
+    SV F = I[i] * D.S[i];
+#pragma unroll
+    for (int j = 0; j <= i; j++) M[tri(i, j)] = is_anc<MD>(j, i) ? dot(D.S[j], F) : 0.f;
+    if (pi >= 0) { f[pi < 0 ? 0 : pi] += f[i]; I[pi < 0 ? 0 : pi] = I[pi < 0 ? 0 : pi] + I[i]; }
+  }
+  // Cholesky M = L L^T (in place, reciprocal diagonal), Linv, Minv = Linv^T Linv
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    float s = M[tri(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) s -= M[tri(j, k)] * M[tri(j, k)];
+    float di = rsqrtf(s);
+    di = di * (1.5f - 0.5f * s * di * di);  // one Newton step: full float accuracy
+    M[tri(j, j)] = di;
+#pragma unroll
+    for (int i = j + 1; i < N; i++) {
+      float t = M[tri(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= M[tri(i, k)] * M[tri(j, k)];
+      M[tri(i, j)] = t * di;
+    }
+  }
+  // Linv (lower) overwrites M column by column: Linv[j][j] = 1/L[j][j]; Linv[i][j] = -sum_{k=j}^{i-1} L[i][k] Linv[k][j] / L[i][i]
+  float Li[N * (N + 1) / 2];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    Li[tri(j, j)] = M[tri(j, j)];
+#pragma unroll
+    for (int i = j + 1; i < N; i++) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = j; k < i; k++) s += M[tri(i, k)] * Li[tri(k, j)];
+      Li[tri(i, j)] = -s * M[tri(i, i)];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = i; k < N; k++) s += Li[tri(k, i)] * Li[tri(k, j)];
+      D.Minv[tri(i, j)] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; j++) s += D.Minv[tri(i, j)] * rhs[j];
+    D.qdu[i] = st.qd[i] + h * s;
+  }
+}
+
+// hand (PyBullet link 9) COM position and linear velocity: getLinkState(arm, 9, computeLinkVelocity=1) (N10)
+template <class T>
+NOINL void hand_state(int a, const ArmState<typename T::MD>& st, V3& pos, V3& vel) {
+  using MD = typename T::MD;
+  M3 Re; V3 pe, org[7], axs[7];
+  arm_fk7<T>(a, st.q, Re, pe, org, axs);
+  pos = pe + Re * MD::hand_com();
+  V3 vv = v3(0, 0, 0);
+#pragma unroll
+  for (int j = 0; j < 7; j++) vv += st.qd[j] * cross(axs[j], pos - org[j]);
+  vel = vv;
+}
+
+// ------------------------------------------------------------------------------------------------ collision (N7)
+struct Box {
+  V3 c;
+  M3 R;  // columns = box axes
+  V3 h;
+};
+struct CPoint {
+  V3 pa, pb, n;
+  float depth;
+};
+
+XD int clip_poly(const float (*in)[2], int n, int axis, float sign, float lim, float (*out)[2]) {
+  int m = 0;
+  for (int i = 0; i < n; i++) {
+    const float* a = in[i];
+    const float* b = in[(i + 1 == n) ? 0 : i + 1];
+    float da = sign * a[axis] - lim, db = sign * b[axis] - lim;
+    if (da <= 0.f) { out[m][0] = a[0]; out[m][1] = a[1]; m++; }
+    if ((da < 0.f && db > 0.f) || (da > 0.f && db < 0.f)) {
+      float s = da / (da - db);
+      out[m][0] = a[0] + s * (b[0] - a[0]); out[m][1] = a[1] + s * (b[1] - a[1]); m++;
+    }
+    if (m >= 8) break;
+  }
+  return m;
+}
+
+// 15-axis SAT + reference-face clipping / edge-edge closest points; normal points from B to A.
+NOINL int box_box(const Box& A, const Box& B, CPoint* out, int max_out) {
+  V3 Aa[3], Ba[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { Aa[i] = col(A.R, i); Ba[i] = col(B.R, i); }
+  V3 Tv = B.c - A.c;
+  float Rm[3][3], Q[3][3], Ta[3];
+  float ah[3] = {A.h.x, A.h.y, A.h.z}, bh[3] = {B.h.x, B.h.y, B.h.z};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Ta[i] = dot(Tv, Aa[i]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { Rm[i][j] = dot(Aa[i], Ba[j]); Q[i][j] = fabsf(Rm[i][j]); }
+  }
+  const float margin = (float)XARM_CONTACT_MARGIN;
+  float best = -1e30f, nsign = 1.f;
+  int code = -1;
+  V3 naxis = v3(0, 0, 0);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float s = fabsf(Ta[i]) - (ah[i] + bh[0] * Q[i][0] + bh[1] * Q[i][1] + bh[2] * Q[i][2]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = i; nsign = Ta[i] < 0.f ? -1.f : 1.f; naxis = Aa[i]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float tb = dot(Tv, Ba[j]);
+    float s = fabsf(tb) - (bh[j] + ah[0] * Q[0][j] + ah[1] * Q[1][j] + ah[2] * Q[2][j]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = 3 + j; nsign = tb < 0.f ? -1.f : 1.f; naxis = Ba[j]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      V3 ax = cross(Aa[i], Ba[j]);
+      float l = norm(ax);
+      if (l < 1e-6f) continue;
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      float tp = dot(Tv, ax);
+      float ra = ah[i1] * Q[i2][j] + ah[i2] * Q[i1][j];
+      float rb = bh[j1] * Q[i][j2] + bh[j2] * Q[i][j1];
+      float s = (fabsf(tp) - (ra + rb)) / l;
+      if (s > margin) return 0;
+      if (s * 1.05f > best) { best = s; code = 6 + 3 * i + j; nsign = tp < 0.f ? -1.f : 1.f; naxis = (1.f / l) * ax; }
+    }
+  if (code < 0 || max_out < 1) return 0;
+  V3 nAB = nsign * naxis;
+  float depth = -best;
+  if (code >= 6) {
+    int i = (code - 6) / 3, j = (code - 6) % 3;
+    V3 pa = A.c, pb = B.c;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (k != i) pa += ((dot(nAB, Aa[k]) > 0.f ? 1.f : -1.f) * ah[k]) * Aa[k];
+      if (k != j) pb += ((dot(nAB, Ba[k]) > 0.f ? -1.f : 1.f) * bh[k]) * Ba[k];
+    }
+    V3 ua = i == 0 ? Aa[0] : (i == 1 ? Aa[1] : Aa[2]);
+    V3 ub = j == 0 ? Ba[0] : (j == 1 ? Ba[1] : Ba[2]);
+    V3 d = pb - pa;
+    float uaub = dot(ua, ub), q1 = dot(ua, d), q2 = -dot(ub, d), den = 1.f - uaub * uaub;
+    float sa = 0.f, sb = 0.f;
+    if (den > 1e-4f) { sa = (q1 + uaub * q2) / den; sb = (uaub * q1 + q2) / den; }
+    out[0].pa = pa + sa * ua; out[0].pb = pb + sb * ub; out[0].n = -nAB; out[0].depth = depth;
+    return 1;
+  }
+  const bool refA = code < 3;
+  const Box& Rf = refA ? A : B;
+  const Box& In = refA ? B : A;
+  const int ra = refA ? code : code - 3;
+  V3 nref = refA ? nAB : -nAB;
+  V3 Ra[3], Ia[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { Ra[i] = col(Rf.R, i); Ia[i] = col(In.R, i); }
+  float rh[3] = {Rf.h.x, Rf.h.y, Rf.h.z}, ih[3] = {In.h.x, In.h.y, In.h.z};
+  int ia = 0; float bd = -1.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { float d = fabsf(dot(nref, Ia[i])); if (d > bd) { bd = d; ia = i; } }
+  V3 Iax = ia == 0 ? Ia[0] : (ia == 1 ? Ia[1] : Ia[2]);
+  float isg = dot(nref, Iax) > 0.f ? -1.f : 1.f;
+  const int i1 = (ia + 1) % 3, i2 = (ia + 2) % 3, r1 = (ra + 1) % 3, r2 = (ra + 2) % 3;
+  V3 I1 = i1 == 0 ? Ia[0] : (i1 == 1 ? Ia[1] : Ia[2]), I2 = i2 == 0 ? Ia[0] : (i2 == 1 ? Ia[1] : Ia[2]);
+  V3 R1 = r1 == 0 ? Ra[0] : (r1 == 1 ? Ra[1] : Ra[2]), R2 = r2 == 0 ? Ra[0] : (r2 == 1 ? Ra[1] : Ra[2]);
+  float h1 = ih[i1], h2 = ih[i2], hr1 = rh[r1], hr2 = rh[r2], hra = rh[ra];
+  V3 fc = In.c + (isg * ih[ia]) * Iax;
+  float poly[8][2], tmp[8][2];
+  const float sg[4][2] = {{1, 1}, {-1, 1}, {-1, -1}, {1, -1}};
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    V3 vtx = fc + (sg[c][0] * h1) * I1 + (sg[c][1] * h2) * I2;
+    V3 d = vtx - Rf.c;
+    poly[c][0] = dot(d, R1); poly[c][1] = dot(d, R2);
+  }
+  int n = 4;
+  n = clip_poly(poly, n, 0, 1.f, hr1, tmp); if (!n) return 0;
+  n = clip_poly(tmp, n, 0, -1.f, hr1, poly); if (!n) return 0;
+  n = clip_poly(poly, n, 1, 1.f, hr2, tmp); if (!n) return 0;
+  n = clip_poly(tmp, n, 1, -1.f, hr2, poly); if (!n) return 0;
+  V3 inorm = isg * Iax;
+  float denom = dot(inorm, nref);
+  CPoint cand[8]; int nc = 0;
+  for (int c = 0; c < n; c++) {
+    V3 base = Rf.c + poly[c][0] * R1 + poly[c][1] * R2;
+    float z = fabsf(denom) > 1e-9f ? dot(fc - base, inorm) / denom : 0.f;
+    V3 pin = base + z * nref;
+    float dep = hra - z;
+    if (dep < -margin) continue;
+    CPoint k;
+    k.depth = dep;
+    if (refA) { k.pb = pin; k.pa = pin + dep * nref; k.n = -nref; }
+    else { k.pa = pin; k.pb = pin + dep * nref; k.n = nref; }
+    cand[nc++] = k;
+  }
+  if (nc > 4) {
+    int keep[4]; int i0 = 0;
+    for (int c = 1; c < nc; c++) if (cand[c].depth > cand[i0].depth) i0 = c;
+    keep[0] = i0;
+    int ib = -1; float bdist = -1.f;
+    for (int c = 0; c < nc; c++) { V3 d = cand[c].pb - cand[i0].pb; float l = dot(d, d); if (c != i0 && l > bdist) { bdist = l; ib = c; } }
+    keep[1] = ib;
+    V3 e1 = cand[ib].pb - cand[i0].pb;
+    int imax = -1, imin = -1; float amax = 0.f, amin = 0.f;
+    for (int c = 0; c < nc; c++) {
+      if (c == i0 || c == ib) continue;
+      float ar = dot(cross(e1, cand[c].pb - cand[i0].pb), nref);
+      if (imax < 0 || ar > amax) { amax = ar; imax = c; }
+      if (imin < 0 || ar < amin) { amin = ar; imin = c; }
+    }
+    keep[2] = imax; keep[3] = imin;
+    CPoint red[4]; int nr = 0;
+    for (int c = 0; c < 4; c++) {
+      bool dup = keep[c] < 0;
+      for (int d = 0; d < c && !dup; d++) if (keep[d] == keep[c]) dup = true;
+      if (!dup) red[nr++] = cand[keep[c]];
+    }
+    for (int c = 0; c < nr; c++) cand[c] = red[c];
+    nc = nr;
+  }
+  if (nc > max_out) nc = max_out;
+  for (int c = 0; c < nc; c++) out[c] = cand[c];
+  return nc;
+}
+
+// ------------------------------------------------------------------------------------------------ substep
+XD void plane_space(V3 n, V3& p, V3& q) {  // btPlaneSpace1
+  if (fabsf(n.z) > 0.7071067811865475244f) {
+    float a = n.y * n.y + n.z * n.z, k = rsqrtf(a);
+    p = v3(0.f, -n.z * k, n.y * k);
+    q = v3(a * k, -n.x * p.z, n.x * p.y);
+  } else {
+    float a = n.x * n.x + n.y * n.y, k = rsqrtf(a);
+    p = v3(-n.y * k, n.x * k, 0.f);
+    q = v3(-n.z * p.y, n.z * p.x, a * k);
+  }
+}
+
+template <class T>
+struct Solver {
+  using MD = typename T::MD;
+  static constexpr int N = MD::N, NA = T::NARM, NO = T::NOBJ > 0 ? T::NOBJ : 1;
+  // contacts
+  int nc, nac;
+  uint8_t ba[XARM_MAXC], bb[XARM_MAXC];
+  int8_t slot[XARM_MAXC];  // arm-side row pool slot (-1: no arm side)
+  V3 dir[XARM_MAXC][3];    // n, t1, t2
+  V3 pa[XARM_MAXC], pb[XARM_MAXC];
+  float depth[XARM_MAXC], mu[XARM_MAXC], erp[XARM_MAXC], cfm0[XARM_MAXC];
+  float rhs[XARM_MAXC][3], dinv[XARM_MAXC][3], app[XARM_MAXC][3], cfmr[XARM_MAXC];
+  float Jarm[XARM_MAXAC][3][N], dVarm[XARM_MAXAC][3][N];
+  // per-arm unit rows
+  float mot_rhs[NA][N], mot_app[NA][N], mot_hi[NA][N];
+  float lim_rhs[NA][N], lim_app[NA][N];
+  uint32_t lim_lo_mask[NA], lim_hi_mask[NA];
+  float gear_rhs[NA], gear_app[NA], gear_dinv[NA], gear_hi;
+  // door rows
+  float door_lim_rhs, door_lim_app, door_lim_sign, door_mot_rhs, door_mot_app;
+  bool door_lim;
+  // accumulated velocity changes
+  float dqd[NA][N];
+  V3 dv[NO], dw[NO];
+  float ddoor;
+  // per object
+  S3 Iinv[NO];
+};
+
+XD V3 door_axis() { const float a[3] = XARM_DOOR_AXIS; return v3(a[0], a[1], a[2]); }
+
+template <class T>
+XD Box arm_box(const ArmDyn<typename T::MD>& D, int which) {  // 0 hand, 1 finger1, 2 finger2
+  Box b;
+  b.R = D.Rh;
+  if (which == 0) { b.c = D.ph + D.Rh * v3(c_pd_hc[0], c_pd_hc[1], c_pd_hc[2]); b.h = v3(c_pd_hh[0], c_pd_hh[1], c_pd_hh[2]); }
+  else if (which == 1) { b.c = D.pf1 + D.Rh * v3(c_pd_f1c[0], c_pd_f1c[1], c_pd_f1c[2]); b.h = v3(c_pd_f1h[0], c_pd_f1h[1], c_pd_f1h[2]); }
+  else { b.c = D.pf2 + D.Rh * v3(c_pd_f2c[0], c_pd_f2c[1], c_pd_f2c[2]); b.h = v3(c_pd_f2h[0], c_pd_f2h[1], c_pd_f2h[2]); }
+  return b;
+}
+
+// collide one pair and append its points (normal from B to A); returns the number of points added
+template <class T>
+XD int add_pair(Solver<T>& S, const Box& A, const Box& B, int ca, int cb, float fa, float fb, bool soft, float erp_override) {
+  V3 d = A.c - B.c;
+  float ra = norm(A.h), rb = norm(B.h), rr = ra + rb + (float)XARM_CONTACT_MARGIN;
+  if (dot(d, d) > rr * rr) return 0;
+  int room = XARM_MAXC - S.nc;
+  const bool with_arm = bc_is_arm(ca) || bc_is_arm(cb);
+  if (with_arm && XARM_MAXAC - S.nac < room) room = XARM_MAXAC - S.nac;
+  if (room <= 0) return 0;
+  CPoint pts[4];
+  int k = box_box(A, B, pts, room < 4 ? room : 4);
+  float mu = fminf(fa * fb, (float)XARM_MAX_FRICTION);
+  float erp = (float)XARM_ERP2, cfm = 0.f;
+  if (erp_override >= 0.f) erp = erp_override;
+  if (soft) {
+    const float h = (float)T::H, ks = (float)XARM_FINGER_STIFFNESS, kd = (float)XARM_FINGER_DAMPING;
+    cfm = 1.f / (h * ks + kd); erp = h * ks / (h * ks + kd); cfm /= h;
+  }
+  for (int i = 0; i < k; i++) {
+    int c = S.nc++;
+    S.ba[c] = (uint8_t)ca; S.bb[c] = (uint8_t)cb;
+    S.pa[c] = pts[i].pa; S.pb[c] = pts[i].pb; S.dir[c][0] = pts[i].n; S.depth[c] = pts[i].depth;
+    S.mu[c] = mu; S.erp[c] = erp; S.cfm0[c] = cfm;
+    S.slot[c] = with_arm ? (int8_t)(S.nac++) : (int8_t)-1;
+  }
+  return k;
+}
+
+// one side of one contact row: fills the arm-side Jacobian / response if the body is an arm link, returns the
+// side's contribution to the row denominator and accumulates the side's relative velocity.
+template <class T>
+XD float row_side(Solver<T>& S, const Env<T>& e, const ArmDyn<typename T::MD>* D, int code, int c, int k, V3 p, V3 d,
+                  float sign, float door_qdu, float& relvel) {
+  using MD = typename T::MD;
+  constexpr int N = MD::N;
+  if (code == BC_STATIC) return 0.f;
+  if (bc_is_arm(code)) {
+    const int a = T::NARM == 1 ? 0 : bc_arm(code);
+    const int which = (code - BC_ARM0_HAND) % 3;  // 0 hand, 1 finger1, 2 finger2
+    const int sl = S.slot[c];
+    const ArmDyn<MD>& Da = D[a];
+    V3 pxd = cross(p, d);
+    float J[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      bool on = j < 7 || (which == 1 && j == MD::F1) || (which == 2 && j == MD::F2);
+      J[j] = on ? sign * (dot(Da.S[j].a, pxd) + dot(Da.S[j].l, d)) : 0.f;
+    }
+    float den = 0.f, rv = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < N; j++) s += Da.Minv[tri(i, j)] * J[j];
+      S.Jarm[sl][k][i] = J[i];
+      S.dVarm[sl][k][i] = s;
+      den += J[i] * s;
+      rv += J[i] * Da.qdu[i];
+    }
+    relvel += rv;
+    return den;
+  }
+  if (bc_is_obj(code)) {
+    const int o = T::NOBJ <= 1 ? 0 : code - BC_OBJ0;
+    V3 r = p - e.obj[o].pos;
+    V3 rxd = cross(r, d);
+    relvel += sign * (dot(d, S.dv[o]) + dot(rxd, S.dw[o]));  // dv/dw hold the unconstrained velocities during setup
+    return 1.f / T::OBJ_MASS + dot(rxd, S.Iinv[o] * rxd);
+  }
+  // door
+  float jd = dot(door_axis(), d);
+  relvel += sign * jd * door_qdu;
+  return jd * jd / (float)XARM_DOOR_MASS;
+}
+
+// J . dqd of one side (sign folded in) during the PGS sweeps
+template <class T>
+XD float side_jv(const Solver<T>& S, int code, int c, int k, V3 r, V3 d, float sign) {
+  constexpr int N = T::MD::N;
+  if (code == BC_STATIC) return 0.f;
+  if (bc_is_arm(code)) {
+    const int sl = S.slot[c];
+    float s = 0.f;
+    if (T::NARM == 1 || bc_arm(code) == 0) {
+#pragma unroll
+      for (int i = 0; i < N; i++) s += S.Jarm[sl][k][i] * S.dqd[0][i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i++) s += S.Jarm[sl][k][i] * S.dqd[T::NARM - 1][i];
+    }
+    return s;
+  }
+  if (bc_is_obj(code)) {
+    const int o = T::NOBJ <= 1 ? 0 : code - BC_OBJ0;
+    return sign * dot(d, S.dv[o] + cross(S.dw[o], r));
+  }
+  return sign * dot(door_axis(), d) * S.ddoor;
+}
+template <class T>
+XD void side_apply(Solver<T>& S, int code, int c, int k, V3 r, V3 d, float sign, float delta) {
+  constexpr int N = T::MD::N;
+  if (code == BC_STATIC) return;
+  if (bc_is_arm(code)) {
+    const int sl = S.slot[c];
+    if (T::NARM == 1 || bc_arm(code) == 0) {
+#pragma unroll
+      for (int i = 0; i < N; i++) S.dqd[0][i] += S.dVarm[sl][k][i] * delta;
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i++) S.dqd[T::NARM - 1][i] += S.dVarm[sl][k][i] * delta;
+    }
+    return;
+  }
+  if (bc_is_obj(code)) {
+    const int o = T::NOBJ <= 1 ? 0 : code - BC_OBJ0;
+    float sd = sign * delta;
+    S.dv[o] += (sd / T::OBJ_MASS) * d;
+    S.dw[o] += sd * (S.Iinv[o] * cross(r, d));
+    return;
+  }
+  S.ddoor += sign * dot(door_axis(), d) * delta / (float)XARM_DOOR_MASS;
+}
+
+template <class T>
+XD void unit_row(Solver<T>& S, const ArmDyn<typename T::MD>& D, int a, int i, float sign, float rhs, float lo, float hi,
+                 float& applied, float& resid) {
+  constexpr int N = T::MD::N;
+  const float den = D.Minv[tri(i, i)];
+  float jv = sign * S.dqd[a][i];
+  float delta = rhs - jv / den;
+  float sum = applied + delta;
+  if (sum < lo) { delta = lo - applied; sum = lo; } else if (sum > hi) { delta = hi - applied; sum = hi; }
+  applied = sum;
+  float sd = sign * delta;
+#pragma unroll
+  for (int k = 0; k < N; k++) S.dqd[a][k] += D.Minv[tri(k, i)] * sd;
+  float rv = delta * den;
+  resid = fmaxf(resid, rv * rv);
+}
+
+template <class T>
+XD void arm_rows_sweep(Solver<T>& S, const ArmDyn<typename T::MD>& D, int a, bool forward, float& resid) {
+  using MD = typename T::MD;
+  constexpr int N = MD::N;
+  const float lim_hi = (float)XARM_LIMIT_MAX_IMPULSE;
+  if (forward) {
+    if (S.lim_lo_mask[a] | S.lim_hi_mask[a]) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (S.lim_lo_mask[a] >> i & 1) unit_row(S, D, a, i, 1.f, S.lim_rhs[a][i], 0.f, lim_hi, S.lim_app[a][i], resid);
+        if (S.lim_hi_mask[a] >> i & 1) unit_row(S, D, a, i, -1.f, S.lim_rhs[a][i], 0.f, lim_hi, S.lim_app[a][i], resid);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) unit_row(S, D, a, i, 1.f, S.mot_rhs[a][i], -S.mot_hi[a][i], S.mot_hi[a][i], S.mot_app[a][i], resid);
+  }
+  if (MD::HAS_GEAR) {
+    const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
+    const float gr = (float)XARM_GEAR_RATIO;
+    float jv = S.dqd[a][f1] + gr * S.dqd[a][f2];
+    float delta = S.gear_rhs[a] - jv * S.gear_dinv[a];
+    float sum = S.gear_app[a] + delta;
+    if (sum < -S.gear_hi) { delta = -S.gear_hi - S.gear_app[a]; sum = -S.gear_hi; }
+    else if (sum > S.gear_hi) { delta = S.gear_hi - S.gear_app[a]; sum = S.gear_hi; }
+    S.gear_app[a] = sum;
+#pragma unroll
+    for (int k = 0; k < N; k++) S.dqd[a][k] += (D.Minv[tri(k, f1)] + gr * D.Minv[tri(k, f2)]) * delta;
+    float rv = delta / S.gear_dinv[a];
+    resid = fmaxf(resid, rv * rv);
+  }
+  if (!forward) {
+#pragma unroll
+    for (int i = N - 1; i >= 0; i--) unit_row(S, D, a, i, 1.f, S.mot_rhs[a][i], -S.mot_hi[a][i], S.mot_hi[a][i], S.mot_app[a][i], resid);
+    if (S.lim_lo_mask[a] | S.lim_hi_mask[a]) {
+#pragma unroll
+      for (int i = N - 1; i >= 0; i--) {
+        if (S.lim_hi_mask[a] >> i & 1) unit_row(S, D, a, i, -1.f, S.lim_rhs[a][i], 0.f, lim_hi, S.lim_app[a][i], resid);
+        if (S.lim_lo_mask[a] >> i & 1) unit_row(S, D, a, i, 1.f, S.lim_rhs[a][i], 0.f, lim_hi, S.lim_app[a][i], resid);
+      }
+    }
+  }
+}
+
+template <class T>
+XD void door_rows_sweep(Solver<T>& S, bool forward, float& resid) {
+  const float den = 1.f / (float)XARM_DOOR_MASS;
+  for (int pass = 0; pass < 2; pass++) {
+    const bool do_lim = forward ? pass == 0 : pass == 1;
+    if (do_lim) {
+      if (!S.door_lim) continue;
+      float jv = S.door_lim_sign * S.ddoor;
+      float delta = S.door_lim_rhs - jv / den;
+      float sum = S.door_lim_app + delta;
+      if (sum < 0.f) { delta = -S.door_lim_app; sum = 0.f; } else if (sum > (float)XARM_LIMIT_MAX_IMPULSE) { delta = (float)XARM_LIMIT_MAX_IMPULSE - S.door_lim_app; sum = (float)XARM_LIMIT_MAX_IMPULSE; }
+      S.door_lim_app = sum;
+      S.ddoor += S.door_lim_sign * delta * den;
+      float rv = delta * den; resid = fmaxf(resid, rv * rv);
+    } else {
+      const float hi = (float)XARM_DEFAULT_MOTOR_MAX_IMPULSE;
+      float delta = S.door_mot_rhs - S.ddoor / den;
+      float sum = S.door_mot_app + delta;
+      if (sum < -hi) { delta = -hi - S.door_mot_app; sum = -hi; } else if (sum > hi) { delta = hi - S.door_mot_app; sum = hi; }
+      S.door_mot_app = sum;
+      S.ddoor += delta * den;
+      float rv = delta * den; resid = fmaxf(resid, rv * rv);
+    }
+  }
+}
+
+// One internal substep: collide -> unconstrained velocities -> rows -> PGS -> integrate.
+template <class T>
+NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
+  using MD = typename T::MD;
+  constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ;
+  const float h = (float)T::H;
+  ArmDyn<MD> D[NA];
+  Solver<T> S;
+#pragma unroll
+  for (int a = 0; a < NA; a++) arm_dynamics<T>(a, e.arm[a], apply_damping, D[a]);
+
+  // ---- 1. collision detection on the current poses (fixed pair order, Appendix G)
+  S.nc = 0; S.nac = 0;
+  if (NOBJ > 0) {
+    Box ob[NOBJ > 0 ? NOBJ : 1];
+    for (int o = 0; o < NOBJ; o++) {
+      ob[o].c = e.obj[o].pos; ob[o].R = quat_to_m3(e.obj[o].quat); ob[o].h = v3(T::OBJ_HX, T::OBJ_HY, T::OBJ_HZ);
+      // world inverse inertia of the box (inertia from its own shape: m/12 (ly^2+lz^2), ...)
+      const float lx = 2 * T::OBJ_HX, ly = 2 * T::OBJ_HY, lz = 2 * T::OBJ_HZ, m12 = T::OBJ_MASS / 12.f;
+      S3 Il = {1.f / (m12 * (ly * ly + lz * lz)), 0, 0, 1.f / (m12 * (lx * lx + lz * lz)), 0, 1.f / (m12 * (lx * lx + ly * ly))};
+      S.Iinv[o] = rotate_sym(ob[o].R, Il);
+    }
+    Box tb[T::NTABLE];
+    for (int k = 0; k < T::NTABLE; k++) {
+      tb[k].c = v3(T::table_x(k), 0.f, -(float)XARM_TABLE_HALF_Z); tb[k].R = m3_identity();
+      tb[k].h = v3((float)XARM_TABLE_HALF_X, (float)XARM_TABLE_HALF_Y, (float)XARM_TABLE_HALF_Z);
+    }
+    Box ground;
+    ground.c = v3(0.f, 0.f, (float)XARM_GROUND_Z - 5.f); ground.R = m3_identity(); ground.h = v3(100.f, 100.f, 5.f);
+    const float fo = (float)XARM_DEFAULT_FRICTION;
+    for (int o = 0; o < NOBJ; o++) {
+      for (int k = 0; k < T::NTABLE; k++) add_pair<T>(S, ob[o], tb[k], BC_OBJ0 + o, BC_STATIC, fo, (float)XARM_TABLE_FRICTION, false, -1.f);
+      if (T::HAS_GROUND) add_pair<T>(S, ob[o], ground, BC_OBJ0 + o, BC_STATIC, fo, 1.0f, false, -1.f);
+    }
+    for (int o = 0; o < NOBJ; o++)
+      for (int p2 = o + 1; p2 < NOBJ; p2++) add_pair<T>(S, ob[o], ob[p2], BC_OBJ0 + o, BC_OBJ0 + p2, fo, fo, false, -1.f);
+    int gcount[2][2][NOBJ > 0 ? NOBJ : 1];
+    if (MD::HAS_BOXES) {
+      for (int a = 0; a < NA; a++) {
+        const float ff = (T::FRICTION_SWITCH && e.grasp[a]) ? (float)XARM_FINGER_FRICTION_GRASP : (float)XARM_FINGER_FRICTION_FREE;
+        Box f1 = arm_box<T>(D[a], 1), f2 = arm_box<T>(D[a], 2), hd = arm_box<T>(D[a], 0);
+        const int c0 = a == 0 ? BC_ARM0_HAND : BC_ARM1_HAND;
+        for (int o = 0; o < NOBJ; o++) {
+          gcount[a][0][o] = add_pair<T>(S, f1, ob[o], c0 + 1, BC_OBJ0 + o, ff, fo, true, -1.f);
+          gcount[a][1][o] = add_pair<T>(S, f2, ob[o], c0 + 2, BC_OBJ0 + o, ff, fo, true, -1.f);
+          add_pair<T>(S, hd, ob[o], c0, BC_OBJ0 + o, fo, fo, false, -1.f);
+        }
+      }
+    }
+    if (T::HAS_DOOR) {
+      const float b1[3] = XARM_DOOR_FIXED_BAR1, b2[3] = XARM_DOOR_FIXED_BAR2, org[3] = XARM_DOOR_ORIGIN, bh[3] = XARM_DOOR_BAR_HALF;
+      Box bar[3];
+      for (int b = 0; b < 3; b++) { bar[b].R = m3_identity(); bar[b].h = v3(bh[0], bh[1], bh[2]); }
+      bar[0].c = v3(b1[0], b1[1], b1[2]); bar[1].c = v3(b2[0], b2[1], b2[2]);
+      bar[2].c = v3(org[0], org[1], org[2]) + e.door_q * door_axis();
+      const float fd = (float)XARM_DOOR_FRICTION;
+      for (int o = 0; o < NOBJ; o++)
+        for (int b = 0; b < 3; b++) add_pair<T>(S, ob[o], bar[b], BC_OBJ0 + o, b == 2 ? BC_DOOR : BC_STATIC, fo, fd, false, 0.f);
+      for (int a = 0; a < NA; a++) {
+        const float ff = (float)XARM_FINGER_FRICTION_FREE;
+        Box f1 = arm_box<T>(D[a], 1), f2 = arm_box<T>(D[a], 2), hd = arm_box<T>(D[a], 0);
+        const int c0 = a == 0 ? BC_ARM0_HAND : BC_ARM1_HAND;
+        for (int b = 0; b < 3; b++) {
+          const int cb = b == 2 ? BC_DOOR : BC_STATIC;
+          add_pair<T>(S, f1, bar[b], c0 + 1, cb, ff, fd, true, 0.f);
+          add_pair<T>(S, f2, bar[b], c0 + 2, cb, ff, fd, true, 0.f);
+          add_pair<T>(S, hd, bar[b], c0, cb, fo, fd, false, 0.f);
+        }
+      }
+    }
+    if (T::FINGER_TABLE) {
+      for (int a = 0; a < NA; a++) {
+        const float ff = (T::FRICTION_SWITCH && e.grasp[a]) ? (float)XARM_FINGER_FRICTION_GRASP : (float)XARM_FINGER_FRICTION_FREE;
+        Box f1 = arm_box<T>(D[a], 1), f2 = arm_box<T>(D[a], 2);
+        const int c0 = a == 0 ? BC_ARM0_HAND : BC_ARM1_HAND;
+        for (int k = 0; k < T::NTABLE; k++) {
+          add_pair<T>(S, f1, tb[k], c0 + 1, BC_STATIC, ff, (float)XARM_TABLE_FRICTION, true, -1.f);
+          add_pair<T>(S, f2, tb[k], c0 + 2, BC_STATIC, ff, (float)XARM_TABLE_FRICTION, true, -1.f);
+        }
+      }
+    }
+    if (last && MD::HAS_BOXES) {  // grasp flags from this (the last) collision pass
+      for (int a = 0; a < NA; a++) {
+        bool g = false;
+        for (int o = 0; o < NOBJ; o++) {
+          if (T::TASK == XARM_TASK_HANDOVER && o > 0) break;
+          g = g || (gcount[a][0][o] > 0 && gcount[a][1][o] > 0);
+        }
+        e.grasp[a] = g;
+      }
+    }
+  }
+
+  // ---- 2. unconstrained velocities of the free bodies (the arms' are in D[a].qdu)
+  float door_qdu = 0.f;
+  for (int o = 0; o < NOBJ; o++) {
+    const ObjState& b = e.obj[o];
+    float kl = (float)XARM_MB_LINEAR_DAMPING * (1.f + norm(b.v)), ka = (float)XARM_MB_ANGULAR_DAMPING * (1.f + norm(b.w));
+    S.dv[o] = b.v + h * ((-kl) * b.v); S.dv[o].z -= h * (float)XARM_GRAVITY;
+    S.dw[o] = b.w + h * ((-ka) * b.w);
+  }
+  if (T::HAS_DOOR) {
+    float v = e.door_qd;
+    float f = (apply_damping ? -(float)XARM_DOOR_DAMPING * v : 0.f) - (float)XARM_DOOR_MASS * v * (float)XARM_MB_LINEAR_DAMPING * (1.f + fabsf(v));
+    door_qdu = v + h * f / (float)XARM_DOOR_MASS;
+  }
+
+  // ---- 3. rows
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    const ArmState<MD>& st = e.arm[a];
+    S.lim_lo_mask[a] = 0; S.lim_hi_mask[a] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const float den = D[a].Minv[tri(i, i)];
+      float pen_lo = st.q[i] - MD::lo(i), pen_hi = MD::hi(i) - st.q[i];
+      S.lim_rhs[a][i] = 0.f; S.lim_app[a][i] = 0.f;
+      if (pen_lo <= 0.f) { S.lim_lo_mask[a] |= 1u << i; S.lim_rhs[a][i] = (-pen_lo * (float)XARM_ERP / h - D[a].qdu[i]) / den; }
+      else if (pen_hi <= 0.f) { S.lim_hi_mask[a] |= 1u << i; S.lim_rhs[a][i] = (-pen_hi * (float)XARM_ERP / h + D[a].qdu[i]) / den; }
+      float target = (float)(XARM_MOTOR_KP * XARM_MOTOR_ERP) * (st.qt[i] - st.q[i]) / h;
+      S.mot_rhs[a][i] = (target - D[a].qdu[i]) / den;
+      S.mot_app[a][i] = 0.f;
+      S.mot_hi[a][i] = (float)((i < 7 ? T::ARM_FORCE : T::FINGER_FORCE) * T::TIME_STEP);
+      S.dqd[a][i] = 0.f;
+    }
+    if (MD::HAS_GEAR) {
+      const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
+      const float gr = (float)XARM_GEAR_RATIO;
+      float den = D[a].Minv[tri(f1, f1)] + 2.f * gr * D[a].Minv[tri(f1, f2)] + gr * gr * D[a].Minv[tri(f2, f2)];
+      float rel = D[a].qdu[f1] + gr * D[a].qdu[f2];
+      float pos_err = (float)XARM_GEAR_ERP * (st.q[f1] + gr * st.q[f2]);
+      S.gear_dinv[a] = 1.f / den;
+      S.gear_rhs[a] = (-pos_err * (float)XARM_ERP / h - rel) / den;
+      S.gear_app[a] = 0.f;
+    }
+  }
+  S.gear_hi = (float)(XARM_GEAR_MAX_FORCE * T::TIME_STEP);
+  S.door_lim = false; S.ddoor = 0.f;
+  if (T::HAS_DOOR) {
+    float pen_lo = e.door_q - (float)XARM_DOOR_LIMIT_LO, pen_hi = (float)XARM_DOOR_LIMIT_HI - e.door_q;
+    const float den = 1.f / (float)XARM_DOOR_MASS;
+    S.door_lim_app = 0.f; S.door_mot_app = 0.f;
+    if (pen_lo <= 0.f) { S.door_lim = true; S.door_lim_sign = 1.f; S.door_lim_rhs = (-pen_lo * (float)XARM_ERP / h - door_qdu) / den; }
+    else if (pen_hi <= 0.f) { S.door_lim = true; S.door_lim_sign = -1.f; S.door_lim_rhs = (-pen_hi * (float)XARM_ERP / h + door_qdu) / den; }
+    S.door_mot_rhs = (0.f - door_qdu) / den;
+  }
+  // contact rows: normal rows of all contacts, then the two friction rows of each
+  for (int c = 0; c < S.nc; c++) {
+    V3 t1, t2;
+    plane_space(S.dir[c][0], t1, t2);
+    S.dir[c][1] = t1; S.dir[c][2] = t2;
+    const int ca = S.ba[c], cb = S.bb[c];
+    for (int k = 0; k < 3; k++) {
+      float rel = 0.f;
+      float den = row_side<T>(S, e, D, ca, c, k, S.pa[c], S.dir[c][k], 1.f, door_qdu, rel);
+      den += row_side<T>(S, e, D, cb, c, k, S.pb[c], S.dir[c][k], -1.f, door_qdu, rel);
+      S.app[c][k] = 0.f;
+      if (k == 0) {
+        float dinv = 1.f / (den + S.cfm0[c]);
+        float pen = -S.depth[c] + (float)XARM_LINEAR_SLOP;
+        float pos_err = 0.f, vel_err = -rel;
+        if (pen > 0.f) vel_err -= pen / h; else pos_err = -pen * S.erp[c] / h;
+        S.rhs[c][0] = (pos_err + vel_err) * dinv;
+        S.dinv[c][0] = dinv;
+        S.cfmr[c] = S.cfm0[c] * dinv;
+      } else {
+        float dinv = 1.f / den;
+        S.rhs[c][k] = -rel * dinv;
+        S.dinv[c][k] = dinv;
+      }
+    }
+  }
+  // from here on dv/dw accumulate velocity CHANGES; keep the unconstrained object velocities aside
+  V3 vu[NOBJ > 0 ? NOBJ : 1], wu[NOBJ > 0 ? NOBJ : 1];
+  for (int o = 0; o < NOBJ; o++) { vu[o] = S.dv[o]; wu[o] = S.dw[o]; S.dv[o] = v3(0, 0, 0); S.dw[o] = v3(0, 0, 0); }
+  // convert contact points to body-relative arms for the object sides
+  for (int c = 0; c < S.nc; c++) {
+    if (bc_is_obj(S.ba[c])) S.pa[c] = S.pa[c] - e.obj[T::NOBJ <= 1 ? 0 : S.ba[c] - BC_OBJ0].pos;
+    if (bc_is_obj(S.bb[c])) S.pb[c] = S.pb[c] - e.obj[T::NOBJ <= 1 ? 0 : S.bb[c] - BC_OBJ0].pos;
+  }
+
+  // ---- 4. PGS sweeps (btMultiBodyConstraintSolver::solveSingleIteration)
+  for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+    float resid = 0.f;
+    const bool forward = it & 1;
+    if (forward) {
+#pragma unroll
+      for (int a = 0; a < NA; a++) arm_rows_sweep<T>(S, D[a], a, true, resid);
+      if (T::HAS_DOOR) door_rows_sweep<T>(S, true, resid);
+    } else {
+      if (T::HAS_DOOR) door_rows_sweep<T>(S, false, resid);
+#pragma unroll
+      for (int a = NA - 1; a >= 0; a--) arm_rows_sweep<T>(S, D[a], a, false, resid);
+    }
+    for (int c = 0; c < S.nc; c++) {
+      const int ca = S.ba[c], cb = S.bb[c];
+      V3 d = S.dir[c][0];
+      float jv = side_jv<T>(S, ca, c, 0, S.pa[c], d, 1.f) + side_jv<T>(S, cb, c, 0, S.pb[c], d, -1.f);
+      float delta = S.rhs[c][0] - S.app[c][0] * S.cfmr[c] - jv * S.dinv[c][0];
+      float sum = S.app[c][0] + delta;
+      if (sum < 0.f) { delta = -S.app[c][0]; sum = 0.f; } else if (sum > (float)XARM_CONTACT_MAX_IMPULSE) { delta = (float)XARM_CONTACT_MAX_IMPULSE - S.app[c][0]; sum = (float)XARM_CONTACT_MAX_IMPULSE; }
+      S.app[c][0] = sum;
+      side_apply<T>(S, ca, c, 0, S.pa[c], d, 1.f, delta);
+      side_apply<T>(S, cb, c, 0, S.pb[c], d, -1.f, delta);
+      float rv = delta / S.dinv[c][0];
+      resid = fmaxf(resid, rv * rv);
+    }
+    for (int c = 0; c < S.nc; c++) {  // cone friction: both deltas from the same state, joint clamp
+      const int ca = S.ba[c], cb = S.bb[c];
+      V3 d1 = S.dir[c][1], d2 = S.dir[c][2];
+      float lim = S.mu[c] * S.app[c][0];
+      float j1 = side_jv<T>(S, ca, c, 1, S.pa[c], d1, 1.f) + side_jv<T>(S, cb, c, 1, S.pb[c], d1, -1.f);
+      float j2 = side_jv<T>(S, ca, c, 2, S.pa[c], d2, 1.f) + side_jv<T>(S, cb, c, 2, S.pb[c], d2, -1.f);
+      float da = S.rhs[c][1] - j1 * S.dinv[c][1], db = S.rhs[c][2] - j2 * S.dinv[c][2];
+      float sa = S.app[c][1] + da, sb = S.app[c][2] + db;
+      float len = sqrtf(sa * sa + sb * sb);
+      if (len > lim) { float sc = len > 0.f ? lim / len : 0.f; sa *= sc; sb *= sc; da = sa - S.app[c][1]; db = sb - S.app[c][2]; }
+      S.app[c][1] = sa; S.app[c][2] = sb;
+      side_apply<T>(S, ca, c, 1, S.pa[c], d1, 1.f, da);
+      side_apply<T>(S, cb, c, 1, S.pb[c], d1, -1.f, da);
+      side_apply<T>(S, ca, c, 2, S.pa[c], d2, 1.f, db);
+      side_apply<T>(S, cb, c, 2, S.pb[c], d2, -1.f, db);
+      float r1 = da / S.dinv[c][1], r2 = db / S.dinv[c][2];
+      resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));
+    }
+    if (resid <= (float)XARM_RESIDUAL_THRESHOLD) break;
+  }
+
+  // ---- 5. integrate (stepPositionsMultiDof)
+#pragma unroll
+  for (int a = 0; a < NA; a++)
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      float qd = D[a].qdu[i] + S.dqd[a][i];
+      e.arm[a].qd[i] = qd;
+      e.arm[a].q[i] += qd * h;
+    }
+  for (int o = 0; o < NOBJ; o++) {
+    ObjState& b = e.obj[o];
+    b.v = vu[o] + S.dv[o]; b.w = wu[o] + S.dw[o];
+    b.pos += h * b.v;
+    float ang = norm(b.w);
+    if (ang * h > (float)XARM_ANGULAR_MOTION_THRESHOLD) ang = (float)XARM_ANGULAR_MOTION_THRESHOLD / h;
+    V3 ax;
+    if (ang < 0.001f) ax = (0.5f * h - h * h * h * 0.020833333333f * ang * ang) * b.w;
+    else ax = (sinf(0.5f * ang * h) / ang) * b.w;
+    Q4 dq = {ax.x, ax.y, ax.z, cosf(ang * h * 0.5f)};
+    Q4 qn = quat_mul(dq, b.quat);
+    float inv = rsqrtf(qn.x * qn.x + qn.y * qn.y + qn.z * qn.z + qn.w * qn.w);
+    b.quat.x = qn.x * inv; b.quat.y = qn.y * inv; b.quat.z = qn.z * inv; b.quat.w = qn.w * inv;
+  }
+  if (T::HAS_DOOR) { e.door_qd = door_qdu + S.ddoor; e.door_q += e.door_qd * h; }
+}
+
+// p.stepSimulation() x calls per env step
+template <class T>
+XD void simulate(Env<T>& e) {
+  for (int s = 0; s < T::NSUB; s++) substep<T>(e, T::DAMP_EACH || s == 0, s == T::NSUB - 1);
+}

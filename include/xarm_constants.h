@@ -22,6 +22,8 @@
 #define XARM_CONTACT_WARMSTART 0         /* multibody contact warm starting is disabled in btMultiBodyConstraintSolver */
 #define XARM_CONTACT_MAX_IMPULSE 1e10
 #define XARM_CONTACT_MARGIN 0.0          /* boxes collide when they overlap (btBoxBoxDetector: no speculative points) */
+#define XARM_MAX_CONTACTS 24             /* per env and substep; pairs are visited in a fixed order, overflow is dropped */
+#define XARM_MAX_ARM_CONTACTS 12         /* of which at most this many touch a gripper link */
 
 /* ---- btMultiBody ---- */
 #define XARM_MB_LINEAR_DAMPING 0.04      /* m_linearDamping: F = m v (k + k|v|)  -- pinned by G1 */

@@ -36,7 +36,7 @@
 #define MAXARM 2
 #define MAXOBJ 3
 #define MAXNV (MAXARM * MAXDOF + MAXOBJ * 6 + 1)
-#define MAXCONTACT 32
+#define MAXCONTACT XARM_MAX_CONTACTS
 #define MAXROW (MAXARM * (2 * MAXDOF + 1) + 4 + 3 * MAXCONTACT)
 #define MAXCOLLIDER 24
 #define MAXPAIR 64
@@ -972,7 +972,7 @@ static void substep(OrEnv* e, int apply_damping, int last) {
   static _Thread_local Row rows[MAXROW];
   world_build(e, &w);
   /* 1. collision detection on the current poses */
-  Contact contacts[MAXCONTACT]; int nc = 0;
+  Contact contacts[MAXCONTACT]; int nc = 0, nac = 0;
   int pair_count[MAXPAIR];
   for (int p = 0; p < w.npair; p++) {
     const Collider *A = &w.col[w.pair[p][0]], *B = &w.col[w.pair[p][1]];
@@ -981,8 +981,11 @@ static void substep(OrEnv* e, int apply_damping, int last) {
     double ra = v3norm(A->h), rb = v3norm(B->h);
     if (v3dot(d, d) > (ra + rb + XARM_CONTACT_MARGIN) * (ra + rb + XARM_CONTACT_MARGIN)) continue;
     int room = MAXCONTACT - nc;
-    if (room <= 0) break;
+    int with_arm = A->body == BODY_ARM || B->body == BODY_ARM;
+    if (with_arm && XARM_MAX_ARM_CONTACTS - nac < room) room = XARM_MAX_ARM_CONTACTS - nac;
+    if (room <= 0) continue;
     int k = box_box(A, B, &contacts[nc], room < 4 ? room : 4);
+    if (with_arm) nac += k;
     for (int i = 0; i < k; i++) { contacts[nc + i].ca = w.pair[p][0]; contacts[nc + i].cb = w.pair[p][1]; }
     pair_count[p] = k; nc += k;
   }

@@ -1,0 +1,145 @@
+// hostsim.cpp - TEST HARNESS ONLY: compiles the per-env bodies of the CUDA kernels (gym_xarm_b200/csrc/*.cuh) for the
+// host with XARM_HOST_SIM, so that the kernel logic can be checked against the oracle on a machine without a GPU
+// (`pytest -m "not gpu"`).  It is not part of the product, is never imported by gym_xarm_b200 and is not a fallback:
+// the product library has no CPU path.  float arithmetic, same code as the device path minus FMA contraction.
+#define XARM_HOST_SIM 1
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../gym_xarm_b200/csrc/xarm_kernels.cuh"
+
+struct Ops {
+  void (*init)(const KArgs&);
+  void (*step)(const KArgs&);
+  void (*reset)(const KArgs&, const uint8_t*, int);
+  void (*obs)(const KArgs&);
+  int A, O, G, S;
+};
+template <class T>
+struct OpsT {
+  static void init(const KArgs& a) { for (int64_t i = 0; i < a.n; i++) body_init<T>(a, i); }
+  static void step(const KArgs& a) {
+    for (int64_t i = 0; i < a.n; i++) {
+      StepStats st = {0, 0, 0, 0, 0};
+      body_step<T>(a, i, st);
+      a.stats[0] += st.eps; a.stats[1] += st.ret; a.stats[2] += st.len; a.stats[3] += st.suc; a.stats[4] += st.div;
+    }
+  }
+  static void reset(const KArgs& a, const uint8_t* mask, int use_flags) {
+    for (int64_t i = 0; i < a.n; i++) {
+      if (use_flags) { if (!a.need_reset[i]) continue; }
+      else if (mask && !mask[i]) continue;
+      body_reset<T>(a, i, !use_flags);
+    }
+  }
+  static void obs(const KArgs& a) { for (int64_t i = 0; i < a.n; i++) body_obs<T>(a, i); }
+  static Ops make() { Ops o = {init, step, reset, obs, T::A, T::O, T::G, state_words<T>()}; return o; }
+};
+static bool get_ops(int task, Ops* out) {
+  switch (task) {
+    case XARM_TASK_REACH: *out = OpsT<TaskT<XARM_TASK_REACH, 0>>::make(); return true;
+    case XARM_TASK_PICK_AND_PLACE: *out = OpsT<TaskT<XARM_TASK_PICK_AND_PLACE, 1>>::make(); return true;
+    case XARM_TASK_STACK_TOWER: *out = OpsT<TaskT<XARM_TASK_STACK_TOWER, 3>>::make(); return true;
+    case XARM_TASK_PUSH_WITH_DOOR: *out = OpsT<TaskT<XARM_TASK_PUSH_WITH_DOOR, 1>>::make(); return true;
+    case XARM_TASK_HANDOVER: *out = OpsT<TaskT<XARM_TASK_HANDOVER, 1>>::make(); return true;
+  }
+  return false;
+}
+
+struct HS {
+  XarmConfig cfg; Ops ops; KArgs k;
+  std::vector<float> state, ep_return, io; std::vector<uint8_t> need_reset, flags; double stats[5];
+};
+
+extern "C" {
+HS* hs_create(const XarmConfig* cfg) {
+  HS* h = new HS();
+  h->cfg = *cfg;
+  if (!get_ops(cfg->task, &h->ops)) { delete h; return nullptr; }
+  const int64_t n = cfg->num_envs; const Ops& o = h->ops;
+  h->state.assign((size_t)n * o.S, 0.f); h->ep_return.assign(n, 0.f); h->need_reset.assign(n, 0); h->flags.assign(2 * n, 0);
+  h->io.assign((size_t)n * (o.A + o.O + 2 * o.G + 2), 0.f);
+  memset(h->stats, 0, sizeof(h->stats));
+  KArgs& k = h->k; memset(&k, 0, sizeof(k));
+  k.state = h->state.data(); k.ep_return = h->ep_return.data(); k.need_reset = h->need_reset.data(); k.stats = h->stats;
+  k.n = n; k.auto_reset = cfg->auto_reset;
+  k.rc.seed = cfg->seed; k.rc.env_index_base = cfg->env_index_base; k.rc.reward_type = cfg->reward_type;
+  k.rc.goal_shape = cfg->goal_shape; k.rc.max_episode_steps = cfg->max_episode_steps;
+  k.rc.init_grasp_rate = cfg->init_grasp_rate; k.rc.goal_ground_rate = cfg->goal_ground_rate; k.rc.same_side_rate = cfg->same_side_rate;
+  float* p = h->io.data();
+  k.b.actions = p; p += n * o.A; k.b.observation = p; p += n * o.O; k.b.achieved_goal = p; p += n * o.G;
+  k.b.desired_goal = p; p += n * o.G; k.b.reward = p; p += n; k.b.success = p; p += n;
+  k.b.done = h->flags.data(); k.b.truncated = h->flags.data() + n; k.b.terminal_observation = nullptr;
+  h->ops.init(k);
+  return h;
+}
+void hs_destroy(HS* h) { delete h; }
+void hs_dims(HS* h, int* A, int* O, int* G, int* S) { *A = h->ops.A; *O = h->ops.O; *G = h->ops.G; *S = h->ops.S; }
+static void copy_out(HS* h, float* obs, float* ag, float* dg) {
+  const int64_t n = h->cfg.num_envs; const Ops& o = h->ops;
+  if (obs) memcpy(obs, h->k.b.observation, sizeof(float) * n * o.O);
+  if (ag) memcpy(ag, h->k.b.achieved_goal, sizeof(float) * n * o.G);
+  if (dg) memcpy(dg, h->k.b.desired_goal, sizeof(float) * n * o.G);
+}
+void hs_reset(HS* h, const uint8_t* mask, float* obs, float* ag, float* dg) { h->ops.reset(h->k, mask, 0); copy_out(h, obs, ag, dg); }
+void hs_get_obs(HS* h, float* obs, float* ag, float* dg) { h->ops.obs(h->k); copy_out(h, obs, ag, dg); }
+void hs_step(HS* h, const float* actions, float* obs, float* ag, float* dg, float* reward, uint8_t* done, float* success, uint8_t* truncated) {
+  const int64_t n = h->cfg.num_envs; const Ops& o = h->ops;
+  memcpy((void*)h->k.b.actions, actions, sizeof(float) * n * o.A);
+  h->ops.step(h->k);
+  if (h->cfg.auto_reset) {
+    // keep the terminal outputs: the reset overwrites observation for finished envs like the CUDA path does
+    h->ops.reset(h->k, nullptr, 1);
+  }
+  copy_out(h, obs, ag, dg);
+  if (reward) memcpy(reward, h->k.b.reward, sizeof(float) * n);
+  if (success) memcpy(success, h->k.b.success, sizeof(float) * n);
+  if (done) memcpy(done, h->k.b.done, n);
+  if (truncated) memcpy(truncated, h->k.b.truncated, n);
+}
+void hs_get_state(HS* h, float* out) {
+  const int64_t n = h->cfg.num_envs; const int S = h->ops.S;
+  for (int64_t i = 0; i < n; i++) for (int w = 0; w < S; w++) out[i * S + w] = h->state[(size_t)w * n + i];
+}
+void hs_set_state(HS* h, const float* in) {
+  const int64_t n = h->cfg.num_envs; const int S = h->ops.S;
+  for (int64_t i = 0; i < n; i++) for (int w = 0; w < S; w++) h->state[(size_t)w * n + i] = in[i * S + w];
+}
+void hs_compute_reward(int task, int reward_type, int num_obj, const float* ag, const float* dg, int64_t n, float* out) {
+  int G = task == XARM_TASK_REACH ? 3 : (task == XARM_TASK_STACK_TOWER ? 9 : 3 * (task == XARM_TASK_PUSH_WITH_DOOR ? 1 : num_obj));
+  for (int64_t i = 0; i < n; i++) out[i] = reward_stateless(task, reward_type, num_obj, task_threshold(task), ag + i * G, dg + i * G, G);
+}
+int hs_box_box(const float* A, const float* B, float* out) {
+  Box a, b; CPoint c[4];
+  a.c = v3(A[0], A[1], A[2]); for (int i = 0; i < 9; i++) a.R.m[i] = A[3 + i]; a.h = v3(A[12], A[13], A[14]);
+  b.c = v3(B[0], B[1], B[2]); for (int i = 0; i < 9; i++) b.R.m[i] = B[3 + i]; b.h = v3(B[12], B[13], B[14]);
+  int n = box_box(a, b, c, 4);
+  for (int i = 0; i < n; i++) {
+    float* o = out + 10 * i;
+    o[0] = c[i].pa.x; o[1] = c[i].pa.y; o[2] = c[i].pa.z; o[3] = c[i].pb.x; o[4] = c[i].pb.y; o[5] = c[i].pb.z;
+    o[6] = c[i].n.x; o[7] = c[i].n.y; o[8] = c[i].n.z; o[9] = c[i].depth;
+  }
+  return n;
+}
+}
+
+// debug exports: joint-space inverse inertia and unconstrained velocity update of arm 0 (first substep semantics)
+template <class T>
+static int dyn_t(const float* q, const float* qd, int damping, float* Minv, float* qdu) {
+  using MD = typename T::MD;
+  ArmState<MD> st; ArmDyn<MD> D;
+  for (int i = 0; i < MD::N; i++) { st.q[i] = q[i]; st.qd[i] = qd[i]; st.qt[i] = q[i]; }
+  arm_dynamics<T>(0, st, damping != 0, D);
+  for (int i = 0; i < MD::N; i++) { qdu[i] = D.qdu[i]; for (int j = 0; j < MD::N; j++) Minv[i * MD::N + j] = D.Minv[tri(i, j)]; }
+  return MD::N;
+}
+extern "C" int hs_dynamics(int task, const float* q, const float* qd, int damping, float* Minv, float* qdu) {
+  if (task == XARM_TASK_REACH) return dyn_t<TaskT<XARM_TASK_REACH, 0>>(q, qd, damping, Minv, qdu);
+  return dyn_t<TaskT<XARM_TASK_PICK_AND_PLACE, 1>>(q, qd, damping, Minv, qdu);
+}
+template <class T>
+static void ik_t(const float* q, const float* target, float* out) { arm_ik<T>(0, q, v3(target[0], target[1], target[2]), out); }
+extern "C" void hs_ik(int task, const float* q, const float* target, float* out) {
+  if (task == XARM_TASK_REACH) ik_t<TaskT<XARM_TASK_REACH, 0>>(q, target, out); else ik_t<TaskT<XARM_TASK_PICK_AND_PLACE, 1>>(q, target, out);
+}

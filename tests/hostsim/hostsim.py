@@ -1,0 +1,126 @@
+"""ctypes binding of tests/hostsim/hostsim.cpp: the CUDA kernels' per-env bodies compiled for the host.
+
+TEST HARNESS ONLY (see the header of hostsim.cpp): it lets `pytest -m "not gpu"` check the kernel logic against the
+oracle where no GPU exists.  Nothing in gym_xarm_b200 imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_hostsim.so")
+_CSRC = os.path.join(_HERE, "..", "..", "gym_xarm_b200", "csrc")
+_INC = os.path.join(_HERE, "..", "..", "include")
+
+
+def build(force=False):
+    deps = [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cuh")]
+    deps += [os.path.join(_INC, f) for f in os.listdir(_INC)]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                               "-Wno-narrowing", "-o", _SO, os.path.join(_HERE, "hostsim.cpp")])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        fp, u8p, ip = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+        L.hs_create.restype = C.c_void_p
+        L.hs_create.argtypes = [C.c_void_p]
+        L.hs_destroy.argtypes = [C.c_void_p]
+        L.hs_dims.argtypes = [C.c_void_p, ip, ip, ip, ip]
+        L.hs_reset.argtypes = [C.c_void_p, u8p, fp, fp, fp]
+        L.hs_get_obs.argtypes = [C.c_void_p, fp, fp, fp]
+        L.hs_step.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, u8p, fp, u8p]
+        L.hs_get_state.argtypes = [C.c_void_p, fp]
+        L.hs_set_state.argtypes = [C.c_void_p, fp]
+        L.hs_compute_reward.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int64, fp]
+        L.hs_box_box.argtypes = [fp, fp, fp]
+        _lib = L
+    return _lib
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+class HostSimVec:
+    """Batched env on the host build of the kernel bodies; same call shapes as the CUDA library wrapper."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.L = lib()
+        self.h = self.L.hs_create(C.addressof(cfg))
+        if not self.h:
+            raise ValueError("hs_create failed")
+        a, o, g, s = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.L.hs_dims(self.h, a, o, g, s)
+        self.A, self.O, self.G, self.S = a.value, o.value, g.value, s.value
+        self.n = cfg.num_envs
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.hs_destroy(self.h)
+            self.h = None
+
+    def _obs(self):
+        return (np.zeros((self.n, self.O), np.float32), np.zeros((self.n, self.G), np.float32), np.zeros((self.n, self.G), np.float32))
+
+    def reset(self, mask=None):
+        o, a, d = self._obs()
+        m = None if mask is None else _u8(np.ascontiguousarray(mask, np.uint8))
+        self.L.hs_reset(self.h, m, _f(o), _f(a), _f(d))
+        return {"observation": o, "achieved_goal": a, "desired_goal": d}
+
+    def get_obs(self):
+        o, a, d = self._obs()
+        self.L.hs_get_obs(self.h, _f(o), _f(a), _f(d))
+        return {"observation": o, "achieved_goal": a, "desired_goal": d}
+
+    def step(self, actions):
+        actions = np.ascontiguousarray(actions, np.float32)
+        assert actions.shape == (self.n, self.A)
+        o, a, d = self._obs()
+        r, s = np.zeros(self.n, np.float32), np.zeros(self.n, np.float32)
+        done, tr = np.zeros(self.n, np.uint8), np.zeros(self.n, np.uint8)
+        self.L.hs_step(self.h, _f(actions), _f(o), _f(a), _f(d), _f(r), _u8(done), _f(s), _u8(tr))
+        return {"observation": o, "achieved_goal": a, "desired_goal": d}, r, done.astype(bool), s, tr.astype(bool)
+
+    def get_state(self):
+        s = np.zeros((self.n, self.S), np.float32)
+        self.L.hs_get_state(self.h, _f(s))
+        return s
+
+    def set_state(self, s):
+        s = np.ascontiguousarray(s, np.float32)
+        assert s.shape == (self.n, self.S)
+        self.L.hs_set_state(self.h, _f(s))
+
+
+def compute_reward(task, reward_type, num_obj, ag, dg):
+    ag = np.ascontiguousarray(ag, np.float32)
+    dg = np.ascontiguousarray(dg, np.float32)
+    n = ag.shape[0]
+    out = np.zeros(n, np.float32)
+    lib().hs_compute_reward(task, reward_type, num_obj, _f(ag), _f(dg), n, _f(out))
+    return out
+
+
+def box_box(A, B):
+    a = np.concatenate([np.asarray(A[0], np.float32), np.asarray(A[1], np.float32).reshape(9), np.asarray(A[2], np.float32)]).astype(np.float32)
+    b = np.concatenate([np.asarray(B[0], np.float32), np.asarray(B[1], np.float32).reshape(9), np.asarray(B[2], np.float32)]).astype(np.float32)
+    out = np.zeros(40, np.float32)
+    n = lib().hs_box_box(_f(a), _f(b), _f(out))
+    return [(out[10 * i:10 * i + 3].copy(), out[10 * i + 3:10 * i + 6].copy(), out[10 * i + 6:10 * i + 9].copy(), out[10 * i + 9]) for i in range(n)]

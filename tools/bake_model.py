@@ -251,6 +251,7 @@ def build_model(path, urdf_inertia):
             d = p.com - com
             I += p.I + p.mass * (d @ d * np.eye(3) - np.outer(d, d))
         M.mass, M.com, M.I = m, com, I
+        M.Ig = sum(p.I for p in ps)  # sum of the parts' central inertias (no parallel-axis terms)
     return links, joints, mov, parts, frame_of, joint_index
 
 
@@ -286,6 +287,7 @@ def emit_model(prefix, mov, parts, extra):
     o.append(f"#define {prefix}_MASS " + arr([m.mass for m in mov]) + "  /* composite of the parts a DoF carries */")
     o.append(f"#define {prefix}_COM " + arr([m.com for m in mov]))
     o.append(f"#define {prefix}_INERTIA " + arr([sym6(m.I) for m in mov]) + "  /* xx xy xz yy yz zz about COM, link frame */")
+    o.append(f"#define {prefix}_CENTRAL_INERTIA " + arr([sym6(m.Ig) for m in mov]) + "  /* sum of part inertias about their own COMs */")
     o.append(f"#define {prefix}_PART_OWNER {{" + ", ".join(str(p.owner) for p in parts) + "}")
     o.append(f"#define {prefix}_PART_MASS " + arr([p.mass for p in parts]))
     o.append(f"#define {prefix}_PART_COM " + arr([p.com for p in parts]))
