@@ -1,0 +1,86 @@
+"""ctypes binding of libxarm_b200.so (include/xarm_abi.h).  There is no fallback: if the library is missing or a call
+fails, this module raises."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+
+class XarmConfig(C.Structure):
+    _fields_ = [
+        ("task", C.c_int32), ("reward_type", C.c_int32), ("num_obj", C.c_int32), ("goal_shape", C.c_int32),
+        ("init_grasp_rate", C.c_float), ("goal_ground_rate", C.c_float), ("same_side_rate", C.c_float),
+        ("use_stand", C.c_int32), ("max_episode_steps", C.c_int32), ("auto_reset", C.c_int32),
+        ("device", C.c_int32), ("reserved", C.c_int32),
+        ("num_envs", C.c_int64), ("env_index_base", C.c_int64), ("seed", C.c_uint64),
+    ]
+
+
+class XarmBuffers(C.Structure):
+    _fields_ = [
+        ("actions", C.c_void_p), ("observation", C.c_void_p), ("achieved_goal", C.c_void_p), ("desired_goal", C.c_void_p),
+        ("reward", C.c_void_p), ("done", C.c_void_p), ("success", C.c_void_p), ("truncated", C.c_void_p),
+        ("terminal_observation", C.c_void_p),
+    ]
+
+
+# every symbol include/xarm_abi.h declares
+ABI_SYMBOLS = [
+    "xarm_task_dims", "xarm_create", "xarm_destroy", "xarm_bind", "xarm_reset", "xarm_step", "xarm_step_host",
+    "xarm_reset_host", "xarm_compute_reward", "xarm_get_state", "xarm_set_state", "xarm_get_obs", "xarm_graph_capture",
+    "xarm_episode_stats", "xarm_launch_count", "xarm_last_error", "xarm_abi_version",
+]
+
+_lib = None
+
+
+class XarmError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load the native library (building it first if the sources are newer and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.is_stale():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on this box and no prebuilt library
+            if not os.path.exists(path):
+                raise XarmError(f"libxarm_b200.so is missing and could not be built ({e}); there is no CPU fallback") from e
+    L = C.CDLL(path)
+    vp, i32p = C.c_void_p, C.POINTER(C.c_int32)
+    L.xarm_task_dims.argtypes = [C.c_int32, C.c_int32, i32p, i32p, i32p, i32p]
+    L.xarm_create.argtypes = [C.POINTER(XarmConfig), C.POINTER(vp)]
+    L.xarm_destroy.argtypes = [vp]
+    L.xarm_bind.argtypes = [vp, C.POINTER(XarmBuffers)]
+    L.xarm_reset.argtypes = [vp, vp, vp]
+    L.xarm_step.argtypes = [vp, vp]
+    L.xarm_step_host.argtypes = [vp] + [vp] * 8 + [vp]
+    L.xarm_reset_host.argtypes = [vp, vp, vp, vp, vp]
+    L.xarm_compute_reward.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int64, vp, vp]
+    L.xarm_get_state.argtypes = [vp, vp]
+    L.xarm_set_state.argtypes = [vp, vp]
+    L.xarm_get_obs.argtypes = [vp, vp]
+    L.xarm_graph_capture.argtypes = [vp, vp]
+    L.xarm_episode_stats.argtypes = [vp, C.POINTER(C.c_double), vp]
+    L.xarm_launch_count.restype = C.c_int64
+    L.xarm_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().xarm_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            if "not implemented" in msg or "reads simulator state" in msg:
+                raise NotImplementedError(msg)
+            raise ValueError(msg)
+        raise XarmError(f"{what} failed ({rc}): {msg}")

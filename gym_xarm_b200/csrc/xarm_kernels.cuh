@@ -12,7 +12,33 @@ struct KArgs {
   ResetCfg rc;
   int64_t n;
   int auto_reset;
+  // load balancing (DESIGN.md "warp homogeneity"): thread t of the step kernel simulates env perm[t]
+  int* perm;             // [N] envs ordered by predicted contact load (nearest gripper-object distance first)
+  int* bin_slot;         // [N] (bin << 24 | slot within bin) scratch of the classify pass
+  int* bin_counts;       // [XARM_LOAD_BINS]
+  int* reset_list;       // [N] compacted list of envs the step kernel finished (auto-reset)
+  int* reset_count;      // [1]
 };
+#define XARM_LOAD_BINS 8
+
+// predicted contact load of env i for the coming step: bin 0 = gripper closest to an object (contacts likely)
+template <class T>
+XD int body_load_bin(const KArgs& a, int64_t i) {
+  using MD = typename T::MD;
+  if (T::NOBJ == 0 || !MD::HAS_BOXES) return 0;
+  Env<T> e;
+  env_load<T>(e, a.state, a.n, i);
+  float dmin = 1e30f;
+#pragma unroll
+  for (int arm = 0; arm < T::NARM; arm++) {
+    M3 Re; V3 pe, org[7], axs[7];
+    arm_fk7<T>(arm, e.arm[arm].q, Re, pe, org, axs);
+    V3 gc = pe + Re * v3(0.f, 0.f, 0.043f);  // middle of the hand + finger hulls along the hand axis
+    for (int o = 0; o < T::NOBJ; o++) dmin = fminf(dmin, norm(gc - e.obj[o].pos));
+  }
+  int bin = (int)((dmin - 0.10f) * 20.f);
+  return bin < 0 ? 0 : (bin >= XARM_LOAD_BINS ? XARM_LOAD_BINS - 1 : bin);
+}
 struct StepStats {
   float eps, ret, len, suc, div;
 };

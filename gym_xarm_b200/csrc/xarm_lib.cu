@@ -19,11 +19,47 @@ __global__ void __launch_bounds__(128) k_init(KArgs a) {
   if (i < a.n) body_init<T>(a, i);
 }
 
+// Load-balancing pass 1: bin every env by predicted contact load; slot = arrival order inside the bin (the order is
+// irrelevant for the results: envs are independent, the permutation only decides which lane simulates which env).
+template <class T>
+__global__ void __launch_bounds__(128) k_classify(KArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < a.n;
+  int bin = valid ? body_load_bin<T>(a, i) : -1;
+  unsigned peers = __match_any_sync(0xffffffffu, bin);
+  int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+  int base = 0;
+  if (valid && lane == leader) base = atomicAdd(&a.bin_counts[bin], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (valid) a.bin_slot[i] = (bin << 24) | (base + __popc(peers & ((1u << lane) - 1u)));
+}
+// pass 2: exclusive prefix over the (8) bins, scatter
+__global__ void __launch_bounds__(128) k_perm(KArgs a) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *a.reset_count = 0;
+  if (i >= a.n) return;
+  int v = a.bin_slot[i], bin = v >> 24, off = 0;
+  for (int b = 0; b < bin; b++) off += a.bin_counts[b];
+  a.perm[off + (v & 0xffffff)] = (int)i;
+}
+
 template <class T>
 __global__ void __launch_bounds__(128) k_step(KArgs a) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = (t < a.n && a.perm) ? a.perm[t] : t;
   StepStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (i < a.n) body_step<T>(a, i, st);
+  if (t < a.n) {
+    body_step<T>(a, i, st);
+    // compact the envs that finished: the reset kernel then runs only full warps of resets
+    bool fin = a.need_reset[i] != 0;
+    unsigned m = __ballot_sync(__activemask(), fin);
+    if (fin) {
+      int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+      if (lane == leader) base = atomicAdd(a.reset_count, __popc(m));
+      base = __shfl_sync(m, base, leader);
+      a.reset_list[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+    }
+  }
   // episode statistics (K8): warp-aggregate, one atomic per warp and counter
   unsigned any = __ballot_sync(0xffffffffu, st.eps != 0.f || st.div != 0.f);
   if (any) {
@@ -48,8 +84,10 @@ template <class T>
 __global__ void __launch_bounds__(128) k_reset(KArgs a, const uint8_t* mask, int use_flags) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
-  if (use_flags) { if (!a.need_reset[i]) return; }
-  else if (mask && !mask[i]) return;
+  if (use_flags) {  // auto-reset: thread t takes the t-th finished env of the compacted list
+    if (i >= *a.reset_count) return;
+    i = a.reset_list[i];
+  } else if (mask && !mask[i]) return;
   body_reset<T>(a, i, !use_flags);
 }
 
@@ -81,6 +119,7 @@ struct Ops {
   void (*step)(const KArgs&, cudaStream_t);
   void (*reset)(const KArgs&, const uint8_t*, int, cudaStream_t);
   void (*obs)(const KArgs&, cudaStream_t);
+  void (*classify)(const KArgs&, cudaStream_t);
   int A, O, G, S;
 };
 
@@ -91,20 +130,42 @@ struct OpsT {
   static void step(const KArgs& a, cudaStream_t s) { k_step<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
   static void reset(const KArgs& a, const uint8_t* m, int f, cudaStream_t s) { k_reset<T><<<grid(a.n), 128, 0, s>>>(a, m, f); g_launches++; }
   static void obs(const KArgs& a, cudaStream_t s) { k_obs<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
-  static Ops make() { Ops o = {init, step, reset, obs, T::A, T::O, T::G, state_words<T>()}; return o; }
+  static void classify(const KArgs& a, cudaStream_t s) {
+    cudaMemsetAsync(a.bin_counts, 0, sizeof(int) * XARM_LOAD_BINS, s);
+    k_classify<T><<<grid(a.n), 128, 0, s>>>(a);
+    k_perm<<<grid(a.n), 128, 0, s>>>(a);
+    g_launches += 2;
+  }
+  static Ops make() { Ops o = {init, step, reset, obs, classify, T::A, T::O, T::G, state_words<T>()}; return o; }
 };
 
+// XARM_ONLY_TASK=<id> builds a single task (development builds: faster compiles); the shipped library has all five.
+#ifdef XARM_ONLY_TASK
+#define XARM_HAS_TASK(t) ((t) == XARM_ONLY_TASK)
+#else
+#define XARM_HAS_TASK(t) 1
+#endif
 static bool get_ops(int task, int num_obj, Ops* out) {
   switch (task) {
+#if XARM_HAS_TASK(0)
     case XARM_TASK_REACH: *out = OpsT<TaskT<XARM_TASK_REACH, 0>>::make(); return true;
+#endif
+#if XARM_HAS_TASK(1)
     case XARM_TASK_PICK_AND_PLACE:
       if (num_obj == 1) { *out = OpsT<TaskT<XARM_TASK_PICK_AND_PLACE, 1>>::make(); return true; }
       return false;
+#endif
+#if XARM_HAS_TASK(2)
     case XARM_TASK_STACK_TOWER: *out = OpsT<TaskT<XARM_TASK_STACK_TOWER, 3>>::make(); return true;
+#endif
+#if XARM_HAS_TASK(3)
     case XARM_TASK_PUSH_WITH_DOOR: *out = OpsT<TaskT<XARM_TASK_PUSH_WITH_DOOR, 1>>::make(); return true;
+#endif
+#if XARM_HAS_TASK(4)
     case XARM_TASK_HANDOVER:
       if (num_obj == 1) { *out = OpsT<TaskT<XARM_TASK_HANDOVER, 1>>::make(); return true; }
       return false;
+#endif
   }
   return false;
 }
@@ -179,11 +240,15 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   cudaError_t e2 = cudaMalloc(&h->k.ep_return, sizeof(float) * n);
   cudaError_t e3 = cudaMalloc(&h->k.need_reset, n);
   cudaError_t e4 = cudaMalloc(&h->k.stats, sizeof(double) * 5);
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
-    cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats);
+  cudaError_t e5 = cudaMalloc(&h->k.perm, sizeof(int) * (3 * n + XARM_LOAD_BINS + 1));
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) {
+    cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.perm);
     delete h; cudaGetLastError();
     return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc failed");
   }
+  h->k.bin_slot = h->k.perm + n; h->k.reset_list = h->k.perm + 2 * n;
+  h->k.bin_counts = h->k.perm + 3 * n; h->k.reset_count = h->k.bin_counts + XARM_LOAD_BINS;
+  CUDA_TRY(cudaMemset(h->k.perm, 0, sizeof(int) * (3 * n + XARM_LOAD_BINS + 1)));
   CUDA_TRY(cudaMemset(h->k.stats, 0, sizeof(double) * 5));
   ops.init(h->k, 0);
   CUDA_TRY(cudaGetLastError());
@@ -196,7 +261,7 @@ int xarm_destroy(XarmHandle* h) {
   if (!h) return XARM_OK;
   cudaSetDevice(h->cfg.device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
-  cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats);
+  cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.perm);
   cudaFree(h->d_io); cudaFree(h->d_flags);
   if (h->h_io) cudaFreeHost(h->h_io);
   if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -214,11 +279,15 @@ int xarm_bind(XarmHandle* h, const XarmBuffers* b) {
   return XARM_OK;
 }
 
-static int launch_step(XarmHandle* h, cudaStream_t s) {
-  h->ops.step(h->k, s);
-  if (h->cfg.auto_reset) h->ops.reset(h->k, nullptr, 1, s);
+// one env step = classify (load-balancing permutation) -> step -> auto-reset of the finished envs
+static int launch_step_with(XarmHandle* h, const KArgs& k, cudaStream_t s) {
+  h->ops.classify(k, s);
+  h->ops.step(k, s);
+  if (h->cfg.auto_reset) h->ops.reset(k, nullptr, 1, s);
   return XARM_OK;
 }
+static int launch_step(XarmHandle* h, cudaStream_t s) { return launch_step_with(h, h->k, s); }
+#define XARM_LAUNCHES_PER_STEP(h) ((h)->cfg.auto_reset ? 4 : 3)
 
 int xarm_reset(XarmHandle* h, const uint8_t* mask, void* stream) {
   if (!h) return fail(XARM_E_INVALID, "xarm_reset: null handle");
@@ -236,7 +305,7 @@ int xarm_step(XarmHandle* h, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (h->graph && s == h->graph_stream) {
     CUDA_TRY(cudaGraphLaunch(h->graph, s));
-    g_launches += h->cfg.auto_reset ? 2 : 1;
+    g_launches += XARM_LAUNCHES_PER_STEP(h);
   } else {
     launch_step(h, s);
     CUDA_TRY(cudaGetLastError());
@@ -303,8 +372,7 @@ int xarm_step_host(XarmHandle* h, const float* actions, float* observation, floa
   float* hp = h->h_io;
   memcpy(hp, actions, sizeof(float) * n * o.A);
   CUDA_TRY(cudaMemcpyAsync((void*)k.b.actions, hp, sizeof(float) * n * o.A, cudaMemcpyHostToDevice, s));
-  h->ops.step(k, s);
-  if (h->cfg.auto_reset) h->ops.reset(k, nullptr, 1, s);
+  launch_step_with(h, k, s);
   CUDA_TRY(cudaGetLastError());
   // one D2H copy of the contiguous float outputs, one of the flags
   const size_t out_fl = (size_t)n * (o.O + 2 * o.G + 2);

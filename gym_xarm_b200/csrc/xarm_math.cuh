@@ -12,6 +12,21 @@
 #define __noinline__
 #define __constant__ static const
 #define __restrict__
+#ifdef XARM_HOST_SIM_DOUBLE
+// diagnostic build: the whole kernel logic in double precision (separates float rounding from logic differences)
+#define float double
+#define sqrtf sqrt
+#define sinf sin
+#define cosf cos
+#define sincosf sincos
+#define atan2f atan2
+#define asinf asin
+#define acosf acos
+#define fabsf fabs
+#define fminf fmin
+#define fmaxf fmax
+#define tanhf tanh
+#endif
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }

@@ -571,36 +571,28 @@ XD void plane_space(V3 n, V3& p, V3& q) {  // btPlaneSpace1
   }
 }
 
-template <class T>
-struct Solver {
-  using MD = typename T::MD;
-  static constexpr int N = MD::N, NA = T::NARM, NO = T::NOBJ > 0 ? T::NOBJ : 1;
-  // contacts
-  int nc, nac;
-  uint8_t ba[XARM_MAXC], bb[XARM_MAXC];
-  int8_t slot[XARM_MAXC];  // arm-side row pool slot (-1: no arm side)
-  V3 dir[XARM_MAXC][3];    // n, t1, t2
-  V3 pa[XARM_MAXC], pb[XARM_MAXC];
-  float depth[XARM_MAXC], mu[XARM_MAXC], erp[XARM_MAXC], cfm0[XARM_MAXC];
-  float rhs[XARM_MAXC][3], dinv[XARM_MAXC][3], app[XARM_MAXC][3], cfmr[XARM_MAXC];
-  float Jarm[XARM_MAXAC][3][N], dVarm[XARM_MAXAC][3][N];
-  // per-arm unit rows
-  float mot_rhs[NA][N], mot_app[NA][N], mot_hi[NA][N];
-  float lim_rhs[NA][N], lim_app[NA][N];
-  uint32_t lim_lo_mask[NA], lim_hi_mask[NA];
-  float gear_rhs[NA], gear_app[NA], gear_dinv[NA], gear_hi;
-  // door rows
-  float door_lim_rhs, door_lim_app, door_lim_sign, door_mot_rhs, door_mot_app;
-  bool door_lim;
-  // accumulated velocity changes
-  float dqd[NA][N];
-  V3 dv[NO], dw[NO];
-  float ddoor;
-  // per object
-  S3 Iinv[NO];
-};
-
 XD V3 door_axis() { const float a[3] = XARM_DOOR_AXIS; return v3(a[0], a[1], a[2]); }
+
+// Contact rows live in thread-local memory (dynamic count and indexing; L1-resident while the PGS sweeps run).
+// Everything the arm rows need (inverse inertia, accumulated velocity change, right-hand sides) is kept in
+// registers by substep() itself.
+template <class T>
+struct Contacts {
+  static constexpr int N = T::MD::N;
+  int nc, nac;
+  uint8_t ba[XARM_MAXC], bb[XARM_MAXC];  // body codes of side A / side B (normal points from B to A)
+  int8_t slot[XARM_MAXC];                // row-pool slot of the arm side (-1: none)
+  int8_t o1[XARM_MAXC], o2[XARM_MAXC];   // object index of the first / second object side (-1: none); o2 only for object-object
+  float s1[XARM_MAXC];                   // sign of the first object side (+1 side A, -1 side B); the second is always -1
+  V3 pa[XARM_MAXC], pb[XARM_MAXC];       // world contact points (row setup only)
+  float depth[XARM_MAXC], mu[XARM_MAXC], erp[XARM_MAXC], cfm0[XARM_MAXC];
+  V3 dir[XARM_MAXC][3];                  // n, t1, t2
+  V3 Jo1[XARM_MAXC][3], dVo1[XARM_MAXC][3];  // first object side: sign * (r x d), sign * Iinv (r x d)
+  V3 Jo2[T::NOBJ > 1 ? XARM_MAXC : 1][3], dVo2[T::NOBJ > 1 ? XARM_MAXC : 1][3];
+  float jdoor[T::HAS_DOOR ? XARM_MAXC : 1][3];  // door side: sign * axis . d
+  float rhs[XARM_MAXC][3], dinv[XARM_MAXC][3], app[XARM_MAXC][3], cfmr[XARM_MAXC];
+  float Jarm[XARM_MAXAC][3][N], dVarm[XARM_MAXAC][3][N];  // arm side: sign * J, Minv (sign * J)
+};
 
 template <class T>
 XD Box arm_box(const ArmDyn<typename T::MD>& D, int which) {  // 0 hand, 1 finger1, 2 finger2
@@ -614,13 +606,13 @@ XD Box arm_box(const ArmDyn<typename T::MD>& D, int which) {  // 0 hand, 1 finge
 
 // collide one pair and append its points (normal from B to A); returns the number of points added
 template <class T>
-XD int add_pair(Solver<T>& S, const Box& A, const Box& B, int ca, int cb, float fa, float fb, bool soft, float erp_override) {
+XD int add_pair(Contacts<T>& C, const Box& A, const Box& B, int ca, int cb, float fa, float fb, bool soft, float erp_override) {
   V3 d = A.c - B.c;
   float ra = norm(A.h), rb = norm(B.h), rr = ra + rb + (float)XARM_CONTACT_MARGIN;
   if (dot(d, d) > rr * rr) return 0;
-  int room = XARM_MAXC - S.nc;
+  int room = XARM_MAXC - C.nc;
   const bool with_arm = bc_is_arm(ca) || bc_is_arm(cb);
-  if (with_arm && XARM_MAXAC - S.nac < room) room = XARM_MAXAC - S.nac;
+  if (with_arm && XARM_MAXAC - C.nac < room) room = XARM_MAXAC - C.nac;
   if (room <= 0) return 0;
   CPoint pts[4];
   int k = box_box(A, B, pts, room < 4 ? room : 4);
@@ -632,217 +624,37 @@ XD int add_pair(Solver<T>& S, const Box& A, const Box& B, int ca, int cb, float 
     cfm = 1.f / (h * ks + kd); erp = h * ks / (h * ks + kd); cfm /= h;
   }
   for (int i = 0; i < k; i++) {
-    int c = S.nc++;
-    S.ba[c] = (uint8_t)ca; S.bb[c] = (uint8_t)cb;
-    S.pa[c] = pts[i].pa; S.pb[c] = pts[i].pb; S.dir[c][0] = pts[i].n; S.depth[c] = pts[i].depth;
-    S.mu[c] = mu; S.erp[c] = erp; S.cfm0[c] = cfm;
-    S.slot[c] = with_arm ? (int8_t)(S.nac++) : (int8_t)-1;
+    int c = C.nc++;
+    C.ba[c] = (uint8_t)ca; C.bb[c] = (uint8_t)cb;
+    C.pa[c] = pts[i].pa; C.pb[c] = pts[i].pb; C.dir[c][0] = pts[i].n; C.depth[c] = pts[i].depth;
+    C.mu[c] = mu; C.erp[c] = erp; C.cfm0[c] = cfm;
+    C.slot[c] = with_arm ? (int8_t)(C.nac++) : (int8_t)-1;
   }
   return k;
-}
-
-// one side of one contact row: fills the arm-side Jacobian / response if the body is an arm link, returns the
-// side's contribution to the row denominator and accumulates the side's relative velocity.
-template <class T>
-XD float row_side(Solver<T>& S, const Env<T>& e, const ArmDyn<typename T::MD>* D, int code, int c, int k, V3 p, V3 d,
-                  float sign, float door_qdu, float& relvel) {
-  using MD = typename T::MD;
-  constexpr int N = MD::N;
-  if (code == BC_STATIC) return 0.f;
-  if (bc_is_arm(code)) {
-    const int a = T::NARM == 1 ? 0 : bc_arm(code);
-    const int which = (code - BC_ARM0_HAND) % 3;  // 0 hand, 1 finger1, 2 finger2
-    const int sl = S.slot[c];
-    const ArmDyn<MD>& Da = D[a];
-    V3 pxd = cross(p, d);
-    float J[N];
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-      bool on = j < 7 || (which == 1 && j == MD::F1) || (which == 2 && j == MD::F2);
-      J[j] = on ? sign * (dot(Da.S[j].a, pxd) + dot(Da.S[j].l, d)) : 0.f;
-    }
-    float den = 0.f, rv = 0.f;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < N; j++) s += Da.Minv[tri(i, j)] * J[j];
-      S.Jarm[sl][k][i] = J[i];
-      S.dVarm[sl][k][i] = s;
-      den += J[i] * s;
-      rv += J[i] * Da.qdu[i];
-    }
-    relvel += rv;
-    return den;
-  }
-  if (bc_is_obj(code)) {
-    const int o = T::NOBJ <= 1 ? 0 : code - BC_OBJ0;
-    V3 r = p - e.obj[o].pos;
-    V3 rxd = cross(r, d);
-    relvel += sign * (dot(d, S.dv[o]) + dot(rxd, S.dw[o]));  // dv/dw hold the unconstrained velocities during setup
-    return 1.f / T::OBJ_MASS + dot(rxd, S.Iinv[o] * rxd);
-  }
-  // door
-  float jd = dot(door_axis(), d);
-  relvel += sign * jd * door_qdu;
-  return jd * jd / (float)XARM_DOOR_MASS;
-}
-
-// J . dqd of one side (sign folded in) during the PGS sweeps
-template <class T>
-XD float side_jv(const Solver<T>& S, int code, int c, int k, V3 r, V3 d, float sign) {
-  constexpr int N = T::MD::N;
-  if (code == BC_STATIC) return 0.f;
-  if (bc_is_arm(code)) {
-    const int sl = S.slot[c];
-    float s = 0.f;
-    if (T::NARM == 1 || bc_arm(code) == 0) {
-#pragma unroll
-      for (int i = 0; i < N; i++) s += S.Jarm[sl][k][i] * S.dqd[0][i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < N; i++) s += S.Jarm[sl][k][i] * S.dqd[T::NARM - 1][i];
-    }
-    return s;
-  }
-  if (bc_is_obj(code)) {
-    const int o = T::NOBJ <= 1 ? 0 : code - BC_OBJ0;
-    return sign * dot(d, S.dv[o] + cross(S.dw[o], r));
-  }
-  return sign * dot(door_axis(), d) * S.ddoor;
-}
-template <class T>
-XD void side_apply(Solver<T>& S, int code, int c, int k, V3 r, V3 d, float sign, float delta) {
-  constexpr int N = T::MD::N;
-  if (code == BC_STATIC) return;
-  if (bc_is_arm(code)) {
-    const int sl = S.slot[c];
-    if (T::NARM == 1 || bc_arm(code) == 0) {
-#pragma unroll
-      for (int i = 0; i < N; i++) S.dqd[0][i] += S.dVarm[sl][k][i] * delta;
-    } else {
-#pragma unroll
-      for (int i = 0; i < N; i++) S.dqd[T::NARM - 1][i] += S.dVarm[sl][k][i] * delta;
-    }
-    return;
-  }
-  if (bc_is_obj(code)) {
-    const int o = T::NOBJ <= 1 ? 0 : code - BC_OBJ0;
-    float sd = sign * delta;
-    S.dv[o] += (sd / T::OBJ_MASS) * d;
-    S.dw[o] += sd * (S.Iinv[o] * cross(r, d));
-    return;
-  }
-  S.ddoor += sign * dot(door_axis(), d) * delta / (float)XARM_DOOR_MASS;
-}
-
-template <class T>
-XD void unit_row(Solver<T>& S, const ArmDyn<typename T::MD>& D, int a, int i, float sign, float rhs, float lo, float hi,
-                 float& applied, float& resid) {
-  constexpr int N = T::MD::N;
-  const float den = D.Minv[tri(i, i)];
-  float jv = sign * S.dqd[a][i];
-  float delta = rhs - jv / den;
-  float sum = applied + delta;
-  if (sum < lo) { delta = lo - applied; sum = lo; } else if (sum > hi) { delta = hi - applied; sum = hi; }
-  applied = sum;
-  float sd = sign * delta;
-#pragma unroll
-  for (int k = 0; k < N; k++) S.dqd[a][k] += D.Minv[tri(k, i)] * sd;
-  float rv = delta * den;
-  resid = fmaxf(resid, rv * rv);
-}
-
-template <class T>
-XD void arm_rows_sweep(Solver<T>& S, const ArmDyn<typename T::MD>& D, int a, bool forward, float& resid) {
-  using MD = typename T::MD;
-  constexpr int N = MD::N;
-  const float lim_hi = (float)XARM_LIMIT_MAX_IMPULSE;
-  if (forward) {
-    if (S.lim_lo_mask[a] | S.lim_hi_mask[a]) {
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        if (S.lim_lo_mask[a] >> i & 1) unit_row(S, D, a, i, 1.f, S.lim_rhs[a][i], 0.f, lim_hi, S.lim_app[a][i], resid);
-        if (S.lim_hi_mask[a] >> i & 1) unit_row(S, D, a, i, -1.f, S.lim_rhs[a][i], 0.f, lim_hi, S.lim_app[a][i], resid);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < N; i++) unit_row(S, D, a, i, 1.f, S.mot_rhs[a][i], -S.mot_hi[a][i], S.mot_hi[a][i], S.mot_app[a][i], resid);
-  }
-  if (MD::HAS_GEAR) {
-    const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
-    const float gr = (float)XARM_GEAR_RATIO;
-    float jv = S.dqd[a][f1] + gr * S.dqd[a][f2];
-    float delta = S.gear_rhs[a] - jv * S.gear_dinv[a];
-    float sum = S.gear_app[a] + delta;
-    if (sum < -S.gear_hi) { delta = -S.gear_hi - S.gear_app[a]; sum = -S.gear_hi; }
-    else if (sum > S.gear_hi) { delta = S.gear_hi - S.gear_app[a]; sum = S.gear_hi; }
-    S.gear_app[a] = sum;
-#pragma unroll
-    for (int k = 0; k < N; k++) S.dqd[a][k] += (D.Minv[tri(k, f1)] + gr * D.Minv[tri(k, f2)]) * delta;
-    float rv = delta / S.gear_dinv[a];
-    resid = fmaxf(resid, rv * rv);
-  }
-  if (!forward) {
-#pragma unroll
-    for (int i = N - 1; i >= 0; i--) unit_row(S, D, a, i, 1.f, S.mot_rhs[a][i], -S.mot_hi[a][i], S.mot_hi[a][i], S.mot_app[a][i], resid);
-    if (S.lim_lo_mask[a] | S.lim_hi_mask[a]) {
-#pragma unroll
-      for (int i = N - 1; i >= 0; i--) {
-        if (S.lim_hi_mask[a] >> i & 1) unit_row(S, D, a, i, -1.f, S.lim_rhs[a][i], 0.f, lim_hi, S.lim_app[a][i], resid);
-        if (S.lim_lo_mask[a] >> i & 1) unit_row(S, D, a, i, 1.f, S.lim_rhs[a][i], 0.f, lim_hi, S.lim_app[a][i], resid);
-      }
-    }
-  }
-}
-
-template <class T>
-XD void door_rows_sweep(Solver<T>& S, bool forward, float& resid) {
-  const float den = 1.f / (float)XARM_DOOR_MASS;
-  for (int pass = 0; pass < 2; pass++) {
-    const bool do_lim = forward ? pass == 0 : pass == 1;
-    if (do_lim) {
-      if (!S.door_lim) continue;
-      float jv = S.door_lim_sign * S.ddoor;
-      float delta = S.door_lim_rhs - jv / den;
-      float sum = S.door_lim_app + delta;
-      if (sum < 0.f) { delta = -S.door_lim_app; sum = 0.f; } else if (sum > (float)XARM_LIMIT_MAX_IMPULSE) { delta = (float)XARM_LIMIT_MAX_IMPULSE - S.door_lim_app; sum = (float)XARM_LIMIT_MAX_IMPULSE; }
-      S.door_lim_app = sum;
-      S.ddoor += S.door_lim_sign * delta * den;
-      float rv = delta * den; resid = fmaxf(resid, rv * rv);
-    } else {
-      const float hi = (float)XARM_DEFAULT_MOTOR_MAX_IMPULSE;
-      float delta = S.door_mot_rhs - S.ddoor / den;
-      float sum = S.door_mot_app + delta;
-      if (sum < -hi) { delta = -hi - S.door_mot_app; sum = -hi; } else if (sum > hi) { delta = hi - S.door_mot_app; sum = hi; }
-      S.door_mot_app = sum;
-      S.ddoor += delta * den;
-      float rv = delta * den; resid = fmaxf(resid, rv * rv);
-    }
-  }
 }
 
 // One internal substep: collide -> unconstrained velocities -> rows -> PGS -> integrate.
 template <class T>
 NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
   using MD = typename T::MD;
-  constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ;
+  constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1, NT = N * (N + 1) / 2;
   const float h = (float)T::H;
   ArmDyn<MD> D[NA];
-  Solver<T> S;
+  Contacts<T> C;
 #pragma unroll
   for (int a = 0; a < NA; a++) arm_dynamics<T>(a, e.arm[a], apply_damping, D[a]);
 
   // ---- 1. collision detection on the current poses (fixed pair order, Appendix G)
-  S.nc = 0; S.nac = 0;
+  C.nc = 0; C.nac = 0;
+  S3 Iinv[NO];
   if (NOBJ > 0) {
-    Box ob[NOBJ > 0 ? NOBJ : 1];
+    Box ob[NO];
     for (int o = 0; o < NOBJ; o++) {
       ob[o].c = e.obj[o].pos; ob[o].R = quat_to_m3(e.obj[o].quat); ob[o].h = v3(T::OBJ_HX, T::OBJ_HY, T::OBJ_HZ);
       // world inverse inertia of the box (inertia from its own shape: m/12 (ly^2+lz^2), ...)
       const float lx = 2 * T::OBJ_HX, ly = 2 * T::OBJ_HY, lz = 2 * T::OBJ_HZ, m12 = T::OBJ_MASS / 12.f;
       S3 Il = {1.f / (m12 * (ly * ly + lz * lz)), 0, 0, 1.f / (m12 * (lx * lx + lz * lz)), 0, 1.f / (m12 * (lx * lx + ly * ly))};
-      S.Iinv[o] = rotate_sym(ob[o].R, Il);
+      Iinv[o] = rotate_sym(ob[o].R, Il);
     }
     Box tb[T::NTABLE];
     for (int k = 0; k < T::NTABLE; k++) {
@@ -853,21 +665,21 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
     ground.c = v3(0.f, 0.f, (float)XARM_GROUND_Z - 5.f); ground.R = m3_identity(); ground.h = v3(100.f, 100.f, 5.f);
     const float fo = (float)XARM_DEFAULT_FRICTION;
     for (int o = 0; o < NOBJ; o++) {
-      for (int k = 0; k < T::NTABLE; k++) add_pair<T>(S, ob[o], tb[k], BC_OBJ0 + o, BC_STATIC, fo, (float)XARM_TABLE_FRICTION, false, -1.f);
-      if (T::HAS_GROUND) add_pair<T>(S, ob[o], ground, BC_OBJ0 + o, BC_STATIC, fo, 1.0f, false, -1.f);
+      for (int k = 0; k < T::NTABLE; k++) add_pair<T>(C, ob[o], tb[k], BC_OBJ0 + o, BC_STATIC, fo, (float)XARM_TABLE_FRICTION, false, -1.f);
+      if (T::HAS_GROUND) add_pair<T>(C, ob[o], ground, BC_OBJ0 + o, BC_STATIC, fo, 1.0f, false, -1.f);
     }
     for (int o = 0; o < NOBJ; o++)
-      for (int p2 = o + 1; p2 < NOBJ; p2++) add_pair<T>(S, ob[o], ob[p2], BC_OBJ0 + o, BC_OBJ0 + p2, fo, fo, false, -1.f);
-    int gcount[2][2][NOBJ > 0 ? NOBJ : 1];
+      for (int p2 = o + 1; p2 < NOBJ; p2++) add_pair<T>(C, ob[o], ob[p2], BC_OBJ0 + o, BC_OBJ0 + p2, fo, fo, false, -1.f);
+    int gcount[2][2][NO];
     if (MD::HAS_BOXES) {
       for (int a = 0; a < NA; a++) {
         const float ff = (T::FRICTION_SWITCH && e.grasp[a]) ? (float)XARM_FINGER_FRICTION_GRASP : (float)XARM_FINGER_FRICTION_FREE;
         Box f1 = arm_box<T>(D[a], 1), f2 = arm_box<T>(D[a], 2), hd = arm_box<T>(D[a], 0);
         const int c0 = a == 0 ? BC_ARM0_HAND : BC_ARM1_HAND;
         for (int o = 0; o < NOBJ; o++) {
-          gcount[a][0][o] = add_pair<T>(S, f1, ob[o], c0 + 1, BC_OBJ0 + o, ff, fo, true, -1.f);
-          gcount[a][1][o] = add_pair<T>(S, f2, ob[o], c0 + 2, BC_OBJ0 + o, ff, fo, true, -1.f);
-          add_pair<T>(S, hd, ob[o], c0, BC_OBJ0 + o, fo, fo, false, -1.f);
+          gcount[a][0][o] = add_pair<T>(C, f1, ob[o], c0 + 1, BC_OBJ0 + o, ff, fo, true, -1.f);
+          gcount[a][1][o] = add_pair<T>(C, f2, ob[o], c0 + 2, BC_OBJ0 + o, ff, fo, true, -1.f);
+          add_pair<T>(C, hd, ob[o], c0, BC_OBJ0 + o, fo, fo, false, -1.f);
         }
       }
     }
@@ -879,16 +691,16 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
       bar[2].c = v3(org[0], org[1], org[2]) + e.door_q * door_axis();
       const float fd = (float)XARM_DOOR_FRICTION;
       for (int o = 0; o < NOBJ; o++)
-        for (int b = 0; b < 3; b++) add_pair<T>(S, ob[o], bar[b], BC_OBJ0 + o, b == 2 ? BC_DOOR : BC_STATIC, fo, fd, false, 0.f);
+        for (int b = 0; b < 3; b++) add_pair<T>(C, ob[o], bar[b], BC_OBJ0 + o, b == 2 ? BC_DOOR : BC_STATIC, fo, fd, false, 0.f);
       for (int a = 0; a < NA; a++) {
         const float ff = (float)XARM_FINGER_FRICTION_FREE;
         Box f1 = arm_box<T>(D[a], 1), f2 = arm_box<T>(D[a], 2), hd = arm_box<T>(D[a], 0);
         const int c0 = a == 0 ? BC_ARM0_HAND : BC_ARM1_HAND;
         for (int b = 0; b < 3; b++) {
           const int cb = b == 2 ? BC_DOOR : BC_STATIC;
-          add_pair<T>(S, f1, bar[b], c0 + 1, cb, ff, fd, true, 0.f);
-          add_pair<T>(S, f2, bar[b], c0 + 2, cb, ff, fd, true, 0.f);
-          add_pair<T>(S, hd, bar[b], c0, cb, fo, fd, false, 0.f);
+          add_pair<T>(C, f1, bar[b], c0 + 1, cb, ff, fd, true, 0.f);
+          add_pair<T>(C, f2, bar[b], c0 + 2, cb, ff, fd, true, 0.f);
+          add_pair<T>(C, hd, bar[b], c0, cb, fo, fd, false, 0.f);
         }
       }
     }
@@ -898,8 +710,8 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
         Box f1 = arm_box<T>(D[a], 1), f2 = arm_box<T>(D[a], 2);
         const int c0 = a == 0 ? BC_ARM0_HAND : BC_ARM1_HAND;
         for (int k = 0; k < T::NTABLE; k++) {
-          add_pair<T>(S, f1, tb[k], c0 + 1, BC_STATIC, ff, (float)XARM_TABLE_FRICTION, true, -1.f);
-          add_pair<T>(S, f2, tb[k], c0 + 2, BC_STATIC, ff, (float)XARM_TABLE_FRICTION, true, -1.f);
+          add_pair<T>(C, f1, tb[k], c0 + 1, BC_STATIC, ff, (float)XARM_TABLE_FRICTION, true, -1.f);
+          add_pair<T>(C, f2, tb[k], c0 + 2, BC_STATIC, ff, (float)XARM_TABLE_FRICTION, true, -1.f);
         }
       }
     }
@@ -915,13 +727,19 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
     }
   }
 
+#ifdef XARM_HOST_SIM
+  if (getenv("XARM_TRACE")) for (int c = 0; c < C.nc; c++)
+    fprintf(stderr, "K c%d (%d,%d) pa %.6f %.6f %.6f pb %.6f %.6f %.6f n %.4f %.4f %.4f d %.6f\n", c, (int)C.ba[c], (int)C.bb[c], (double)C.pa[c].x, (double)C.pa[c].y, (double)C.pa[c].z,
+            (double)C.pb[c].x, (double)C.pb[c].y, (double)C.pb[c].z, (double)C.dir[c][0].x, (double)C.dir[c][0].y, (double)C.dir[c][0].z, (double)C.depth[c]);
+#endif
   // ---- 2. unconstrained velocities of the free bodies (the arms' are in D[a].qdu)
+  V3 vu[NO], wu[NO];
   float door_qdu = 0.f;
   for (int o = 0; o < NOBJ; o++) {
     const ObjState& b = e.obj[o];
     float kl = (float)XARM_MB_LINEAR_DAMPING * (1.f + norm(b.v)), ka = (float)XARM_MB_ANGULAR_DAMPING * (1.f + norm(b.w));
-    S.dv[o] = b.v + h * ((-kl) * b.v); S.dv[o].z -= h * (float)XARM_GRAVITY;
-    S.dw[o] = b.w + h * ((-ka) * b.w);
+    vu[o] = b.v + h * ((-kl) * b.v); vu[o].z -= h * (float)XARM_GRAVITY;
+    wu[o] = b.w + h * ((-ka) * b.w);
   }
   if (T::HAS_DOOR) {
     float v = e.door_qd;
@@ -929,139 +747,320 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
     door_qdu = v + h * f / (float)XARM_DOOR_MASS;
   }
 
-  // ---- 3. rows
-#pragma unroll
-  for (int a = 0; a < NA; a++) {
-    const ArmState<MD>& st = e.arm[a];
-    S.lim_lo_mask[a] = 0; S.lim_hi_mask[a] = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      const float den = D[a].Minv[tri(i, i)];
-      float pen_lo = st.q[i] - MD::lo(i), pen_hi = MD::hi(i) - st.q[i];
-      S.lim_rhs[a][i] = 0.f; S.lim_app[a][i] = 0.f;
-      if (pen_lo <= 0.f) { S.lim_lo_mask[a] |= 1u << i; S.lim_rhs[a][i] = (-pen_lo * (float)XARM_ERP / h - D[a].qdu[i]) / den; }
-      else if (pen_hi <= 0.f) { S.lim_hi_mask[a] |= 1u << i; S.lim_rhs[a][i] = (-pen_hi * (float)XARM_ERP / h + D[a].qdu[i]) / den; }
-      float target = (float)(XARM_MOTOR_KP * XARM_MOTOR_ERP) * (st.qt[i] - st.q[i]) / h;
-      S.mot_rhs[a][i] = (target - D[a].qdu[i]) / den;
-      S.mot_app[a][i] = 0.f;
-      S.mot_hi[a][i] = (float)((i < 7 ? T::ARM_FORCE : T::FINGER_FORCE) * T::TIME_STEP);
-      S.dqd[a][i] = 0.f;
-    }
-    if (MD::HAS_GEAR) {
-      const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
-      const float gr = (float)XARM_GEAR_RATIO;
-      float den = D[a].Minv[tri(f1, f1)] + 2.f * gr * D[a].Minv[tri(f1, f2)] + gr * gr * D[a].Minv[tri(f2, f2)];
-      float rel = D[a].qdu[f1] + gr * D[a].qdu[f2];
-      float pos_err = (float)XARM_GEAR_ERP * (st.q[f1] + gr * st.q[f2]);
-      S.gear_dinv[a] = 1.f / den;
-      S.gear_rhs[a] = (-pos_err * (float)XARM_ERP / h - rel) / den;
-      S.gear_app[a] = 0.f;
-    }
-  }
-  S.gear_hi = (float)(XARM_GEAR_MAX_FORCE * T::TIME_STEP);
-  S.door_lim = false; S.ddoor = 0.f;
-  if (T::HAS_DOOR) {
-    float pen_lo = e.door_q - (float)XARM_DOOR_LIMIT_LO, pen_hi = (float)XARM_DOOR_LIMIT_HI - e.door_q;
-    const float den = 1.f / (float)XARM_DOOR_MASS;
-    S.door_lim_app = 0.f; S.door_mot_app = 0.f;
-    if (pen_lo <= 0.f) { S.door_lim = true; S.door_lim_sign = 1.f; S.door_lim_rhs = (-pen_lo * (float)XARM_ERP / h - door_qdu) / den; }
-    else if (pen_hi <= 0.f) { S.door_lim = true; S.door_lim_sign = -1.f; S.door_lim_rhs = (-pen_hi * (float)XARM_ERP / h + door_qdu) / den; }
-    S.door_mot_rhs = (0.f - door_qdu) / den;
-  }
-  // contact rows: normal rows of all contacts, then the two friction rows of each
-  for (int c = 0; c < S.nc; c++) {
+  // ---- 3. contact rows (setupMultiBodyContactConstraint): normal row and two friction rows per point
+  for (int c = 0; c < C.nc; c++) {
     V3 t1, t2;
-    plane_space(S.dir[c][0], t1, t2);
-    S.dir[c][1] = t1; S.dir[c][2] = t2;
-    const int ca = S.ba[c], cb = S.bb[c];
+    plane_space(C.dir[c][0], t1, t2);
+    C.dir[c][1] = t1; C.dir[c][2] = t2;
+    const int ca = C.ba[c], cb = C.bb[c];
+    int o1 = -1, o2 = -1; float s1 = 1.f;
+    if (bc_is_obj(ca)) { o1 = NOBJ <= 1 ? 0 : ca - BC_OBJ0; s1 = 1.f; if (bc_is_obj(cb)) o2 = NOBJ <= 1 ? 0 : cb - BC_OBJ0; }
+    else if (bc_is_obj(cb)) { o1 = NOBJ <= 1 ? 0 : cb - BC_OBJ0; s1 = -1.f; }
+    C.o1[c] = (int8_t)o1; C.o2[c] = (int8_t)o2; C.s1[c] = s1;
     for (int k = 0; k < 3; k++) {
-      float rel = 0.f;
-      float den = row_side<T>(S, e, D, ca, c, k, S.pa[c], S.dir[c][k], 1.f, door_qdu, rel);
-      den += row_side<T>(S, e, D, cb, c, k, S.pb[c], S.dir[c][k], -1.f, door_qdu, rel);
-      S.app[c][k] = 0.f;
+      const V3 d = C.dir[c][k];
+      float den = 0.f, rel = 0.f;
+      if (o1 >= 0) {
+        const int o = NOBJ <= 1 ? 0 : o1;
+        V3 r = (s1 > 0.f ? C.pa[c] : C.pb[c]) - e.obj[o].pos;
+        V3 rxd = cross(r, d), ir = Iinv[o] * rxd;
+        C.Jo1[c][k] = s1 * rxd; C.dVo1[c][k] = s1 * ir;
+        den += 1.f / T::OBJ_MASS + dot(rxd, ir);
+        rel += s1 * (dot(d, vu[o]) + dot(rxd, wu[o]));
+      }
+      if (NOBJ > 1 && o2 >= 0) {
+        V3 r = C.pb[c] - e.obj[o2].pos;
+        V3 rxd = cross(r, d), ir = Iinv[o2] * rxd;
+        C.Jo2[NOBJ > 1 ? c : 0][k] = -rxd; C.dVo2[NOBJ > 1 ? c : 0][k] = -ir;
+        den += 1.f / T::OBJ_MASS + dot(rxd, ir);
+        rel -= dot(d, vu[o2]) + dot(rxd, wu[o2]);
+      }
+      if (C.slot[c] >= 0) {  // gripper link side: J_j = S_j . [p x d ; d] over the link's ancestors, response Minv J
+        const int code = bc_is_arm(ca) ? ca : cb;
+        const float sign = bc_is_arm(ca) ? 1.f : -1.f;
+        const V3 p = bc_is_arm(ca) ? C.pa[c] : C.pb[c];
+        const int a = NA == 1 ? 0 : bc_arm(code);
+        const int which = (code - BC_ARM0_HAND) % 3;
+        const int sl = C.slot[c];
+        const ArmDyn<MD>& Da = D[a];
+        V3 pxd = cross(p, d);
+        float J[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+          bool on = j < 7 || (which == 1 && j == MD::F1) || (which == 2 && j == MD::F2);
+          J[j] = on ? sign * (dot(Da.S[j].a, pxd) + dot(Da.S[j].l, d)) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int j = 0; j < N; j++) sacc += Da.Minv[tri(i, j)] * J[j];
+          C.Jarm[sl][k][i] = J[i];
+          C.dVarm[sl][k][i] = sacc;
+          den += J[i] * sacc;
+          rel += J[i] * Da.qdu[i];
+        }
+      }
+      if (T::HAS_DOOR) {
+        float jd = 0.f;
+        if (ca == BC_DOOR) jd = dot(door_axis(), d); else if (cb == BC_DOOR) jd = -dot(door_axis(), d);
+        C.jdoor[T::HAS_DOOR ? c : 0][k] = jd;
+        den += jd * jd / (float)XARM_DOOR_MASS;
+        rel += jd * door_qdu;
+      }
+      C.app[c][k] = 0.f;
       if (k == 0) {
-        float dinv = 1.f / (den + S.cfm0[c]);
-        float pen = -S.depth[c] + (float)XARM_LINEAR_SLOP;
+        float dinv = 1.f / (den + C.cfm0[c]);
+        float pen = -C.depth[c] + (float)XARM_LINEAR_SLOP;
         float pos_err = 0.f, vel_err = -rel;
-        if (pen > 0.f) vel_err -= pen / h; else pos_err = -pen * S.erp[c] / h;
-        S.rhs[c][0] = (pos_err + vel_err) * dinv;
-        S.dinv[c][0] = dinv;
-        S.cfmr[c] = S.cfm0[c] * dinv;
+        if (pen > 0.f) vel_err -= pen / h; else pos_err = -pen * C.erp[c] / h;
+        C.rhs[c][0] = (pos_err + vel_err) * dinv;
+        C.dinv[c][0] = dinv;
+        C.cfmr[c] = C.cfm0[c] * dinv;
       } else {
         float dinv = 1.f / den;
-        S.rhs[c][k] = -rel * dinv;
-        S.dinv[c][k] = dinv;
+        C.rhs[c][k] = -rel * dinv;
+        C.dinv[c][k] = dinv;
       }
     }
   }
-  // from here on dv/dw accumulate velocity CHANGES; keep the unconstrained object velocities aside
-  V3 vu[NOBJ > 0 ? NOBJ : 1], wu[NOBJ > 0 ? NOBJ : 1];
-  for (int o = 0; o < NOBJ; o++) { vu[o] = S.dv[o]; wu[o] = S.dw[o]; S.dv[o] = v3(0, 0, 0); S.dw[o] = v3(0, 0, 0); }
-  // convert contact points to body-relative arms for the object sides
-  for (int c = 0; c < S.nc; c++) {
-    if (bc_is_obj(S.ba[c])) S.pa[c] = S.pa[c] - e.obj[T::NOBJ <= 1 ? 0 : S.ba[c] - BC_OBJ0].pos;
-    if (bc_is_obj(S.bb[c])) S.pb[c] = S.pb[c] - e.obj[T::NOBJ <= 1 ? 0 : S.bb[c] - BC_OBJ0].pos;
+
+  // ---- 4. arm / door rows in registers, then the PGS sweeps (btMultiBodyConstraintSolver::solveSingleIteration)
+  float Mi[NA][NT], iden[NA][N], dqd[NA][N], mrhs[NA][N], mapp[NA][N], lrhs[NA][N], lapp[NA][N];
+  uint32_t lim_lo[NA], lim_hi[NA];
+  float grhs[NA], gapp[NA], gdinv[NA];
+  const float hi_arm = (float)(T::ARM_FORCE * T::TIME_STEP), hi_fin = (float)(T::FINGER_FORCE * T::TIME_STEP);
+  const float hi_gear = (float)(XARM_GEAR_MAX_FORCE * T::TIME_STEP), hi_lim = (float)XARM_LIMIT_MAX_IMPULSE;
+  const float gr = (float)XARM_GEAR_RATIO;
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    const ArmState<MD>& st = e.arm[a];
+#pragma unroll
+    for (int i = 0; i < NT; i++) Mi[a][i] = D[a].Minv[i];
+    lim_lo[a] = 0; lim_hi[a] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const float den = Mi[a][tri(i, i)], qdu = D[a].qdu[i];
+      iden[a][i] = 1.f / den;
+      float pen_lo = st.q[i] - MD::lo(i), pen_hi = MD::hi(i) - st.q[i];
+      lrhs[a][i] = 0.f; lapp[a][i] = 0.f;
+      if (pen_lo <= 0.f) { lim_lo[a] |= 1u << i; lrhs[a][i] = (-pen_lo * (float)XARM_ERP / h - qdu) / den; }
+      else if (pen_hi <= 0.f) { lim_hi[a] |= 1u << i; lrhs[a][i] = (-pen_hi * (float)XARM_ERP / h + qdu) / den; }
+      float target = (float)(XARM_MOTOR_KP * XARM_MOTOR_ERP) * (st.qt[i] - st.q[i]) / h;
+      mrhs[a][i] = (target - qdu) / den;
+      mapp[a][i] = 0.f; dqd[a][i] = 0.f;
+    }
+    grhs[a] = 0.f; gapp[a] = 0.f; gdinv[a] = 0.f;
+    if (MD::HAS_GEAR) {
+      const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
+      float den = Mi[a][tri(f1, f1)] + 2.f * gr * Mi[a][tri(f1, f2)] + gr * gr * Mi[a][tri(f2, f2)];
+      float rel = D[a].qdu[f1] + gr * D[a].qdu[f2];
+      float pos_err = (float)XARM_GEAR_ERP * (st.q[f1] + gr * st.q[f2]);
+      gdinv[a] = 1.f / den;
+      grhs[a] = (-pos_err * (float)XARM_ERP / h - rel) / den;
+    }
+  }
+  bool door_lim = false; float ddoor = 0.f, dl_rhs = 0.f, dl_app = 0.f, dl_sign = 1.f, dm_rhs = 0.f, dm_app = 0.f;
+  const float door_den = 1.f / (float)XARM_DOOR_MASS;
+  if (T::HAS_DOOR) {
+    float pen_lo = e.door_q - (float)XARM_DOOR_LIMIT_LO, pen_hi = (float)XARM_DOOR_LIMIT_HI - e.door_q;
+    if (pen_lo <= 0.f) { door_lim = true; dl_sign = 1.f; dl_rhs = (-pen_lo * (float)XARM_ERP / h - door_qdu) / door_den; }
+    else if (pen_hi <= 0.f) { door_lim = true; dl_sign = -1.f; dl_rhs = (-pen_hi * (float)XARM_ERP / h + door_qdu) / door_den; }
+    dm_rhs = (0.f - door_qdu) / door_den;
+  }
+  V3 dv[NO], dw[NO];
+#pragma unroll
+  for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
+
+// one unit row (J = sign * e_i) of arm a: motors and joint limits
+#define UNIT_ROW(a, i, sign, rhs_, lo_, hi_, app_)                                   \
+  {                                                                                   \
+    float delta = (rhs_) - (sign) * dqd[a][i] * iden[a][i];                           \
+    float sum = (app_) + delta;                                                       \
+    if (sum < (lo_)) { delta = (lo_) - (app_); sum = (lo_); }                         \
+    else if (sum > (hi_)) { delta = (hi_) - (app_); sum = (hi_); }                    \
+    (app_) = sum;                                                                     \
+    const float sd = (sign) * delta;                                                  \
+    _Pragma("unroll") for (int k_ = 0; k_ < N; k_++) dqd[a][k_] += Mi[a][tri(k_, i)] * sd; \
+    const float rv = delta * Mi[a][tri(i, i)];                                        \
+    resid = fmaxf(resid, rv * rv);                                                    \
+  }
+#define GEAR_ROW(a)                                                                   \
+  if (MD::HAS_GEAR) {                                                                 \
+    const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;                              \
+    float delta = grhs[a] - (dqd[a][f1] + gr * dqd[a][f2]) * gdinv[a];                \
+    float sum = gapp[a] + delta;                                                      \
+    if (sum < -hi_gear) { delta = -hi_gear - gapp[a]; sum = -hi_gear; }               \
+    else if (sum > hi_gear) { delta = hi_gear - gapp[a]; sum = hi_gear; }             \
+    gapp[a] = sum;                                                                    \
+    _Pragma("unroll") for (int k_ = 0; k_ < N; k_++) dqd[a][k_] += (Mi[a][tri(k_, f1)] + gr * Mi[a][tri(k_, f2)]) * delta; \
+    const float rv = delta / gdinv[a];                                                \
+    resid = fmaxf(resid, rv * rv);                                                    \
+  }
+#define DOOR_LIMIT_ROW()                                                              \
+  if (door_lim) {                                                                     \
+    float delta = dl_rhs - dl_sign * ddoor / door_den;                                \
+    float sum = dl_app + delta;                                                       \
+    if (sum < 0.f) { delta = -dl_app; sum = 0.f; } else if (sum > hi_lim) { delta = hi_lim - dl_app; sum = hi_lim; } \
+    dl_app = sum; ddoor += dl_sign * delta * door_den;                                \
+    const float rv = delta * door_den; resid = fmaxf(resid, rv * rv);                 \
+  }
+#define DOOR_MOTOR_ROW()                                                              \
+  {                                                                                   \
+    const float hi_ = (float)XARM_DEFAULT_MOTOR_MAX_IMPULSE;                          \
+    float delta = dm_rhs - ddoor / door_den;                                          \
+    float sum = dm_app + delta;                                                       \
+    if (sum < -hi_) { delta = -hi_ - dm_app; sum = -hi_; } else if (sum > hi_) { delta = hi_ - dm_app; sum = hi_; } \
+    dm_app = sum; ddoor += delta * door_den;                                          \
+    const float rv = delta * door_den; resid = fmaxf(resid, rv * rv);                 \
   }
 
-  // ---- 4. PGS sweeps (btMultiBodyConstraintSolver::solveSingleIteration)
-  for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
-    float resid = 0.f;
-    const bool forward = it & 1;
-    if (forward) {
-#pragma unroll
-      for (int a = 0; a < NA; a++) arm_rows_sweep<T>(S, D[a], a, true, resid);
-      if (T::HAS_DOOR) door_rows_sweep<T>(S, true, resid);
-    } else {
-      if (T::HAS_DOOR) door_rows_sweep<T>(S, false, resid);
-#pragma unroll
-      for (int a = NA - 1; a >= 0; a--) arm_rows_sweep<T>(S, D[a], a, false, resid);
-    }
-    for (int c = 0; c < S.nc; c++) {
-      const int ca = S.ba[c], cb = S.bb[c];
-      V3 d = S.dir[c][0];
-      float jv = side_jv<T>(S, ca, c, 0, S.pa[c], d, 1.f) + side_jv<T>(S, cb, c, 0, S.pb[c], d, -1.f);
-      float delta = S.rhs[c][0] - S.app[c][0] * S.cfmr[c] - jv * S.dinv[c][0];
-      float sum = S.app[c][0] + delta;
-      if (sum < 0.f) { delta = -S.app[c][0]; sum = 0.f; } else if (sum > (float)XARM_CONTACT_MAX_IMPULSE) { delta = (float)XARM_CONTACT_MAX_IMPULSE - S.app[c][0]; sum = (float)XARM_CONTACT_MAX_IMPULSE; }
-      S.app[c][0] = sum;
-      side_apply<T>(S, ca, c, 0, S.pa[c], d, 1.f, delta);
-      side_apply<T>(S, cb, c, 0, S.pb[c], d, -1.f, delta);
-      float rv = delta / S.dinv[c][0];
-      resid = fmaxf(resid, rv * rv);
-    }
-    for (int c = 0; c < S.nc; c++) {  // cone friction: both deltas from the same state, joint clamp
-      const int ca = S.ba[c], cb = S.bb[c];
-      V3 d1 = S.dir[c][1], d2 = S.dir[c][2];
-      float lim = S.mu[c] * S.app[c][0];
-      float j1 = side_jv<T>(S, ca, c, 1, S.pa[c], d1, 1.f) + side_jv<T>(S, cb, c, 1, S.pb[c], d1, -1.f);
-      float j2 = side_jv<T>(S, ca, c, 2, S.pa[c], d2, 1.f) + side_jv<T>(S, cb, c, 2, S.pb[c], d2, -1.f);
-      float da = S.rhs[c][1] - j1 * S.dinv[c][1], db = S.rhs[c][2] - j2 * S.dinv[c][2];
-      float sa = S.app[c][1] + da, sb = S.app[c][2] + db;
-      float len = sqrtf(sa * sa + sb * sb);
-      if (len > lim) { float sc = len > 0.f ? lim / len : 0.f; sa *= sc; sb *= sc; da = sa - S.app[c][1]; db = sb - S.app[c][2]; }
-      S.app[c][1] = sa; S.app[c][2] = sb;
-      side_apply<T>(S, ca, c, 1, S.pa[c], d1, 1.f, da);
-      side_apply<T>(S, cb, c, 1, S.pb[c], d1, -1.f, da);
-      side_apply<T>(S, ca, c, 2, S.pa[c], d2, 1.f, db);
-      side_apply<T>(S, cb, c, 2, S.pb[c], d2, -1.f, db);
-      float r1 = da / S.dinv[c][1], r2 = db / S.dinv[c][2];
-      resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));
-    }
-    if (resid <= (float)XARM_RESIDUAL_THRESHOLD) break;
+// one sweep over the non-contact rows: forward on odd iterations, exact reverse on even ones
+#define ARM_ROWS_SWEEP(it)                                                                                      \
+  if ((it) & 1) {                                                                                                \
+    _Pragma("unroll") for (int a = 0; a < NA; a++) {                                                             \
+      if (lim_lo[a] | lim_hi[a]) {                                                                               \
+        _Pragma("unroll") for (int i = 0; i < N; i++) {                                                          \
+          if (lim_lo[a] >> i & 1) UNIT_ROW(a, i, 1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                       \
+          if (lim_hi[a] >> i & 1) UNIT_ROW(a, i, -1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                      \
+        }                                                                                                        \
+      }                                                                                                          \
+      _Pragma("unroll") for (int i = 0; i < N; i++) { const float hi_ = i < 7 ? hi_arm : hi_fin; UNIT_ROW(a, i, 1.f, mrhs[a][i], -hi_, hi_, mapp[a][i]) } \
+      GEAR_ROW(a)                                                                                                \
+    }                                                                                                            \
+    if (T::HAS_DOOR) { DOOR_LIMIT_ROW() DOOR_MOTOR_ROW() }                                                       \
+  } else {                                                                                                       \
+    if (T::HAS_DOOR) { DOOR_MOTOR_ROW() DOOR_LIMIT_ROW() }                                                       \
+    _Pragma("unroll") for (int a = NA - 1; a >= 0; a--) {                                                        \
+      GEAR_ROW(a)                                                                                                \
+      _Pragma("unroll") for (int i = N - 1; i >= 0; i--) { const float hi_ = i < 7 ? hi_arm : hi_fin; UNIT_ROW(a, i, 1.f, mrhs[a][i], -hi_, hi_, mapp[a][i]) } \
+      if (lim_lo[a] | lim_hi[a]) {                                                                               \
+        _Pragma("unroll") for (int i = N - 1; i >= 0; i--) {                                                     \
+          if (lim_hi[a] >> i & 1) UNIT_ROW(a, i, -1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                      \
+          if (lim_lo[a] >> i & 1) UNIT_ROW(a, i, 1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                       \
+        }                                                                                                        \
+      }                                                                                                          \
+    }                                                                                                            \
   }
+
+// the contact rows of one iteration: all normal rows, then the friction pairs (implicit cone).  COUPLED=false is the
+// object-only form used when no contact touches an arm link or the door (single-object tasks).
+#define CONTACT_ROWS_SWEEP(COUPLED)                                                                              \
+  for (int phase = 0; phase < 2; phase++) {                                                                      \
+    for (int c = 0; c < C.nc; c++) {                                                                             \
+      const int o1 = NOBJ <= 1 ? (C.o1[c] >= 0 ? 0 : -1) : C.o1[c];                                              \
+      const int o2 = NOBJ > 1 ? C.o2[c] : -1;                                                                    \
+      const int sl = (COUPLED) ? C.slot[c] : -1;                                                                 \
+      const float s1 = C.s1[c];                                                                                  \
+      const int arm_of = ((COUPLED) && NA > 1 && sl >= 0) ? bc_arm(bc_is_arm(C.ba[c]) ? C.ba[c] : C.bb[c]) : 0;  \
+      float delta[3] = {0.f, 0.f, 0.f};                                                                          \
+      const int k0 = phase == 0 ? 0 : 1, k1 = phase == 0 ? 1 : 3;                                                \
+      float jv[3] = {0.f, 0.f, 0.f};                                                                             \
+      for (int k = k0; k < k1; k++) {                                                                            \
+        const V3 d = C.dir[c][k];                                                                                \
+        float s_ = 0.f;                                                                                          \
+        if (o1 >= 0) s_ += s1 * dot(d, dv[NOBJ <= 1 ? 0 : o1]) + dot(C.Jo1[c][k], dw[NOBJ <= 1 ? 0 : o1]);       \
+        if (NOBJ > 1 && o2 >= 0) s_ += -dot(d, dv[o2 < 0 ? 0 : o2]) + dot(C.Jo2[NOBJ > 1 ? c : 0][k], dw[o2 < 0 ? 0 : o2]); \
+        if ((COUPLED) && sl >= 0) {                                                                              \
+          if (NA == 1 || arm_of == 0) { _Pragma("unroll") for (int i = 0; i < N; i++) s_ += C.Jarm[sl][k][i] * dqd[0][i]; } \
+          else { _Pragma("unroll") for (int i = 0; i < N; i++) s_ += C.Jarm[sl][k][i] * dqd[NA - 1][i]; }        \
+        }                                                                                                        \
+        if ((COUPLED) && T::HAS_DOOR) s_ += C.jdoor[T::HAS_DOOR ? c : 0][k] * ddoor;                             \
+        jv[k] = s_;                                                                                              \
+      }                                                                                                          \
+      if (phase == 0) {                                                                                          \
+        float d0 = C.rhs[c][0] - C.app[c][0] * C.cfmr[c] - jv[0] * C.dinv[c][0];                                 \
+        float sum = C.app[c][0] + d0;                                                                            \
+        if (sum < 0.f) { d0 = -C.app[c][0]; sum = 0.f; }                                                         \
+        else if (sum > (float)XARM_CONTACT_MAX_IMPULSE) { d0 = (float)XARM_CONTACT_MAX_IMPULSE - C.app[c][0]; sum = (float)XARM_CONTACT_MAX_IMPULSE; } \
+        C.app[c][0] = sum;                                                                                       \
+        delta[0] = d0;                                                                                           \
+        float rv = d0 / C.dinv[c][0];                                                                            \
+        resid = fmaxf(resid, rv * rv);                                                                           \
+      } else {                                                                                                   \
+        float lim = C.mu[c] * C.app[c][0];                                                                       \
+        float da = C.rhs[c][1] - jv[1] * C.dinv[c][1], db = C.rhs[c][2] - jv[2] * C.dinv[c][2];                  \
+        float sa = C.app[c][1] + da, sb = C.app[c][2] + db;                                                      \
+        float len = sqrtf(sa * sa + sb * sb);                                                                    \
+        if (len > lim) { float sc = len > 0.f ? lim / len : 0.f; sa *= sc; sb *= sc; da = sa - C.app[c][1]; db = sb - C.app[c][2]; } \
+        C.app[c][1] = sa; C.app[c][2] = sb;                                                                      \
+        delta[1] = da; delta[2] = db;                                                                            \
+        float r1 = da / C.dinv[c][1], r2 = db / C.dinv[c][2];                                                    \
+        resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));                                                           \
+      }                                                                                                          \
+      for (int k = k0; k < k1; k++) {                                                                            \
+        const V3 d = C.dir[c][k];                                                                                \
+        const float dl = delta[k];                                                                               \
+        if (o1 >= 0) { dv[NOBJ <= 1 ? 0 : o1] += (s1 * dl / T::OBJ_MASS) * d; dw[NOBJ <= 1 ? 0 : o1] += dl * C.dVo1[c][k]; } \
+        if (NOBJ > 1 && o2 >= 0) { dv[o2 < 0 ? 0 : o2] += (-dl / T::OBJ_MASS) * d; dw[o2 < 0 ? 0 : o2] += dl * C.dVo2[NOBJ > 1 ? c : 0][k]; } \
+        if ((COUPLED) && sl >= 0) {                                                                              \
+          if (NA == 1 || arm_of == 0) { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[0][i] += C.dVarm[sl][k][i] * dl; } \
+          else { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[NA - 1][i] += C.dVarm[sl][k][i] * dl; }       \
+        }                                                                                                        \
+        if ((COUPLED) && T::HAS_DOOR) ddoor += C.jdoor[T::HAS_DOOR ? c : 0][k] * dl / (float)XARM_DOOR_MASS;     \
+      }                                                                                                          \
+    }                                                                                                            \
+  }
+
+  // Islands: when no contact touches an arm link (and the task has one arm and no door) the arm rows and the object
+  // rows never read each other's velocities, so sweeping them in two separate loops gives bit-identical impulses.
+  // Only the early-exit test couples them (max residual over ALL rows); it is reproduced from per-iteration masks
+  // and, in the (never observed) case that it would have fired before the last iteration, the joint loop is re-run.
+  bool joint_loop = true;
+  if (NA == 1 && !T::HAS_DOOR && C.nac == 0) {
+    joint_loop = false;
+    const float thr = (float)XARM_RESIDUAL_THRESHOLD;
+    unsigned long long ok_arm = 0ull, ok_obj = 0ull;
+    for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+      float resid = 0.f;
+      ARM_ROWS_SWEEP(it)
+      if (resid <= thr) { ok_arm |= 1ull << it; if (C.nc == 0) break; }
+    }
+    if (C.nc > 0) {
+      for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+        float resid = 0.f;
+        CONTACT_ROWS_SWEEP(false)
+        if (resid <= thr) ok_obj |= 1ull << it;
+      }
+      const unsigned long long both = ok_arm & ok_obj & ((1ull << (XARM_SOLVER_ITERATIONS - 1)) - 1ull);
+      if (both) {  // the joint loop would have stopped early: redo it exactly
+        joint_loop = true;
+#pragma unroll
+        for (int i = 0; i < N; i++) { dqd[0][i] = 0.f; mapp[0][i] = 0.f; lapp[0][i] = 0.f; }
+        gapp[0] = 0.f;
+#pragma unroll
+        for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
+        for (int c = 0; c < C.nc; c++) { C.app[c][0] = 0.f; C.app[c][1] = 0.f; C.app[c][2] = 0.f; }
+      }
+    }
+  }
+  if (joint_loop) {
+    for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+      float resid = 0.f;
+      ARM_ROWS_SWEEP(it)
+      CONTACT_ROWS_SWEEP(true)
+      if (resid <= (float)XARM_RESIDUAL_THRESHOLD) break;
+    }
+  }
+#undef ARM_ROWS_SWEEP
+#undef CONTACT_ROWS_SWEEP
+#undef UNIT_ROW
+#undef GEAR_ROW
+#undef DOOR_LIMIT_ROW
+#undef DOOR_MOTOR_ROW
 
   // ---- 5. integrate (stepPositionsMultiDof)
 #pragma unroll
   for (int a = 0; a < NA; a++)
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      float qd = D[a].qdu[i] + S.dqd[a][i];
+      float qd = D[a].qdu[i] + dqd[a][i];
       e.arm[a].qd[i] = qd;
       e.arm[a].q[i] += qd * h;
     }
   for (int o = 0; o < NOBJ; o++) {
     ObjState& b = e.obj[o];
-    b.v = vu[o] + S.dv[o]; b.w = wu[o] + S.dw[o];
+    b.v = vu[o] + dv[o]; b.w = wu[o] + dw[o];
     b.pos += h * b.v;
     float ang = norm(b.w);
     if (ang * h > (float)XARM_ANGULAR_MOTION_THRESHOLD) ang = (float)XARM_ANGULAR_MOTION_THRESHOLD / h;
@@ -1073,7 +1072,15 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
     float inv = rsqrtf(qn.x * qn.x + qn.y * qn.y + qn.z * qn.z + qn.w * qn.w);
     b.quat.x = qn.x * inv; b.quat.y = qn.y * inv; b.quat.z = qn.z * inv; b.quat.w = qn.w * inv;
   }
-  if (T::HAS_DOOR) { e.door_qd = door_qdu + S.ddoor; e.door_q += e.door_qd * h; }
+  if (T::HAS_DOOR) { e.door_qd = door_qdu + ddoor; e.door_q += e.door_qd * h; }
+#ifdef XARM_HOST_SIM
+  if (getenv("XARM_TRACE")) {
+    fprintf(stderr, "KS nc %d qd", C.nc);
+    for (int a = 0; a < NA; a++) for (int i = 0; i < N; i++) fprintf(stderr, " %.10f", (double)e.arm[a].qd[i]);
+    for (int o = 0; o < NOBJ; o++) fprintf(stderr, " %.10f %.10f %.10f %.10f %.10f %.10f", (double)e.obj[o].v.x, (double)e.obj[o].v.y, (double)e.obj[o].v.z, (double)e.obj[o].w.x, (double)e.obj[o].w.y, (double)e.obj[o].w.z);
+    fprintf(stderr, "\n");
+  }
+#endif
 }
 
 // p.stepSimulation() x calls per env step

@@ -54,6 +54,8 @@ def lib():
         L.or_set_state.argtypes = [C.c_void_p, fp]
         L.or_get_state_d.argtypes = [C.c_void_p, dp]
         L.or_set_state_d.argtypes = [C.c_void_p, dp]
+        L.or_arm_contacts.restype = C.c_long
+        L.or_arm_contacts.argtypes = [C.c_void_p, C.c_int]
         L.or_flops.restype = C.c_double
         L.or_flops.argtypes = [C.c_void_p, C.c_int]
         L.or_compute_reward.argtypes = [C.c_int32, C.c_int32, C.c_int32, fp, fp, C.c_int64, fp]
@@ -62,6 +64,9 @@ def lib():
         L.or_ik.argtypes = [C.c_int32, C.c_int, dp, dp, dp]
         L.or_box_box.argtypes = [dp, dp, dp]
         L.or_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.or_debug_assemble_obs.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, fp, fp, fp, fp]
+        L.or_debug_command.argtypes = [C.c_int32, C.c_int, fp, dp, C.c_double, dp, C.POINTER(C.c_double)]
+        L.or_debug_lego_clamp.argtypes = [dp, dp]
         L.or_bench.restype = C.c_double
         L.or_bench.argtypes = [C.POINTER(XarmConfig), C.c_int64, C.c_int, C.c_int, dp]
         _lib = L
@@ -158,6 +163,10 @@ class OracleEnv:
         s = np.ascontiguousarray(s, np.float64)
         self.L.or_set_state_d(self.h, _d(s))
 
+    def arm_contacts(self, reset=True):
+        """gripper-link contact points since the last call (parity tests: contact-free steps get the strict tolerance)"""
+        return self.L.or_arm_contacts(self.h, int(reset))
+
     def flops(self, reset=True):
         return self.L.or_flops(self.h, int(reset))
 
@@ -203,6 +212,33 @@ def box_box(A, B):
     out = np.zeros(40)
     n = lib().or_box_box(_d(a), _d(b), _d(out))
     return [(out[10 * i:10 * i + 3].copy(), out[10 * i + 3:10 * i + 6].copy(), out[10 * i + 6:10 * i + 9].copy(), out[10 * i + 9]) for i in range(n)]
+
+
+def assemble_obs(task, num_obj, hand_pos, hand_vel, finger_q, finger_qd, obj, goal):
+    t = TASKS[task]
+    a, o, g, _ = dims(t, max(num_obj, 1) if t in (1, 4) else num_obj)
+    hp, hv = np.ascontiguousarray(hand_pos, np.float64), np.ascontiguousarray(hand_vel, np.float64)
+    fq, fqd = np.ascontiguousarray(finger_q, np.float64), np.ascontiguousarray(finger_qd, np.float64)
+    ob = np.ascontiguousarray(obj, np.float64) if obj is not None and len(obj) else np.zeros(13)
+    gl = np.ascontiguousarray(goal, np.float32)
+    obs, ag, dg = np.zeros(o, np.float32), np.zeros(g, np.float32), np.zeros(g, np.float32)
+    rc = lib().or_debug_assemble_obs(t, num_obj, _d(hp), _d(hv), _d(fq), _d(fqd), _d(ob), _f(gl), _f(obs), _f(ag), _f(dg))
+    assert rc == 0
+    return {"observation": obs, "achieved_goal": ag, "desired_goal": dg}
+
+
+def command(task, arm, action, eef, finger_q):
+    action = np.ascontiguousarray(action, np.float32)
+    eef = np.ascontiguousarray(eef, np.float64)
+    tgt, g = np.zeros(3), C.c_double()
+    assert lib().or_debug_command(TASKS[task], arm, _f(action), _d(eef), float(finger_q), _d(tgt), C.byref(g)) == 0
+    return tgt, g.value
+
+
+def lego_clamp(pos, quat):
+    pos, quat = np.array(pos, np.float64), np.array(quat, np.float64)
+    lib().or_debug_lego_clamp(_d(pos), _d(quat))
+    return pos, quat
 
 
 def philox(seed, env, episode, block):

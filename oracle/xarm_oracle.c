@@ -309,6 +309,9 @@ typedef struct OrEnv {
   int grasp[MAXARM];
   uint32_t rng_draw; /* draws consumed in the current episode */
   double flops;      /* instrumented flop counter (FMA=2) over PGS/ABA inner loops: see or_flops() */
+  long st_substeps, st_iters, st_rows, st_contacts; /* solver statistics (or_solver_stats) */
+  long st_hist_nc[XARM_MAX_CONTACTS + 1], st_hist_nac[XARM_MAX_ARM_CONTACTS + 1];
+  long arm_contacts; /* contact points that involved a gripper link since the last or_arm_contacts() (test aid) */
 } OrEnv;
 
 /* ------------------------------------------------------------------------------------------------ RNG (Appendix E) */
@@ -985,10 +988,13 @@ static void substep(OrEnv* e, int apply_damping, int last) {
     if (with_arm && XARM_MAX_ARM_CONTACTS - nac < room) room = XARM_MAX_ARM_CONTACTS - nac;
     if (room <= 0) continue;
     int k = box_box(A, B, &contacts[nc], room < 4 ? room : 4);
-    if (with_arm) nac += k;
+    if (with_arm) { nac += k; e->arm_contacts += k; }
     for (int i = 0; i < k; i++) { contacts[nc + i].ca = w.pair[p][0]; contacts[nc + i].cb = w.pair[p][1]; }
     pair_count[p] = k; nc += k;
   }
+  if (getenv("XARM_TRACE")) for (int c = 0; c < nc; c++)
+    fprintf(stderr, "O env %ld c%d (%d,%d) pa %.6f %.6f %.6f pb %.6f %.6f %.6f n %.4f %.4f %.4f d %.6f\n", (long)e->env_index, c, w.col[contacts[c].ca].body * 10 + w.col[contacts[c].ca].link, w.col[contacts[c].cb].body,
+            contacts[c].pa[0], contacts[c].pa[1], contacts[c].pa[2], contacts[c].pb[0], contacts[c].pb[1], contacts[c].pb[2], contacts[c].n[0], contacts[c].n[1], contacts[c].n[2], contacts[c].depth);
   /* grasp flags = "both finger links hold >= 1 manifold point with lego 0 / any lego" at the time of the last
    * collision pass [REF xarm_pick_and_place.py:212, xarm_handover.py:263-264] */
   if (last && m->has_gripper_boxes)
@@ -1175,8 +1181,10 @@ static void substep(OrEnv* e, int apply_damping, int last) {
         j += 1;
       }
     }
+    e->st_iters += 1;
     if (resid <= XARM_RESIDUAL_THRESHOLD) break;
   }
+  e->st_substeps += 1; e->st_rows += nr; e->st_contacts += nc; e->st_hist_nc[nc] += 1; e->st_hist_nac[nac] += 1;
   for (int i = 0; i < w.nv; i++) w.qd[i] += dqd[i];
   /* 5. integrate positions (stepPositionsMultiDof) */
   for (int a = 0; a < t->n_arms; a++)
@@ -1199,6 +1207,11 @@ static void substep(OrEnv* e, int apply_damping, int last) {
     for (int i = 0; i < 4; i++) s->quat[i] = qn[i] / nn;
   }
   if (t->has_door) { e->door_qd = w.qd[w.door_off]; e->door_q += e->door_qd * h; }
+  if (getenv("XARM_TRACE")) {
+    fprintf(stderr, "OS env %ld nc %d qd", (long)e->env_index, nc);
+    for (int i = 0; i < w.nv; i++) fprintf(stderr, " %.10f", w.qd[i]);
+    fprintf(stderr, "\n");
+  }
 }
 
 /* p.stepSimulation() x (number of calls per env step) */
@@ -1270,28 +1283,32 @@ static void hand_state(const OrEnv* e, int arm, v3 pos, v3 vel) {
   link_point_vel(t->model, &k, t->model->eef_dof, e->arm[arm].qd, pos, vel);
 }
 
-static void get_obs(const OrEnv* e, ObsOut* o) {
-  const Task* t = &e->t;
+/* pure assembly of the observation dict from the quantities the reference reads through PyBullet getters */
+typedef struct {
+  v3 hand_pos[MAXARM], hand_vel[MAXARM];
+  double finger_q[MAXARM], finger_qd[MAXARM];
+  ObjState obj[MAXOBJ];
+  float goal[3 * MAXOBJ];
+} ObsIn;
+
+static void assemble_obs(const Task* t, const ObsIn* in, ObsOut* o) {
   int n = 0;
-  v3 hp[MAXARM], hv[MAXARM];
-  for (int a = 0; a < t->n_arms; a++) hand_state(e, a, hp[a], hv[a]);
+  const v3* hp = in->hand_pos; const v3* hv = in->hand_vel;
   if (t->task == XARM_TASK_REACH) { /* [REF xarm_reach.py:144-161] */
-    const Model* m = t->model;
     for (int c = 0; c < 3; c++) o->obs[n++] = (float)hp[0][c];
     for (int c = 0; c < 3; c++) o->obs[n++] = (float)hv[0][c];
-    o->obs[n++] = (float)e->arm[0].q[m->finger1];
-    o->obs[n++] = (float)e->arm[0].qd[m->finger1];
-    for (int c = 0; c < 3; c++) { o->ag[c] = (float)hp[0][c]; o->dg[c] = e->goal[c]; }
+    o->obs[n++] = (float)in->finger_q[0];
+    o->obs[n++] = (float)in->finger_qd[0];
+    for (int c = 0; c < 3; c++) { o->ag[c] = (float)hp[0][c]; o->dg[c] = in->goal[c]; }
     return;
   }
-  const Model* m = t->model;
   if (t->task == XARM_TASK_PICK_AND_PLACE) { /* [REF xarm_pick_and_place.py:220-248] */
     for (int c = 0; c < 3; c++) o->obs[n++] = (float)hp[0][c];
     for (int c = 0; c < 3; c++) o->obs[n++] = (float)hv[0][c];
-    o->obs[n++] = (float)e->arm[0].q[m->finger1];
-    o->obs[n++] = (float)e->arm[0].qd[m->finger1];
+    o->obs[n++] = (float)in->finger_q[0];
+    o->obs[n++] = (float)in->finger_qd[0];
     for (int i = 0; i < t->n_obj; i++) {
-      const ObjState* s = &e->obj[i];
+      const ObjState* s = &in->obj[i];
       for (int c = 0; c < 3; c++) o->obs[n++] = (float)s->pos[c];
       for (int c = 0; c < 4; c++) o->obs[n++] = (float)s->quat[c];
       for (int c = 0; c < 3; c++) o->obs[n++] = (float)(s->v[c] - hv[0][c]);
@@ -1300,21 +1317,34 @@ static void get_obs(const OrEnv* e, ObsOut* o) {
       for (int c = 0; c < 3; c++) o->ag[3 * i + c] = (float)s->pos[c];
     }
   } else { /* StackTower / PushWithDoor / Handover [REF xarm_stack_tower.py:164-199; xarm_push_with_door.py:162-193; xarm_handover.py:299-336] */
-    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 3; c++) o->obs[n++] = (float)e->obj[i].pos[c];
-    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 4; c++) o->obs[n++] = (float)e->obj[i].quat[c];
-    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 3; c++) o->obs[n++] = (float)e->obj[i].v[c];
-    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 3; c++) o->obs[n++] = (float)e->obj[i].w[c];
+    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 3; c++) o->obs[n++] = (float)in->obj[i].pos[c];
+    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 4; c++) o->obs[n++] = (float)in->obj[i].quat[c];
+    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 3; c++) o->obs[n++] = (float)in->obj[i].v[c];
+    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 3; c++) o->obs[n++] = (float)in->obj[i].w[c];
     for (int a = 0; a < t->n_arms; a++) {
       for (int c = 0; c < 3; c++) o->obs[n++] = (float)(hp[a][c] - t->hand_offset[c]);
       for (int c = 0; c < 3; c++) o->obs[n++] = (float)hv[a][c];
       if (t->task != XARM_TASK_PUSH_WITH_DOOR) {
-        o->obs[n++] = (float)e->arm[a].q[m->finger1];
-        o->obs[n++] = (float)e->arm[a].qd[m->finger1];
+        o->obs[n++] = (float)in->finger_q[a];
+        o->obs[n++] = (float)in->finger_qd[a];
       }
     }
-    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 3; c++) o->ag[3 * i + c] = (float)e->obj[i].pos[c];
+    for (int i = 0; i < t->n_obj; i++) for (int c = 0; c < 3; c++) o->ag[3 * i + c] = (float)in->obj[i].pos[c];
   }
-  for (int c = 0; c < t->goal_dim; c++) o->dg[c] = e->goal[c];
+  for (int c = 0; c < t->goal_dim; c++) o->dg[c] = in->goal[c];
+}
+
+static void get_obs(const OrEnv* e, ObsOut* o) {
+  const Task* t = &e->t;
+  ObsIn in;
+  for (int a = 0; a < t->n_arms; a++) {
+    hand_state(e, a, in.hand_pos[a], in.hand_vel[a]);
+    in.finger_q[a] = e->arm[a].q[t->model->finger1];
+    in.finger_qd[a] = e->arm[a].qd[t->model->finger1];
+  }
+  for (int i = 0; i < t->n_obj; i++) in.obj[i] = e->obj[i];
+  memcpy(in.goal, e->goal, sizeof(in.goal));
+  assemble_obs(t, &in, o);
 }
 
 /* staged dense rewards that read the live simulator (not batch-safe in the reference either) */
@@ -1499,6 +1529,36 @@ static void env_reset(OrEnv* e) {
 }
 
 /* ------------------------------------------------------------------------------------------------ step (_set_action + step) */
+/* pure part of _set_action: eef target and finger target of one arm from the current eef position / finger joint */
+static void arm_command(const Task* t, int a, const float* u, const v3 eef, double finger_q, v3 target, double* grip) {
+  for (int c = 0; c < 3; c++) { /* [REF xarm_pick_and_place.py:202-204] float64 arithmetic, float32 bounds */
+    double np_ = eef[c] + (double)u[c] * t->max_vel * t->dt_cmd;
+    double lo = t->pos_lo[a][c], hi = t->pos_hi[a][c];
+    target[c] = np_ < lo ? lo : (np_ > hi ? hi : np_);
+  }
+  double g = finger_q;
+  if (t->grip_cmd) {
+    g = finger_q + (double)u[3] * t->dt_cmd * t->max_grip_vel; /* [REF :205-206] */
+    if (t->grip_clip) { double lo = t->grip_lo, hi = t->grip_hi; g = g < lo ? lo : (g > hi ? hi : g); }
+  }
+  *grip = g;
+}
+/* Handover: clamp |x|,|y| and keep only pitch, zeroing velocity [REF xarm_handover.py:282-297] */
+static void lego_clamp(ObjState* s) {
+  double x = s->pos[0], y = s->pos[1];
+  const double hx = (float)0.28f, hy = (float)0.2f;
+  int neg = x < 0; if (neg) x = -x;
+  x = x < -hx ? -hx : (x > hx ? hx : x); y = y < -hy ? -hy : (y > hy ? hy : y);
+  if (neg) x = -x;
+  m3 R; quat_to_m3(R, s->quat);
+  /* getEulerFromQuaternion -> pitch; getQuaternionFromEuler([0,pitch,0]) */
+  double sp = -R[6]; sp = sp < -1 ? -1 : (sp > 1 ? 1 : sp);
+  double pitch = asin(sp);
+  s->pos[0] = x; s->pos[1] = y;
+  s->quat[0] = 0; s->quat[1] = sin(pitch / 2); s->quat[2] = 0; s->quat[3] = cos(pitch / 2);
+  memset(s->v, 0, sizeof(v3)); memset(s->w, 0, sizeof(v3));
+}
+
 static void set_action(OrEnv* e, const float* act_in) {
   const Task* t = &e->t;
   const Model* m = t->model;
@@ -1508,38 +1568,17 @@ static void set_action(OrEnv* e, const float* act_in) {
     const float* u = t->task == XARM_TASK_PUSH_WITH_DOOR ? act + 3 * a : act + 4 * a;
     Kin k;
     arm_fk(t, a, e->arm[a].q, &k);
-    v3 target;
-    for (int c = 0; c < 3; c++) { /* [REF xarm_pick_and_place.py:202-204] float64 arithmetic, float32 bounds */
-      double np_ = k.p[m->eef_dof][c] + (double)u[c] * t->max_vel * t->dt_cmd;
-      double lo = t->pos_lo[a][c], hi = t->pos_hi[a][c];
-      target[c] = np_ < lo ? lo : (np_ > hi ? hi : np_);
-    }
+    v3 target; double g;
+    arm_command(t, a, u, k.p[m->eef_dof], e->arm[a].q[m->finger1], target, &g);
     double qn[MAXDOF];
     arm_ik(t, a, e->arm[a].q, target, qn);
     for (int i = 0; i < 7; i++) e->arm[a].qt[i] = qn[i];
     if (t->grip_cmd) {
-      double g = e->arm[a].q[m->finger1] + (double)u[3] * t->dt_cmd * t->max_grip_vel; /* [REF :205-206] */
-      if (t->grip_clip) { double lo = t->grip_lo, hi = t->grip_hi; g = g < lo ? lo : (g > hi ? hi : g); }
       if (m->finger2 >= 0) { e->arm[a].qt[m->finger1] = g; e->arm[a].qt[m->finger2] = g; }
       else for (int i = m->finger1; i < m->ndof; i++) e->arm[a].qt[i] = g; /* Reach: joints 10..16 [REF xarm_reach.py:141-142] */
     }
   }
-  if (t->lego_clamp) /* Handover: clamp |x|,|y| and keep only pitch, zeroing velocity [REF xarm_handover.py:282-297] */
-    for (int i = 0; i < t->n_obj; i++) {
-      ObjState* s = &e->obj[i];
-      double x = s->pos[0], y = s->pos[1];
-      const double hx = (float)0.28f, hy = (float)0.2f;
-      int neg = x < 0; if (neg) x = -x;
-      x = x < -hx ? -hx : (x > hx ? hx : x); y = y < -hy ? -hy : (y > hy ? hy : y);
-      if (neg) x = -x;
-      m3 R; quat_to_m3(R, s->quat);
-      /* getEulerFromQuaternion -> pitch; getQuaternionFromEuler([0,pitch,0]) */
-      double sp = -R[6]; sp = sp < -1 ? -1 : (sp > 1 ? 1 : sp);
-      double pitch = asin(sp);
-      s->pos[0] = x; s->pos[1] = y;
-      s->quat[0] = 0; s->quat[1] = sin(pitch / 2); s->quat[2] = 0; s->quat[3] = cos(pitch / 2);
-      memset(s->v, 0, sizeof(v3)); memset(s->w, 0, sizeof(v3));
-    }
+  if (t->lego_clamp) for (int i = 0; i < t->n_obj; i++) lego_clamp(&e->obj[i]);
 }
 
 typedef struct { float reward; uint8_t done, truncated; float success; } StepOut;
@@ -1660,6 +1699,11 @@ void or_get_state(OrEnv* e, float* out) { double b[256]; int n = state_io(e, b, 
 void or_set_state(OrEnv* e, const float* in) { double b[256]; int n = state_words(&e->t); for (int i = 0; i < n; i++) b[i] = in[i]; state_io(e, b, 1); }
 void or_get_state_d(OrEnv* e, double* out) { state_io(e, out, 0); }
 void or_set_state_d(OrEnv* e, const double* in) { double b[256]; memcpy(b, in, sizeof(double) * state_words(&e->t)); state_io(e, b, 1); }
+void or_contact_hist(OrEnv* e, long* nc_hist, long* nac_hist) {
+  memcpy(nc_hist, e->st_hist_nc, sizeof(e->st_hist_nc)); memcpy(nac_hist, e->st_hist_nac, sizeof(e->st_hist_nac));
+}
+void or_solver_stats(OrEnv* e, long out[4]) { out[0] = e->st_substeps; out[1] = e->st_iters; out[2] = e->st_rows; out[3] = e->st_contacts; }
+long or_arm_contacts(OrEnv* e, int reset) { long c = e->arm_contacts; if (reset) e->arm_contacts = 0; return c; }
 double or_flops(OrEnv* e, int reset) { double f = e->flops; if (reset) e->flops = 0; return f; }
 
 /* known-answer helpers: FK of one arm at base (0,0,0) */
@@ -1704,6 +1748,42 @@ int or_box_box(const double* A, const double* B, double* out /* up to 4 x [pa(3)
     v3cpy(out + 10 * i, c[i].pa); v3cpy(out + 10 * i + 3, c[i].pb); v3cpy(out + 10 * i + 6, c[i].n); out[10 * i + 9] = c[i].depth;
   }
   return n;
+}
+/* pure gym-logic hooks checked against tests/golden/reference_logic.npz (outputs of the reference's own methods) */
+int or_debug_assemble_obs(int32_t task, int32_t num_obj, const double* hand_pos, const double* hand_vel, const double* finger_q,
+                          const double* finger_qd, const double* obj /* n_obj x 13 */, const float* goal, float* obs, float* ag, float* dg) {
+  Task t;
+  if (task_fill(&t, task, num_obj)) return -1;
+  ObsIn in; memset(&in, 0, sizeof(in));
+  for (int a = 0; a < t.n_arms; a++) {
+    v3cpy(in.hand_pos[a], hand_pos + 3 * a); v3cpy(in.hand_vel[a], hand_vel + 3 * a);
+    in.finger_q[a] = finger_q[a]; in.finger_qd[a] = finger_qd[a];
+  }
+  for (int i = 0; i < t.n_obj; i++) {
+    const double* b = obj + 13 * i;
+    v3cpy(in.obj[i].pos, b); memcpy(in.obj[i].quat, b + 3, 4 * sizeof(double)); v3cpy(in.obj[i].v, b + 7); v3cpy(in.obj[i].w, b + 10);
+  }
+  memcpy(in.goal, goal, sizeof(float) * t.goal_dim);
+  ObsOut o; memset(&o, 0, sizeof(o));
+  assemble_obs(&t, &in, &o);
+  memcpy(obs, o.obs, sizeof(float) * t.obs_dim); memcpy(ag, o.ag, sizeof(float) * t.goal_dim); memcpy(dg, o.dg, sizeof(float) * t.goal_dim);
+  return 0;
+}
+int or_debug_command(int32_t task, int arm, const float* action /* full action vector */, const double* eef, double finger_q,
+                     double* target, double* grip) {
+  Task t;
+  if (task_fill(&t, task, 1)) return -1;
+  float act[8];
+  for (int i = 0; i < t.act_dim; i++) act[i] = action[i] < -1 ? -1 : (action[i] > 1 ? 1 : action[i]);
+  const float* u = t.task == XARM_TASK_PUSH_WITH_DOOR ? act + 3 * arm : act + 4 * arm;
+  arm_command(&t, arm, u, eef, finger_q, target, grip);
+  return 0;
+}
+void or_debug_lego_clamp(double* pos, double* quat) {
+  ObjState s; memset(&s, 0, sizeof(s));
+  v3cpy(s.pos, pos); memcpy(s.quat, quat, 4 * sizeof(double));
+  lego_clamp(&s);
+  v3cpy(pos, s.pos); memcpy(quat, s.quat, 4 * sizeof(double));
 }
 void or_philox(uint64_t seed, uint64_t env, uint32_t episode, uint32_t block, uint32_t out[4]) {
   uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), episode, block};

