@@ -144,11 +144,12 @@ XD void set_action(Env<T>& e, const float* act_in) {
     const float* u = T::TASK == XARM_TASK_PUSH_WITH_DOOR ? act + 3 * a : act + 4 * a;
     M3 Re; V3 pe, org[7], axs[7];
     arm_fk7<T>(a, e.arm[a].q, Re, pe, org, axs);  // getLinkState(arm, 8)[0]
-    const float step = (float)(T::MAX_VEL * T::DT_CMD);
+    // `a[:3] * max_vel * dt` is float32 array arithmetic in the reference: two separately rounded products
+    const float mv = (float)T::MAX_VEL, dtc = (float)T::DT_CMD;
     V3 target;
-    target.x = fminf(T::pos_hi(a, 0), fmaxf(T::pos_lo(a, 0), pe.x + u[0] * step));
-    target.y = fminf(T::pos_hi(a, 1), fmaxf(T::pos_lo(a, 1), pe.y + u[1] * step));
-    target.z = fminf(T::pos_hi(a, 2), fmaxf(T::pos_lo(a, 2), pe.z + u[2] * step));
+    target.x = fminf(T::pos_hi(a, 0), fmaxf(T::pos_lo(a, 0), pe.x + __fmul_rn(__fmul_rn(u[0], mv), dtc)));
+    target.y = fminf(T::pos_hi(a, 1), fmaxf(T::pos_lo(a, 1), pe.y + __fmul_rn(__fmul_rn(u[1], mv), dtc)));
+    target.z = fminf(T::pos_hi(a, 2), fmaxf(T::pos_lo(a, 2), pe.z + __fmul_rn(__fmul_rn(u[2], mv), dtc)));
     float qn[7];
     arm_ik<T>(a, e.arm[a].q, target, qn);
 #pragma unroll

@@ -1531,14 +1531,18 @@ static void env_reset(OrEnv* e) {
 /* ------------------------------------------------------------------------------------------------ step (_set_action + step) */
 /* pure part of _set_action: eef target and finger target of one arm from the current eef position / finger joint */
 static void arm_command(const Task* t, int a, const float* u, const v3 eef, double finger_q, v3 target, double* grip) {
-  for (int c = 0; c < 3; c++) { /* [REF xarm_pick_and_place.py:202-204] float64 arithmetic, float32 bounds */
-    double np_ = eef[c] + (double)u[c] * t->max_vel * t->dt_cmd;
+  for (int c = 0; c < 3; c++) {
+    /* [REF xarm_pick_and_place.py:202-204] `np.array(a[:3]) * max_vel * dt` is float32-array x Python-scalar
+     * arithmetic (two float32 roundings); the sum with the float64 eef position and the clip are float64 */
+    float stepf = (float)(u[c] * (float)t->max_vel);
+    stepf = (float)(stepf * (float)t->dt_cmd);
+    double np_ = eef[c] + (double)stepf;
     double lo = t->pos_lo[a][c], hi = t->pos_hi[a][c];
     target[c] = np_ < lo ? lo : (np_ > hi ? hi : np_);
   }
   double g = finger_q;
   if (t->grip_cmd) {
-    g = finger_q + (double)u[3] * t->dt_cmd * t->max_grip_vel; /* [REF :205-206] */
+    g = finger_q + (double)u[3] * t->dt_cmd * t->max_grip_vel; /* [REF :205-206] float32 scalar x Python floats: float64 (NumPy 1.x) */
     if (t->grip_clip) { double lo = t->grip_lo, hi = t->grip_hi; g = g < lo ? lo : (g > hi ? hi : g); }
   }
   *grip = g;

@@ -22,8 +22,9 @@ def _mk(task, n, **kw):
 
 def _actions(rng, task, n, adim):
     a = rng.uniform(-1, 1, (n, adim)).astype(np.float32)
-    if task == "reach":
-        a[:, 3] = np.abs(a[:, 3])  # a negative xArm-gripper command drives its joints through the lower limit: chaotic in any solver
+    if task == "handover":  # keep the fingertips above the table and the lego (eef z can go down to 0.1 there)
+        a[:, 2] = 0.5 + 0.5 * np.abs(a[:, 2])
+        a[:, 6] = 0.5 + 0.5 * np.abs(a[:, 6])
     return a
 
 
@@ -45,6 +46,11 @@ def test_step_parity_50_steps(task):
     clean = np.array([r.arm_contacts() == 0 for r in ref])
     # re-synchronise the envs whose reset already had gripper contacts, so that all 16 start the tape identical
     st0 = np.stack([r.get_state() for r in ref])
+    if task == "pick_and_place":
+        # park the lego of half the envs on the table outside the gripper's workspace (x<=0.5, |y|<=0.3): their whole
+        # tape is gripper-contact-free while the lego-table contact rows stay active
+        st0[::2, 27:30] = [0.65, 0.42, 0.04]
+        st0[::2, 30:40] = [0, 0, 0, 1, 0, 0, 0, 0, 0, 0]
     env.set_state(st0)
     for r, s in zip(ref, st0):
         r.set_state(s)
@@ -65,8 +71,11 @@ def test_step_parity_50_steps(task):
         assert np.isfinite(st).all()
         c = clean
         for arm in range(narm):
-            sl = slice(arm * 3 * ndof, arm * 3 * ndof + (9 if ndof == 9 else 7))
+            sl = slice(arm * 3 * ndof, arm * 3 * ndof + (9 if ndof == 9 else 7))  # Reach: the 7 arm joints (DESIGN.md on its gripper)
             np.testing.assert_allclose(st[c][:, sl], rst[c][:, sl], atol=TOL, err_msg=f"{task} step {t} arm {arm} q")
+        if task == "reach":  # hand position within 1e-3 m; the xArm-gripper knuckles (driven through their limits) only loosely
+            np.testing.assert_allclose(obs["observation"].cpu().numpy()[:, :3], np.stack([r[0]["observation"][:3] for r in res]), atol=TOL)
+            np.testing.assert_allclose(st[:, 7:13], rst[:, 7:13], atol=0.1)
         for o in range(nobj):
             sl = slice(nq + 13 * o, nq + 13 * o + 7)
             np.testing.assert_allclose(st[c][:, sl], rst[c][:, sl], atol=TOL, err_msg=f"{task} step {t} obj {o} pose")
