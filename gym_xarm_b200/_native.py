@@ -47,8 +47,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if _build.is_stale():
+    path = os.environ.get("XARM_B200_LIB") or _build.LIB   # XARM_B200_LIB: development override (A/B builds)
+    if path == _build.LIB and _build.is_stale():
         try:
             _build.build()
         except Exception as e:  # no nvcc on this box and no prebuilt library

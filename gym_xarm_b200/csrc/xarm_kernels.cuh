@@ -25,9 +25,11 @@ struct KArgs {
 template <class T>
 XD int body_load_bin(const KArgs& a, int64_t i) {
   using MD = typename T::MD;
-  if (T::NOBJ == 0 || !MD::HAS_BOXES) return 0;
   Env<T> e;
   env_load<T>(e, a.state, a.n, i);
+  const int limit = a.rc.max_episode_steps > 0 ? a.rc.max_episode_steps : T::MAX_STEPS;
+  if (a.auto_reset && e.step_count + 1 >= limit) return 0;  // will hit the time limit: step + reset in this launch
+  if (T::NOBJ == 0 || !MD::HAS_BOXES) return 1;
   float dmin = 1e30f;
 #pragma unroll
   for (int arm = 0; arm < T::NARM; arm++) {
@@ -36,8 +38,8 @@ XD int body_load_bin(const KArgs& a, int64_t i) {
     V3 gc = pe + Re * v3(0.f, 0.f, 0.043f);  // middle of the hand + finger hulls along the hand axis
     for (int o = 0; o < T::NOBJ; o++) dmin = fminf(dmin, norm(gc - e.obj[o].pos));
   }
-  int bin = (int)((dmin - 0.10f) * 20.f);
-  return bin < 0 ? 0 : (bin >= XARM_LOAD_BINS ? XARM_LOAD_BINS - 1 : bin);
+  int bin = 1 + (int)((dmin - 0.10f) * 20.f);
+  return bin < 1 ? 1 : (bin >= XARM_LOAD_BINS ? XARM_LOAD_BINS - 1 : bin);
 }
 struct StepStats {
   float eps, ret, len, suc, div;
@@ -79,7 +81,7 @@ XD void body_init(const KArgs& a, int64_t i) {
 
 // Env.step for env i
 template <class T>
-XD void body_step(const KArgs& a, int64_t i, StepStats& st) {
+XD void body_step(const KArgs& a, int64_t i, StepStats& st, bool block_sync = false, bool valid = true) {
   Env<T> e;
   env_load<T>(e, a.state, a.n, i);
   float act[T::A];
@@ -87,7 +89,8 @@ XD void body_step(const KArgs& a, int64_t i, StepStats& st) {
   for (int k = 0; k < T::A; k++) act[k] = a.b.actions[i * T::A + k];
   Obs<T> o;
   StepOut so;
-  env_step<T>(e, act, a.rc, o, so);
+  env_step<T>(e, act, a.rc, o, so, block_sync);
+  if (!valid) return;  // padding lane of a phase-synchronised block: simulated a copy, stores nothing
   if (!env_finite<T>(e)) {  // NaN guard: rebuild the env, end the episode
     uint32_t ep = e.episode;
     env_construct<T>(e, a.rc, a.rc.env_index_base + i);
@@ -114,7 +117,17 @@ XD void body_step(const KArgs& a, int64_t i, StepStats& st) {
     ret = 0.f;
   }
   a.ep_return[i] = ret;
-  a.need_reset[i] = (so.done && a.auto_reset) ? 1 : 0;
+  a.need_reset[i] = 0;
+  if (so.done && a.auto_reset) {
+    // VecEnv auto-reset, fused: the finishing lane runs Env.reset() right away (its warp finishes later, the other
+    // warps of the grid keep the SMs busy meanwhile - a separate reset kernel over the few finished envs would add its
+    // whole 6-sim-step latency to every step).  Envs that reach their time limit are grouped into the same warps by
+    // the load-balancing permutation.
+    env_reset<T>(e, a.rc, a.rc.env_index_base + i);
+    get_obs<T>(e, o);
+    e.d_old = np_dist(o.ag, o.dg, T::G);
+    write_obs<T>(a, i, o);
+  }
   env_store<T>(e, a.state, a.n, i);
 }
 

@@ -43,23 +43,27 @@ __global__ void __launch_bounds__(128) k_perm(KArgs a) {
   a.perm[off + (v & 0xffffff)] = (int)i;
 }
 
+#ifndef XARM_STEP_BLOCK
+#define XARM_STEP_BLOCK 128
+#endif
+#ifndef XARM_STEP_MIN_BLOCKS
+#define XARM_STEP_MIN_BLOCKS (256 / XARM_STEP_BLOCK)
+#endif
 template <class T>
-__global__ void __launch_bounds__(128) k_step(KArgs a) {
+__global__ void __launch_bounds__(XARM_STEP_BLOCK, XARM_STEP_MIN_BLOCKS) k_step(KArgs a) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t i = (t < a.n && a.perm) ? a.perm[t] : t;
   StepStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
-  if (t < a.n) {
-    body_step<T>(a, i, st);
-    // compact the envs that finished: the reset kernel then runs only full warps of resets
-    bool fin = a.need_reset[i] != 0;
-    unsigned m = __ballot_sync(__activemask(), fin);
-    if (fin) {
-      int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
-      if (lane == leader) base = atomicAdd(a.reset_count, __popc(m));
-      base = __shfl_sync(m, base, leader);
-      a.reset_list[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
-    }
+#ifdef XARM_PHASE_SYNC
+  {  // every thread of the block runs the step (block barriers inside); lanes past the end simulate a copy of the last env
+    const bool valid = t < a.n;
+    const int64_t tt = valid ? t : a.n - 1;
+    const int64_t i = a.perm ? a.perm[tt] : tt;
+    body_step<T>(a, i, st, true, valid);
   }
+#else
+  int64_t i = (t < a.n && a.perm) ? a.perm[t] : t;
+  if (t < a.n) body_step<T>(a, i, st);
+#endif
   // episode statistics (K8): warp-aggregate, one atomic per warp and counter
   unsigned any = __ballot_sync(0xffffffffu, st.eps != 0.f || st.div != 0.f);
   if (any) {
@@ -84,10 +88,8 @@ template <class T>
 __global__ void __launch_bounds__(128) k_reset(KArgs a, const uint8_t* mask, int use_flags) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
-  if (use_flags) {  // auto-reset: thread t takes the t-th finished env of the compacted list
-    if (i >= *a.reset_count) return;
-    i = a.reset_list[i];
-  } else if (mask && !mask[i]) return;
+  if (use_flags) { if (!a.need_reset[i]) return; }
+  else if (mask && !mask[i]) return;
   body_reset<T>(a, i, !use_flags);
 }
 
@@ -127,7 +129,7 @@ template <class T>
 struct OpsT {
   static dim3 grid(int64_t n) { return dim3((unsigned)((n + 127) / 128)); }
   static void init(const KArgs& a, cudaStream_t s) { k_init<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
-  static void step(const KArgs& a, cudaStream_t s) { k_step<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
+  static void step(const KArgs& a, cudaStream_t s) { k_step<T><<<dim3((unsigned)((a.n + XARM_STEP_BLOCK - 1) / XARM_STEP_BLOCK)), XARM_STEP_BLOCK, 0, s>>>(a); g_launches++; }
   static void reset(const KArgs& a, const uint8_t* m, int f, cudaStream_t s) { k_reset<T><<<grid(a.n), 128, 0, s>>>(a, m, f); g_launches++; }
   static void obs(const KArgs& a, cudaStream_t s) { k_obs<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
   static void classify(const KArgs& a, cudaStream_t s) {
@@ -279,15 +281,14 @@ int xarm_bind(XarmHandle* h, const XarmBuffers* b) {
   return XARM_OK;
 }
 
-// one env step = classify (load-balancing permutation) -> step -> auto-reset of the finished envs
+// one env step = classify (load-balancing permutation) -> step (with the auto-reset of finished envs fused in)
 static int launch_step_with(XarmHandle* h, const KArgs& k, cudaStream_t s) {
   h->ops.classify(k, s);
   h->ops.step(k, s);
-  if (h->cfg.auto_reset) h->ops.reset(k, nullptr, 1, s);
   return XARM_OK;
 }
 static int launch_step(XarmHandle* h, cudaStream_t s) { return launch_step_with(h, h->k, s); }
-#define XARM_LAUNCHES_PER_STEP(h) ((h)->cfg.auto_reset ? 4 : 3)
+#define XARM_LAUNCHES_PER_STEP(h) 3
 
 int xarm_reset(XarmHandle* h, const uint8_t* mask, void* stream) {
   if (!h) return fail(XARM_E_INVALID, "xarm_reset: null handle");

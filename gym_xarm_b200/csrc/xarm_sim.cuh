@@ -144,7 +144,7 @@ XD void arm_fk7(int a, const float* q, M3& Re, V3& pe, V3* org, V3* axs) {
   using MD = typename T::MD;
   M3 R; V3 p;
   arm_base<T>(a, R, p);
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 7; i++) {
     const float* r0 = MD::R0(i);
     M3 R0;
@@ -181,16 +181,16 @@ NOINL void arm_ik(int a, const float* q_in, V3 target, float* q_out) {
     float an = vn > 1e-30f ? angle / vn : 0.f;
     e[3] = an * dq.x; e[4] = an * dq.y; e[5] = an * dq.z;
     float J[6][7];
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 7; j++) {
       V3 lin = cross(axs[j], pe - org[j]);
       J[0][j] = lin.x; J[1][j] = lin.y; J[2][j] = lin.z; J[3][j] = axs[j].x; J[4][j] = axs[j].y; J[5][j] = axs[j].z;
     }
-    // A = J^T J + 0.5 I (packed lower), b = J^T e; Cholesky solve (A is SPD)
+    // A = J^T J + 0.5 I (packed lower), b = J^T e; Cholesky solve (A is SPD).  Rolled loops: small code, see arm_dynamics.
     float A[28], b[7];
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 7; i++) {
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j <= i; j++) {
         float s = (i == j) ? (float)XARM_IK_DAMPING : 0.f;
 #pragma unroll
@@ -202,32 +202,28 @@ NOINL void arm_ik(int a, const float* q_in, V3 target, float* q_out) {
       for (int r = 0; r < 6; r++) s += J[r][i] * e[r];
       b[i] = s;
     }
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 7; j++) {
       float s = A[tri(j, j)];
-#pragma unroll
       for (int k = 0; k < j; k++) s -= A[tri(j, k)] * A[tri(j, k)];
       float d = sqrtf(s), di = 1.f / d;
       A[tri(j, j)] = di;  // store the reciprocal of the diagonal
-#pragma unroll
+#pragma unroll 1
       for (int i = j + 1; i < 7; i++) {
         float t = A[tri(i, j)];
-#pragma unroll
         for (int k = 0; k < j; k++) t -= A[tri(i, k)] * A[tri(j, k)];
         A[tri(i, j)] = t * di;
       }
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 7; i++) {
       float s = b[i];
-#pragma unroll
       for (int k = 0; k < i; k++) s -= A[tri(i, k)] * b[k];
       b[i] = s * A[tri(i, i)];
     }
-#pragma unroll
+#pragma unroll 1
     for (int i = 6; i >= 0; i--) {
       float s = b[i];
-#pragma unroll
       for (int k = i + 1; k < 7; k++) s -= A[tri(k, i)] * b[k];
       b[i] = s * A[tri(i, i)];
     }
@@ -246,130 +242,136 @@ NOINL void arm_ik(int a, const float* q_in, V3 target, float* q_out) {
 
 // Full-arm pass: FK, spatial velocities, bias forces (world-frame RNEA), joint-space inertia (CRBA), its inverse
 // (Cholesky) and the unconstrained velocity update qdu = qd + h * Minv (tau - bias).  Equivalent to the ABA +
-// calcAccelerationDeltas pair Bullet runs per substep (N3); with_bias=false skips the velocity update.
+// calcAccelerationDeltas pair Bullet runs per substep (N3).
+// Written as ROLLED loops over links with thread-local arrays: this pass runs once per substep, and a fully
+// unrolled version (~10k straight-line instructions) is instruction-fetch bound on the SM (profiles/: every
+// 128-byte line costs an L2 round trip), while the rolled form stays in the instruction cache.
 template <class T>
 NOINL void arm_dynamics(int a, const ArmState<typename T::MD>& st, bool apply_damping, ArmDyn<typename T::MD>& D) {
   using MD = typename T::MD;
-  constexpr int N = MD::N;
+  constexpr int N = MD::N, NT = N * (N + 1) / 2;
   const float h = (float)T::H;
   M3 R[N]; V3 p[N];
   SV v[N], f[N];
   SI I[N];
   M3 Rb; V3 pb;
   arm_base<T>(a, Rb, pb);
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < N; i++) {
     const int pi = MD::parent(i);
-    M3 Rp = pi < 0 ? Rb : R[pi < 0 ? 0 : pi];
-    V3 pp = pi < 0 ? pb : p[pi < 0 ? 0 : pi];
+    const M3 Rp = pi < 0 ? Rb : R[pi < 0 ? 0 : pi];
+    const V3 pp = pi < 0 ? pb : p[pi < 0 ? 0 : pi];
     const float* r0 = MD::R0(i);
     M3 R0;
 #pragma unroll
     for (int k = 0; k < 9; k++) R0.m[k] = r0[k];
-    M3 Rj = Rp * R0;
-    V3 tj = pp + Rp * MD::t0(i);
-    V3 ax = Rj * MD::axis(i);
+    const M3 Rj = Rp * R0;
+    const V3 tj = pp + Rp * MD::t0(i);
+    const V3 ax = Rj * MD::axis(i);
+    SV Si;
     if (!MD::prismatic(i)) {
       R[i] = Rj * m3_axis_angle(MD::axis(i), st.q[i]);
       p[i] = tj;
-      D.S[i].a = ax; D.S[i].l = cross(tj, ax);
+      Si.a = ax; Si.l = cross(tj, ax);
     } else {
       R[i] = Rj;
       p[i] = tj + st.q[i] * ax;
-      D.S[i].a = v3(0, 0, 0); D.S[i].l = ax;
+      Si.a = v3(0, 0, 0); Si.l = ax;
     }
-    SV vj = st.qd[i] * D.S[i];
-    SV vp = pi < 0 ? sv_zero() : v[pi < 0 ? 0 : pi];
-    v[i] = vp + vj;
-    // bias acceleration a_i = a_parent + v_i x vj is accumulated into f[] below through the parent chain
-    SV ai = motion_cross(v[i], vj);
-    if (pi >= 0) ai += f[pi < 0 ? 0 : pi];  // f[] temporarily holds the bias acceleration of each link
+    D.S[i] = Si;
+    const SV vj = st.qd[i] * Si;
+    const SV vi = (pi < 0 ? sv_zero() : v[pi < 0 ? 0 : pi]) + vj;
+    v[i] = vi;
+    // bias acceleration a_i = a_parent + v_i x vj (f[] holds it until the force pass below)
+    SV ai = motion_cross(vi, vj);
+    if (pi >= 0) ai += f[pi < 0 ? 0 : pi];
+    // link force: f_i = I a + v x* I v - gyro + angular damping; gravity and linear damping per URDF part below
+    const M3 Ri = R[i];
+    const SI Ii = si_make(MD::mass(i), p[i] + Ri * MD::com(i), rotate_sym(Ri, MD::inertia(i)));
+    I[i] = Ii;
     f[i] = ai;
-    V3 cw = p[i] + R[i] * MD::com(i);
-    I[i] = si_make(MD::mass(i), cw, rotate_sym(R[i], MD::inertia(i)));
   }
   D.Rh = R[MD::EEF]; D.ph = p[MD::EEF];
   if (MD::HAS_BOXES) { D.pf1 = p[MD::F1]; D.pf2 = p[MD::F2 < 0 ? 0 : MD::F2]; }
-  // link forces: f_i = I a + v x* I v - gyro - external (gravity + Bullet's velocity damping per URDF link)
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < N; i++) {
-    SV Iv = I[i] * v[i];
-    SV fi = I[i] * f[i] + force_cross(v[i], Iv);
-    V3 w = v[i].a;
-    S3 Gw = rotate_sym(R[i], MD::central(i));
-    V3 Gww = Gw * w;
+    const SV vi = v[i];
+    const SI Ii = I[i];
+    SV fi = Ii * f[i] + force_cross(vi, Ii * vi);
+    const V3 w = vi.a;
+    const V3 Gww = rotate_sym(R[i], MD::central(i)) * w;
     if (!XARM_MB_USE_GYRO) fi.a -= cross(w, Gww);
-    float ka = (float)XARM_MB_ANGULAR_DAMPING * (1.f + norm(w));
-    fi.a += ka * Gww;  // minus the external damping torque -(G w) ka
-#pragma unroll
-    for (int pt = 0; pt < MD::NPART; pt++) {
-      if (MD::part_owner(pt) != i) continue;
-      V3 c = p[i] + R[i] * MD::part_com(pt);
-      V3 vc = v[i].l + cross(w, c);
-      float m = MD::part_mass(pt);
-      float kl = (float)XARM_MB_LINEAR_DAMPING * (1.f + norm(vc));
-      V3 F = (-m * kl) * vc;
-      F.z -= m * (float)XARM_GRAVITY;
-      fi.a -= cross(c, F);
-      fi.l -= F;
-    }
+    fi.a += ((float)XARM_MB_ANGULAR_DAMPING * (1.f + norm(w))) * Gww;  // minus the external damping torque -(G w) ka
+    f[i] = fi;
+  }
+#pragma unroll 1
+  for (int pt = 0; pt < MD::NPART; pt++) {  // gravity + Bullet's linear velocity damping of every URDF link
+    const int i = MD::part_owner(pt);
+    const V3 c = p[i] + R[i] * MD::part_com(pt);
+    const V3 w = v[i].a;
+    const V3 vc = v[i].l + cross(w, c);
+    const float m = MD::part_mass(pt);
+    V3 F = (-m * (float)XARM_MB_LINEAR_DAMPING * (1.f + norm(vc))) * vc;
+    F.z -= m * (float)XARM_GRAVITY;
+    SV fi = f[i];
+    fi.a -= cross(c, F);
+    fi.l -= F;
     f[i] = fi;
   }
   // backward: bias torques, composite inertias, joint-space inertia matrix
-  float M[N * (N + 1) / 2], rhs[N];
-#pragma unroll
+  float M[NT], rhs[N];
+#pragma unroll 1
   for (int i = N - 1; i >= 0; i--) {
     const int pi = MD::parent(i);
-    float tau = apply_damping ? -MD::damping(i) * st.qd[i] : 0.f;
-    rhs[i] = tau - dot(D.S[i], f[i]);
-    SV F = I[i] * D.S[i];
-#pragma unroll
-    for (int j = 0; j <= i; j++) M[tri(i, j)] = is_anc<MD>(j, i) ? dot(D.S[j], F) : 0.f;
-    if (pi >= 0) { f[pi < 0 ? 0 : pi] += f[i]; I[pi < 0 ? 0 : pi] = I[pi < 0 ? 0 : pi] + I[i]; }
+    const SV Si = D.S[i], fi = f[i];
+    const float tau = apply_damping ? -MD::damping(i) * st.qd[i] : 0.f;
+    rhs[i] = tau - dot(Si, fi);
+    const SI Ii = I[i];
+    const SV F = Ii * Si;
+    unsigned anc = 0u;
+    for (int k = i; k >= 0; k = MD::parent(k)) anc |= 1u << k;
+    for (int j = 0; j <= i; j++) M[tri(i, j)] = (anc >> j & 1u) ? dot(D.S[j], F) : 0.f;
+    if (pi >= 0) { f[pi] += fi; I[pi] = I[pi] + Ii; }
   }
-  // Cholesky M = L L^T (in place, reciprocal diagonal), Linv, Minv = Linv^T Linv
-#pragma unroll
+  // Cholesky M = L L^T in place (reciprocal diagonal)
+#pragma unroll 1
   for (int j = 0; j < N; j++) {
     float s = M[tri(j, j)];
-#pragma unroll
     for (int k = 0; k < j; k++) s -= M[tri(j, k)] * M[tri(j, k)];
     float di = rsqrtf(s);
     di = di * (1.5f - 0.5f * s * di * di);  // one Newton step: full float accuracy
     M[tri(j, j)] = di;
-#pragma unroll
+#pragma unroll 1
     for (int i = j + 1; i < N; i++) {
       float t = M[tri(i, j)];
-#pragma unroll
       for (int k = 0; k < j; k++) t -= M[tri(i, k)] * M[tri(j, k)];
       M[tri(i, j)] = t * di;
     }
   }
-  // Linv (lower) overwrites M column by column: Linv[j][j] = 1/L[j][j]; Linv[i][j] = -sum_{k=j}^{i-1} L[i][k] Linv[k][j] / L[i][i]
-  float Li[N * (N + 1) / 2];
-#pragma unroll
+  // Linv (lower): Linv[j][j] = 1/L[j][j]; Linv[i][j] = -sum_{k=j}^{i-1} L[i][k] Linv[k][j] / L[i][i]
+  float Li[NT];
+#pragma unroll 1
   for (int j = 0; j < N; j++) {
     Li[tri(j, j)] = M[tri(j, j)];
-#pragma unroll
+#pragma unroll 1
     for (int i = j + 1; i < N; i++) {
       float s = 0.f;
-#pragma unroll
       for (int k = j; k < i; k++) s += M[tri(i, k)] * Li[tri(k, j)];
       Li[tri(i, j)] = -s * M[tri(i, i)];
     }
   }
-#pragma unroll
+  // Minv = Linv^T Linv
+#pragma unroll 1
   for (int i = 0; i < N; i++)
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j <= i; j++) {
       float s = 0.f;
-#pragma unroll
       for (int k = i; k < N; k++) s += Li[tri(k, i)] * Li[tri(k, j)];
       D.Minv[tri(i, j)] = s;
     }
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < N; i++) {
     float s = 0.f;
-#pragma unroll
     for (int j = 0; j < N; j++) s += D.Minv[tri(i, j)] * rhs[j];
     D.qdu[i] = st.qd[i] + h * s;
   }
@@ -579,7 +581,7 @@ XD V3 door_axis() { const float a[3] = XARM_DOOR_AXIS; return v3(a[0], a[1], a[2
 template <class T>
 struct Contacts {
   static constexpr int N = T::MD::N;
-  int nc, nac;
+  int nc, nac, npair;                    // contact points, points on gripper links, pairs that produced points
   uint8_t ba[XARM_MAXC], bb[XARM_MAXC];  // body codes of side A / side B (normal points from B to A)
   int8_t slot[XARM_MAXC];                // row-pool slot of the arm side (-1: none)
   int8_t o1[XARM_MAXC], o2[XARM_MAXC];   // object index of the first / second object side (-1: none); o2 only for object-object
@@ -590,7 +592,7 @@ struct Contacts {
   V3 Jo1[XARM_MAXC][3], dVo1[XARM_MAXC][3];  // first object side: sign * (r x d), sign * Iinv (r x d)
   V3 Jo2[T::NOBJ > 1 ? XARM_MAXC : 1][3], dVo2[T::NOBJ > 1 ? XARM_MAXC : 1][3];
   float jdoor[T::HAS_DOOR ? XARM_MAXC : 1][3];  // door side: sign * axis . d
-  float rhs[XARM_MAXC][3], dinv[XARM_MAXC][3], app[XARM_MAXC][3], cfmr[XARM_MAXC];
+  float rhs[XARM_MAXC][3], dinv[XARM_MAXC][3], den[XARM_MAXC][3], app[XARM_MAXC][3], cfmr[XARM_MAXC];
   float Jarm[XARM_MAXAC][3][N], dVarm[XARM_MAXAC][3][N];  // arm side: sign * J, Minv (sign * J)
 };
 
@@ -616,6 +618,7 @@ XD int add_pair(Contacts<T>& C, const Box& A, const Box& B, int ca, int cb, floa
   if (room <= 0) return 0;
   CPoint pts[4];
   int k = box_box(A, B, pts, room < 4 ? room : 4);
+  if (k > 0) C.npair++;
   float mu = fminf(fa * fb, (float)XARM_MAX_FRICTION);
   float erp = (float)XARM_ERP2, cfm = 0.f;
   if (erp_override >= 0.f) erp = erp_override;
@@ -634,18 +637,28 @@ XD int add_pair(Contacts<T>& C, const Box& A, const Box& B, int ca, int cb, floa
 }
 
 // One internal substep: collide -> unconstrained velocities -> rows -> PGS -> integrate.
+// PHASE_SYNC(): optional block barrier between the phases of a substep.  All warps of a block then run the same
+// loop at the same time, so its instructions are fetched once and shared (the step kernel is instruction-fetch
+// bound: profiles/).  Only legal where every thread of the block executes the same number of substeps.
+#if defined(__CUDA_ARCH__) && defined(XARM_PHASE_SYNC)
+#define PHASE_SYNC(on) do { if (on) __syncthreads(); } while (0)
+#else
+#define PHASE_SYNC(on) do { } while (0)
+#endif
 template <class T>
-NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
+NOINL void substep(Env<T>& e, bool apply_damping, bool last, bool block_sync = false) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1, NT = N * (N + 1) / 2;
   const float h = (float)T::H;
   ArmDyn<MD> D[NA];
   Contacts<T> C;
+  PHASE_SYNC(block_sync);
 #pragma unroll
   for (int a = 0; a < NA; a++) arm_dynamics<T>(a, e.arm[a], apply_damping, D[a]);
+  PHASE_SYNC(block_sync);
 
   // ---- 1. collision detection on the current poses (fixed pair order, Appendix G)
-  C.nc = 0; C.nac = 0;
+  C.nc = 0; C.nac = 0; C.npair = 0;
   S3 Iinv[NO];
   if (NOBJ > 0) {
     Box ob[NO];
@@ -815,12 +828,12 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
         float pos_err = 0.f, vel_err = -rel;
         if (pen > 0.f) vel_err -= pen / h; else pos_err = -pen * C.erp[c] / h;
         C.rhs[c][0] = (pos_err + vel_err) * dinv;
-        C.dinv[c][0] = dinv;
+        C.dinv[c][0] = dinv; C.den[c][0] = den + C.cfm0[c];
         C.cfmr[c] = C.cfm0[c] * dinv;
       } else {
         float dinv = 1.f / den;
         C.rhs[c][k] = -rel * dinv;
-        C.dinv[c][k] = dinv;
+        C.dinv[c][k] = dinv; C.den[c][k] = den;
       }
     }
   }
@@ -828,7 +841,7 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
   // ---- 4. arm / door rows in registers, then the PGS sweeps (btMultiBodyConstraintSolver::solveSingleIteration)
   float Mi[NA][NT], iden[NA][N], dqd[NA][N], mrhs[NA][N], mapp[NA][N], lrhs[NA][N], lapp[NA][N];
   uint32_t lim_lo[NA], lim_hi[NA];
-  float grhs[NA], gapp[NA], gdinv[NA];
+  float grhs[NA], gapp[NA], gdinv[NA], gden[NA];
   const float hi_arm = (float)(T::ARM_FORCE * T::TIME_STEP), hi_fin = (float)(T::FINGER_FORCE * T::TIME_STEP);
   const float hi_gear = (float)(XARM_GEAR_MAX_FORCE * T::TIME_STEP), hi_lim = (float)XARM_LIMIT_MAX_IMPULSE;
   const float gr = (float)XARM_GEAR_RATIO;
@@ -850,13 +863,13 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
       mrhs[a][i] = (target - qdu) / den;
       mapp[a][i] = 0.f; dqd[a][i] = 0.f;
     }
-    grhs[a] = 0.f; gapp[a] = 0.f; gdinv[a] = 0.f;
+    grhs[a] = 0.f; gapp[a] = 0.f; gdinv[a] = 0.f; gden[a] = 0.f;
     if (MD::HAS_GEAR) {
       const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
       float den = Mi[a][tri(f1, f1)] + 2.f * gr * Mi[a][tri(f1, f2)] + gr * gr * Mi[a][tri(f2, f2)];
       float rel = D[a].qdu[f1] + gr * D[a].qdu[f2];
       float pos_err = (float)XARM_GEAR_ERP * (st.q[f1] + gr * st.q[f2]);
-      gdinv[a] = 1.f / den;
+      gdinv[a] = 1.f / den; gden[a] = den;
       grhs[a] = (-pos_err * (float)XARM_ERP / h - rel) / den;
     }
   }
@@ -871,31 +884,32 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
   V3 dv[NO], dw[NO];
 #pragma unroll
   for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
+  const float inv_obj_mass = 1.f / T::OBJ_MASS;
+  // exit test of Bullet: max over rows of (delta / dinv)^2 <= threshold  <=>  no row has |delta| > sqrt(threshold) * dinv
+  const float sthr_ = sqrtf((float)XARM_RESIDUAL_THRESHOLD);
 
 // one unit row (J = sign * e_i) of arm a: motors and joint limits
 #define UNIT_ROW(a, i, sign, rhs_, lo_, hi_, app_)                                   \
   {                                                                                   \
     float delta = (rhs_) - (sign) * dqd[a][i] * iden[a][i];                           \
-    float sum = (app_) + delta;                                                       \
-    if (sum < (lo_)) { delta = (lo_) - (app_); sum = (lo_); }                         \
-    else if (sum > (hi_)) { delta = (hi_) - (app_); sum = (hi_); }                    \
-    (app_) = sum;                                                                     \
+    const float sum = (app_) + delta;                                                 \
+    const float sumc = fminf(fmaxf(sum, (lo_)), (hi_));   /* branch-free clamp; delta is recomputed only when it bites */ \
+    delta = (sumc == sum) ? delta : sumc - (app_);                                    \
+    (app_) = sumc;                                                                    \
     const float sd = (sign) * delta;                                                  \
     _Pragma("unroll") for (int k_ = 0; k_ < N; k_++) dqd[a][k_] += Mi[a][tri(k_, i)] * sd; \
-    const float rv = delta * Mi[a][tri(i, i)];                                        \
-    resid = fmaxf(resid, rv * rv);                                                    \
+    resid_bad = resid_bad || fabsf(delta) > sthr_ * iden[a][i];                       \
   }
 #define GEAR_ROW(a)                                                                   \
   if (MD::HAS_GEAR) {                                                                 \
     const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;                              \
     float delta = grhs[a] - (dqd[a][f1] + gr * dqd[a][f2]) * gdinv[a];                \
-    float sum = gapp[a] + delta;                                                      \
-    if (sum < -hi_gear) { delta = -hi_gear - gapp[a]; sum = -hi_gear; }               \
-    else if (sum > hi_gear) { delta = hi_gear - gapp[a]; sum = hi_gear; }             \
-    gapp[a] = sum;                                                                    \
+    const float sum = gapp[a] + delta;                                                \
+    const float sumc = fminf(fmaxf(sum, -hi_gear), hi_gear);                          \
+    delta = (sumc == sum) ? delta : sumc - gapp[a];                                   \
+    gapp[a] = sumc;                                                                   \
     _Pragma("unroll") for (int k_ = 0; k_ < N; k_++) dqd[a][k_] += (Mi[a][tri(k_, f1)] + gr * Mi[a][tri(k_, f2)]) * delta; \
-    const float rv = delta / gdinv[a];                                                \
-    resid = fmaxf(resid, rv * rv);                                                    \
+    resid_bad = resid_bad || fabsf(delta) > sthr_ * gdinv[a];                         \
   }
 #define DOOR_LIMIT_ROW()                                                              \
   if (door_lim) {                                                                     \
@@ -903,7 +917,7 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
     float sum = dl_app + delta;                                                       \
     if (sum < 0.f) { delta = -dl_app; sum = 0.f; } else if (sum > hi_lim) { delta = hi_lim - dl_app; sum = hi_lim; } \
     dl_app = sum; ddoor += dl_sign * delta * door_den;                                \
-    const float rv = delta * door_den; resid = fmaxf(resid, rv * rv);                 \
+    resid_bad = resid_bad || fabsf(delta * door_den) > sthr_;                         \
   }
 #define DOOR_MOTOR_ROW()                                                              \
   {                                                                                   \
@@ -912,35 +926,40 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
     float sum = dm_app + delta;                                                       \
     if (sum < -hi_) { delta = -hi_ - dm_app; sum = -hi_; } else if (sum > hi_) { delta = hi_ - dm_app; sum = hi_; } \
     dm_app = sum; ddoor += delta * door_den;                                          \
-    const float rv = delta * door_den; resid = fmaxf(resid, rv * rv);                 \
+    resid_bad = resid_bad || fabsf(delta * door_den) > sthr_;                         \
   }
 
-// one sweep over the non-contact rows: forward on odd iterations, exact reverse on even ones
-#define ARM_ROWS_SWEEP(it)                                                                                      \
-  if ((it) & 1) {                                                                                                \
-    _Pragma("unroll") for (int a = 0; a < NA; a++) {                                                             \
-      if (lim_lo[a] | lim_hi[a]) {                                                                               \
-        _Pragma("unroll") for (int i = 0; i < N; i++) {                                                          \
-          if (lim_lo[a] >> i & 1) UNIT_ROW(a, i, 1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                       \
-          if (lim_hi[a] >> i & 1) UNIT_ROW(a, i, -1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                      \
-        }                                                                                                        \
+// One sweep over the non-contact rows: forward on odd iterations, exact reverse on even ones.  Every row body
+// exists ONCE in the code (the kernel is instruction-fetch bound, profiles/): a warp-uniform switch picks the row and
+// the loop runs the slots [limit dof 0..N-1 | motor dof 0..N-1 | gear] up or down.  Case labels: limit i -> i,
+// motor i -> 16 + i, gear -> 32; dofs >= N of the smaller model compile to nothing.
+#define CI_(i) ((i) < N ? (i) : 0)
+#define ARM_ROW_CASE(a, i)                                                                                       \
+      case (i): if ((i) < N) { if (lim_lo[a] >> (i) & 1) UNIT_ROW(a, CI_(i), 1.f, lrhs[a][CI_(i)], 0.f, hi_lim, lapp[a][CI_(i)]) \
+                else if (lim_hi[a] >> (i) & 1) UNIT_ROW(a, CI_(i), -1.f, lrhs[a][CI_(i)], 0.f, hi_lim, lapp[a][CI_(i)]) }       \
+                break;                                                                                           \
+      case (16 + (i)): if ((i) < N) { const float hi_ = (i) < 7 ? hi_arm : hi_fin; UNIT_ROW(a, CI_(i), 1.f, mrhs[a][CI_(i)], -hi_, hi_, mapp[a][CI_(i)]) } break;
+#define ARM_ROWS_ONE(a, fwd)                                                                                     \
+  {                                                                                                              \
+    const int first_ = (lim_lo[a] | lim_hi[a]) ? 0 : N;   /* skip the limit slots when no limit is active */     \
+    for (int s_ = first_; s_ <= 2 * N; s_++) {                                                                   \
+      const int r_ = (fwd) ? s_ : 2 * N + first_ - s_;                                                           \
+      const int code_ = r_ < N ? r_ : (r_ < 2 * N ? 16 + (r_ - N) : 32);                                         \
+      switch (code_) {                                                                                           \
+        ARM_ROW_CASE(a, 0) ARM_ROW_CASE(a, 1) ARM_ROW_CASE(a, 2) ARM_ROW_CASE(a, 3) ARM_ROW_CASE(a, 4)           \
+        ARM_ROW_CASE(a, 5) ARM_ROW_CASE(a, 6) ARM_ROW_CASE(a, 7) ARM_ROW_CASE(a, 8) ARM_ROW_CASE(a, 9)           \
+        ARM_ROW_CASE(a, 10) ARM_ROW_CASE(a, 11) ARM_ROW_CASE(a, 12)                                              \
+        default: GEAR_ROW(a) break;                                                                              \
       }                                                                                                          \
-      _Pragma("unroll") for (int i = 0; i < N; i++) { const float hi_ = i < 7 ? hi_arm : hi_fin; UNIT_ROW(a, i, 1.f, mrhs[a][i], -hi_, hi_, mapp[a][i]) } \
-      GEAR_ROW(a)                                                                                                \
     }                                                                                                            \
+  }
+#define ARM_ROWS_SWEEP(it)                                                                                       \
+  if ((it) & 1) {                                                                                                \
+    _Pragma("unroll") for (int a = 0; a < NA; a++) ARM_ROWS_ONE(a, true)                                         \
     if (T::HAS_DOOR) { DOOR_LIMIT_ROW() DOOR_MOTOR_ROW() }                                                       \
   } else {                                                                                                       \
     if (T::HAS_DOOR) { DOOR_MOTOR_ROW() DOOR_LIMIT_ROW() }                                                       \
-    _Pragma("unroll") for (int a = NA - 1; a >= 0; a--) {                                                        \
-      GEAR_ROW(a)                                                                                                \
-      _Pragma("unroll") for (int i = N - 1; i >= 0; i--) { const float hi_ = i < 7 ? hi_arm : hi_fin; UNIT_ROW(a, i, 1.f, mrhs[a][i], -hi_, hi_, mapp[a][i]) } \
-      if (lim_lo[a] | lim_hi[a]) {                                                                               \
-        _Pragma("unroll") for (int i = N - 1; i >= 0; i--) {                                                     \
-          if (lim_hi[a] >> i & 1) UNIT_ROW(a, i, -1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                      \
-          if (lim_lo[a] >> i & 1) UNIT_ROW(a, i, 1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                       \
-        }                                                                                                        \
-      }                                                                                                          \
-    }                                                                                                            \
+    _Pragma("unroll") for (int a = NA - 1; a >= 0; a--) ARM_ROWS_ONE(a, false)                                   \
   }
 
 // the contact rows of one iteration: all normal rows, then the friction pairs (implicit cone).  COUPLED=false is the
@@ -975,8 +994,7 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
         else if (sum > (float)XARM_CONTACT_MAX_IMPULSE) { d0 = (float)XARM_CONTACT_MAX_IMPULSE - C.app[c][0]; sum = (float)XARM_CONTACT_MAX_IMPULSE; } \
         C.app[c][0] = sum;                                                                                       \
         delta[0] = d0;                                                                                           \
-        float rv = d0 / C.dinv[c][0];                                                                            \
-        resid = fmaxf(resid, rv * rv);                                                                           \
+        resid_bad = resid_bad || fabsf(d0) > sthr_ * C.dinv[c][0];                                               \
       } else {                                                                                                   \
         float lim = C.mu[c] * C.app[c][0];                                                                       \
         float da = C.rhs[c][1] - jv[1] * C.dinv[c][1], db = C.rhs[c][2] - jv[2] * C.dinv[c][2];                  \
@@ -985,14 +1003,13 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
         if (len > lim) { float sc = len > 0.f ? lim / len : 0.f; sa *= sc; sb *= sc; da = sa - C.app[c][1]; db = sb - C.app[c][2]; } \
         C.app[c][1] = sa; C.app[c][2] = sb;                                                                      \
         delta[1] = da; delta[2] = db;                                                                            \
-        float r1 = da / C.dinv[c][1], r2 = db / C.dinv[c][2];                                                    \
-        resid = fmaxf(resid, fmaxf(r1 * r1, r2 * r2));                                                           \
+        resid_bad = resid_bad || fabsf(da) > sthr_ * C.dinv[c][1] || fabsf(db) > sthr_ * C.dinv[c][2];           \
       }                                                                                                          \
       for (int k = k0; k < k1; k++) {                                                                            \
         const V3 d = C.dir[c][k];                                                                                \
         const float dl = delta[k];                                                                               \
-        if (o1 >= 0) { dv[NOBJ <= 1 ? 0 : o1] += (s1 * dl / T::OBJ_MASS) * d; dw[NOBJ <= 1 ? 0 : o1] += dl * C.dVo1[c][k]; } \
-        if (NOBJ > 1 && o2 >= 0) { dv[o2 < 0 ? 0 : o2] += (-dl / T::OBJ_MASS) * d; dw[o2 < 0 ? 0 : o2] += dl * C.dVo2[NOBJ > 1 ? c : 0][k]; } \
+        if (o1 >= 0) { dv[NOBJ <= 1 ? 0 : o1] += (s1 * dl * inv_obj_mass) * d; dw[NOBJ <= 1 ? 0 : o1] += dl * C.dVo1[c][k]; } \
+        if (NOBJ > 1 && o2 >= 0) { dv[o2 < 0 ? 0 : o2] += (-dl * inv_obj_mass) * d; dw[o2 < 0 ? 0 : o2] += dl * C.dVo2[NOBJ > 1 ? c : 0][k]; } \
         if ((COUPLED) && sl >= 0) {                                                                              \
           if (NA == 1 || arm_of == 0) { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[0][i] += C.dVarm[sl][k][i] * dl; } \
           else { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[NA - 1][i] += C.dVarm[sl][k][i] * dl; }       \
@@ -1002,47 +1019,93 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
     }                                                                                                            \
   }
 
+  PHASE_SYNC(block_sync);
   // Islands: when no contact touches an arm link (and the task has one arm and no door) the arm rows and the object
   // rows never read each other's velocities, so sweeping them in two separate loops gives bit-identical impulses.
-  // Only the early-exit test couples them (max residual over ALL rows); it is reproduced from per-iteration masks
-  // and, in the (never observed) case that it would have fired before the last iteration, the joint loop is re-run.
-  bool joint_loop = true;
-  if (NA == 1 && !T::HAS_DOOR && C.nac == 0) {
-    joint_loop = false;
-    const float thr = (float)XARM_RESIDUAL_THRESHOLD;
-    unsigned long long ok_arm = 0ull, ok_obj = 0ull;
+  // Only the early-exit test couples them (a sweep ends the solve when NO row of either island moved more than the
+  // threshold); it is reproduced from per-sweep masks and, in the (never observed) case that it would have fired
+  // before the last sweep, the joint loop is run instead.  phase 0: arm rows only; 1: contact rows only; 2: joint.
+  // One expansion of each sweep serves all three phases (code size).
+  const bool decoupled = NA == 1 && !T::HAS_DOOR && C.nac == 0;
+  // single manifold of the one object against a static box (the resting / landing lego: by far the most common case)
+  const bool manifold = decoupled && NOBJ == 1 && C.nc > 0 && C.nc <= 4 && C.npair == 1 && C.o1[0] == 0 && C.s1[0] > 0.f && C.cfm0[0] == 0.f;
+  unsigned long long ok_arm = 0ull, ok_obj = 0ull;
+  int phase = decoupled ? 0 : 2;
+  while (true) {
     for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
-      float resid = 0.f;
-      ARM_ROWS_SWEEP(it)
-      if (resid <= thr) { ok_arm |= 1ull << it; if (C.nc == 0) break; }
+      bool resid_bad = false;
+      if (phase != 1) { ARM_ROWS_SWEEP(it) }
+      if (phase != 0) { CONTACT_ROWS_SWEEP(true) }
+      if (!resid_bad) {
+        if (phase == 2) break;
+        if (phase == 0) { ok_arm |= 1ull << it; if (C.nc == 0) break; } else ok_obj |= 1ull << it;
+      }
     }
-    if (C.nc > 0) {
+    if (phase == 2 || C.nc == 0) break;
+    if (phase == 0) {
+      if (!manifold) { phase = 1; continue; }
+      // <= 4 points sharing n, t1, t2: all row data in registers, fully unrolled, same row order and updates
+      const V3 n = C.dir[0][0], t1 = C.dir[0][1], t2 = C.dir[0][2];
+      const float mu = C.mu[0], sthr = sthr_;
+      V3 Jn[4], Jt1[4], Jt2[4], Vn[4], Vt1[4], Vt2[4];
+      float rn[4], r1[4], r2[4], dn[4], d1[4], d2[4], an[4], a1[4], a2[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const bool on = c < C.nc;
+        const V3 z = v3(0, 0, 0);
+        Jn[c] = on ? C.Jo1[c][0] : z; Jt1[c] = on ? C.Jo1[c][1] : z; Jt2[c] = on ? C.Jo1[c][2] : z;
+        Vn[c] = on ? C.dVo1[c][0] : z; Vt1[c] = on ? C.dVo1[c][1] : z; Vt2[c] = on ? C.dVo1[c][2] : z;
+        rn[c] = on ? C.rhs[c][0] : 0.f; r1[c] = on ? C.rhs[c][1] : 0.f; r2[c] = on ? C.rhs[c][2] : 0.f;
+        dn[c] = on ? C.dinv[c][0] : 0.f; d1[c] = on ? C.dinv[c][1] : 0.f; d2[c] = on ? C.dinv[c][2] : 0.f;
+        an[c] = 0.f; a1[c] = 0.f; a2[c] = 0.f;
+      }
+      V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
+      const V3 nm = inv_obj_mass * n, t1m = inv_obj_mass * t1, t2m = inv_obj_mass * t2;
       for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
-        float resid = 0.f;
-        CONTACT_ROWS_SWEEP(false)
-        if (resid <= thr) ok_obj |= 1ull << it;
-      }
-      const unsigned long long both = ok_arm & ok_obj & ((1ull << (XARM_SOLVER_ITERATIONS - 1)) - 1ull);
-      if (both) {  // the joint loop would have stopped early: redo it exactly
-        joint_loop = true;
+        bool bad = false;
 #pragma unroll
-        for (int i = 0; i < N; i++) { dqd[0][i] = 0.f; mapp[0][i] = 0.f; lapp[0][i] = 0.f; }
-        gapp[0] = 0.f;
+        for (int c = 0; c < 4; c++) {  // normal rows
+          float delta = rn[c] - (dot(n, v) + dot(Jn[c], w)) * dn[c];
+          const float sum = an[c] + delta;
+          const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
+          delta = (sumc == sum) ? delta : sumc - an[c];
+          an[c] = sumc;
+          v += delta * nm; w += delta * Vn[c];
+          bad = bad || fabsf(delta) > sthr * dn[c];
+        }
 #pragma unroll
-        for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
-        for (int c = 0; c < C.nc; c++) { C.app[c][0] = 0.f; C.app[c][1] = 0.f; C.app[c][2] = 0.f; }
+        for (int c = 0; c < 4; c++) {  // friction pairs, implicit cone
+          const float lim = mu * an[c];
+          float da = r1[c] - (dot(t1, v) + dot(Jt1[c], w)) * d1[c], db = r2[c] - (dot(t2, v) + dot(Jt2[c], w)) * d2[c];
+          float sa = a1[c] + da, sb = a2[c] + db;
+          const float l2 = sa * sa + sb * sb;
+          if (l2 > lim * lim) {
+            const float len = sqrtf(l2);
+            if (len > lim) { const float sc = lim / len; sa *= sc; sb *= sc; da = sa - a1[c]; db = sb - a2[c]; }
+          }
+          a1[c] = sa; a2[c] = sb;
+          v += da * t1m; w += da * Vt1[c];
+          v += db * t2m; w += db * Vt2[c];
+          bad = bad || fabsf(da) > sthr * d1[c] || fabsf(db) > sthr * d2[c];
+        }
+        if (!bad) ok_obj |= 1ull << it;
       }
+      dv[0] = v; dw[0] = w;
     }
-  }
-  if (joint_loop) {
-    for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
-      float resid = 0.f;
-      ARM_ROWS_SWEEP(it)
-      CONTACT_ROWS_SWEEP(true)
-      if (resid <= (float)XARM_RESIDUAL_THRESHOLD) break;
-    }
+    // both islands solved separately: would the joint loop have stopped before its last sweep?
+    if (!(ok_arm & ok_obj & ((1ull << (XARM_SOLVER_ITERATIONS - 1)) - 1ull))) break;
+#pragma unroll
+    for (int i = 0; i < N; i++) { dqd[0][i] = 0.f; mapp[0][i] = 0.f; lapp[0][i] = 0.f; }
+    gapp[0] = 0.f;
+#pragma unroll
+    for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
+    for (int c = 0; c < C.nc; c++) { C.app[c][0] = 0.f; C.app[c][1] = 0.f; C.app[c][2] = 0.f; }
+    phase = 2;
   }
 #undef ARM_ROWS_SWEEP
+#undef ARM_ROWS_ONE
+#undef ARM_ROW_CASE
+#undef CI_
 #undef CONTACT_ROWS_SWEEP
 #undef UNIT_ROW
 #undef GEAR_ROW
@@ -1085,6 +1148,6 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
 
 // p.stepSimulation() x calls per env step
 template <class T>
-XD void simulate(Env<T>& e) {
-  for (int s = 0; s < T::NSUB; s++) substep<T>(e, T::DAMP_EACH || s == 0, s == T::NSUB - 1);
+XD void simulate(Env<T>& e, bool block_sync = false) {
+  for (int s = 0; s < T::NSUB; s++) substep<T>(e, T::DAMP_EACH || s == 0, s == T::NSUB - 1, block_sync);
 }

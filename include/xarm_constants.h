@@ -10,7 +10,9 @@
 
 /* ---- world (PhysicsServerCommandProcessor::createEmptyDynamicsWorld) ---- */
 #define XARM_GRAVITY 9.8                 /* [REF xarm_pick_and_place.py:110] setGravity(0,0,-9.8) */
+#ifndef XARM_SOLVER_ITERATIONS
 #define XARM_SOLVER_ITERATIONS 50        /* numSolverIterations default */
+#endif
 #define XARM_RESIDUAL_THRESHOLD 1e-7     /* leastSquaresResidualThreshold: exit when max (delta v)^2 <= this */
 #define XARM_ERP 0.2                     /* btContactSolverInfo::m_erp (joint-limit rows) */
 #define XARM_ERP2 0.08                   /* m_erp2 as set by pybullet (contact rows) */

@@ -100,11 +100,7 @@ void hs_get_obs(HS* h, float* obs, float* ag, float* dg) { h->ops.obs(h->k); cop
 void hs_step(HS* h, const float* actions, float* obs, float* ag, float* dg, float* reward, uint8_t* done, float* success, uint8_t* truncated) {
   const int64_t n = h->cfg.num_envs; const Ops& o = h->ops;
   memcpy((void*)h->k.b.actions, actions, sizeof(float) * n * o.A);
-  h->ops.step(h->k);
-  if (h->cfg.auto_reset) {
-    // keep the terminal outputs: the reset overwrites observation for finished envs like the CUDA path does
-    h->ops.reset(h->k, nullptr, 1);
-  }
+  h->ops.step(h->k);  // auto-reset is fused into the step body
   copy_out(h, obs, ag, dg);
   if (reward) memcpy(reward, h->k.b.reward, sizeof(float) * n);
   if (success) memcpy(success, h->k.b.success, sizeof(float) * n);
