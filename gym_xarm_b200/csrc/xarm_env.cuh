@@ -359,10 +359,10 @@ struct StepOut {
 };
 
 template <class T>
-XD void env_step(Env<T>& e, const float* action, const ResetCfg& cfg, Obs<T>& o, StepOut& so, bool block_sync = false) {
+XD void env_step(Env<T>& e, const float* action, const ResetCfg& cfg, Obs<T>& o, StepOut& so) {
   e.step_count += 1;
   set_action<T>(e, action);
-  simulate<T>(e, block_sync);
+  simulate<T>(e);
   get_obs<T>(e, o);
   const float thr = T::THRESHOLD;
   float succ;

@@ -89,7 +89,7 @@ XD void body_step(const KArgs& a, int64_t i, StepStats& st, bool block_sync = fa
   for (int k = 0; k < T::A; k++) act[k] = a.b.actions[i * T::A + k];
   Obs<T> o;
   StepOut so;
-  env_step<T>(e, act, a.rc, o, so, block_sync);
+  env_step<T>(e, act, a.rc, o, so);
   if (!valid) return;  // padding lane of a phase-synchronised block: simulated a copy, stores nothing
   if (!env_finite<T>(e)) {  // NaN guard: rebuild the env, end the episode
     uint32_t ep = e.episode;

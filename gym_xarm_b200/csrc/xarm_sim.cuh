@@ -637,25 +637,42 @@ XD int add_pair(Contacts<T>& C, const Box& A, const Box& B, int ca, int cb, floa
 }
 
 // One internal substep: collide -> unconstrained velocities -> rows -> PGS -> integrate.
-// PHASE_SYNC(): optional block barrier between the phases of a substep.  All warps of a block then run the same
-// loop at the same time, so its instructions are fetched once and shared (the step kernel is instruction-fetch
-// bound: profiles/).  Only legal where every thread of the block executes the same number of substeps.
-#if defined(__CUDA_ARCH__) && defined(XARM_PHASE_SYNC)
-#define PHASE_SYNC(on) do { if (on) __syncthreads(); } while (0)
-#else
-#define PHASE_SYNC(on) do { } while (0)
-#endif
+// ------------------------------------------------------------------------------------------------ substep pieces
+// A substep is split into three pieces so that the CUDA path can run them as separate small kernels (the fused
+// per-env kernel is instruction-fetch bound, profiles/): sub_setup -> sub_solve_light / sub_solve_generic -> sub_integrate.
+// tests/hostsim and the fused fallback compose them back into substep().
 template <class T>
-NOINL void substep(Env<T>& e, bool apply_damping, bool last, bool block_sync = false) {
+struct ArmRows {  // non-contact rows of the PGS, per arm (btMultiBodyJointMotor / JointLimit / Gear) + the door rows
+  static constexpr int N = T::MD::N, NA = T::NARM, NT = N * (N + 1) / 2;
+  float Mi[NA][NT], mrhs[NA][N], lrhs[NA][N];
+  uint32_t lim_lo[NA], lim_hi[NA];
+  float grhs[NA], gdinv[NA], gden[NA];
+  float dl_rhs, dl_sign, dm_rhs;
+  int door_lim;
+};
+template <class T>
+struct SubBase {  // unconstrained velocities of the substep (what the solved changes are added to)
+  float qdu[T::NARM][T::MD::N];
+  V3 vu[T::NOBJ > 0 ? T::NOBJ : 1], wu[T::NOBJ > 0 ? T::NOBJ : 1];
+  float door_qdu;
+};
+template <class T>
+struct SubSol {  // velocity changes produced by the solver
+  float dqd[T::NARM][T::MD::N];
+  V3 dv[T::NOBJ > 0 ? T::NOBJ : 1], dw[T::NOBJ > 0 ? T::NOBJ : 1];
+  float ddoor;
+};
+enum { SOLVE_LIGHT = 0, SOLVE_GENERIC_DECOUPLED = 1, SOLVE_GENERIC_JOINT = 2 };
+
+// collide -> unconstrained velocities -> rows.  Returns which solver form applies.
+template <class T>
+XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Contacts<T>& C, SubBase<T>& B) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1, NT = N * (N + 1) / 2;
   const float h = (float)T::H;
   ArmDyn<MD> D[NA];
-  Contacts<T> C;
-  PHASE_SYNC(block_sync);
 #pragma unroll
   for (int a = 0; a < NA; a++) arm_dynamics<T>(a, e.arm[a], apply_damping, D[a]);
-  PHASE_SYNC(block_sync);
 
   // ---- 1. collision detection on the current poses (fixed pair order, Appendix G)
   C.nc = 0; C.nac = 0; C.npair = 0;
@@ -746,7 +763,7 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last, bool block_sync = f
             (double)C.pb[c].x, (double)C.pb[c].y, (double)C.pb[c].z, (double)C.dir[c][0].x, (double)C.dir[c][0].y, (double)C.dir[c][0].z, (double)C.depth[c]);
 #endif
   // ---- 2. unconstrained velocities of the free bodies (the arms' are in D[a].qdu)
-  V3 vu[NO], wu[NO];
+  V3 (&vu)[NO] = B.vu; V3 (&wu)[NO] = B.wu;
   float door_qdu = 0.f;
   for (int o = 0; o < NOBJ; o++) {
     const ObjState& b = e.obj[o];
@@ -838,56 +855,52 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last, bool block_sync = f
     }
   }
 
-  // ---- 4. arm / door rows in registers, then the PGS sweeps (btMultiBodyConstraintSolver::solveSingleIteration)
-  float Mi[NA][NT], iden[NA][N], dqd[NA][N], mrhs[NA][N], mapp[NA][N], lrhs[NA][N], lapp[NA][N];
-  uint32_t lim_lo[NA], lim_hi[NA];
-  float grhs[NA], gapp[NA], gdinv[NA], gden[NA];
-  const float hi_arm = (float)(T::ARM_FORCE * T::TIME_STEP), hi_fin = (float)(T::FINGER_FORCE * T::TIME_STEP);
-  const float hi_gear = (float)(XARM_GEAR_MAX_FORCE * T::TIME_STEP), hi_lim = (float)XARM_LIMIT_MAX_IMPULSE;
+  // ---- 4. arm / door rows (btMultiBodyJointLimitConstraint, JointMotor, GearConstraint)
   const float gr = (float)XARM_GEAR_RATIO;
-#pragma unroll
+#pragma unroll 1
   for (int a = 0; a < NA; a++) {
     const ArmState<MD>& st = e.arm[a];
-#pragma unroll
-    for (int i = 0; i < NT; i++) Mi[a][i] = D[a].Minv[i];
-    lim_lo[a] = 0; lim_hi[a] = 0;
-#pragma unroll
+    for (int i = 0; i < NT; i++) AR.Mi[a][i] = D[a].Minv[i];
+    uint32_t lo = 0, hi = 0;
     for (int i = 0; i < N; i++) {
-      const float den = Mi[a][tri(i, i)], qdu = D[a].qdu[i];
-      iden[a][i] = 1.f / den;
+      const float den = D[a].Minv[tri(i, i)], qdu = D[a].qdu[i];
+      B.qdu[a][i] = qdu;
       float pen_lo = st.q[i] - MD::lo(i), pen_hi = MD::hi(i) - st.q[i];
-      lrhs[a][i] = 0.f; lapp[a][i] = 0.f;
-      if (pen_lo <= 0.f) { lim_lo[a] |= 1u << i; lrhs[a][i] = (-pen_lo * (float)XARM_ERP / h - qdu) / den; }
-      else if (pen_hi <= 0.f) { lim_hi[a] |= 1u << i; lrhs[a][i] = (-pen_hi * (float)XARM_ERP / h + qdu) / den; }
+      float lr = 0.f;
+      if (pen_lo <= 0.f) { lo |= 1u << i; lr = (-pen_lo * (float)XARM_ERP / h - qdu) / den; }
+      else if (pen_hi <= 0.f) { hi |= 1u << i; lr = (-pen_hi * (float)XARM_ERP / h + qdu) / den; }
+      AR.lrhs[a][i] = lr;
       float target = (float)(XARM_MOTOR_KP * XARM_MOTOR_ERP) * (st.qt[i] - st.q[i]) / h;
-      mrhs[a][i] = (target - qdu) / den;
-      mapp[a][i] = 0.f; dqd[a][i] = 0.f;
+      AR.mrhs[a][i] = (target - qdu) / den;
     }
-    grhs[a] = 0.f; gapp[a] = 0.f; gdinv[a] = 0.f; gden[a] = 0.f;
+    AR.lim_lo[a] = lo; AR.lim_hi[a] = hi;
+    AR.grhs[a] = 0.f; AR.gdinv[a] = 0.f; AR.gden[a] = 0.f;
     if (MD::HAS_GEAR) {
       const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
-      float den = Mi[a][tri(f1, f1)] + 2.f * gr * Mi[a][tri(f1, f2)] + gr * gr * Mi[a][tri(f2, f2)];
+      float den = D[a].Minv[tri(f1, f1)] + 2.f * gr * D[a].Minv[tri(f1, f2)] + gr * gr * D[a].Minv[tri(f2, f2)];
       float rel = D[a].qdu[f1] + gr * D[a].qdu[f2];
       float pos_err = (float)XARM_GEAR_ERP * (st.q[f1] + gr * st.q[f2]);
-      gdinv[a] = 1.f / den; gden[a] = den;
-      grhs[a] = (-pos_err * (float)XARM_ERP / h - rel) / den;
+      AR.gdinv[a] = 1.f / den; AR.gden[a] = den;
+      AR.grhs[a] = (-pos_err * (float)XARM_ERP / h - rel) / den;
     }
   }
-  bool door_lim = false; float ddoor = 0.f, dl_rhs = 0.f, dl_app = 0.f, dl_sign = 1.f, dm_rhs = 0.f, dm_app = 0.f;
-  const float door_den = 1.f / (float)XARM_DOOR_MASS;
+  AR.door_lim = 0; AR.dl_rhs = 0.f; AR.dl_sign = 1.f; AR.dm_rhs = 0.f;
+  B.door_qdu = door_qdu;
   if (T::HAS_DOOR) {
+    const float door_den = 1.f / (float)XARM_DOOR_MASS;
     float pen_lo = e.door_q - (float)XARM_DOOR_LIMIT_LO, pen_hi = (float)XARM_DOOR_LIMIT_HI - e.door_q;
-    if (pen_lo <= 0.f) { door_lim = true; dl_sign = 1.f; dl_rhs = (-pen_lo * (float)XARM_ERP / h - door_qdu) / door_den; }
-    else if (pen_hi <= 0.f) { door_lim = true; dl_sign = -1.f; dl_rhs = (-pen_hi * (float)XARM_ERP / h + door_qdu) / door_den; }
-    dm_rhs = (0.f - door_qdu) / door_den;
+    if (pen_lo <= 0.f) { AR.door_lim = 1; AR.dl_sign = 1.f; AR.dl_rhs = (-pen_lo * (float)XARM_ERP / h - door_qdu) / door_den; }
+    else if (pen_hi <= 0.f) { AR.door_lim = 1; AR.dl_sign = -1.f; AR.dl_rhs = (-pen_hi * (float)XARM_ERP / h + door_qdu) / door_den; }
+    AR.dm_rhs = (0.f - door_qdu) / door_den;
   }
-  V3 dv[NO], dw[NO];
-#pragma unroll
-  for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
-  const float inv_obj_mass = 1.f / T::OBJ_MASS;
-  // exit test of Bullet: max over rows of (delta / dinv)^2 <= threshold  <=>  no row has |delta| > sqrt(threshold) * dinv
-  const float sthr_ = sqrtf((float)XARM_RESIDUAL_THRESHOLD);
+  // which solver form: islands (one arm, no door, no gripper contact) decouple the arm rows from the object rows
+  const bool decoupled = NA == 1 && !T::HAS_DOOR && C.nac == 0;
+  const bool manifold = decoupled && NOBJ == 1 && C.nc > 0 && C.nc <= 4 && C.npair == 1 && C.o1[0] == 0 && C.s1[0] > 0.f && C.cfm0[0] == 0.f;
+  if (decoupled && (C.nc == 0 || manifold)) return SOLVE_LIGHT;
+  return decoupled ? SOLVE_GENERIC_DECOUPLED : SOLVE_GENERIC_JOINT;
+}
 
+// ---- row updates shared by the solver forms (they act on the local register arrays Mi, iden, dqd, ... of the caller)
 // one unit row (J = sign * e_i) of arm a: motors and joint limits
 #define UNIT_ROW(a, i, sign, rhs_, lo_, hi_, app_)                                   \
   {                                                                                   \
@@ -1019,18 +1032,127 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last, bool block_sync = f
     }                                                                                                            \
   }
 
-  PHASE_SYNC(block_sync);
-  // Islands: when no contact touches an arm link (and the task has one arm and no door) the arm rows and the object
-  // rows never read each other's velocities, so sweeping them in two separate loops gives bit-identical impulses.
-  // Only the early-exit test couples them (a sweep ends the solve when NO row of either island moved more than the
-  // threshold); it is reproduced from per-sweep masks and, in the (never observed) case that it would have fired
-  // before the last sweep, the joint loop is run instead.  phase 0: arm rows only; 1: contact rows only; 2: joint.
-  // One expansion of each sweep serves all three phases (code size).
-  const bool decoupled = NA == 1 && !T::HAS_DOOR && C.nac == 0;
-  // single manifold of the one object against a static box (the resting / landing lego: by far the most common case)
-  const bool manifold = decoupled && NOBJ == 1 && C.nc > 0 && C.nc <= 4 && C.npair == 1 && C.o1[0] == 0 && C.s1[0] > 0.f && C.cfm0[0] == 0.f;
+#define SOLVER_LOCALS_FROM(AR)                                                                                   \
+  float Mi[NA][NT], iden[NA][N], dqd[NA][N], mrhs[NA][N], mapp[NA][N], lrhs[NA][N], lapp[NA][N];                 \
+  uint32_t lim_lo[NA], lim_hi[NA];                                                                               \
+  float grhs[NA], gapp[NA], gdinv[NA], gden[NA];                                                                 \
+  const float hi_arm = (float)(T::ARM_FORCE * T::TIME_STEP), hi_fin = (float)(T::FINGER_FORCE * T::TIME_STEP);   \
+  const float hi_gear = (float)(XARM_GEAR_MAX_FORCE * T::TIME_STEP), hi_lim = (float)XARM_LIMIT_MAX_IMPULSE;     \
+  const float gr = (float)XARM_GEAR_RATIO;                                                                       \
+  _Pragma("unroll") for (int a = 0; a < NA; a++) {                                                               \
+    _Pragma("unroll") for (int i = 0; i < NT; i++) Mi[a][i] = (AR).Mi[a][i];                                     \
+    _Pragma("unroll") for (int i = 0; i < N; i++) {                                                              \
+      iden[a][i] = 1.f / Mi[a][tri(i, i)]; mrhs[a][i] = (AR).mrhs[a][i]; lrhs[a][i] = (AR).lrhs[a][i];           \
+      mapp[a][i] = 0.f; lapp[a][i] = 0.f; dqd[a][i] = 0.f;                                                       \
+    }                                                                                                            \
+    lim_lo[a] = (AR).lim_lo[a]; lim_hi[a] = (AR).lim_hi[a];                                                      \
+    grhs[a] = (AR).grhs[a]; gdinv[a] = (AR).gdinv[a]; gden[a] = (AR).gden[a]; gapp[a] = 0.f;                     \
+  }                                                                                                              \
+  const bool door_lim = (AR).door_lim != 0;                                                                      \
+  float ddoor = 0.f, dl_app = 0.f, dm_app = 0.f;                                                                 \
+  const float dl_rhs = (AR).dl_rhs, dl_sign = (AR).dl_sign, dm_rhs = (AR).dm_rhs;                                \
+  const float door_den = 1.f / (float)XARM_DOOR_MASS;                                                            \
+  const float inv_obj_mass = 1.f / T::OBJ_MASS;                                                                  \
+  /* exit test of Bullet: max over rows of (delta / dinv)^2 <= threshold <=> no row has |delta| > sqrt(thr) dinv */ \
+  const float sthr_ = sqrtf((float)XARM_RESIDUAL_THRESHOLD);                                                     \
+  (void)door_lim; (void)dl_rhs; (void)dl_sign; (void)dm_rhs; (void)door_den; (void)hi_lim; (void)hi_gear; (void)gr; (void)inv_obj_mass;
+
+// Register-resident rows of a single manifold (<= 4 points sharing n, t1, t2) of the one object against a static box.
+template <class T>
+struct ManifoldRows {
+  V3 n, t1, t2;
+  float mu;
+  V3 Jn[4], Jt1[4], Jt2[4], Vn[4], Vt1[4], Vt2[4];
+  float rn[4], r1[4], r2[4], dn[4], d1[4], d2[4];
+};
+template <class T>
+XD void manifold_from_contacts(const Contacts<T>& C, ManifoldRows<T>& Mf) {
+  Mf.n = C.dir[0][0]; Mf.t1 = C.dir[0][1]; Mf.t2 = C.dir[0][2]; Mf.mu = C.mu[0];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const bool on = c < C.nc;
+    const V3 z = v3(0, 0, 0);
+    Mf.Jn[c] = on ? C.Jo1[c][0] : z; Mf.Jt1[c] = on ? C.Jo1[c][1] : z; Mf.Jt2[c] = on ? C.Jo1[c][2] : z;
+    Mf.Vn[c] = on ? C.dVo1[c][0] : z; Mf.Vt1[c] = on ? C.dVo1[c][1] : z; Mf.Vt2[c] = on ? C.dVo1[c][2] : z;
+    Mf.rn[c] = on ? C.rhs[c][0] : 0.f; Mf.r1[c] = on ? C.rhs[c][1] : 0.f; Mf.r2[c] = on ? C.rhs[c][2] : 0.f;
+    Mf.dn[c] = on ? C.dinv[c][0] : 0.f; Mf.d1[c] = on ? C.dinv[c][1] : 0.f; Mf.d2[c] = on ? C.dinv[c][2] : 0.f;
+  }
+}
+
+// Light form (SOLVE_LIGHT): the arm rows and, if present, one manifold of the object, swept as two independent
+// islands - bit-identical impulses to the joint loop.  Only the early-exit test couples the islands (a sweep ends the
+// solve when NO row of either island moved more than the threshold); it is reproduced from per-sweep masks.  Returns
+// false in the (never observed) case that the joint loop would have stopped before its last sweep: the caller then
+// runs the joint loop instead.
+template <class T>
+XD bool sub_solve_light(const ArmRows<T>& AR, int nc, const ManifoldRows<T>& Mf, SubSol<T>& S) {
+  using MD = typename T::MD;
+  constexpr int N = MD::N, NA = T::NARM, NT = N * (N + 1) / 2;
+  SOLVER_LOCALS_FROM(AR)
   unsigned long long ok_arm = 0ull, ok_obj = 0ull;
-  int phase = decoupled ? 0 : 2;
+  for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+    bool resid_bad = false;
+    ARM_ROWS_SWEEP(it)
+    if (!resid_bad) { ok_arm |= 1ull << it; if (nc == 0) break; }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) S.dqd[0][i] = dqd[0][i];
+  S.dv[0] = v3(0, 0, 0); S.dw[0] = v3(0, 0, 0); S.ddoor = 0.f;
+  if (nc == 0) return true;
+  {
+    const V3 n = Mf.n, t1 = Mf.t1, t2 = Mf.t2;
+    const float mu = Mf.mu, sthr = sthr_;
+    float an[4], a1[4], a2[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) { an[c] = 0.f; a1[c] = 0.f; a2[c] = 0.f; }
+    V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
+    const V3 nm = inv_obj_mass * n, t1m = inv_obj_mass * t1, t2m = inv_obj_mass * t2;
+    for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+      bool bad = false;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {  // normal rows
+        float delta = Mf.rn[c] - (dot(n, v) + dot(Mf.Jn[c], w)) * Mf.dn[c];
+        const float sum = an[c] + delta;
+        const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
+        delta = (sumc == sum) ? delta : sumc - an[c];
+        an[c] = sumc;
+        v += delta * nm; w += delta * Mf.Vn[c];
+        bad = bad || fabsf(delta) > sthr * Mf.dn[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++) {  // friction pairs, implicit cone
+        const float lim = mu * an[c];
+        float da = Mf.r1[c] - (dot(t1, v) + dot(Mf.Jt1[c], w)) * Mf.d1[c], db = Mf.r2[c] - (dot(t2, v) + dot(Mf.Jt2[c], w)) * Mf.d2[c];
+        float sa = a1[c] + da, sb = a2[c] + db;
+        const float l2 = sa * sa + sb * sb;
+        if (l2 > lim * lim) {
+          const float len = sqrtf(l2);
+          if (len > lim) { const float sc = lim / len; sa *= sc; sb *= sc; da = sa - a1[c]; db = sb - a2[c]; }
+        }
+        a1[c] = sa; a2[c] = sb;
+        v += da * t1m; w += da * Mf.Vt1[c];
+        v += db * t2m; w += db * Mf.Vt2[c];
+        bad = bad || fabsf(da) > sthr * Mf.d1[c] || fabsf(db) > sthr * Mf.d2[c];
+      }
+      if (!bad) ok_obj |= 1ull << it;
+    }
+    S.dv[0] = v; S.dw[0] = w;
+  }
+  return !(ok_arm & ok_obj & ((1ull << (XARM_SOLVER_ITERATIONS - 1)) - 1ull));
+}
+
+// Generic form: phase 0 = arm rows only, 1 = contact rows only (the two islands of a decoupled env), 2 = the joint
+// loop of btMultiBodyConstraintSolver::solveSingleIteration.  One expansion of each sweep serves all phases.
+template <class T>
+XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, int form) {
+  using MD = typename T::MD;
+  constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1, NT = N * (N + 1) / 2;
+  SOLVER_LOCALS_FROM(AR)
+  V3 dv[NO], dw[NO];
+#pragma unroll
+  for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
+  unsigned long long ok_arm = 0ull, ok_obj = 0ull;
+  int phase = form == SOLVE_GENERIC_DECOUPLED ? 0 : 2;
   while (true) {
     for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
       bool resid_bad = false;
@@ -1042,66 +1164,28 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last, bool block_sync = f
       }
     }
     if (phase == 2 || C.nc == 0) break;
-    if (phase == 0) {
-      if (!manifold) { phase = 1; continue; }
-      // <= 4 points sharing n, t1, t2: all row data in registers, fully unrolled, same row order and updates
-      const V3 n = C.dir[0][0], t1 = C.dir[0][1], t2 = C.dir[0][2];
-      const float mu = C.mu[0], sthr = sthr_;
-      V3 Jn[4], Jt1[4], Jt2[4], Vn[4], Vt1[4], Vt2[4];
-      float rn[4], r1[4], r2[4], dn[4], d1[4], d2[4], an[4], a1[4], a2[4];
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const bool on = c < C.nc;
-        const V3 z = v3(0, 0, 0);
-        Jn[c] = on ? C.Jo1[c][0] : z; Jt1[c] = on ? C.Jo1[c][1] : z; Jt2[c] = on ? C.Jo1[c][2] : z;
-        Vn[c] = on ? C.dVo1[c][0] : z; Vt1[c] = on ? C.dVo1[c][1] : z; Vt2[c] = on ? C.dVo1[c][2] : z;
-        rn[c] = on ? C.rhs[c][0] : 0.f; r1[c] = on ? C.rhs[c][1] : 0.f; r2[c] = on ? C.rhs[c][2] : 0.f;
-        dn[c] = on ? C.dinv[c][0] : 0.f; d1[c] = on ? C.dinv[c][1] : 0.f; d2[c] = on ? C.dinv[c][2] : 0.f;
-        an[c] = 0.f; a1[c] = 0.f; a2[c] = 0.f;
-      }
-      V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
-      const V3 nm = inv_obj_mass * n, t1m = inv_obj_mass * t1, t2m = inv_obj_mass * t2;
-      for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
-        bool bad = false;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {  // normal rows
-          float delta = rn[c] - (dot(n, v) + dot(Jn[c], w)) * dn[c];
-          const float sum = an[c] + delta;
-          const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
-          delta = (sumc == sum) ? delta : sumc - an[c];
-          an[c] = sumc;
-          v += delta * nm; w += delta * Vn[c];
-          bad = bad || fabsf(delta) > sthr * dn[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 4; c++) {  // friction pairs, implicit cone
-          const float lim = mu * an[c];
-          float da = r1[c] - (dot(t1, v) + dot(Jt1[c], w)) * d1[c], db = r2[c] - (dot(t2, v) + dot(Jt2[c], w)) * d2[c];
-          float sa = a1[c] + da, sb = a2[c] + db;
-          const float l2 = sa * sa + sb * sb;
-          if (l2 > lim * lim) {
-            const float len = sqrtf(l2);
-            if (len > lim) { const float sc = lim / len; sa *= sc; sb *= sc; da = sa - a1[c]; db = sb - a2[c]; }
-          }
-          a1[c] = sa; a2[c] = sb;
-          v += da * t1m; w += da * Vt1[c];
-          v += db * t2m; w += db * Vt2[c];
-          bad = bad || fabsf(da) > sthr * d1[c] || fabsf(db) > sthr * d2[c];
-        }
-        if (!bad) ok_obj |= 1ull << it;
-      }
-      dv[0] = v; dw[0] = w;
-    }
+    if (phase == 0) { phase = 1; continue; }
     // both islands solved separately: would the joint loop have stopped before its last sweep?
     if (!(ok_arm & ok_obj & ((1ull << (XARM_SOLVER_ITERATIONS - 1)) - 1ull))) break;
 #pragma unroll
-    for (int i = 0; i < N; i++) { dqd[0][i] = 0.f; mapp[0][i] = 0.f; lapp[0][i] = 0.f; }
-    gapp[0] = 0.f;
+    for (int a = 0; a < NA; a++) {
+#pragma unroll
+      for (int i = 0; i < N; i++) { dqd[a][i] = 0.f; mapp[a][i] = 0.f; lapp[a][i] = 0.f; }
+      gapp[a] = 0.f;
+    }
 #pragma unroll
     for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
     for (int c = 0; c < C.nc; c++) { C.app[c][0] = 0.f; C.app[c][1] = 0.f; C.app[c][2] = 0.f; }
     phase = 2;
   }
+#pragma unroll
+  for (int a = 0; a < NA; a++)
+#pragma unroll
+    for (int i = 0; i < N; i++) S.dqd[a][i] = dqd[a][i];
+#pragma unroll
+  for (int o = 0; o < NO; o++) { S.dv[o] = dv[o]; S.dw[o] = dw[o]; }
+  S.ddoor = ddoor;
+}
 #undef ARM_ROWS_SWEEP
 #undef ARM_ROWS_ONE
 #undef ARM_ROW_CASE
@@ -1112,18 +1196,23 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last, bool block_sync = f
 #undef DOOR_LIMIT_ROW
 #undef DOOR_MOTOR_ROW
 
-  // ---- 5. integrate (stepPositionsMultiDof)
+// stepPositionsMultiDof: add the solved velocity changes, integrate joints and boxes
+template <class T>
+XD void sub_integrate(Env<T>& e, const SubBase<T>& B, const SubSol<T>& S) {
+  using MD = typename T::MD;
+  constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ;
+  const float h = (float)T::H;
 #pragma unroll
   for (int a = 0; a < NA; a++)
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      float qd = D[a].qdu[i] + dqd[a][i];
+      float qd = B.qdu[a][i] + S.dqd[a][i];
       e.arm[a].qd[i] = qd;
       e.arm[a].q[i] += qd * h;
     }
   for (int o = 0; o < NOBJ; o++) {
     ObjState& b = e.obj[o];
-    b.v = vu[o] + dv[o]; b.w = wu[o] + dw[o];
+    b.v = B.vu[o] + S.dv[o]; b.w = B.wu[o] + S.dw[o];
     b.pos += h * b.v;
     float ang = norm(b.w);
     if (ang * h > (float)XARM_ANGULAR_MOTION_THRESHOLD) ang = (float)XARM_ANGULAR_MOTION_THRESHOLD / h;
@@ -1135,10 +1224,10 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last, bool block_sync = f
     float inv = rsqrtf(qn.x * qn.x + qn.y * qn.y + qn.z * qn.z + qn.w * qn.w);
     b.quat.x = qn.x * inv; b.quat.y = qn.y * inv; b.quat.z = qn.z * inv; b.quat.w = qn.w * inv;
   }
-  if (T::HAS_DOOR) { e.door_qd = door_qdu + ddoor; e.door_q += e.door_qd * h; }
+  if (T::HAS_DOOR) { e.door_qd = B.door_qdu + S.ddoor; e.door_q += e.door_qd * h; }
 #ifdef XARM_HOST_SIM
   if (getenv("XARM_TRACE")) {
-    fprintf(stderr, "KS nc %d qd", C.nc);
+    fprintf(stderr, "KS qd");
     for (int a = 0; a < NA; a++) for (int i = 0; i < N; i++) fprintf(stderr, " %.10f", (double)e.arm[a].qd[i]);
     for (int o = 0; o < NOBJ; o++) fprintf(stderr, " %.10f %.10f %.10f %.10f %.10f %.10f", (double)e.obj[o].v.x, (double)e.obj[o].v.y, (double)e.obj[o].v.z, (double)e.obj[o].w.x, (double)e.obj[o].w.y, (double)e.obj[o].w.z);
     fprintf(stderr, "\n");
@@ -1146,8 +1235,26 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last, bool block_sync = f
 #endif
 }
 
+// One internal substep, fused: collide -> unconstrained velocities -> rows -> PGS -> integrate.
+template <class T>
+NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
+  ArmRows<T> AR;
+  Contacts<T> C;
+  SubBase<T> B;
+  SubSol<T> S;
+  const int form = sub_setup<T>(e, apply_damping, last, AR, C, B);
+  bool done = false;
+  if (form == SOLVE_LIGHT) {
+    ManifoldRows<T> Mf;
+    if (C.nc > 0) manifold_from_contacts<T>(C, Mf);
+    done = sub_solve_light<T>(AR, C.nc, Mf, S);
+  }
+  if (!done) sub_solve_generic<T>(AR, C, S, form == SOLVE_GENERIC_DECOUPLED ? SOLVE_GENERIC_DECOUPLED : SOLVE_GENERIC_JOINT);
+  sub_integrate<T>(e, B, S);
+}
+
 // p.stepSimulation() x calls per env step
 template <class T>
-XD void simulate(Env<T>& e, bool block_sync = false) {
-  for (int s = 0; s < T::NSUB; s++) substep<T>(e, T::DAMP_EACH || s == 0, s == T::NSUB - 1, block_sync);
+XD void simulate(Env<T>& e) {
+  for (int s = 0; s < T::NSUB; s++) substep<T>(e, T::DAMP_EACH || s == 0, s == T::NSUB - 1);
 }
