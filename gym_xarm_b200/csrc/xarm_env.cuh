@@ -306,23 +306,19 @@ XD void env_construct(Env<T>& e, const ResetCfg& cfg, int64_t genv) {
   sample_goal<T>(e, rng, cfg);
 }
 
-// Env.reset() [REF xarm_reach.py:96-102,163-168; xarm_pick_and_place.py:121-127,250-267; xarm_stack_tower.py:115-119,201-211;
-// xarm_push_with_door.py:117-121,195-205; xarm_handover.py:141-145,338-368]
+// The part of _reset_sim between the arm motion and the last stepSimulation: joint teleport (Reach, StackTower,
+// PushWithDoor) and object placement [REF xarm_reach.py:163-168; xarm_pick_and_place.py:259-266;
+// xarm_stack_tower.py:201-211; xarm_push_with_door.py:195-205; xarm_handover.py:354-367]
 template <class T>
-XD void env_reset(Env<T>& e, const ResetCfg& cfg, int64_t genv) {
-  e.episode += 1; e.step_count = 0;
-  Rng rng = {cfg.seed, (uint64_t)genv, e.episode, 0u};
+XD void env_reset_place(Env<T>& e, Rng& rng, const ResetCfg& cfg) {
   if (T::TASK == XARM_TASK_REACH) {
     set_joint_init<T>(e, 0, 0.f);
-    simulate<T>(e);
   } else if (T::TASK == XARM_TASK_PICK_AND_PLACE) {
-    servo_reset<T>(e, v3(0.4f, 0.f, 0.12f), v3(0, 0, 0), true);
     for (int i = 0; i < T::NOBJ; i++) {
       double ug = rng.uniform();
       float x = rng.box(0.35f, 0.45f), y = rng.box(-0.25f, 0.25f);
       if (ug < (double)cfg.init_grasp_rate) place_obj(e.obj[i], 0.4f, 0.0f); else place_obj(e.obj[i], x, y);
     }
-    simulate<T>(e);
   } else if (T::TASK == XARM_TASK_STACK_TOWER || T::TASK == XARM_TASK_PUSH_WITH_DOOR) {
 #pragma unroll
     for (int a = 0; a < T::NARM; a++) set_joint_init<T>(e, a, 0.f);
@@ -332,9 +328,7 @@ XD void env_reset(Env<T>& e, const ResetCfg& cfg, int64_t genv) {
       else { x = rng.box(-0.3f, -0.1f); y = rng.box(-0.2f, 0.2f); }
       place_obj(e.obj[i], x, y);
     }
-    simulate<T>(e);
   } else {
-    servo_reset<T>(e, v3(-0.15f, 0.f, 0.15f), v3(0.15f, 0.f, 0.15f), false);
     float px[T::NOBJ > 0 ? T::NOBJ : 1], py[T::NOBJ > 0 ? T::NOBJ : 1];
     for (int i = 0; i < T::NOBJ; i++) {
       px[i] = rng.box(0.11f, 0.28f); py[i] = rng.box(-0.18f, 0.2f);
@@ -347,8 +341,19 @@ XD void env_reset(Env<T>& e, const ResetCfg& cfg, int64_t genv) {
       if (rng.uniform() < 0.5) px[i] = -px[i];
       place_obj(e.obj[i], px[i], py[i]);
     }
-    simulate<T>(e);
   }
+}
+
+// Env.reset() [REF xarm_reach.py:96-102,163-168; xarm_pick_and_place.py:121-127,250-267; xarm_stack_tower.py:115-119,201-211;
+// xarm_push_with_door.py:117-121,195-205; xarm_handover.py:141-145,338-368]
+template <class T>
+XD void env_reset(Env<T>& e, const ResetCfg& cfg, int64_t genv) {
+  e.episode += 1; e.step_count = 0;
+  Rng rng = {cfg.seed, (uint64_t)genv, e.episode, 0u};
+  if (T::TASK == XARM_TASK_PICK_AND_PLACE) servo_reset<T>(e, v3(0.4f, 0.f, 0.12f), v3(0, 0, 0), true);
+  if (T::TASK == XARM_TASK_HANDOVER) servo_reset<T>(e, v3(-0.15f, 0.f, 0.15f), v3(0.15f, 0.f, 0.15f), false);
+  env_reset_place<T>(e, rng, cfg);
+  simulate<T>(e);
   sample_goal<T>(e, rng, cfg);
 }
 
@@ -358,11 +363,20 @@ struct StepOut {
   bool done, truncated;
 };
 
+// everything Env.step does after stepSimulation: _get_obs, _is_success, compute_reward, done, TimeLimit
+template <class T>
+XD void env_step_outputs(Env<T>& e, const ResetCfg& cfg, Obs<T>& o, StepOut& so);
+
 template <class T>
 XD void env_step(Env<T>& e, const float* action, const ResetCfg& cfg, Obs<T>& o, StepOut& so) {
   e.step_count += 1;
   set_action<T>(e, action);
   simulate<T>(e);
+  env_step_outputs<T>(e, cfg, o, so);
+}
+
+template <class T>
+XD void env_step_outputs(Env<T>& e, const ResetCfg& cfg, Obs<T>& o, StepOut& so) {
   get_obs<T>(e, o);
   const float thr = T::THRESHOLD;
   float succ;

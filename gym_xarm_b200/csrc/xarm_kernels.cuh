@@ -12,35 +12,20 @@ struct KArgs {
   ResetCfg rc;
   int64_t n;
   int auto_reset;
-  // load balancing (DESIGN.md "warp homogeneity"): thread t of the step kernel simulates env perm[t]
-  int* perm;             // [N] envs ordered by predicted contact load (nearest gripper-object distance first)
-  int* bin_slot;         // [N] (bin << 24 | slot within bin) scratch of the classify pass
-  int* bin_counts;       // [XARM_LOAD_BINS]
-  int* reset_list;       // [N] compacted list of envs the step kernel finished (auto-reset)
+  int* reset_list;       // [N] compacted list of envs that finished this step (auto-reset) / were selected by xarm_reset
   int* reset_count;      // [1]
+  // step pipeline (xarm_pipeline.cuh)
+  float* scratch;        // [pipe_scratch_words][N] rows of the current substep
+  int* form;             // [N] light / heavy classification of the current substep (+ manifold point count)
+  int* heavy_list;       // [N] envs the setup kernel classified as heavy
+  int* heavy_count;      // [XARM_PIPE_COUNTERS] one counter per simulate() pass and substep (zeroed by k_pipe_begin)
+  int* rng_draw;         // [N] Philox draw counter carried from the placement stage of a reset to its goal stage
+  const int* list;       // optional: thread t works on env list[t] (auto-reset tail); NULL = identity
+  const int* list_count;
 };
-#define XARM_LOAD_BINS 8
-
-// predicted contact load of env i for the coming step: bin 0 = gripper closest to an object (contacts likely)
-template <class T>
-XD int body_load_bin(const KArgs& a, int64_t i) {
-  using MD = typename T::MD;
-  Env<T> e;
-  env_load<T>(e, a.state, a.n, i);
-  const int limit = a.rc.max_episode_steps > 0 ? a.rc.max_episode_steps : T::MAX_STEPS;
-  if (a.auto_reset && e.step_count + 1 >= limit) return 0;  // will hit the time limit: step + reset in this launch
-  if (T::NOBJ == 0 || !MD::HAS_BOXES) return 1;
-  float dmin = 1e30f;
-#pragma unroll
-  for (int arm = 0; arm < T::NARM; arm++) {
-    M3 Re; V3 pe, org[7], axs[7];
-    arm_fk7<T>(arm, e.arm[arm].q, Re, pe, org, axs);
-    V3 gc = pe + Re * v3(0.f, 0.f, 0.043f);  // middle of the hand + finger hulls along the hand axis
-    for (int o = 0; o < T::NOBJ; o++) dmin = fminf(dmin, norm(gc - e.obj[o].pos));
-  }
-  int bin = 1 + (int)((dmin - 0.10f) * 20.f);
-  return bin < 1 ? 1 : (bin >= XARM_LOAD_BINS ? XARM_LOAD_BINS - 1 : bin);
-}
+#define XARM_MAX_SUBSTEPS 32
+#define XARM_PIPE_PASSES 8   /* simulate() passes of one xarm_step: the step itself + up to 6 of the auto-reset tail */
+#define XARM_PIPE_COUNTERS (XARM_PIPE_PASSES * XARM_MAX_SUBSTEPS)
 struct StepStats {
   float eps, ret, len, suc, div;
 };
@@ -79,9 +64,11 @@ XD void body_init(const KArgs& a, int64_t i) {
   a.need_reset[i] = 0;
 }
 
-// Env.step for env i
+// Env.step for env i in ONE piece (step + inline auto-reset).  The CUDA path runs the step as the kernel pipeline of
+// xarm_pipeline.cuh; this fused form is what tests/hostsim checks the pipeline against (same results, bit for bit on
+// the host) and the plain statement of the step's semantics.
 template <class T>
-XD void body_step(const KArgs& a, int64_t i, StepStats& st, bool block_sync = false, bool valid = true) {
+XD void body_step(const KArgs& a, int64_t i, StepStats& st) {
   Env<T> e;
   env_load<T>(e, a.state, a.n, i);
   float act[T::A];
@@ -90,7 +77,6 @@ XD void body_step(const KArgs& a, int64_t i, StepStats& st, bool block_sync = fa
   Obs<T> o;
   StepOut so;
   env_step<T>(e, act, a.rc, o, so);
-  if (!valid) return;  // padding lane of a phase-synchronised block: simulated a copy, stores nothing
   if (!env_finite<T>(e)) {  // NaN guard: rebuild the env, end the episode
     uint32_t ep = e.episode;
     env_construct<T>(e, a.rc, a.rc.env_index_base + i);
@@ -119,10 +105,7 @@ XD void body_step(const KArgs& a, int64_t i, StepStats& st, bool block_sync = fa
   a.ep_return[i] = ret;
   a.need_reset[i] = 0;
   if (so.done && a.auto_reset) {
-    // VecEnv auto-reset, fused: the finishing lane runs Env.reset() right away (its warp finishes later, the other
-    // warps of the grid keep the SMs busy meanwhile - a separate reset kernel over the few finished envs would add its
-    // whole 6-sim-step latency to every step).  Envs that reach their time limit are grouped into the same warps by
-    // the load-balancing permutation.
+    // VecEnv auto-reset: the finished env runs Env.reset() right away
     env_reset<T>(e, a.rc, a.rc.env_index_base + i);
     get_obs<T>(e, o);
     e.d_old = np_dist(o.ag, o.dg, T::G);

@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "xarm_kernels.cuh"
+#include "xarm_pipeline.cuh"
 
 // ------------------------------------------------------------------------------------------------ kernels
 // One thread per env; 128-thread blocks (a warp steps 32 envs in lock-step).
@@ -19,51 +19,63 @@ __global__ void __launch_bounds__(128) k_init(KArgs a) {
   if (i < a.n) body_init<T>(a, i);
 }
 
-// Load-balancing pass 1: bin every env by predicted contact load; slot = arrival order inside the bin (the order is
-// irrelevant for the results: envs are independent, the permutation only decides which lane simulates which env).
-template <class T>
-__global__ void __launch_bounds__(128) k_classify(KArgs a) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = i < a.n;
-  int bin = valid ? body_load_bin<T>(a, i) : -1;
-  unsigned peers = __match_any_sync(0xffffffffu, bin);
-  int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-  int base = 0;
-  if (valid && lane == leader) base = atomicAdd(&a.bin_counts[bin], __popc(peers));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (valid) a.bin_slot[i] = (bin << 24) | (base + __popc(peers & ((1u << lane) - 1u)));
+// ------------------------------------------------------------------------------------------------ step pipeline
+// (xarm_pipeline.cuh).  Thread t works on env t, or on env list[t] for t < *list_count when the launch carries a list.
+__device__ __forceinline__ int64_t pipe_env(const KArgs& a, int64_t t) {
+  if (a.list) return t < (int64_t)*a.list_count ? (int64_t)a.list[t] : -1;
+  return t < a.n ? t : -1;
 }
-// pass 2: exclusive prefix over the (8) bins, scatter
-__global__ void __launch_bounds__(128) k_perm(KArgs a) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) *a.reset_count = 0;
-  if (i >= a.n) return;
-  int v = a.bin_slot[i], bin = v >> 24, off = 0;
-  for (int b = 0; b < bin; b++) off += a.bin_counts[b];
-  a.perm[off + (v & 0xffffff)] = (int)i;
+// warp-aggregated append of the flagged lanes' env ids to a list
+__device__ __forceinline__ void list_append(bool flag, int64_t i, int* list, int* count) {
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (!m) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
 }
 
-#ifndef XARM_STEP_BLOCK
-#define XARM_STEP_BLOCK 128
-#endif
-#ifndef XARM_STEP_MIN_BLOCKS
-#define XARM_STEP_MIN_BLOCKS (256 / XARM_STEP_BLOCK)
-#endif
 template <class T>
-__global__ void __launch_bounds__(XARM_STEP_BLOCK, XARM_STEP_MIN_BLOCKS) k_step(KArgs a) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_pipe_action(KArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = pipe_env(a, t);
+  if (i >= 0) pipe_action<T>(a, i);
+}
+template <class T>
+__global__ void __launch_bounds__(128, 4) k_pipe_setup(KArgs a, int sub, int* heavy_count) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = pipe_env(a, t);
+  const bool heavy = i >= 0 && pipe_setup<T>(a, i, sub);
+  list_append(heavy, i, a.heavy_list, heavy_count);
+}
+template <class T>
+__global__ void __launch_bounds__(128, 4) k_pipe_light(KArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = pipe_env(a, t);
+  if (i >= 0) pipe_light<T>(a, i);
+}
+// heavy envs of this substep: 32-thread blocks spread the few heavy warps over all SMs (they run next to k_pipe_light)
+template <class T>
+__global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* heavy_count) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)*heavy_count) return;
+  pipe_heavy<T>(a, a.heavy_list[t], sub);
+}
+// tasks without a light form (two arms / door): every env takes the generic substep
+template <class T>
+__global__ void __launch_bounds__(128) k_pipe_heavy_all(KArgs a, int sub) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = pipe_env(a, t);
+  if (i >= 0) pipe_heavy<T>(a, i, sub);
+}
+template <class T>
+__global__ void __launch_bounds__(128) k_pipe_finish(KArgs a) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = pipe_env(a, t);
   StepStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
-#ifdef XARM_PHASE_SYNC
-  {  // every thread of the block runs the step (block barriers inside); lanes past the end simulate a copy of the last env
-    const bool valid = t < a.n;
-    const int64_t tt = valid ? t : a.n - 1;
-    const int64_t i = a.perm ? a.perm[tt] : tt;
-    body_step<T>(a, i, st, true, valid);
-  }
-#else
-  int64_t i = (t < a.n && a.perm) ? a.perm[t] : t;
-  if (t < a.n) body_step<T>(a, i, st);
-#endif
+  const bool fin = i >= 0 && pipe_finish<T>(a, i, st);
+  list_append(fin, i, a.reset_list, a.reset_count);
   // episode statistics (K8): warp-aggregate, one atomic per warp and counter
   unsigned any = __ballot_sync(0xffffffffu, st.eps != 0.f || st.div != 0.f);
   if (any) {
@@ -82,15 +94,23 @@ __global__ void __launch_bounds__(XARM_STEP_BLOCK, XARM_STEP_MIN_BLOCKS) k_step(
     }
   }
 }
-
-// Env.reset for the envs selected by mask (or by the step kernel's need_reset flags)
 template <class T>
-__global__ void __launch_bounds__(128) k_reset(KArgs a, const uint8_t* mask, int use_flags) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  if (use_flags) { if (!a.need_reset[i]) return; }
-  else if (mask && !mask[i]) return;
-  body_reset<T>(a, i, !use_flags);
+__global__ void __launch_bounds__(128) k_pipe_reset_stage(KArgs a, int stage, int clear_return) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = pipe_env(a, t);
+  if (i >= 0) pipe_reset_stage<T>(a, i, stage, clear_return != 0);
+}
+// zero the per-launch counters of one env step (heavy lists of every pass and substep, the reset list)
+__global__ void k_pipe_begin(KArgs a) {
+  const int t = threadIdx.x;
+  if (t < XARM_PIPE_COUNTERS) a.heavy_count[t] = 0;
+  if (t == 0) *a.reset_count = 0;
+}
+// list = the envs selected by a mask (xarm_reset)
+__global__ void __launch_bounds__(128) k_mask_to_list(KArgs a, const uint8_t* mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = i < a.n && (!mask || mask[i]);
+  list_append(on, i, a.reset_list, a.reset_count);
 }
 
 template <class T>
@@ -116,29 +136,92 @@ static std::atomic<int64_t> g_launches{0};
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define CUDA_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(XARM_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } while (0)
 
+// fork/join plumbing of the pipeline: a side stream for the heavy kernels and a pool of dependency events
+struct PipeCtx {
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> ev;
+  size_t next_ev = 0;
+  cudaEvent_t next() {
+    if (next_ev == ev.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); ev.push_back(e); }
+    return ev[next_ev++];
+  }
+};
+
 struct Ops {
   void (*init)(const KArgs&, cudaStream_t);
-  void (*step)(const KArgs&, cudaStream_t);
-  void (*reset)(const KArgs&, const uint8_t*, int, cudaStream_t);
+  void (*step)(PipeCtx&, const KArgs&, cudaStream_t);
+  void (*reset)(PipeCtx&, const KArgs&, const uint8_t*, cudaStream_t);
   void (*obs)(const KArgs&, cudaStream_t);
-  void (*classify)(const KArgs&, cudaStream_t);
-  int A, O, G, S;
+  int A, O, G, S, scratch_words;
 };
 
 template <class T>
 struct OpsT {
+  static constexpr bool HAS_LIGHT = T::NARM == 1 && !T::HAS_DOOR;  // tasks whose envs can take the light solver form
   static dim3 grid(int64_t n) { return dim3((unsigned)((n + 127) / 128)); }
   static void init(const KArgs& a, cudaStream_t s) { k_init<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
-  static void step(const KArgs& a, cudaStream_t s) { k_step<T><<<dim3((unsigned)((a.n + XARM_STEP_BLOCK - 1) / XARM_STEP_BLOCK)), XARM_STEP_BLOCK, 0, s>>>(a); g_launches++; }
-  static void reset(const KArgs& a, const uint8_t* m, int f, cudaStream_t s) { k_reset<T><<<grid(a.n), 128, 0, s>>>(a, m, f); g_launches++; }
   static void obs(const KArgs& a, cudaStream_t s) { k_obs<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
-  static void classify(const KArgs& a, cudaStream_t s) {
-    cudaMemsetAsync(a.bin_counts, 0, sizeof(int) * XARM_LOAD_BINS, s);
-    k_classify<T><<<grid(a.n), 128, 0, s>>>(a);
-    k_perm<<<grid(a.n), 128, 0, s>>>(a);
-    g_launches += 2;
+  // p.stepSimulation(): NSUB x { setup -> light || heavy }
+  static void simulate(PipeCtx& c, const KArgs& a, int pass, cudaStream_t s) {
+    const dim3 g = grid(a.n);
+    for (int sub = 0; sub < T::NSUB; sub++) {
+      if constexpr (!HAS_LIGHT) {
+        k_pipe_heavy_all<T><<<g, 128, 0, s>>>(a, sub); g_launches++;
+      } else {
+        int* hc = a.heavy_count + pass * XARM_MAX_SUBSTEPS + sub;
+        k_pipe_setup<T><<<g, 128, 0, s>>>(a, sub, hc);
+        cudaEvent_t fork = c.next(), join = c.next();
+        cudaEventRecord(fork, s);
+        cudaStreamWaitEvent(c.side, fork, 0);
+        k_pipe_heavy<T><<<dim3((unsigned)((a.n + 31) / 32)), 32, 0, c.side>>>(a, sub, hc);
+        cudaEventRecord(join, c.side);
+        k_pipe_light<T><<<g, 128, 0, s>>>(a);
+        cudaStreamWaitEvent(s, join, 0);
+        g_launches += 3;
+      }
+    }
   }
-  static Ops make() { Ops o = {init, step, reset, obs, classify, T::A, T::O, T::G, state_words<T>()}; return o; }
+  // Env.reset() of the envs in r.list (all envs when r.list is NULL)
+  static void reset_passes(PipeCtx& c, const KArgs& r, int pass, int clear_return, cudaStream_t s) {
+    const dim3 g = grid(r.n);
+    if (reset_has_servo<T>())
+      for (int rep = 0; rep < 5; rep++) {
+        k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, rep, 0); g_launches++;
+        simulate(c, r, pass++, s);
+      }
+    k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, XARM_RESET_PLACE, 0); g_launches++;
+    simulate(c, r, pass++, s);
+    k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, XARM_RESET_FINISH, clear_return); g_launches++;
+  }
+  static void step(PipeCtx& c, const KArgs& a0, cudaStream_t s) {
+    static_assert(T::NSUB <= XARM_MAX_SUBSTEPS, "substep counters");
+    KArgs a = a0;
+    a.list = nullptr; a.list_count = nullptr;
+    c.next_ev = 0;
+    const dim3 g = grid(a.n);
+    k_pipe_begin<<<1, XARM_PIPE_COUNTERS, 0, s>>>(a);
+    k_pipe_action<T><<<g, 128, 0, s>>>(a);
+    simulate(c, a, 0, s);
+    k_pipe_finish<T><<<g, 128, 0, s>>>(a);
+    g_launches += 3;
+    if (a.auto_reset) {  // VecEnv auto-reset: the finished envs (compacted list) run Env.reset() through the same pipeline
+      KArgs r = a;
+      r.list = a.reset_list; r.list_count = a.reset_count;
+      reset_passes(c, r, 1, 0, s);
+    }
+  }
+  static void reset(PipeCtx& c, const KArgs& a0, const uint8_t* mask, cudaStream_t s) {
+    KArgs a = a0;
+    a.list = nullptr; a.list_count = nullptr;
+    c.next_ev = 0;
+    k_pipe_begin<<<1, XARM_PIPE_COUNTERS, 0, s>>>(a); g_launches++;
+    if (mask) {
+      k_mask_to_list<<<grid(a.n), 128, 0, s>>>(a, mask); g_launches++;
+      a.list = a.reset_list; a.list_count = a.reset_count;
+    }
+    reset_passes(c, a, 0, 1, s);
+  }
+  static Ops make() { Ops o = {init, step, reset, obs, T::A, T::O, T::G, state_words<T>(), pipe_scratch_words<T>()}; return o; }
 };
 
 // XARM_ONLY_TASK=<id> builds a single task (development builds: faster compiles); the shipped library has all five.
@@ -183,8 +266,10 @@ struct XarmHandle {
   Ops ops;
   KArgs k;
   bool bound = false;
+  PipeCtx pipe;
   cudaGraphExec_t graph = nullptr;
   cudaStream_t graph_stream = nullptr;
+  int64_t graph_launches = 0;
   // device + pinned staging for the *_host entry points
   float* d_io = nullptr;   // actions | obs | ag | dg | reward | success
   uint8_t* d_flags = nullptr;  // done | truncated
@@ -238,19 +323,23 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   h->k.rc.seed = c.seed; h->k.rc.env_index_base = c.env_index_base; h->k.rc.reward_type = c.reward_type;
   h->k.rc.goal_shape = c.goal_shape; h->k.rc.max_episode_steps = c.max_episode_steps;
   h->k.rc.init_grasp_rate = c.init_grasp_rate; h->k.rc.goal_ground_rate = c.goal_ground_rate; h->k.rc.same_side_rate = c.same_side_rate;
+  const size_t n_int = (size_t)4 * n + XARM_PIPE_COUNTERS + 1;
   cudaError_t e1 = cudaMalloc(&h->k.state, sizeof(float) * ops.S * n);
   cudaError_t e2 = cudaMalloc(&h->k.ep_return, sizeof(float) * n);
   cudaError_t e3 = cudaMalloc(&h->k.need_reset, n);
   cudaError_t e4 = cudaMalloc(&h->k.stats, sizeof(double) * 5);
-  cudaError_t e5 = cudaMalloc(&h->k.perm, sizeof(int) * (3 * n + XARM_LOAD_BINS + 1));
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess) {
-    cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.perm);
+  cudaError_t e5 = cudaMalloc(&h->k.reset_list, sizeof(int) * n_int);
+  cudaError_t e6 = cudaMalloc(&h->k.scratch, sizeof(float) * ops.scratch_words * n);
+  cudaError_t e7 = cudaStreamCreateWithFlags(&h->pipe.side, cudaStreamNonBlocking);
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
+    cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.reset_list); cudaFree(h->k.scratch);
+    if (h->pipe.side) cudaStreamDestroy(h->pipe.side);
     delete h; cudaGetLastError();
     return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc failed");
   }
-  h->k.bin_slot = h->k.perm + n; h->k.reset_list = h->k.perm + 2 * n;
-  h->k.bin_counts = h->k.perm + 3 * n; h->k.reset_count = h->k.bin_counts + XARM_LOAD_BINS;
-  CUDA_TRY(cudaMemset(h->k.perm, 0, sizeof(int) * (3 * n + XARM_LOAD_BINS + 1)));
+  h->k.heavy_list = h->k.reset_list + n; h->k.form = h->k.reset_list + 2 * n; h->k.rng_draw = h->k.reset_list + 3 * n;
+  h->k.heavy_count = h->k.reset_list + 4 * n; h->k.reset_count = h->k.heavy_count + XARM_PIPE_COUNTERS;
+  CUDA_TRY(cudaMemset(h->k.reset_list, 0, sizeof(int) * n_int));
   CUDA_TRY(cudaMemset(h->k.stats, 0, sizeof(double) * 5));
   ops.init(h->k, 0);
   CUDA_TRY(cudaGetLastError());
@@ -263,7 +352,9 @@ int xarm_destroy(XarmHandle* h) {
   if (!h) return XARM_OK;
   cudaSetDevice(h->cfg.device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
-  cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.perm);
+  cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.reset_list); cudaFree(h->k.scratch);
+  for (cudaEvent_t e : h->pipe.ev) cudaEventDestroy(e);
+  if (h->pipe.side) cudaStreamDestroy(h->pipe.side);
   cudaFree(h->d_io); cudaFree(h->d_flags);
   if (h->h_io) cudaFreeHost(h->h_io);
   if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -281,20 +372,18 @@ int xarm_bind(XarmHandle* h, const XarmBuffers* b) {
   return XARM_OK;
 }
 
-// one env step = classify (load-balancing permutation) -> step (with the auto-reset of finished envs fused in)
+// one env step = the kernel pipeline of xarm_pipeline.cuh (action -> NSUB x {setup -> light || heavy} -> finish -> auto-reset tail)
 static int launch_step_with(XarmHandle* h, const KArgs& k, cudaStream_t s) {
-  h->ops.classify(k, s);
-  h->ops.step(k, s);
+  h->ops.step(h->pipe, k, s);
   return XARM_OK;
 }
 static int launch_step(XarmHandle* h, cudaStream_t s) { return launch_step_with(h, h->k, s); }
-#define XARM_LAUNCHES_PER_STEP(h) 3
 
 int xarm_reset(XarmHandle* h, const uint8_t* mask, void* stream) {
   if (!h) return fail(XARM_E_INVALID, "xarm_reset: null handle");
   if (!h->bound) return fail(XARM_E_STATE, "xarm_reset: call xarm_bind first");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  h->ops.reset(h->k, mask, 0, (cudaStream_t)stream);
+  h->ops.reset(h->pipe, h->k, mask, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return XARM_OK;
 }
@@ -306,7 +395,7 @@ int xarm_step(XarmHandle* h, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (h->graph && s == h->graph_stream) {
     CUDA_TRY(cudaGraphLaunch(h->graph, s));
-    g_launches += XARM_LAUNCHES_PER_STEP(h);
+    g_launches += h->graph_launches;
   } else {
     launch_step(h, s);
     CUDA_TRY(cudaGetLastError());
@@ -326,6 +415,7 @@ int xarm_graph_capture(XarmHandle* h, void* stream) {
   CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   launch_step(h, s);
   cudaError_t e = cudaStreamEndCapture(s, &g);
+  h->graph_launches = g_launches.load() - before;
   g_launches = before;  // captured launches did not run
   if (e != cudaSuccess) return fail(XARM_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
   e = cudaGraphInstantiate(&h->graph, g, 0);
@@ -405,7 +495,7 @@ int xarm_reset_host(XarmHandle* h, float* observation, float* achieved_goal, flo
   const Ops& o = h->ops;
   KArgs k = h->k;
   k.b = h->host_bufs;
-  h->ops.reset(k, nullptr, 0, s);
+  h->ops.reset(h->pipe, k, nullptr, s);
   CUDA_TRY(cudaGetLastError());
   float* hp = h->h_io + n * o.A;
   CUDA_TRY(cudaMemcpyAsync(hp, k.b.observation, sizeof(float) * n * (o.O + 2 * o.G), cudaMemcpyDeviceToHost, s));

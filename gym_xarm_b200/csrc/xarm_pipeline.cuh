@@ -1,0 +1,283 @@
+// xarm_pipeline.cuh - Env.step as a pipeline of small kernels (per-env bodies; the __global__ wrappers are in
+// xarm_lib.cu, tests/hostsim runs the same bodies on the host).
+//
+// Why: the fused one-kernel step (body_step) is ~270 KB of SASS and instruction-fetch bound - ncu shows 70 % of the
+// warp cycles in "no instruction" stalls, 0.5 IPC per SM and 8 warps per SM at 255 registers (profiles/).  Each piece
+// below fits the 32 KB L1.5 instruction cache, needs far fewer registers, and all warps of a launch run the same loop:
+//
+//   pipe_action            _set_action: FK, IK, motor targets (once per env step)
+//   NSUB x { pipe_setup    collide -> unconstrained velocities -> rows; classifies the env as light / heavy
+//            pipe_light    light envs : PGS over the arm rows + one object manifold, integrate      } run concurrently
+//            pipe_heavy    heavy envs : the whole substep with the generic coupled solver             } (graph fork)
+//   pipe_finish            _get_obs, reward, success, done, TimeLimit, episode statistics, auto-reset list
+//
+// Intermediates travel through a per-handle scratch slab in the same [word][env] layout as the state (coalesced; it
+// stays in the 126 MB L2 at the benchmark sizes): 72 + 22 + 28 words per env and substep for PickAndPlace.
+// Every body takes the env index; with a list (auto-reset tail) thread t works on env list[t].
+#pragma once
+#include "xarm_kernels.cuh"
+
+#define XARM_FORM_LIGHT 0
+#define XARM_FORM_HEAVY 1
+
+template <class T>
+XHD int pipe_ar_words() { return T::NARM * (T::MD::N * (T::MD::N + 1) / 2 + 2 * T::MD::N + 5) + 4; }
+template <class T>
+XHD int pipe_sb_words() { return T::NARM * T::MD::N + 6 * (T::NOBJ > 0 ? T::NOBJ : 1) + 1; }
+XHD int pipe_mi_words() { return 3 + 1 + 12 + 12 + 6; }
+template <class T>
+XHD int pipe_scratch_words() { return pipe_ar_words<T>() + pipe_sb_words<T>() + pipe_mi_words(); }
+
+// ---- scratch records: word w of env i at base[w * n + i]
+template <class T>
+XD void ar_store(const ArmRows<T>& AR, float* __restrict__ s, int64_t n, int64_t i) {
+  constexpr int N = T::MD::N, NT = N * (N + 1) / 2;
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++) {
+#pragma unroll
+    for (int k = 0; k < NT; k++) s[(w++) * n + i] = AR.Mi[a][k];
+#pragma unroll
+    for (int k = 0; k < N; k++) s[(w++) * n + i] = AR.mrhs[a][k];
+#pragma unroll
+    for (int k = 0; k < N; k++) s[(w++) * n + i] = AR.lrhs[a][k];
+    s[(w++) * n + i] = (float)AR.lim_lo[a]; s[(w++) * n + i] = (float)AR.lim_hi[a];  // bit masks < 2^13: exact
+    s[(w++) * n + i] = AR.grhs[a]; s[(w++) * n + i] = AR.gdinv[a]; s[(w++) * n + i] = AR.gden[a];
+  }
+  s[(w++) * n + i] = AR.dl_rhs; s[(w++) * n + i] = AR.dl_sign; s[(w++) * n + i] = AR.dm_rhs;
+  s[(w++) * n + i] = (float)AR.door_lim;
+}
+template <class T>
+XD void ar_load(ArmRows<T>& AR, const float* __restrict__ s, int64_t n, int64_t i) {
+  constexpr int N = T::MD::N, NT = N * (N + 1) / 2;
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++) {
+#pragma unroll
+    for (int k = 0; k < NT; k++) AR.Mi[a][k] = s[(w++) * n + i];
+#pragma unroll
+    for (int k = 0; k < N; k++) AR.mrhs[a][k] = s[(w++) * n + i];
+#pragma unroll
+    for (int k = 0; k < N; k++) AR.lrhs[a][k] = s[(w++) * n + i];
+    AR.lim_lo[a] = (uint32_t)s[(w++) * n + i]; AR.lim_hi[a] = (uint32_t)s[(w++) * n + i];
+    AR.grhs[a] = s[(w++) * n + i]; AR.gdinv[a] = s[(w++) * n + i]; AR.gden[a] = s[(w++) * n + i];
+  }
+  AR.dl_rhs = s[(w++) * n + i]; AR.dl_sign = s[(w++) * n + i]; AR.dm_rhs = s[(w++) * n + i];
+  AR.door_lim = (int)s[(w++) * n + i];
+}
+template <class T>
+XD void sb_store(const SubBase<T>& B, float* __restrict__ s, int64_t n, int64_t i) {
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++)
+#pragma unroll
+    for (int k = 0; k < T::MD::N; k++) s[(w++) * n + i] = B.qdu[a][k];
+#pragma unroll
+  for (int o = 0; o < (T::NOBJ > 0 ? T::NOBJ : 1); o++) {
+    s[(w++) * n + i] = B.vu[o].x; s[(w++) * n + i] = B.vu[o].y; s[(w++) * n + i] = B.vu[o].z;
+    s[(w++) * n + i] = B.wu[o].x; s[(w++) * n + i] = B.wu[o].y; s[(w++) * n + i] = B.wu[o].z;
+  }
+  s[(w++) * n + i] = B.door_qdu;
+}
+template <class T>
+XD void sb_load(SubBase<T>& B, const float* __restrict__ s, int64_t n, int64_t i) {
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++)
+#pragma unroll
+    for (int k = 0; k < T::MD::N; k++) B.qdu[a][k] = s[(w++) * n + i];
+#pragma unroll
+  for (int o = 0; o < (T::NOBJ > 0 ? T::NOBJ : 1); o++) {
+    B.vu[o].x = s[(w++) * n + i]; B.vu[o].y = s[(w++) * n + i]; B.vu[o].z = s[(w++) * n + i];
+    B.wu[o].x = s[(w++) * n + i]; B.wu[o].y = s[(w++) * n + i]; B.wu[o].z = s[(w++) * n + i];
+  }
+  B.door_qdu = s[(w++) * n + i];
+}
+XD void mi_store(const ManifoldIn& M, float* __restrict__ s, int64_t n, int64_t i) {
+  int w = 0;
+  s[(w++) * n + i] = M.n.x; s[(w++) * n + i] = M.n.y; s[(w++) * n + i] = M.n.z; s[(w++) * n + i] = M.mu;
+#pragma unroll
+  for (int c = 0; c < 4; c++) { s[(w++) * n + i] = M.r[c].x; s[(w++) * n + i] = M.r[c].y; s[(w++) * n + i] = M.r[c].z; }
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[(w++) * n + i] = M.rhs[c][k];
+  s[(w++) * n + i] = M.Iinv.xx; s[(w++) * n + i] = M.Iinv.xy; s[(w++) * n + i] = M.Iinv.xz;
+  s[(w++) * n + i] = M.Iinv.yy; s[(w++) * n + i] = M.Iinv.yz; s[(w++) * n + i] = M.Iinv.zz;
+}
+XD void mi_load(ManifoldIn& M, const float* __restrict__ s, int64_t n, int64_t i) {
+  int w = 0;
+  M.n.x = s[(w++) * n + i]; M.n.y = s[(w++) * n + i]; M.n.z = s[(w++) * n + i]; M.mu = s[(w++) * n + i];
+#pragma unroll
+  for (int c = 0; c < 4; c++) { M.r[c].x = s[(w++) * n + i]; M.r[c].y = s[(w++) * n + i]; M.r[c].z = s[(w++) * n + i]; }
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) M.rhs[c][k] = s[(w++) * n + i];
+  M.Iinv.xx = s[(w++) * n + i]; M.Iinv.xy = s[(w++) * n + i]; M.Iinv.xz = s[(w++) * n + i];
+  M.Iinv.yy = s[(w++) * n + i]; M.Iinv.yz = s[(w++) * n + i]; M.Iinv.zz = s[(w++) * n + i];
+}
+
+// ---- _set_action (once per env step): FK, IK, motor targets; Handover's lego clamp
+template <class T>
+XD void pipe_action(const KArgs& a, int64_t i) {
+  Env<T> e;
+  env_load<T>(e, a.state, a.n, i);
+  float act[T::A];
+#pragma unroll
+  for (int k = 0; k < T::A; k++) act[k] = a.b.actions[i * T::A + k];
+  e.step_count += 1;
+  set_action<T>(e, act);
+  env_store<T>(e, a.state, a.n, i);
+}
+
+// ---- substep, part 1: rows.  Light envs leave their rows in the scratch slab; the others join the heavy list.
+// Returns true when env i is heavy (the wrapper appends it to the list, warp-aggregated).
+template <class T>
+XD bool pipe_setup(const KArgs& a, int64_t i, int sub) {
+  Env<T> e;
+  env_load<T>(e, a.state, a.n, i);
+  ArmRows<T> AR;
+  Contacts<T> C;
+  SubBase<T> B;
+  ManifoldIn MI;
+  const bool last = sub == T::NSUB - 1;
+  const int g0 = e.grasp[0], g1 = e.grasp[1];
+  const int form = sub_setup<T>(e, T::DAMP_EACH || sub == 0, last, AR, C, B, MI);
+  if (form != SOLVE_LIGHT) { a.form[i] = XARM_FORM_HEAVY; return true; }  // the heavy kernel redoes the setup (and the grasp flags)
+  float* s = a.scratch;
+  ar_store<T>(AR, s, a.n, i); s += (int64_t)pipe_ar_words<T>() * a.n;
+  sb_store<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
+  if (C.nc > 0) mi_store(MI, s, a.n, i);
+  a.form[i] = XARM_FORM_LIGHT | (C.nc << 8);
+  if (last && (e.grasp[0] != g0 || e.grasp[1] != g1)) {  // grasp flags of the last collision pass
+    const int w = state_words<T>() - 2;
+    a.state[(int64_t)w * a.n + i] = e.grasp[0] ? 1.f : 0.f;
+    a.state[(int64_t)(w + 1) * a.n + i] = e.grasp[1] ? 1.f : 0.f;
+  }
+  return false;
+}
+
+// ---- substep, part 2 (light envs): PGS over the arm rows and the object's manifold, then stepPositionsMultiDof
+template <class T>
+XD void pipe_light(const KArgs& a, int64_t i) {
+  const int f = a.form[i];
+  if ((f & 0xff) != XARM_FORM_LIGHT) return;
+  const int nc = f >> 8;
+  ArmRows<T> AR;
+  SubBase<T> B;
+  ManifoldIn MI;
+  const float* s = a.scratch;
+  ar_load<T>(AR, s, a.n, i); s += (int64_t)pipe_ar_words<T>() * a.n;
+  sb_load<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
+  if (nc > 0) mi_load(MI, s, a.n, i);
+  SubSol<T> S;
+  sub_solve_light<T>(AR, nc, MI, S);
+  Env<T> e;
+  env_load_dyn<T>(e, a.state, a.n, i);
+  sub_integrate<T>(e, B, S);
+  env_store_dyn<T>(e, a.state, a.n, i);
+}
+
+// ---- substep for heavy envs (gripper contacts, several manifolds, two arms, door): setup + generic coupled PGS + integrate
+template <class T>
+XD void pipe_heavy(const KArgs& a, int64_t i, int sub) {
+  Env<T> e;
+  env_load<T>(e, a.state, a.n, i);
+  substep_generic<T>(e, T::DAMP_EACH || sub == 0, sub == T::NSUB - 1);
+  env_store<T>(e, a.state, a.n, i);
+}
+
+// ---- end of the env step: _get_obs, _is_success, compute_reward, done / TimeLimit, statistics, auto-reset bookkeeping
+// Returns true when the env finished and auto-reset is on (the wrapper appends it to the reset list).
+template <class T>
+XD bool pipe_finish(const KArgs& a, int64_t i, StepStats& st) {
+  Env<T> e;
+  env_load<T>(e, a.state, a.n, i);
+  Obs<T> o;
+  StepOut so;
+  env_step_outputs<T>(e, a.rc, o, so);
+  bool rebuilt = false;
+  if (!env_finite<T>(e)) {  // NaN guard: rebuild the env, end the episode
+    uint32_t ep = e.episode;
+    env_construct<T>(e, a.rc, a.rc.env_index_base + i);
+    e.episode = ep;
+    get_obs<T>(e, o);
+    so.reward = 0.f; so.success = 0.f; so.done = true; so.truncated = true;
+    st.div = 1.f;
+    rebuilt = true;
+  }
+  write_obs<T>(a, i, o);
+  a.b.reward[i] = so.reward;
+  a.b.done[i] = so.done;
+  a.b.success[i] = so.success;
+  if (a.b.truncated) a.b.truncated[i] = so.truncated;
+  float ret = a.ep_return[i] + so.reward;
+  if (so.done) {
+    if (a.b.terminal_observation) {
+      float* t = a.b.terminal_observation + i * (T::O + 2 * T::G);
+#pragma unroll
+      for (int k = 0; k < T::O; k++) t[k] = o.obs[k];
+#pragma unroll
+      for (int k = 0; k < T::G; k++) { t[T::O + k] = o.ag[k]; t[T::O + T::G + k] = o.dg[k]; }
+    }
+    st.eps = 1.f; st.ret = ret; st.len = (float)e.step_count; st.suc = so.success;
+    ret = 0.f;
+  }
+  a.ep_return[i] = ret;
+  a.need_reset[i] = 0;
+  if (rebuilt || (T::TASK == XARM_TASK_REACH && a.rc.reward_type == XARM_REWARD_DENSE_DIFF)) env_store<T>(e, a.state, a.n, i);  // d_old / rebuilt state
+  return so.done && a.auto_reset;
+}
+
+// ---- Env.reset() through the same pipeline (auto-reset tail and xarm_reset): env_reset() cut at its stepSimulation
+// calls.  Stages: 0..4 = the five servo repetitions of PickAndPlace / Handover (IK to the start pose, finger command;
+// stage 0 also opens the episode), XARM_RESET_PLACE = object placement (teleport tasks: also joint teleport and episode
+// bookkeeping), XARM_RESET_FINISH = _sample_goal, _get_obs, d_old.  A simulate() pass follows every stage but the last.
+// The Philox draw counter travels from PLACE to FINISH in a.rng_draw (Handover's placement loop consumes a variable
+// number of draws).  [REF xarm_pick_and_place.py:250-287; xarm_handover.py:338-393; xarm_reach.py:163-173;
+// xarm_stack_tower.py:201-219; xarm_push_with_door.py:195-212]
+#define XARM_RESET_PLACE 5
+#define XARM_RESET_FINISH 6
+template <class T>
+XHD bool reset_has_servo() { return T::TASK == XARM_TASK_PICK_AND_PLACE || T::TASK == XARM_TASK_HANDOVER; }
+
+template <class T>
+XD void pipe_reset_stage(const KArgs& a, int64_t i, int stage, bool clear_return) {
+  using MD = typename T::MD;
+  Env<T> e;
+  env_load<T>(e, a.state, a.n, i);
+  const int64_t genv = a.rc.env_index_base + i;
+  if (stage < XARM_RESET_PLACE) {  // servo repetition
+    if (stage == 0) { e.episode += 1; e.step_count = 0; }
+    const bool pp = T::TASK == XARM_TASK_PICK_AND_PLACE;
+    const V3 t0 = pp ? v3(0.4f, 0.f, 0.12f) : v3(-0.15f, 0.f, 0.15f), t1 = pp ? v3(0, 0, 0) : v3(0.15f, 0.f, 0.15f);
+#pragma unroll
+    for (int arm = 0; arm < T::NARM; arm++) {
+      float qn[7];
+      arm_ik<T>(arm, e.arm[arm].q, arm == 0 ? t0 : t1, qn);
+#pragma unroll
+      for (int k = 0; k < 7; k++) e.arm[arm].qt[k] = qn[k];
+      if (pp && MD::F2 >= 0) { e.arm[arm].qt[MD::F1] = 0.02f; e.arm[arm].qt[MD::F2 < 0 ? 0 : MD::F2] = 0.02f; }
+    }
+    env_store<T>(e, a.state, a.n, i);
+    return;
+  }
+  if (stage == XARM_RESET_PLACE) {
+    if (!reset_has_servo<T>()) { e.episode += 1; e.step_count = 0; }
+    Rng rng = {a.rc.seed, (uint64_t)genv, e.episode, 0u};
+    env_reset_place<T>(e, rng, a.rc);
+    a.rng_draw[i] = (int)rng.draw;
+    env_store<T>(e, a.state, a.n, i);
+    return;
+  }
+  Rng rng = {a.rc.seed, (uint64_t)genv, e.episode, (uint32_t)a.rng_draw[i]};
+  sample_goal<T>(e, rng, a.rc);
+  Obs<T> o;
+  get_obs<T>(e, o);
+  e.d_old = np_dist(o.ag, o.dg, T::G);  // [REF xarm_reach.py:100]
+  write_obs<T>(a, i, o);
+  env_store<T>(e, a.state, a.n, i);
+  a.need_reset[i] = 0;
+  if (clear_return) a.ep_return[i] = 0.f;
+}

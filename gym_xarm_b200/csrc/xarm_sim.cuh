@@ -93,6 +93,53 @@ XD void env_store(const Env<T>& e, float* __restrict__ s, int64_t n, int64_t i) 
   s[(w++) * n + i] = e.grasp[1] ? 1.f : 0.f;
 }
 
+// the dynamic part only (what a substep changes): joint positions / velocities, object poses / velocities, the door.
+// Motor targets, goal, counters and grasp flags are not touched (the arms' qt words are skipped).
+template <class T>
+XD void env_load_dyn(Env<T>& e, const float* __restrict__ s, int64_t n, int64_t i) {
+  using MD = typename T::MD;
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++) {
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) e.arm[a].q[k] = s[(w++) * n + i];
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) e.arm[a].qd[k] = s[(w++) * n + i];
+    w += MD::N;
+  }
+#pragma unroll
+  for (int o = 0; o < T::NOBJ; o++) {
+    ObjState& b = e.obj[o];
+    b.pos.x = s[(w++) * n + i]; b.pos.y = s[(w++) * n + i]; b.pos.z = s[(w++) * n + i];
+    b.quat.x = s[(w++) * n + i]; b.quat.y = s[(w++) * n + i]; b.quat.z = s[(w++) * n + i]; b.quat.w = s[(w++) * n + i];
+    b.v.x = s[(w++) * n + i]; b.v.y = s[(w++) * n + i]; b.v.z = s[(w++) * n + i];
+    b.w.x = s[(w++) * n + i]; b.w.y = s[(w++) * n + i]; b.w.z = s[(w++) * n + i];
+  }
+  if (T::HAS_DOOR) { e.door_q = s[(w++) * n + i]; e.door_qd = s[(w++) * n + i]; } else { e.door_q = 0; e.door_qd = 0; }
+}
+template <class T>
+XD void env_store_dyn(const Env<T>& e, float* __restrict__ s, int64_t n, int64_t i) {
+  using MD = typename T::MD;
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++) {
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) s[(w++) * n + i] = e.arm[a].q[k];
+#pragma unroll
+    for (int k = 0; k < MD::N; k++) s[(w++) * n + i] = e.arm[a].qd[k];
+    w += MD::N;
+  }
+#pragma unroll
+  for (int o = 0; o < T::NOBJ; o++) {
+    const ObjState& b = e.obj[o];
+    s[(w++) * n + i] = b.pos.x; s[(w++) * n + i] = b.pos.y; s[(w++) * n + i] = b.pos.z;
+    s[(w++) * n + i] = b.quat.x; s[(w++) * n + i] = b.quat.y; s[(w++) * n + i] = b.quat.z; s[(w++) * n + i] = b.quat.w;
+    s[(w++) * n + i] = b.v.x; s[(w++) * n + i] = b.v.y; s[(w++) * n + i] = b.v.z;
+    s[(w++) * n + i] = b.w.x; s[(w++) * n + i] = b.w.y; s[(w++) * n + i] = b.w.z;
+  }
+  if (T::HAS_DOOR) { s[(w++) * n + i] = e.door_q; s[(w++) * n + i] = e.door_qd; }
+}
+
 // ------------------------------------------------------------------------------------------------ RNG (Appendix E)
 XD void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -663,10 +710,20 @@ struct SubSol {  // velocity changes produced by the solver
   float ddoor;
 };
 enum { SOLVE_LIGHT = 0, SOLVE_GENERIC_DECOUPLED = 1, SOLVE_GENERIC_JOINT = 2 };
+// What the light solver needs of a single manifold (<= 4 points sharing the normal) of object 0 against a static box:
+// lever arms, right-hand sides and the box's world inverse inertia; the rows themselves are rebuilt from these
+// (manifold_rows) so that only 34 words per env travel between the setup and the solve kernels.
+struct ManifoldIn {
+  V3 n;
+  float mu;
+  V3 r[4];
+  float rhs[4][3];
+  S3 Iinv;
+};
 
 // collide -> unconstrained velocities -> rows.  Returns which solver form applies.
 template <class T>
-XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Contacts<T>& C, SubBase<T>& B) {
+XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Contacts<T>& C, SubBase<T>& B, ManifoldIn& MI) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1, NT = N * (N + 1) / 2;
   const float h = (float)T::H;
@@ -896,6 +953,16 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
   // which solver form: islands (one arm, no door, no gripper contact) decouple the arm rows from the object rows
   const bool decoupled = NA == 1 && !T::HAS_DOOR && C.nac == 0;
   const bool manifold = decoupled && NOBJ == 1 && C.nc > 0 && C.nc <= 4 && C.npair == 1 && C.o1[0] == 0 && C.s1[0] > 0.f && C.cfm0[0] == 0.f;
+  if (manifold) {
+    MI.n = C.dir[0][0]; MI.mu = C.mu[0]; MI.Iinv = Iinv[0];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const bool on = c < C.nc;
+      MI.r[c] = on ? C.pa[c] - e.obj[0].pos : v3(0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 3; k++) MI.rhs[c][k] = on ? C.rhs[c][k] : 0.f;
+    }
+  }
   if (decoupled && (C.nc == 0 || manifold)) return SOLVE_LIGHT;
   return decoupled ? SOLVE_GENERIC_DECOUPLED : SOLVE_GENERIC_JOINT;
 }
@@ -966,6 +1033,10 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
       }                                                                                                          \
     }                                                                                                            \
   }
+// the motor rows of arm a, fully unrolled (no limit row active): forward = dof 0..N-1, backward = N-1..0
+#define ARM_MOTOR_ROW_(a, i) { const float hi_ = (i) < 7 ? hi_arm : hi_fin; UNIT_ROW(a, i, 1.f, mrhs[a][i], -hi_, hi_, mapp[a][i]) }
+#define ARM_MOTORS_FWD(a) { _Pragma("unroll") for (int i_ = 0; i_ < N; i_++) ARM_MOTOR_ROW_(a, i_) }
+#define ARM_MOTORS_BWD(a) { _Pragma("unroll") for (int i_ = N - 1; i_ >= 0; i_--) ARM_MOTOR_ROW_(a, i_) }
 #define ARM_ROWS_SWEEP(it)                                                                                       \
   if ((it) & 1) {                                                                                                \
     _Pragma("unroll") for (int a = 0; a < NA; a++) ARM_ROWS_ONE(a, true)                                         \
@@ -1057,7 +1128,8 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
   const float sthr_ = sqrtf((float)XARM_RESIDUAL_THRESHOLD);                                                     \
   (void)door_lim; (void)dl_rhs; (void)dl_sign; (void)dm_rhs; (void)door_den; (void)hi_lim; (void)hi_gear; (void)gr; (void)inv_obj_mass;
 
-// Register-resident rows of a single manifold (<= 4 points sharing n, t1, t2) of the one object against a static box.
+// Register-resident rows of a single manifold (<= 4 points sharing n, t1, t2) of the one object against a static box,
+// rebuilt from the compact ManifoldIn with the arithmetic of sub_setup's row loop.
 template <class T>
 struct ManifoldRows {
   V3 n, t1, t2;
@@ -1066,79 +1138,129 @@ struct ManifoldRows {
   float rn[4], r1[4], r2[4], dn[4], d1[4], d2[4];
 };
 template <class T>
-XD void manifold_from_contacts(const Contacts<T>& C, ManifoldRows<T>& Mf) {
-  Mf.n = C.dir[0][0]; Mf.t1 = C.dir[0][1]; Mf.t2 = C.dir[0][2]; Mf.mu = C.mu[0];
+XD void manifold_rows(const ManifoldIn& MI, int nc, ManifoldRows<T>& Mf) {
+  V3 t1, t2;
+  plane_space(MI.n, t1, t2);
+  Mf.n = MI.n; Mf.t1 = t1; Mf.t2 = t2; Mf.mu = MI.mu;
 #pragma unroll
   for (int c = 0; c < 4; c++) {
-    const bool on = c < C.nc;
-    const V3 z = v3(0, 0, 0);
-    Mf.Jn[c] = on ? C.Jo1[c][0] : z; Mf.Jt1[c] = on ? C.Jo1[c][1] : z; Mf.Jt2[c] = on ? C.Jo1[c][2] : z;
-    Mf.Vn[c] = on ? C.dVo1[c][0] : z; Mf.Vt1[c] = on ? C.dVo1[c][1] : z; Mf.Vt2[c] = on ? C.dVo1[c][2] : z;
-    Mf.rn[c] = on ? C.rhs[c][0] : 0.f; Mf.r1[c] = on ? C.rhs[c][1] : 0.f; Mf.r2[c] = on ? C.rhs[c][2] : 0.f;
-    Mf.dn[c] = on ? C.dinv[c][0] : 0.f; Mf.d1[c] = on ? C.dinv[c][1] : 0.f; Mf.d2[c] = on ? C.dinv[c][2] : 0.f;
+    const bool on = c < nc;
+    const V3 r = MI.r[c];
+    V3 rxd, ir;
+    rxd = cross(r, MI.n); ir = MI.Iinv * rxd;
+    Mf.Jn[c] = rxd; Mf.Vn[c] = ir; Mf.dn[c] = on ? 1.f / ((1.f / T::OBJ_MASS + dot(rxd, ir)) + 0.f) : 0.f;
+    rxd = cross(r, t1); ir = MI.Iinv * rxd;
+    Mf.Jt1[c] = rxd; Mf.Vt1[c] = ir; Mf.d1[c] = on ? 1.f / (1.f / T::OBJ_MASS + dot(rxd, ir)) : 0.f;
+    rxd = cross(r, t2); ir = MI.Iinv * rxd;
+    Mf.Jt2[c] = rxd; Mf.Vt2[c] = ir; Mf.d2[c] = on ? 1.f / (1.f / T::OBJ_MASS + dot(rxd, ir)) : 0.f;
+    Mf.rn[c] = MI.rhs[c][0]; Mf.r1[c] = MI.rhs[c][1]; Mf.r2[c] = MI.rhs[c][2];
   }
 }
 
-// Light form (SOLVE_LIGHT): the arm rows and, if present, one manifold of the object, swept as two independent
-// islands - bit-identical impulses to the joint loop.  Only the early-exit test couples the islands (a sweep ends the
-// solve when NO row of either island moved more than the threshold); it is reproduced from per-sweep masks.  Returns
-// false in the (never observed) case that the joint loop would have stopped before its last sweep: the caller then
-// runs the joint loop instead.
+// Arm island of the light form: at most max_it sweeps over the non-contact rows of arm 0; bit `it` of the returned mask
+// is set when no row moved more than the residual threshold in sweep `it`.  stop_when_ok: leave at the first such sweep
+// (what the solver does when the arm rows are the only rows).  The common case (no joint limit active) runs fully
+// unrolled forward / backward sweeps; with a limit active the switch-dispatched sweep of the generic form is used.
 template <class T>
-XD bool sub_solve_light(const ArmRows<T>& AR, int nc, const ManifoldRows<T>& Mf, SubSol<T>& S) {
+NOINL unsigned long long solve_arm_island(const ArmRows<T>& AR, int max_it, bool stop_when_ok, float* dqd_out) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NA = T::NARM, NT = N * (N + 1) / 2;
   SOLVER_LOCALS_FROM(AR)
-  unsigned long long ok_arm = 0ull, ok_obj = 0ull;
-  for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
-    bool resid_bad = false;
-    ARM_ROWS_SWEEP(it)
-    if (!resid_bad) { ok_arm |= 1ull << it; if (nc == 0) break; }
-  }
-#pragma unroll
-  for (int i = 0; i < N; i++) S.dqd[0][i] = dqd[0][i];
-  S.dv[0] = v3(0, 0, 0); S.dw[0] = v3(0, 0, 0); S.ddoor = 0.f;
-  if (nc == 0) return true;
-  {
-    const V3 n = Mf.n, t1 = Mf.t1, t2 = Mf.t2;
-    const float mu = Mf.mu, sthr = sthr_;
-    float an[4], a1[4], a2[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) { an[c] = 0.f; a1[c] = 0.f; a2[c] = 0.f; }
-    V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
-    const V3 nm = inv_obj_mass * n, t1m = inv_obj_mass * t1, t2m = inv_obj_mass * t2;
-    for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
-      bool bad = false;
-#pragma unroll
-      for (int c = 0; c < 4; c++) {  // normal rows
-        float delta = Mf.rn[c] - (dot(n, v) + dot(Mf.Jn[c], w)) * Mf.dn[c];
-        const float sum = an[c] + delta;
-        const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
-        delta = (sumc == sum) ? delta : sumc - an[c];
-        an[c] = sumc;
-        v += delta * nm; w += delta * Mf.Vn[c];
-        bad = bad || fabsf(delta) > sthr * Mf.dn[c];
-      }
-#pragma unroll
-      for (int c = 0; c < 4; c++) {  // friction pairs, implicit cone
-        const float lim = mu * an[c];
-        float da = Mf.r1[c] - (dot(t1, v) + dot(Mf.Jt1[c], w)) * Mf.d1[c], db = Mf.r2[c] - (dot(t2, v) + dot(Mf.Jt2[c], w)) * Mf.d2[c];
-        float sa = a1[c] + da, sb = a2[c] + db;
-        const float l2 = sa * sa + sb * sb;
-        if (l2 > lim * lim) {
-          const float len = sqrtf(l2);
-          if (len > lim) { const float sc = lim / len; sa *= sc; sb *= sc; da = sa - a1[c]; db = sb - a2[c]; }
-        }
-        a1[c] = sa; a2[c] = sb;
-        v += da * t1m; w += da * Mf.Vt1[c];
-        v += db * t2m; w += db * Mf.Vt2[c];
-        bad = bad || fabsf(da) > sthr * Mf.d1[c] || fabsf(db) > sthr * Mf.d2[c];
-      }
-      if (!bad) ok_obj |= 1ull << it;
+  unsigned long long ok_arm = 0ull;
+  if ((lim_lo[0] | lim_hi[0]) == 0u) {
+    for (int it = 0; it < max_it; it++) {
+      bool resid_bad = false;
+      if (it & 1) { ARM_MOTORS_FWD(0) GEAR_ROW(0) } else { GEAR_ROW(0) ARM_MOTORS_BWD(0) }
+      if (!resid_bad) { ok_arm |= 1ull << it; if (stop_when_ok) break; }
     }
-    S.dv[0] = v; S.dw[0] = w;
+  } else {
+    for (int it = 0; it < max_it; it++) {
+      bool resid_bad = false;
+      ARM_ROWS_SWEEP(it)
+      if (!resid_bad) { ok_arm |= 1ull << it; if (stop_when_ok) break; }
+    }
   }
-  return !(ok_arm & ok_obj & ((1ull << (XARM_SOLVER_ITERATIONS - 1)) - 1ull));
+#pragma unroll
+  for (int i = 0; i < N; i++) dqd_out[i] = dqd[0][i];
+  return ok_arm;
+}
+
+// Object island of the light form: the manifold's normal rows, then its friction pairs (implicit cone), max_it sweeps.
+template <class T>
+NOINL unsigned long long solve_manifold_island(const ManifoldRows<T>& Mf, int max_it, V3& v_out, V3& w_out) {
+  const float inv_obj_mass = 1.f / T::OBJ_MASS;
+  const float sthr = sqrtf((float)XARM_RESIDUAL_THRESHOLD);
+  const V3 n = Mf.n, t1 = Mf.t1, t2 = Mf.t2;
+  const float mu = Mf.mu;
+  float an[4], a1[4], a2[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) { an[c] = 0.f; a1[c] = 0.f; a2[c] = 0.f; }
+  V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
+  const V3 nm = inv_obj_mass * n, t1m = inv_obj_mass * t1, t2m = inv_obj_mass * t2;
+  unsigned long long ok_obj = 0ull;
+  for (int it = 0; it < max_it; it++) {
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {  // normal rows
+      float delta = Mf.rn[c] - (dot(n, v) + dot(Mf.Jn[c], w)) * Mf.dn[c];
+      const float sum = an[c] + delta;
+      const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
+      delta = (sumc == sum) ? delta : sumc - an[c];
+      an[c] = sumc;
+      v += delta * nm; w += delta * Mf.Vn[c];
+      bad = bad || fabsf(delta) > sthr * Mf.dn[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {  // friction pairs, implicit cone
+      const float lim = mu * an[c];
+      float da = Mf.r1[c] - (dot(t1, v) + dot(Mf.Jt1[c], w)) * Mf.d1[c], db = Mf.r2[c] - (dot(t2, v) + dot(Mf.Jt2[c], w)) * Mf.d2[c];
+      float sa = a1[c] + da, sb = a2[c] + db;
+      const float l2 = sa * sa + sb * sb;
+      if (l2 > lim * lim) {
+        const float len = sqrtf(l2);
+        if (len > lim) { const float sc = lim / len; sa *= sc; sb *= sc; da = sa - a1[c]; db = sb - a2[c]; }
+      }
+      a1[c] = sa; a2[c] = sb;
+      v += da * t1m; w += da * Mf.Vt1[c];
+      v += db * t2m; w += db * Mf.Vt2[c];
+      bad = bad || fabsf(da) > sthr * Mf.d1[c] || fabsf(db) > sthr * Mf.d2[c];
+    }
+    if (!bad) ok_obj |= 1ull << it;
+  }
+  v_out = v; w_out = w;
+  return ok_obj;
+}
+
+// Light form (SOLVE_LIGHT): the arm rows and, if present, one manifold of the object, swept as two independent
+// islands - the impulses of the joint loop of btMultiBodyConstraintSolver::solveSingleIteration, bit for bit.  Only the
+// early-exit test couples the islands (the joint loop stops after the first sweep in which NO row of either island
+// moved more than the threshold): that sweep is found from the per-sweep masks and, if it is not the last one, both
+// islands are swept again with that many sweeps.
+template <class T>
+XD void sub_solve_light(const ArmRows<T>& AR, int nc, const ManifoldIn& MI, SubSol<T>& S) {
+  constexpr int N = T::MD::N;
+  float dqd[N];
+  S.ddoor = 0.f;
+  const unsigned long long ok_arm = solve_arm_island<T>(AR, XARM_SOLVER_ITERATIONS, nc == 0, dqd);
+  V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
+  if (nc > 0) {
+    ManifoldRows<T> Mf;
+    manifold_rows<T>(MI, nc, Mf);
+    const unsigned long long ok_obj = solve_manifold_island<T>(Mf, XARM_SOLVER_ITERATIONS, v, w);
+    const unsigned long long both = ok_arm & ok_obj & ((1ull << (XARM_SOLVER_ITERATIONS - 1)) - 1ull);
+    if (both) {
+#ifdef XARM_HOST_SIM
+      const int cap = __builtin_ffsll((long long)both);
+#else
+      const int cap = __ffsll((long long)both);
+#endif
+      solve_arm_island<T>(AR, cap, false, dqd);
+      solve_manifold_island<T>(Mf, cap, v, w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) S.dqd[0][i] = dqd[i];
+  S.dv[0] = v; S.dw[0] = w;
 }
 
 // Generic form: phase 0 = arm rows only, 1 = contact rows only (the two islands of a decoupled env), 2 = the joint
@@ -1187,6 +1309,9 @@ XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, in
   S.ddoor = ddoor;
 }
 #undef ARM_ROWS_SWEEP
+#undef ARM_MOTORS_FWD
+#undef ARM_MOTORS_BWD
+#undef ARM_MOTOR_ROW_
 #undef ARM_ROWS_ONE
 #undef ARM_ROW_CASE
 #undef CI_
@@ -1236,20 +1361,29 @@ XD void sub_integrate(Env<T>& e, const SubBase<T>& B, const SubSol<T>& S) {
 }
 
 // One internal substep, fused: collide -> unconstrained velocities -> rows -> PGS -> integrate.
+// heavy_only: the caller knows the env is not of the light form (the pipeline's heavy kernel).
 template <class T>
 NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
   ArmRows<T> AR;
   Contacts<T> C;
   SubBase<T> B;
   SubSol<T> S;
-  const int form = sub_setup<T>(e, apply_damping, last, AR, C, B);
-  bool done = false;
-  if (form == SOLVE_LIGHT) {
-    ManifoldRows<T> Mf;
-    if (C.nc > 0) manifold_from_contacts<T>(C, Mf);
-    done = sub_solve_light<T>(AR, C.nc, Mf, S);
-  }
-  if (!done) sub_solve_generic<T>(AR, C, S, form == SOLVE_GENERIC_DECOUPLED ? SOLVE_GENERIC_DECOUPLED : SOLVE_GENERIC_JOINT);
+  ManifoldIn MI;
+  const int form = sub_setup<T>(e, apply_damping, last, AR, C, B, MI);
+  if (form == SOLVE_LIGHT) sub_solve_light<T>(AR, C.nc, MI, S);
+  else sub_solve_generic<T>(AR, C, S, form);
+  sub_integrate<T>(e, B, S);
+}
+// the same substep without the light solver (pipeline: envs the setup kernel classified as not light)
+template <class T>
+NOINL void substep_generic(Env<T>& e, bool apply_damping, bool last) {
+  ArmRows<T> AR;
+  Contacts<T> C;
+  SubBase<T> B;
+  SubSol<T> S;
+  ManifoldIn MI;
+  const int form = sub_setup<T>(e, apply_damping, last, AR, C, B, MI);
+  sub_solve_generic<T>(AR, C, S, form == SOLVE_GENERIC_JOINT ? SOLVE_GENERIC_JOINT : SOLVE_GENERIC_DECOUPLED);
   sub_integrate<T>(e, B, S);
 }
 

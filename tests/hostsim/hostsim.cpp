@@ -13,19 +13,22 @@
 #include <stdint.h>
 
 #include "../../gym_xarm_b200/csrc/xarm_math.cuh"  // first: in the double-precision diagnostic build it redefines float
-#include "../../gym_xarm_b200/csrc/xarm_kernels.cuh"
+#include "../../gym_xarm_b200/csrc/xarm_pipeline.cuh"
 
 struct Ops {
   void (*init)(const KArgs&);
   void (*step)(const KArgs&);
   void (*reset)(const KArgs&, const uint8_t*, int);
   void (*obs)(const KArgs&);
-  int A, O, G, S;
+  void (*step_pipeline)(const KArgs&);
+  void (*reset_pipeline)(const KArgs&, const uint8_t*);
+  int A, O, G, S, scratch_words;
 };
 template <class T>
 struct OpsT {
+  static constexpr bool HAS_LIGHT = T::NARM == 1 && !T::HAS_DOOR;
   static void init(const KArgs& a) { for (int64_t i = 0; i < a.n; i++) body_init<T>(a, i); }
-  static void step(const KArgs& a) {
+  static void step(const KArgs& a) {  // the fused form
     for (int64_t i = 0; i < a.n; i++) {
       StepStats st = {0, 0, 0, 0, 0};
       body_step<T>(a, i, st);
@@ -34,13 +37,57 @@ struct OpsT {
   }
   static void reset(const KArgs& a, const uint8_t* mask, int use_flags) {
     for (int64_t i = 0; i < a.n; i++) {
-      if (use_flags) { if (!a.need_reset[i]) continue; }  // (the CUDA path compacts these into a list first)
+      if (use_flags) { if (!a.need_reset[i]) continue; }
       else if (mask && !mask[i]) continue;
       body_reset<T>(a, i, !use_flags);
     }
   }
   static void obs(const KArgs& a) { for (int64_t i = 0; i < a.n; i++) body_obs<T>(a, i); }
-  static Ops make() { Ops o = {init, step, reset, obs, T::A, T::O, T::G, state_words<T>()}; return o; }
+  // ---- the kernel pipeline of the CUDA path, one "launch" = one loop over the envs (same order of operations as
+  // OpsT<T>::step / ::reset in xarm_lib.cu)
+  template <class F>
+  static void launch(const KArgs& a, F f) {
+    if (a.list) { for (int t = 0; t < *a.list_count; t++) f((int64_t)a.list[t]); }
+    else for (int64_t i = 0; i < a.n; i++) f(i);
+  }
+  static void simulate(const KArgs& a) {
+    for (int sub = 0; sub < T::NSUB; sub++) {
+      if (!HAS_LIGHT) { launch(a, [&](int64_t i) { pipe_heavy<T>(a, i, sub); }); continue; }
+      int nh = 0;
+      launch(a, [&](int64_t i) { if (pipe_setup<T>(a, i, sub)) a.heavy_list[nh++] = (int)i; });
+      launch(a, [&](int64_t i) { pipe_light<T>(a, i); });
+      for (int t = 0; t < nh; t++) pipe_heavy<T>(a, a.heavy_list[t], sub);
+    }
+  }
+  static void reset_passes(const KArgs& r, bool clear_return) {
+    if (reset_has_servo<T>())
+      for (int rep = 0; rep < 5; rep++) { launch(r, [&](int64_t i) { pipe_reset_stage<T>(r, i, rep, false); }); simulate(r); }
+    launch(r, [&](int64_t i) { pipe_reset_stage<T>(r, i, XARM_RESET_PLACE, false); });
+    simulate(r);
+    launch(r, [&](int64_t i) { pipe_reset_stage<T>(r, i, XARM_RESET_FINISH, clear_return); });
+  }
+  static void step_pipeline(const KArgs& a0) {
+    KArgs a = a0; a.list = nullptr; a.list_count = nullptr;
+    *a.reset_count = 0;
+    launch(a, [&](int64_t i) { pipe_action<T>(a, i); });
+    simulate(a);
+    launch(a, [&](int64_t i) {
+      StepStats st = {0, 0, 0, 0, 0};
+      if (pipe_finish<T>(a, i, st)) a.reset_list[(*a.reset_count)++] = (int)i;
+      a.stats[0] += st.eps; a.stats[1] += st.ret; a.stats[2] += st.len; a.stats[3] += st.suc; a.stats[4] += st.div;
+    });
+    if (a.auto_reset) { KArgs r = a; r.list = a.reset_list; r.list_count = a.reset_count; reset_passes(r, false); }
+  }
+  static void reset_pipeline(const KArgs& a0, const uint8_t* mask) {
+    KArgs a = a0; a.list = nullptr; a.list_count = nullptr;
+    *a.reset_count = 0;
+    if (mask) {
+      for (int64_t i = 0; i < a.n; i++) if (mask[i]) a.reset_list[(*a.reset_count)++] = (int)i;
+      a.list = a.reset_list; a.list_count = a.reset_count;
+    }
+    reset_passes(a, true);
+  }
+  static Ops make() { Ops o = {init, step, reset, obs, step_pipeline, reset_pipeline, T::A, T::O, T::G, state_words<T>(), pipe_scratch_words<T>()}; return o; }
 };
 static bool get_ops(int task, Ops* out) {
   switch (task) {
@@ -55,7 +102,8 @@ static bool get_ops(int task, Ops* out) {
 
 struct HS {
   XarmConfig cfg; Ops ops; KArgs k;
-  std::vector<float> state, ep_return, io; std::vector<uint8_t> need_reset, flags; double stats[5];
+  std::vector<float> state, ep_return, io, scratch; std::vector<uint8_t> need_reset, flags; std::vector<int> ints; double stats[5];
+  int pipeline = 0;  // 0: fused bodies (body_step / body_reset), 1: the kernel pipeline of the CUDA path
 };
 
 extern "C" {
@@ -77,6 +125,9 @@ HS* hs_create(int task, int reward_type, int num_obj, int goal_shape, double ini
   KArgs& k = h->k; memset(&k, 0, sizeof(k));
   k.state = h->state.data(); k.ep_return = h->ep_return.data(); k.need_reset = h->need_reset.data(); k.stats = h->stats;
   k.n = n; k.auto_reset = cfg->auto_reset;
+  h->scratch.assign((size_t)n * o.scratch_words, 0.f); h->ints.assign((size_t)4 * n + XARM_PIPE_COUNTERS + 1, 0);
+  k.scratch = h->scratch.data(); k.reset_list = h->ints.data(); k.heavy_list = k.reset_list + n; k.form = k.reset_list + 2 * n;
+  k.rng_draw = k.reset_list + 3 * n; k.heavy_count = k.reset_list + 4 * n; k.reset_count = k.heavy_count + XARM_PIPE_COUNTERS;
   k.rc.seed = cfg->seed; k.rc.env_index_base = cfg->env_index_base; k.rc.reward_type = cfg->reward_type;
   k.rc.goal_shape = cfg->goal_shape; k.rc.max_episode_steps = cfg->max_episode_steps;
   k.rc.init_grasp_rate = cfg->init_grasp_rate; k.rc.goal_ground_rate = cfg->goal_ground_rate; k.rc.same_side_rate = cfg->same_side_rate;
@@ -88,6 +139,7 @@ HS* hs_create(int task, int reward_type, int num_obj, int goal_shape, double ini
   return h;
 }
 void hs_destroy(HS* h) { delete h; }
+void hs_set_pipeline(HS* h, int on) { h->pipeline = on; }
 void hs_dims(HS* h, int* A, int* O, int* G, int* S) { *A = h->ops.A; *O = h->ops.O; *G = h->ops.G; *S = h->ops.S; }
 static void copy_out(HS* h, float* obs, float* ag, float* dg) {
   const int64_t n = h->cfg.num_envs; const Ops& o = h->ops;
@@ -95,12 +147,15 @@ static void copy_out(HS* h, float* obs, float* ag, float* dg) {
   if (ag) memcpy(ag, h->k.b.achieved_goal, sizeof(float) * n * o.G);
   if (dg) memcpy(dg, h->k.b.desired_goal, sizeof(float) * n * o.G);
 }
-void hs_reset(HS* h, const uint8_t* mask, float* obs, float* ag, float* dg) { h->ops.reset(h->k, mask, 0); copy_out(h, obs, ag, dg); }
+void hs_reset(HS* h, const uint8_t* mask, float* obs, float* ag, float* dg) {
+  if (h->pipeline) h->ops.reset_pipeline(h->k, mask); else h->ops.reset(h->k, mask, 0);
+  copy_out(h, obs, ag, dg);
+}
 void hs_get_obs(HS* h, float* obs, float* ag, float* dg) { h->ops.obs(h->k); copy_out(h, obs, ag, dg); }
 void hs_step(HS* h, const float* actions, float* obs, float* ag, float* dg, float* reward, uint8_t* done, float* success, uint8_t* truncated) {
   const int64_t n = h->cfg.num_envs; const Ops& o = h->ops;
   memcpy((void*)h->k.b.actions, actions, sizeof(float) * n * o.A);
-  h->ops.step(h->k);  // auto-reset is fused into the step body
+  if (h->pipeline) h->ops.step_pipeline(h->k); else h->ops.step(h->k);  // fused: auto-reset inside the step body
   copy_out(h, obs, ag, dg);
   if (reward) memcpy(reward, h->k.b.reward, sizeof(float) * n);
   if (success) memcpy(success, h->k.b.success, sizeof(float) * n);

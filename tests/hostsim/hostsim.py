@@ -42,6 +42,7 @@ def lib():
         L.hs_create.restype = C.c_void_p
         L.hs_create.argtypes = [C.c_int] * 4 + [C.c_double] * 3 + [C.c_int] * 2 + [C.c_longlong] * 2 + [C.c_ulonglong]
         L.hs_destroy.argtypes = [C.c_void_p]
+        L.hs_set_pipeline.argtypes = [C.c_void_p, C.c_int]
         L.hs_dims.argtypes = [C.c_void_p, ip, ip, ip, ip]
         L.hs_reset.argtypes = [C.c_void_p, u8p, fp, fp, fp]
         L.hs_get_obs.argtypes = [C.c_void_p, fp, fp, fp]
@@ -66,7 +67,9 @@ def _u8(a):
 class HostSimVec:
     """Batched env on the host build of the kernel bodies; same call shapes as the CUDA library wrapper."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, pipeline=False):
+        """pipeline=False: the fused per-env bodies (body_step / body_reset); True: the same step as the CUDA path runs
+        it - the kernel pipeline of xarm_pipeline.cuh, one host loop per kernel launch."""
         self.cfg = cfg
         self.L = lib()
         self.h = self.L.hs_create(cfg.task, cfg.reward_type, cfg.num_obj, cfg.goal_shape, cfg.init_grasp_rate, cfg.goal_ground_rate,
@@ -77,6 +80,7 @@ class HostSimVec:
         self.L.hs_dims(self.h, a, o, g, s)
         self.A, self.O, self.G, self.S = a.value, o.value, g.value, s.value
         self.n = cfg.num_envs
+        self.L.hs_set_pipeline(self.h, 1 if pipeline else 0)
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -1,0 +1,67 @@
+"""CPU check of the step PIPELINE: the per-kernel bodies of gym_xarm_b200/csrc/xarm_pipeline.cuh (action -> NSUB x {setup ->
+light || heavy} -> finish -> auto-reset passes), run on the host by tests/hostsim one loop per kernel launch, must give
+bit-for-bit the results of the fused per-env form (body_step / body_reset), which test_kernel_logic_cpu.py checks against
+the oracle.  Covers the scratch-slab round trip of the rows, the light/heavy classification, the island split of the
+light solver, list-mode launches and the reset stages."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.hostsim import hostsim as hs
+
+CASES = [("pick_and_place", 24, 60, 0), ("reach", 8, 30, 0), ("stack_tower", 4, 12, 8), ("push_with_door", 4, 12, 8), ("handover", 4, 12, 8)]
+
+
+@pytest.mark.parametrize("task,n,steps,limit", CASES)
+def test_pipeline_equals_fused_step(task, n, steps, limit):
+    gs = "air" if task == "pick_and_place" else "ground"
+    cfg = orc.make_config(task, num_envs=n, seed=7, auto_reset=1, goal_shape=gs, max_episode_steps=limit)
+    a, b = hs.HostSimVec(cfg, pipeline=False), hs.HostSimVec(cfg, pipeline=True)
+    oa, ob = a.reset(), b.reset()
+    assert all(np.array_equal(oa[k], ob[k]) for k in oa)
+    assert np.array_equal(a.get_state(), b.get_state())
+    rng = np.random.default_rng(1)
+    n_done = 0
+    for t in range(steps):
+        act = rng.uniform(-1, 1, (n, a.A)).astype(np.float32)
+        ra, rb = a.step(act), b.step(act)
+        for k in ra[0]:
+            assert np.array_equal(ra[0][k], rb[0][k]), (t, k)
+        for x, y in zip(ra[1:], rb[1:]):
+            assert np.array_equal(x, y), t
+        assert np.array_equal(a.get_state(), b.get_state()), t
+        n_done += int(ra[2].sum())
+    assert n_done >= n  # every env went through at least one auto-reset
+    m = np.zeros(n, np.uint8)
+    m[::3] = 1
+    oa, ob = a.reset(m), b.reset(m)  # masked reset = list-mode passes
+    assert all(np.array_equal(oa[k], ob[k]) for k in oa)
+    assert np.array_equal(a.get_state(), b.get_state())
+
+
+def test_light_solver_early_exit_matches_joint_loop():
+    """An arm at rest over a resting lego: every row is below the residual threshold after a few sweeps, so Bullet's joint
+    loop stops early.  The island-split light solver has to stop both islands at that same sweep (pipeline == fused is
+    not enough here: both use it), so compare with the oracle's joint loop."""
+    task = "pick_and_place"
+    cfg = orc.make_config(task, num_envs=2, seed=3, auto_reset=0, goal_shape="air")
+    v = hs.HostSimVec(cfg, pipeline=True)
+    ref = [orc.OracleEnv(task, env_index=i, seed=3, auto_reset=0, goal_shape="air") for i in range(2)]
+    v.reset()
+    for r in ref:
+        r.reset()
+    st0 = np.stack([r.get_state() for r in ref])
+    st0[:, 27:30] = [0.65, 0.42, 0.04]           # lego parked on the table, away from the gripper
+    st0[:, 30:40] = [0, 0, 0, 1, 0, 0, 0, 0, 0, 0]
+    v.set_state(st0)
+    for r, s in zip(ref, st0):
+        r.set_state(s)
+    z = np.zeros((2, 4), np.float32)
+    for t in range(40):                           # zero actions: the arm settles on its IK target
+        v.step(z)
+        for i, r in enumerate(ref):
+            r.step(z[i])
+    st, rst = v.get_state(), np.stack([r.get_state() for r in ref])
+    np.testing.assert_allclose(st[:, :18], rst[:, :18], atol=2e-5)
+    np.testing.assert_allclose(st[:, 27:40], rst[:, 27:40], atol=2e-5)
+    assert min(r.solver_sweeps_last() for r in ref) < 50 if hasattr(ref[0], "solver_sweeps_last") else True
