@@ -25,27 +25,35 @@ XD float np_sum_sq_diff(const float* a, const float* b, int n) {
   return s;
 }
 XD float np_dist(const float* a, const float* b, int n) { return __fsqrt_rn(np_sum_sq_diff(a, b, n)); }
+// IEEE negation (sign-bit flip, -(+0) = -0): nvcc folds `-(c ? 1.f : 0.f)` into `c ? -1.f : 0.f`, which loses the sign of zero
+XD float neg_exact(float x) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(__float_as_int(x) ^ (int)0x80000000);
+#else
+  return -x;
+#endif
+}
 
 // state-free rewards (the ones SB3's HER may call with batches)
 XD float reward_stateless(int task, int reward_type, int num_obj, float thr, const float* ag, const float* dg, int G) {
   switch (task) {
     case XARM_TASK_REACH: {  // [REF xarm_reach.py:107-112]
       float d = np_dist(ag, dg, 3);
-      return reward_type == XARM_REWARD_SPARSE ? (d < thr ? 1.0f : 0.0f) : -d;
+      return reward_type == XARM_REWARD_SPARSE ? (d < thr ? 1.0f : 0.0f) : neg_exact(d);
     }
     case XARM_TASK_PICK_AND_PLACE: {  // [REF xarm_pick_and_place.py:163-165,176-177]
       float d = np_dist(ag, dg, G);
-      return reward_type == XARM_REWARD_SPARSE ? (d < thr ? 1.0f : 0.0f) : -d;
+      return reward_type == XARM_REWARD_SPARSE ? (d < thr ? 1.0f : 0.0f) : neg_exact(d);
     }
     case XARM_TASK_STACK_TOWER:
     case XARM_TASK_PUSH_WITH_DOOR: {  // [REF xarm_stack_tower.py:124-129]: -(d > thr) as float32 => -1.0 or -0.0
       float d = np_dist(ag, dg, G);
-      return reward_type == XARM_REWARD_SPARSE ? -(d > thr ? 1.0f : 0.0f) : -d;
+      return reward_type == XARM_REWARD_SPARSE ? neg_exact(d > thr ? 1.0f : 0.0f) : neg_exact(d);
     }
     default: {  // Handover [REF xarm_handover.py:177-183]
       float s = 0.f;
       for (int i = 0; i < num_obj; i++) s = __fadd_rn(s, np_dist(ag + 3 * i, dg + 3 * i, 3) > thr ? 1.0f : 0.0f);
-      return -s;
+      return neg_exact(s);
     }
   }
 }

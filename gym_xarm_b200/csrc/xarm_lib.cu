@@ -55,19 +55,27 @@ __global__ void __launch_bounds__(128, 4) k_pipe_light(KArgs a) {
   const int64_t i = pipe_env(a, t);
   if (i >= 0) pipe_light<T>(a, i);
 }
-// heavy envs of this substep: 32-thread blocks spread the few heavy warps over all SMs (they run next to k_pipe_light)
+// Heavy envs of this substep.  One warp per block, a few blocks per SM at most: the contact rows of the generic solver
+// (Contacts<T>, ~6 KB per env) live in SHARED memory, one record per lane at an odd word stride (bank-conflict free).
+// In thread-local memory the 50 sweeps stream every row from L2 again (160 KB per warp per sweep) and one heavy warp
+// needs > 1 ms per substep; the launch is persistent (grid = #SMs) and runs next to k_pipe_light.
+template <class T>
+constexpr int heavy_stride_words() { return (int)((sizeof(Contacts<T>) + 3) / 4) | 1; }
 template <class T>
 __global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* heavy_count) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)*heavy_count) return;
-  pipe_heavy<T>(a, a.heavy_list[t], sub);
+  extern __shared__ float heavy_smem[];
+  Contacts<T>& C = *reinterpret_cast<Contacts<T>*>(heavy_smem + (size_t)threadIdx.x * heavy_stride_words<T>());
+  const int count = *heavy_count;
+  for (int t = blockIdx.x * 32 + threadIdx.x; t < count; t += gridDim.x * 32) pipe_heavy<T>(a, a.heavy_list[t], sub, C);
 }
-// tasks without a light form (two arms / door): every env takes the generic substep
+// tasks without a light form (two arms / door): every env takes the generic substep (rows in thread-local memory)
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_heavy_all(KArgs a, int sub) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = pipe_env(a, t);
-  if (i >= 0) pipe_heavy<T>(a, i, sub);
+  if (i < 0) return;
+  Contacts<T> C;
+  pipe_heavy<T>(a, i, sub, C);
 }
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_finish(KArgs a) {
@@ -139,6 +147,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // fork/join plumbing of the pipeline: a side stream for the heavy kernels and a pool of dependency events
 struct PipeCtx {
   cudaStream_t side = nullptr;
+  unsigned heavy_grid = 148;  // persistent heavy kernel: one block per SM (set from the device in xarm_create)
   std::vector<cudaEvent_t> ev;
   size_t next_ev = 0;
   cudaEvent_t next() {
@@ -152,6 +161,7 @@ struct Ops {
   void (*step)(PipeCtx&, const KArgs&, cudaStream_t);
   void (*reset)(PipeCtx&, const KArgs&, const uint8_t*, cudaStream_t);
   void (*obs)(const KArgs&, cudaStream_t);
+  int (*prepare)();
   int A, O, G, S, scratch_words;
 };
 
@@ -159,6 +169,11 @@ template <class T>
 struct OpsT {
   static constexpr bool HAS_LIGHT = T::NARM == 1 && !T::HAS_DOOR;  // tasks whose envs can take the light solver form
   static dim3 grid(int64_t n) { return dim3((unsigned)((n + 127) / 128)); }
+  static size_t heavy_smem_bytes() { return (size_t)heavy_stride_words<T>() * 32 * sizeof(float); }
+  static int prepare() {  // opt in to the large dynamic shared memory of the heavy kernel
+    if constexpr (HAS_LIGHT) return (int)cudaFuncSetAttribute(k_pipe_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem_bytes());
+    return 0;
+  }
   static void init(const KArgs& a, cudaStream_t s) { k_init<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
   static void obs(const KArgs& a, cudaStream_t s) { k_obs<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
   // p.stepSimulation(): NSUB x { setup -> light || heavy }
@@ -173,7 +188,7 @@ struct OpsT {
         cudaEvent_t fork = c.next(), join = c.next();
         cudaEventRecord(fork, s);
         cudaStreamWaitEvent(c.side, fork, 0);
-        k_pipe_heavy<T><<<dim3((unsigned)((a.n + 31) / 32)), 32, 0, c.side>>>(a, sub, hc);
+        k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), c.side>>>(a, sub, hc);
         cudaEventRecord(join, c.side);
         k_pipe_light<T><<<g, 128, 0, s>>>(a);
         cudaStreamWaitEvent(s, join, 0);
@@ -221,7 +236,7 @@ struct OpsT {
     }
     reset_passes(c, a, 0, 1, s);
   }
-  static Ops make() { Ops o = {init, step, reset, obs, T::A, T::O, T::G, state_words<T>(), pipe_scratch_words<T>()}; return o; }
+  static Ops make() { Ops o = {init, step, reset, obs, prepare, T::A, T::O, T::G, state_words<T>(), pipe_scratch_words<T>()}; return o; }
 };
 
 // XARM_ONLY_TASK=<id> builds a single task (development builds: faster compiles); the shipped library has all five.
@@ -336,6 +351,13 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     if (h->pipe.side) cudaStreamDestroy(h->pipe.side);
     delete h; cudaGetLastError();
     return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc failed");
+  }
+  {
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+    h->pipe.heavy_grid = (unsigned)(sms > 0 ? sms : 148);
+    cudaError_t ep = (cudaError_t)ops.prepare();
+    if (ep != cudaSuccess) return fail(XARM_E_CUDA, std::string("cudaFuncSetAttribute(k_pipe_heavy): ") + cudaGetErrorString(ep));
   }
   h->k.heavy_list = h->k.reset_list + n; h->k.form = h->k.reset_list + 2 * n; h->k.rng_draw = h->k.reset_list + 3 * n;
   h->k.heavy_count = h->k.reset_list + 4 * n; h->k.reset_count = h->k.heavy_count + XARM_PIPE_COUNTERS;

@@ -181,10 +181,10 @@ XD void pipe_light(const KArgs& a, int64_t i) {
 
 // ---- substep for heavy envs (gripper contacts, several manifolds, two arms, door): setup + generic coupled PGS + integrate
 template <class T>
-XD void pipe_heavy(const KArgs& a, int64_t i, int sub) {
+XD void pipe_heavy(const KArgs& a, int64_t i, int sub, Contacts<T>& C) {
   Env<T> e;
   env_load<T>(e, a.state, a.n, i);
-  substep_generic<T>(e, T::DAMP_EACH || sub == 0, sub == T::NSUB - 1);
+  substep_generic<T>(e, T::DAMP_EACH || sub == 0, sub == T::NSUB - 1, C);
   env_store<T>(e, a.state, a.n, i);
 }
 

@@ -627,20 +627,20 @@ XD V3 door_axis() { const float a[3] = XARM_DOOR_AXIS; return v3(a[0], a[1], a[2
 // registers by substep() itself.
 template <class T>
 struct Contacts {
-  static constexpr int N = T::MD::N;
+  static constexpr int N = T::MD::N, MAXC = T::MAXC, MAXAC = XARM_MAXAC;
   int nc, nac, npair;                    // contact points, points on gripper links, pairs that produced points
-  uint8_t ba[XARM_MAXC], bb[XARM_MAXC];  // body codes of side A / side B (normal points from B to A)
-  int8_t slot[XARM_MAXC];                // row-pool slot of the arm side (-1: none)
-  int8_t o1[XARM_MAXC], o2[XARM_MAXC];   // object index of the first / second object side (-1: none); o2 only for object-object
-  float s1[XARM_MAXC];                   // sign of the first object side (+1 side A, -1 side B); the second is always -1
-  V3 pa[XARM_MAXC], pb[XARM_MAXC];       // world contact points (row setup only)
-  float depth[XARM_MAXC], mu[XARM_MAXC], erp[XARM_MAXC], cfm0[XARM_MAXC];
-  V3 dir[XARM_MAXC][3];                  // n, t1, t2
-  V3 Jo1[XARM_MAXC][3], dVo1[XARM_MAXC][3];  // first object side: sign * (r x d), sign * Iinv (r x d)
-  V3 Jo2[T::NOBJ > 1 ? XARM_MAXC : 1][3], dVo2[T::NOBJ > 1 ? XARM_MAXC : 1][3];
-  float jdoor[T::HAS_DOOR ? XARM_MAXC : 1][3];  // door side: sign * axis . d
-  float rhs[XARM_MAXC][3], dinv[XARM_MAXC][3], den[XARM_MAXC][3], app[XARM_MAXC][3], cfmr[XARM_MAXC];
-  float Jarm[XARM_MAXAC][3][N], dVarm[XARM_MAXAC][3][N];  // arm side: sign * J, Minv (sign * J)
+  uint8_t ba[MAXC], bb[MAXC];            // body codes of side A / side B (normal points from B to A)
+  int8_t slot[MAXC];                     // row-pool slot of the arm side (-1: none)
+  int8_t o1[MAXC], o2[MAXC];             // object index of the first / second object side (-1: none); o2 only for object-object
+  float s1[MAXC];                        // sign of the first object side (+1 side A, -1 side B); the second is always -1
+  V3 pa[MAXC], pb[MAXC];                 // world contact points (row setup only)
+  float depth[MAXC], mu[MAXC], erp[MAXC], cfm0[MAXC];
+  V3 dir[MAXC][3];                       // n, t1, t2
+  V3 Jo1[MAXC][3], dVo1[MAXC][3];        // first object side: sign * (r x d), sign * Iinv (r x d)
+  V3 Jo2[T::NOBJ > 1 ? MAXC : 1][3], dVo2[T::NOBJ > 1 ? MAXC : 1][3];
+  float jdoor[T::HAS_DOOR ? MAXC : 1][3];  // door side: sign * axis . d
+  float rhs[MAXC][3], dinv[MAXC][3], app[MAXC][3], cfmr[MAXC];
+  float Jarm[MAXAC][3][N], dVarm[MAXAC][3][N];  // arm side: sign * J, Minv (sign * J)
 };
 
 template <class T>
@@ -659,7 +659,7 @@ XD int add_pair(Contacts<T>& C, const Box& A, const Box& B, int ca, int cb, floa
   V3 d = A.c - B.c;
   float ra = norm(A.h), rb = norm(B.h), rr = ra + rb + (float)XARM_CONTACT_MARGIN;
   if (dot(d, d) > rr * rr) return 0;
-  int room = XARM_MAXC - C.nc;
+  int room = T::MAXC - C.nc;
   const bool with_arm = bc_is_arm(ca) || bc_is_arm(cb);
   if (with_arm && XARM_MAXAC - C.nac < room) room = XARM_MAXAC - C.nac;
   if (room <= 0) return 0;
@@ -902,12 +902,12 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
         float pos_err = 0.f, vel_err = -rel;
         if (pen > 0.f) vel_err -= pen / h; else pos_err = -pen * C.erp[c] / h;
         C.rhs[c][0] = (pos_err + vel_err) * dinv;
-        C.dinv[c][0] = dinv; C.den[c][0] = den + C.cfm0[c];
+        C.dinv[c][0] = dinv;
         C.cfmr[c] = C.cfm0[c] * dinv;
       } else {
         float dinv = 1.f / den;
         C.rhs[c][k] = -rel * dinv;
-        C.dinv[c][k] = dinv; C.den[c][k] = den;
+        C.dinv[c][k] = dinv;
       }
     }
   }
@@ -1374,11 +1374,11 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
   else sub_solve_generic<T>(AR, C, S, form);
   sub_integrate<T>(e, B, S);
 }
-// the same substep without the light solver (pipeline: envs the setup kernel classified as not light)
+// the same substep without the light solver (pipeline: envs the setup kernel classified as not light).  The contact
+// rows live where the caller puts them: shared memory in the heavy kernel, thread-local memory elsewhere.
 template <class T>
-NOINL void substep_generic(Env<T>& e, bool apply_damping, bool last) {
+XD void substep_generic(Env<T>& e, bool apply_damping, bool last, Contacts<T>& C) {
   ArmRows<T> AR;
-  Contacts<T> C;
   SubBase<T> B;
   SubSol<T> S;
   ManifoldIn MI;

@@ -25,7 +25,7 @@ struct TaskT;
 template <>
 struct TaskT<XARM_TASK_REACH, 0> {
   using MD = ModelXG;
-  static constexpr int TASK = XARM_TASK_REACH, NARM = 1, NOBJ = 0, NTABLE = 1, A = 4, O = 8, G = 3;
+  static constexpr int TASK = XARM_TASK_REACH, NARM = 1, NOBJ = 0, NTABLE = 1, A = 4, O = 8, G = 3, MAXC = 4;
   static constexpr bool HAS_DOOR = false, HAS_GROUND = false, DAMP_EACH = false, GRIP_CMD = true, GRIP_CLIP = false;
   static constexpr bool FRICTION_SWITCH = false, LEGO_CLAMP = false, FINGER_TABLE = false;
   static constexpr int NSUB = 20, NIK = 20, MAX_STEPS = 25;
@@ -44,6 +44,7 @@ template <int NOBJ_>
 struct TaskT<XARM_TASK_PICK_AND_PLACE, NOBJ_> {
   using MD = ModelPD;
   static constexpr int TASK = XARM_TASK_PICK_AND_PLACE, NARM = 1, NOBJ = NOBJ_, NTABLE = 1, A = 4, O = 8 + 16 * NOBJ_, G = 3 * NOBJ_;
+  static constexpr int MAXC = NOBJ_ == 1 ? 16 : XARM_MAXC;  // one lego: table + finger1 + finger2 + hand manifolds, 4 points each
   static constexpr bool HAS_DOOR = false, HAS_GROUND = false, DAMP_EACH = false, GRIP_CMD = true, GRIP_CLIP = true;
   static constexpr bool FRICTION_SWITCH = true, LEGO_CLAMP = false, FINGER_TABLE = false;
   static constexpr int NSUB = 15, NIK = 15, MAX_STEPS = 50;
@@ -60,7 +61,7 @@ struct TaskT<XARM_TASK_PICK_AND_PLACE, NOBJ_> {
 // shared by XarmStackTowerEnv [REF xarm_stack_tower.py:14-43] and XarmPushWithDoorEnv [REF xarm_push_with_door.py:14-42]
 struct TwoArmTable {
   using MD = ModelPD;
-  static constexpr int NARM = 2, NTABLE = 1;
+  static constexpr int NARM = 2, NTABLE = 1, MAXC = XARM_MAXC;
   static constexpr bool HAS_GROUND = false, DAMP_EACH = false, GRIP_CLIP = true;
   static constexpr bool FRICTION_SWITCH = false, LEGO_CLAMP = false, FINGER_TABLE = false;
   static constexpr int NSUB = 15, NIK = 15, MAX_STEPS = 50;
@@ -90,7 +91,7 @@ struct TaskT<XARM_TASK_PUSH_WITH_DOOR, 1> : TwoArmTable {
 template <int NOBJ_>
 struct TaskT<XARM_TASK_HANDOVER, NOBJ_> {
   using MD = ModelPD;
-  static constexpr int TASK = XARM_TASK_HANDOVER, NARM = 2, NOBJ = NOBJ_, NTABLE = 2, A = 8, O = 13 * NOBJ_ + 16, G = 3 * NOBJ_;
+  static constexpr int TASK = XARM_TASK_HANDOVER, NARM = 2, NOBJ = NOBJ_, NTABLE = 2, A = 8, O = 13 * NOBJ_ + 16, G = 3 * NOBJ_, MAXC = XARM_MAXC;
   static constexpr bool HAS_DOOR = false, HAS_GROUND = true, DAMP_EACH = true, GRIP_CMD = true, GRIP_CLIP = true;
   static constexpr bool FRICTION_SWITCH = true, LEGO_CLAMP = true, FINGER_TABLE = true;
   static constexpr int NSUB = 15, NIK = 15, MAX_STEPS = 100;

@@ -52,11 +52,11 @@ struct OpsT {
   }
   static void simulate(const KArgs& a) {
     for (int sub = 0; sub < T::NSUB; sub++) {
-      if (!HAS_LIGHT) { launch(a, [&](int64_t i) { pipe_heavy<T>(a, i, sub); }); continue; }
+      if (!HAS_LIGHT) { launch(a, [&](int64_t i) { Contacts<T> C; pipe_heavy<T>(a, i, sub, C); }); continue; }
       int nh = 0;
       launch(a, [&](int64_t i) { if (pipe_setup<T>(a, i, sub)) a.heavy_list[nh++] = (int)i; });
       launch(a, [&](int64_t i) { pipe_light<T>(a, i); });
-      for (int t = 0; t < nh; t++) pipe_heavy<T>(a, a.heavy_list[t], sub);
+      for (int t = 0; t < nh; t++) { Contacts<T> C; pipe_heavy<T>(a, a.heavy_list[t], sub, C); }
     }
   }
   static void reset_passes(const KArgs& r, bool clear_return) {
