@@ -50,10 +50,11 @@ __global__ void __launch_bounds__(128, 4) k_pipe_setup(KArgs a, int sub, int* he
   list_append(heavy, i, a.heavy_list, heavy_count);
 }
 template <class T>
-__global__ void __launch_bounds__(128, 4) k_pipe_light(KArgs a) {
+__global__ void __launch_bounds__(128, 3) k_pipe_light(KArgs a) {
+  extern __shared__ float light_mrows[];  // [XARM_MROW_WORDS][128]: the manifold rows of this block's envs
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = pipe_env(a, t);
-  if (i >= 0) pipe_light<T>(a, i);
+  if (i >= 0) pipe_light<T>(a, i, light_mrows + threadIdx.x, 128);
 }
 // Heavy envs of this substep.  One warp per block, a few blocks per SM at most: the contact rows of the generic solver
 // (Contacts<T>, ~6 KB per env) live in SHARED memory, one record per lane at an odd word stride (bank-conflict free).
@@ -167,7 +168,7 @@ struct Ops {
 
 template <class T>
 struct OpsT {
-  static constexpr bool HAS_LIGHT = T::NARM == 1 && !T::HAS_DOOR;  // tasks whose envs can take the light solver form
+  static constexpr bool HAS_LIGHT = task_has_light<T>();  // tasks whose envs can take the light solver form
   static dim3 grid(int64_t n) { return dim3((unsigned)((n + 127) / 128)); }
   static size_t heavy_smem_bytes() { return (size_t)heavy_stride_words<T>() * 32 * sizeof(float); }
   static int prepare() {  // opt in to the large dynamic shared memory of the heavy kernel
@@ -190,7 +191,7 @@ struct OpsT {
         cudaStreamWaitEvent(c.side, fork, 0);
         k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), c.side>>>(a, sub, hc);
         cudaEventRecord(join, c.side);
-        k_pipe_light<T><<<g, 128, 0, s>>>(a);
+        k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(a);
         cudaStreamWaitEvent(s, join, 0);
         g_launches += 3;
       }

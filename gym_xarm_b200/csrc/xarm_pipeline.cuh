@@ -138,29 +138,25 @@ XD bool pipe_setup(const KArgs& a, int64_t i, int sub) {
   Env<T> e;
   env_load<T>(e, a.state, a.n, i);
   ArmRows<T> AR;
-  Contacts<T> C;
   SubBase<T> B;
   ManifoldIn MI;
   const bool last = sub == T::NSUB - 1;
-  const int g0 = e.grasp[0], g1 = e.grasp[1];
-  const int form = sub_setup<T>(e, T::DAMP_EACH || sub == 0, last, AR, C, B, MI);
-  if (form != SOLVE_LIGHT) { a.form[i] = XARM_FORM_HEAVY; return true; }  // the heavy kernel redoes the setup (and the grasp flags)
+  const int g0 = e.grasp[0];
+  int nc = 0;
+  if (!sub_setup_lean<T>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc)) { a.form[i] = XARM_FORM_HEAVY; return true; }
   float* s = a.scratch;
   ar_store<T>(AR, s, a.n, i); s += (int64_t)pipe_ar_words<T>() * a.n;
   sb_store<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
-  if (C.nc > 0) mi_store(MI, s, a.n, i);
-  a.form[i] = XARM_FORM_LIGHT | (C.nc << 8);
-  if (last && (e.grasp[0] != g0 || e.grasp[1] != g1)) {  // grasp flags of the last collision pass
-    const int w = state_words<T>() - 2;
-    a.state[(int64_t)w * a.n + i] = e.grasp[0] ? 1.f : 0.f;
-    a.state[(int64_t)(w + 1) * a.n + i] = e.grasp[1] ? 1.f : 0.f;
-  }
+  if (nc > 0) mi_store(MI, s, a.n, i);
+  a.form[i] = XARM_FORM_LIGHT | (nc << 8);
+  if (last && e.grasp[0] != g0) a.state[(int64_t)(state_words<T>() - 2) * a.n + i] = e.grasp[0] ? 1.f : 0.f;  // grasp flag of the last collision pass
   return false;
 }
 
-// ---- substep, part 2 (light envs): PGS over the arm rows and the object's manifold, then stepPositionsMultiDof
+// ---- substep, part 2 (light envs): PGS over the arm rows and the object's manifold, then stepPositionsMultiDof.
+// mrows: per-thread manifold rows, word w at mrows[w * stride] (shared memory in the kernel)
 template <class T>
-XD void pipe_light(const KArgs& a, int64_t i) {
+XD void pipe_light(const KArgs& a, int64_t i, float* mrows, int stride) {
   const int f = a.form[i];
   if ((f & 0xff) != XARM_FORM_LIGHT) return;
   const int nc = f >> 8;
@@ -172,7 +168,7 @@ XD void pipe_light(const KArgs& a, int64_t i) {
   sb_load<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
   if (nc > 0) mi_load(MI, s, a.n, i);
   SubSol<T> S;
-  sub_solve_light<T>(AR, nc, MI, S);
+  sub_solve_light<T>(AR, nc, MI, mrows, stride, S);
   Env<T> e;
   env_load_dyn<T>(e, a.state, a.n, i);
   sub_integrate<T>(e, B, S);

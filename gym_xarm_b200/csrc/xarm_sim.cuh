@@ -721,6 +721,52 @@ struct ManifoldIn {
   S3 Iinv;
 };
 
+// arm / door rows (btMultiBodyJointLimitConstraint, JointMotor, GearConstraint) and the arms' unconstrained
+// velocities, from the per-arm dynamics pass
+template <class T>
+XD void arm_rows(const Env<T>& e, const ArmDyn<typename T::MD>* D, float door_qdu, ArmRows<T>& AR, SubBase<T>& B) {
+  using MD = typename T::MD;
+  constexpr int N = MD::N, NA = T::NARM, NT = N * (N + 1) / 2;
+  const float h = (float)T::H;
+  const float gr = (float)XARM_GEAR_RATIO;
+#pragma unroll 1
+  for (int a = 0; a < NA; a++) {
+    const ArmState<MD>& st = e.arm[a];
+    for (int i = 0; i < NT; i++) AR.Mi[a][i] = D[a].Minv[i];
+    uint32_t lo = 0, hi = 0;
+    for (int i = 0; i < N; i++) {
+      const float den = D[a].Minv[tri(i, i)], qdu = D[a].qdu[i];
+      B.qdu[a][i] = qdu;
+      float pen_lo = st.q[i] - MD::lo(i), pen_hi = MD::hi(i) - st.q[i];
+      float lr = 0.f;
+      if (pen_lo <= 0.f) { lo |= 1u << i; lr = (-pen_lo * (float)XARM_ERP / h - qdu) / den; }
+      else if (pen_hi <= 0.f) { hi |= 1u << i; lr = (-pen_hi * (float)XARM_ERP / h + qdu) / den; }
+      AR.lrhs[a][i] = lr;
+      float target = (float)(XARM_MOTOR_KP * XARM_MOTOR_ERP) * (st.qt[i] - st.q[i]) / h;
+      AR.mrhs[a][i] = (target - qdu) / den;
+    }
+    AR.lim_lo[a] = lo; AR.lim_hi[a] = hi;
+    AR.grhs[a] = 0.f; AR.gdinv[a] = 0.f; AR.gden[a] = 0.f;
+    if (MD::HAS_GEAR) {
+      const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
+      float den = D[a].Minv[tri(f1, f1)] + 2.f * gr * D[a].Minv[tri(f1, f2)] + gr * gr * D[a].Minv[tri(f2, f2)];
+      float rel = D[a].qdu[f1] + gr * D[a].qdu[f2];
+      float pos_err = (float)XARM_GEAR_ERP * (st.q[f1] + gr * st.q[f2]);
+      AR.gdinv[a] = 1.f / den; AR.gden[a] = den;
+      AR.grhs[a] = (-pos_err * (float)XARM_ERP / h - rel) / den;
+    }
+  }
+  AR.door_lim = 0; AR.dl_rhs = 0.f; AR.dl_sign = 1.f; AR.dm_rhs = 0.f;
+  B.door_qdu = door_qdu;
+  if (T::HAS_DOOR) {
+    const float door_den = 1.f / (float)XARM_DOOR_MASS;
+    float pen_lo = e.door_q - (float)XARM_DOOR_LIMIT_LO, pen_hi = (float)XARM_DOOR_LIMIT_HI - e.door_q;
+    if (pen_lo <= 0.f) { AR.door_lim = 1; AR.dl_sign = 1.f; AR.dl_rhs = (-pen_lo * (float)XARM_ERP / h - door_qdu) / door_den; }
+    else if (pen_hi <= 0.f) { AR.door_lim = 1; AR.dl_sign = -1.f; AR.dl_rhs = (-pen_hi * (float)XARM_ERP / h + door_qdu) / door_den; }
+    AR.dm_rhs = (0.f - door_qdu) / door_den;
+  }
+}
+
 // collide -> unconstrained velocities -> rows.  Returns which solver form applies.
 template <class T>
 XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Contacts<T>& C, SubBase<T>& B, ManifoldIn& MI) {
@@ -912,44 +958,8 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
     }
   }
 
-  // ---- 4. arm / door rows (btMultiBodyJointLimitConstraint, JointMotor, GearConstraint)
-  const float gr = (float)XARM_GEAR_RATIO;
-#pragma unroll 1
-  for (int a = 0; a < NA; a++) {
-    const ArmState<MD>& st = e.arm[a];
-    for (int i = 0; i < NT; i++) AR.Mi[a][i] = D[a].Minv[i];
-    uint32_t lo = 0, hi = 0;
-    for (int i = 0; i < N; i++) {
-      const float den = D[a].Minv[tri(i, i)], qdu = D[a].qdu[i];
-      B.qdu[a][i] = qdu;
-      float pen_lo = st.q[i] - MD::lo(i), pen_hi = MD::hi(i) - st.q[i];
-      float lr = 0.f;
-      if (pen_lo <= 0.f) { lo |= 1u << i; lr = (-pen_lo * (float)XARM_ERP / h - qdu) / den; }
-      else if (pen_hi <= 0.f) { hi |= 1u << i; lr = (-pen_hi * (float)XARM_ERP / h + qdu) / den; }
-      AR.lrhs[a][i] = lr;
-      float target = (float)(XARM_MOTOR_KP * XARM_MOTOR_ERP) * (st.qt[i] - st.q[i]) / h;
-      AR.mrhs[a][i] = (target - qdu) / den;
-    }
-    AR.lim_lo[a] = lo; AR.lim_hi[a] = hi;
-    AR.grhs[a] = 0.f; AR.gdinv[a] = 0.f; AR.gden[a] = 0.f;
-    if (MD::HAS_GEAR) {
-      const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
-      float den = D[a].Minv[tri(f1, f1)] + 2.f * gr * D[a].Minv[tri(f1, f2)] + gr * gr * D[a].Minv[tri(f2, f2)];
-      float rel = D[a].qdu[f1] + gr * D[a].qdu[f2];
-      float pos_err = (float)XARM_GEAR_ERP * (st.q[f1] + gr * st.q[f2]);
-      AR.gdinv[a] = 1.f / den; AR.gden[a] = den;
-      AR.grhs[a] = (-pos_err * (float)XARM_ERP / h - rel) / den;
-    }
-  }
-  AR.door_lim = 0; AR.dl_rhs = 0.f; AR.dl_sign = 1.f; AR.dm_rhs = 0.f;
-  B.door_qdu = door_qdu;
-  if (T::HAS_DOOR) {
-    const float door_den = 1.f / (float)XARM_DOOR_MASS;
-    float pen_lo = e.door_q - (float)XARM_DOOR_LIMIT_LO, pen_hi = (float)XARM_DOOR_LIMIT_HI - e.door_q;
-    if (pen_lo <= 0.f) { AR.door_lim = 1; AR.dl_sign = 1.f; AR.dl_rhs = (-pen_lo * (float)XARM_ERP / h - door_qdu) / door_den; }
-    else if (pen_hi <= 0.f) { AR.door_lim = 1; AR.dl_sign = -1.f; AR.dl_rhs = (-pen_hi * (float)XARM_ERP / h + door_qdu) / door_den; }
-    AR.dm_rhs = (0.f - door_qdu) / door_den;
-  }
+  // ---- 4. arm / door rows
+  arm_rows<T>(e, D, door_qdu, AR, B);
   // which solver form: islands (one arm, no door, no gripper contact) decouple the arm rows from the object rows
   const bool decoupled = NA == 1 && !T::HAS_DOOR && C.nac == 0;
   const bool manifold = decoupled && NOBJ == 1 && C.nc > 0 && C.nc <= 4 && C.npair == 1 && C.o1[0] == 0 && C.s1[0] > 0.f && C.cfm0[0] == 0.f;
@@ -965,6 +975,112 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
   }
   if (decoupled && (C.nc == 0 || manifold)) return SOLVE_LIGHT;
   return decoupled ? SOLVE_GENERIC_DECOUPLED : SOLVE_GENERIC_JOINT;
+}
+
+// Lean form of sub_setup for the tasks with one arm, no door and at most one object (Reach, PickAndPlace): the common
+// case there is "the gripper touches nothing and the object rests on (or falls towards) one static box", i.e. the
+// light solver form.  This version never builds the Contacts record (5.8 KB of thread-local memory per env - in the
+// batched setup kernel those writes alone were 720 MB of DRAM traffic per launch): the one object-static manifold goes
+// straight into ManifoldIn, the gripper pairs are only tested for ANY contact.  Returns false when the env is not of
+// the light form (the caller then takes the generic path: sub_setup with a Contacts record); true with nc = number of
+// manifold points otherwise.  Row arithmetic = sub_setup's row loop (setupMultiBodyContactConstraint).
+template <class T>
+XD bool sub_setup_lean(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, SubBase<T>& B, ManifoldIn& MI, int& nc_out) {
+  using MD = typename T::MD;
+  static_assert(T::NARM == 1 && !T::HAS_DOOR && T::NOBJ <= 1, "lean setup: one arm, no door, at most one object");
+  const float h = (float)T::H;
+  ArmDyn<MD> D[1];
+  arm_dynamics<T>(0, e.arm[0], apply_damping, D[0]);
+  nc_out = 0;
+  if (T::NOBJ == 1) {
+    Box ob;
+    ob.c = e.obj[0].pos; ob.R = quat_to_m3(e.obj[0].quat); ob.h = v3(T::OBJ_HX, T::OBJ_HY, T::OBJ_HZ);
+    const float r_ob = norm(ob.h);
+    // gripper links against the object: any contact point makes the env heavy
+    if (MD::HAS_BOXES) {
+#pragma unroll 1
+      for (int which = 1; which <= 3; which++) {
+        const Box g = arm_box<T>(D[0], which == 3 ? 0 : which);
+        const V3 d = g.c - ob.c;
+        const float rr = norm(g.h) + r_ob + (float)XARM_CONTACT_MARGIN;
+        if (dot(d, d) > rr * rr) continue;
+        CPoint one[1];
+        if (box_box(g, ob, one, 1) > 0) return false;
+      }
+    }
+    // object against the static boxes (tables, ground): at most one of them may produce points
+    CPoint pts[4];
+    int npts = 0, npair = 0;
+#pragma unroll 1
+    for (int k = 0; k < T::NTABLE + (T::HAS_GROUND ? 1 : 0); k++) {
+      Box tb;
+      tb.R = m3_identity();
+      if (k < T::NTABLE) {
+        tb.c = v3(T::table_x(k), 0.f, -(float)XARM_TABLE_HALF_Z);
+        tb.h = v3((float)XARM_TABLE_HALF_X, (float)XARM_TABLE_HALF_Y, (float)XARM_TABLE_HALF_Z);
+      } else {
+        tb.c = v3(0.f, 0.f, (float)XARM_GROUND_Z - 5.f); tb.h = v3(100.f, 100.f, 5.f);
+      }
+      const V3 d = ob.c - tb.c;
+      const float rr = r_ob + norm(tb.h) + (float)XARM_CONTACT_MARGIN;
+      if (dot(d, d) > rr * rr) continue;
+      CPoint p4[4];
+      const int kk = box_box(ob, tb, p4, 4);
+      if (kk > 0) {
+        if (++npair > 1) return false;
+        npts = kk;
+        MI.mu = fminf((float)XARM_DEFAULT_FRICTION * (k < T::NTABLE ? (float)XARM_TABLE_FRICTION : 1.0f), (float)XARM_MAX_FRICTION);
+#pragma unroll
+        for (int c = 0; c < 4; c++) pts[c] = p4[c];
+      }
+    }
+    // unconstrained velocity of the object
+    const ObjState& b = e.obj[0];
+    const float kl = (float)XARM_MB_LINEAR_DAMPING * (1.f + norm(b.v)), ka = (float)XARM_MB_ANGULAR_DAMPING * (1.f + norm(b.w));
+    V3 vu = b.v + h * ((-kl) * b.v); vu.z -= h * (float)XARM_GRAVITY;
+    const V3 wu = b.w + h * ((-ka) * b.w);
+    B.vu[0] = vu; B.wu[0] = wu;
+    if (npts > 0) {
+      const float lx = 2 * T::OBJ_HX, ly = 2 * T::OBJ_HY, lz = 2 * T::OBJ_HZ, m12 = T::OBJ_MASS / 12.f;
+      const S3 Il = {1.f / (m12 * (ly * ly + lz * lz)), 0, 0, 1.f / (m12 * (lx * lx + lz * lz)), 0, 1.f / (m12 * (lx * lx + ly * ly))};
+      const S3 Iinv = rotate_sym(ob.R, Il);
+      MI.Iinv = Iinv;
+      MI.n = pts[0].n;
+      V3 t1, t2;
+      plane_space(MI.n, t1, t2);
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const bool on = c < npts;
+        const V3 r = on ? pts[c].pa - b.pos : v3(0, 0, 0);
+        MI.r[c] = r;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const V3 d = k == 0 ? MI.n : (k == 1 ? t1 : t2);
+          const V3 rxd = cross(r, d), ir = Iinv * rxd;
+          float den = 0.f, rel = 0.f;
+          den += 1.f / T::OBJ_MASS + dot(rxd, ir);
+          rel += 1.f * (dot(d, vu) + dot(rxd, wu));
+          float rhs;
+          if (k == 0) {
+            const float dinv = 1.f / (den + 0.f);
+            const float pen = -pts[c].depth + (float)XARM_LINEAR_SLOP;
+            float pos_err = 0.f, vel_err = -rel;
+            if (pen > 0.f) vel_err -= pen / h; else pos_err = -pen * (float)XARM_ERP2 / h;
+            rhs = (pos_err + vel_err) * dinv;
+          } else {
+            rhs = -rel * (1.f / den);
+          }
+          MI.rhs[c][k] = on ? rhs : 0.f;
+        }
+      }
+    }
+    nc_out = npts;
+    if (last && MD::HAS_BOXES) e.grasp[0] = 0;  // no gripper contact in this (the last) collision pass
+  } else {
+    B.vu[0] = v3(0, 0, 0); B.wu[0] = v3(0, 0, 0);
+  }
+  arm_rows<T>(e, D, 0.f, AR, B);
+  return true;
 }
 
 // ---- row updates shared by the solver forms (they act on the local register arrays Mi, iden, dqd, ... of the caller)
@@ -1037,6 +1153,12 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
 #define ARM_MOTOR_ROW_(a, i) { const float hi_ = (i) < 7 ? hi_arm : hi_fin; UNIT_ROW(a, i, 1.f, mrhs[a][i], -hi_, hi_, mapp[a][i]) }
 #define ARM_MOTORS_FWD(a) { _Pragma("unroll") for (int i_ = 0; i_ < N; i_++) ARM_MOTOR_ROW_(a, i_) }
 #define ARM_MOTORS_BWD(a) { _Pragma("unroll") for (int i_ = N - 1; i_ >= 0; i_--) ARM_MOTOR_ROW_(a, i_) }
+// the joint-limit rows of arm a (only the violated limits have a row)
+#define ARM_LIMIT_ROW_(a, i)                                                                                     \
+  { if (lim_lo[a] >> (i) & 1) UNIT_ROW(a, i, 1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                           \
+    else if (lim_hi[a] >> (i) & 1) UNIT_ROW(a, i, -1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i]) }
+#define ARM_LIMITS_FWD(a) { _Pragma("unroll") for (int i_ = 0; i_ < N; i_++) ARM_LIMIT_ROW_(a, i_) }
+#define ARM_LIMITS_BWD(a) { _Pragma("unroll") for (int i_ = N - 1; i_ >= 0; i_--) ARM_LIMIT_ROW_(a, i_) }
 #define ARM_ROWS_SWEEP(it)                                                                                       \
   if ((it) & 1) {                                                                                                \
     _Pragma("unroll") for (int a = 0; a < NA; a++) ARM_ROWS_ONE(a, true)                                         \
@@ -1157,110 +1279,96 @@ XD void manifold_rows(const ManifoldIn& MI, int nc, ManifoldRows<T>& Mf) {
   }
 }
 
-// Arm island of the light form: at most max_it sweeps over the non-contact rows of arm 0; bit `it` of the returned mask
-// is set when no row moved more than the residual threshold in sweep `it`.  stop_when_ok: leave at the first such sweep
-// (what the solver does when the arm rows are the only rows).  The common case (no joint limit active) runs fully
-// unrolled forward / backward sweeps; with a limit active the switch-dispatched sweep of the generic form is used.
+// Light form (SOLVE_LIGHT): the joint loop of btMultiBodyConstraintSolver::solveSingleIteration over the arm's
+// non-contact rows and, if present, the one object manifold - non-contact rows (forward on odd sweeps, backward on even
+// ones), normal rows, friction pairs; leave after the first sweep in which no row moved more than the residual
+// threshold.  The arm rows live in registers; the manifold rows are read from `mrows` (shared memory in the kernel,
+// word w of this env at mrows[w * stride]) so that both row sets fit without spilling and the two independent row
+// chains of a sweep can overlap in the pipeline.
+#define XARM_MROW_WORDS 96
 template <class T>
-NOINL unsigned long long solve_arm_island(const ArmRows<T>& AR, int max_it, bool stop_when_ok, float* dqd_out) {
+XD void manifold_rows_store(const ManifoldIn& MI, int nc, float* mrows, int stride) {
+  ManifoldRows<T> Mf;
+  manifold_rows<T>(MI, nc, Mf);
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    float* m = mrows + (size_t)(24 * c) * stride;
+    m[0 * stride] = Mf.Jn[c].x; m[1 * stride] = Mf.Jn[c].y; m[2 * stride] = Mf.Jn[c].z;
+    m[3 * stride] = Mf.Vn[c].x; m[4 * stride] = Mf.Vn[c].y; m[5 * stride] = Mf.Vn[c].z;
+    m[6 * stride] = Mf.Jt1[c].x; m[7 * stride] = Mf.Jt1[c].y; m[8 * stride] = Mf.Jt1[c].z;
+    m[9 * stride] = Mf.Vt1[c].x; m[10 * stride] = Mf.Vt1[c].y; m[11 * stride] = Mf.Vt1[c].z;
+    m[12 * stride] = Mf.Jt2[c].x; m[13 * stride] = Mf.Jt2[c].y; m[14 * stride] = Mf.Jt2[c].z;
+    m[15 * stride] = Mf.Vt2[c].x; m[16 * stride] = Mf.Vt2[c].y; m[17 * stride] = Mf.Vt2[c].z;
+    m[18 * stride] = Mf.rn[c]; m[19 * stride] = Mf.dn[c];
+    m[20 * stride] = Mf.r1[c]; m[21 * stride] = Mf.d1[c];
+    m[22 * stride] = Mf.r2[c]; m[23 * stride] = Mf.d2[c];
+  }
+}
+template <class T>
+XD void sub_solve_light(const ArmRows<T>& AR, int nc, const ManifoldIn& MI, float* mrows, int stride, SubSol<T>& S) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NA = T::NARM, NT = N * (N + 1) / 2;
   SOLVER_LOCALS_FROM(AR)
-  unsigned long long ok_arm = 0ull;
-  if ((lim_lo[0] | lim_hi[0]) == 0u) {
-    for (int it = 0; it < max_it; it++) {
-      bool resid_bad = false;
-      if (it & 1) { ARM_MOTORS_FWD(0) GEAR_ROW(0) } else { GEAR_ROW(0) ARM_MOTORS_BWD(0) }
-      if (!resid_bad) { ok_arm |= 1ull << it; if (stop_when_ok) break; }
-    }
-  } else {
-    for (int it = 0; it < max_it; it++) {
-      bool resid_bad = false;
-      ARM_ROWS_SWEEP(it)
-      if (!resid_bad) { ok_arm |= 1ull << it; if (stop_when_ok) break; }
-    }
+  V3 n = v3(0, 0, 0), t1 = v3(0, 0, 0), t2 = v3(0, 0, 0), nm = n, t1m = n, t2m = n;
+  float mu = 0.f;
+  if (nc > 0) {
+    manifold_rows_store<T>(MI, nc, mrows, stride);
+    n = MI.n; mu = MI.mu;
+    plane_space(n, t1, t2);
+    nm = inv_obj_mass * n; t1m = inv_obj_mass * t1; t2m = inv_obj_mass * t2;
   }
-#pragma unroll
-  for (int i = 0; i < N; i++) dqd_out[i] = dqd[0][i];
-  return ok_arm;
-}
-
-// Object island of the light form: the manifold's normal rows, then its friction pairs (implicit cone), max_it sweeps.
-template <class T>
-NOINL unsigned long long solve_manifold_island(const ManifoldRows<T>& Mf, int max_it, V3& v_out, V3& w_out) {
-  const float inv_obj_mass = 1.f / T::OBJ_MASS;
-  const float sthr = sqrtf((float)XARM_RESIDUAL_THRESHOLD);
-  const V3 n = Mf.n, t1 = Mf.t1, t2 = Mf.t2;
-  const float mu = Mf.mu;
   float an[4], a1[4], a2[4];
 #pragma unroll
   for (int c = 0; c < 4; c++) { an[c] = 0.f; a1[c] = 0.f; a2[c] = 0.f; }
   V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
-  const V3 nm = inv_obj_mass * n, t1m = inv_obj_mass * t1, t2m = inv_obj_mass * t2;
-  unsigned long long ok_obj = 0ull;
-  for (int it = 0; it < max_it; it++) {
-    bool bad = false;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {  // normal rows
-      float delta = Mf.rn[c] - (dot(n, v) + dot(Mf.Jn[c], w)) * Mf.dn[c];
-      const float sum = an[c] + delta;
-      const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
-      delta = (sumc == sum) ? delta : sumc - an[c];
-      an[c] = sumc;
-      v += delta * nm; w += delta * Mf.Vn[c];
-      bad = bad || fabsf(delta) > sthr * Mf.dn[c];
+  const bool any_lim = (lim_lo[0] | lim_hi[0]) != 0u;
+#define MR(c, k) mrows[(size_t)(24 * (c) + (k)) * stride]
+#define MRV(c, k) v3(MR(c, k), MR(c, (k) + 1), MR(c, (k) + 2))
+  for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+    bool resid_bad = false;
+    if (it & 1) {
+      if (any_lim) ARM_LIMITS_FWD(0)
+      ARM_MOTORS_FWD(0) GEAR_ROW(0)
+    } else {
+      GEAR_ROW(0) ARM_MOTORS_BWD(0)
+      if (any_lim) ARM_LIMITS_BWD(0)
     }
+    if (nc > 0) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) {  // friction pairs, implicit cone
-      const float lim = mu * an[c];
-      float da = Mf.r1[c] - (dot(t1, v) + dot(Mf.Jt1[c], w)) * Mf.d1[c], db = Mf.r2[c] - (dot(t2, v) + dot(Mf.Jt2[c], w)) * Mf.d2[c];
-      float sa = a1[c] + da, sb = a2[c] + db;
-      const float l2 = sa * sa + sb * sb;
-      if (l2 > lim * lim) {
-        const float len = sqrtf(l2);
-        if (len > lim) { const float sc = lim / len; sa *= sc; sb *= sc; da = sa - a1[c]; db = sb - a2[c]; }
+      for (int c = 0; c < 4; c++) {  // normal rows
+        const float dn = MR(c, 19);
+        float delta = MR(c, 18) - (dot(n, v) + dot(MRV(c, 0), w)) * dn;
+        const float sum = an[c] + delta;
+        const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
+        delta = (sumc == sum) ? delta : sumc - an[c];
+        an[c] = sumc;
+        v += delta * nm; w += delta * MRV(c, 3);
+        resid_bad = resid_bad || fabsf(delta) > sthr_ * dn;
       }
-      a1[c] = sa; a2[c] = sb;
-      v += da * t1m; w += da * Mf.Vt1[c];
-      v += db * t2m; w += db * Mf.Vt2[c];
-      bad = bad || fabsf(da) > sthr * Mf.d1[c] || fabsf(db) > sthr * Mf.d2[c];
-    }
-    if (!bad) ok_obj |= 1ull << it;
-  }
-  v_out = v; w_out = w;
-  return ok_obj;
-}
-
-// Light form (SOLVE_LIGHT): the arm rows and, if present, one manifold of the object, swept as two independent
-// islands - the impulses of the joint loop of btMultiBodyConstraintSolver::solveSingleIteration, bit for bit.  Only the
-// early-exit test couples the islands (the joint loop stops after the first sweep in which NO row of either island
-// moved more than the threshold): that sweep is found from the per-sweep masks and, if it is not the last one, both
-// islands are swept again with that many sweeps.
-template <class T>
-XD void sub_solve_light(const ArmRows<T>& AR, int nc, const ManifoldIn& MI, SubSol<T>& S) {
-  constexpr int N = T::MD::N;
-  float dqd[N];
-  S.ddoor = 0.f;
-  const unsigned long long ok_arm = solve_arm_island<T>(AR, XARM_SOLVER_ITERATIONS, nc == 0, dqd);
-  V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
-  if (nc > 0) {
-    ManifoldRows<T> Mf;
-    manifold_rows<T>(MI, nc, Mf);
-    const unsigned long long ok_obj = solve_manifold_island<T>(Mf, XARM_SOLVER_ITERATIONS, v, w);
-    const unsigned long long both = ok_arm & ok_obj & ((1ull << (XARM_SOLVER_ITERATIONS - 1)) - 1ull);
-    if (both) {
-#ifdef XARM_HOST_SIM
-      const int cap = __builtin_ffsll((long long)both);
-#else
-      const int cap = __ffsll((long long)both);
-#endif
-      solve_arm_island<T>(AR, cap, false, dqd);
-      solve_manifold_island<T>(Mf, cap, v, w);
-    }
-  }
 #pragma unroll
-  for (int i = 0; i < N; i++) S.dqd[0][i] = dqd[i];
-  S.dv[0] = v; S.dw[0] = w;
+      for (int c = 0; c < 4; c++) {  // friction pairs, implicit cone
+        const float lim = mu * an[c];
+        const float d1 = MR(c, 21), d2 = MR(c, 23);
+        float da = MR(c, 20) - (dot(t1, v) + dot(MRV(c, 6), w)) * d1, db = MR(c, 22) - (dot(t2, v) + dot(MRV(c, 12), w)) * d2;
+        float sa = a1[c] + da, sb = a2[c] + db;
+        const float l2 = sa * sa + sb * sb;
+        if (l2 > lim * lim) {
+          const float len = sqrtf(l2);
+          if (len > lim) { const float sc = lim / len; sa *= sc; sb *= sc; da = sa - a1[c]; db = sb - a2[c]; }
+        }
+        a1[c] = sa; a2[c] = sb;
+        v += da * t1m; w += da * MRV(c, 9);
+        v += db * t2m; w += db * MRV(c, 15);
+        resid_bad = resid_bad || fabsf(da) > sthr_ * d1 || fabsf(db) > sthr_ * d2;
+      }
+    }
+    if (!resid_bad) break;
+  }
+#undef MR
+#undef MRV
+#pragma unroll
+  for (int i = 0; i < N; i++) S.dqd[0][i] = dqd[0][i];
+  S.dv[0] = v; S.dw[0] = w; S.ddoor = 0.f;
 }
 
 // Generic form: phase 0 = arm rows only, 1 = contact rows only (the two islands of a decoupled env), 2 = the joint
@@ -1312,6 +1420,9 @@ XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, in
 #undef ARM_MOTORS_FWD
 #undef ARM_MOTORS_BWD
 #undef ARM_MOTOR_ROW_
+#undef ARM_LIMITS_FWD
+#undef ARM_LIMITS_BWD
+#undef ARM_LIMIT_ROW_
 #undef ARM_ROWS_ONE
 #undef ARM_ROW_CASE
 #undef CI_
@@ -1361,17 +1472,26 @@ XD void sub_integrate(Env<T>& e, const SubBase<T>& B, const SubSol<T>& S) {
 }
 
 // One internal substep, fused: collide -> unconstrained velocities -> rows -> PGS -> integrate.
-// heavy_only: the caller knows the env is not of the light form (the pipeline's heavy kernel).
+template <class T>
+constexpr bool task_has_light() { return T::NARM == 1 && !T::HAS_DOOR && T::NOBJ <= 1; }
 template <class T>
 NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
   ArmRows<T> AR;
-  Contacts<T> C;
   SubBase<T> B;
   SubSol<T> S;
   ManifoldIn MI;
+  if constexpr (task_has_light<T>()) {
+    int nc = 0;
+    if (sub_setup_lean<T>(e, apply_damping, last, AR, B, MI, nc)) {
+      float mrows[XARM_MROW_WORDS];
+      sub_solve_light<T>(AR, nc, MI, mrows, 1, S);
+      sub_integrate<T>(e, B, S);
+      return;
+    }
+  }
+  Contacts<T> C;
   const int form = sub_setup<T>(e, apply_damping, last, AR, C, B, MI);
-  if (form == SOLVE_LIGHT) sub_solve_light<T>(AR, C.nc, MI, S);
-  else sub_solve_generic<T>(AR, C, S, form);
+  sub_solve_generic<T>(AR, C, S, form == SOLVE_GENERIC_JOINT ? SOLVE_GENERIC_JOINT : SOLVE_GENERIC_DECOUPLED);
   sub_integrate<T>(e, B, S);
 }
 // the same substep without the light solver (pipeline: envs the setup kernel classified as not light).  The contact

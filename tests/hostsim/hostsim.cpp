@@ -26,7 +26,7 @@ struct Ops {
 };
 template <class T>
 struct OpsT {
-  static constexpr bool HAS_LIGHT = T::NARM == 1 && !T::HAS_DOOR;
+  static constexpr bool HAS_LIGHT = task_has_light<T>();
   static void init(const KArgs& a) { for (int64_t i = 0; i < a.n; i++) body_init<T>(a, i); }
   static void step(const KArgs& a) {  // the fused form
     for (int64_t i = 0; i < a.n; i++) {
@@ -52,11 +52,14 @@ struct OpsT {
   }
   static void simulate(const KArgs& a) {
     for (int sub = 0; sub < T::NSUB; sub++) {
-      if (!HAS_LIGHT) { launch(a, [&](int64_t i) { Contacts<T> C; pipe_heavy<T>(a, i, sub, C); }); continue; }
-      int nh = 0;
-      launch(a, [&](int64_t i) { if (pipe_setup<T>(a, i, sub)) a.heavy_list[nh++] = (int)i; });
-      launch(a, [&](int64_t i) { pipe_light<T>(a, i); });
-      for (int t = 0; t < nh; t++) { Contacts<T> C; pipe_heavy<T>(a, a.heavy_list[t], sub, C); }
+      if constexpr (!HAS_LIGHT) {
+        launch(a, [&](int64_t i) { Contacts<T> C; pipe_heavy<T>(a, i, sub, C); });
+      } else {
+        int nh = 0;
+        launch(a, [&](int64_t i) { if (pipe_setup<T>(a, i, sub)) a.heavy_list[nh++] = (int)i; });
+        launch(a, [&](int64_t i) { float mrows[XARM_MROW_WORDS]; pipe_light<T>(a, i, mrows, 1); });
+        for (int t = 0; t < nh; t++) { Contacts<T> C; pipe_heavy<T>(a, a.heavy_list[t], sub, C); }
+      }
     }
   }
   static void reset_passes(const KArgs& r, bool clear_return) {
