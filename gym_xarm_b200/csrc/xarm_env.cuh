@@ -25,10 +25,16 @@ XD float np_sum_sq_diff(const float* a, const float* b, int n) {
   return s;
 }
 XD float np_dist(const float* a, const float* b, int n) { return __fsqrt_rn(np_sum_sq_diff(a, b, n)); }
-// IEEE negation (sign-bit flip, -(+0) = -0): nvcc folds `-(c ? 1.f : 0.f)` into `c ? -1.f : 0.f`, which loses the sign of zero
+// IEEE negation (sign-bit flip, -(+0) = -0).  nvcc 12.9 / ptxas turn select(c, -1.0f, -0.0f) - however it is spelled:
+// -(c ? 1.f : 0.f), an xor with 0x80000000, an explicit select of the two constants - into I2FP(c ? -1 : 0), which
+// yields +0.0 and loses the reference's -0.0 sparse reward.  The sign bit therefore comes from constant
+// memory, which the compiler cannot fold.
+#if defined(__CUDACC__) && !defined(XARM_HOST_SIM)
+__constant__ float c_neg_zero = -0.0f;
+#endif
 XD float neg_exact(float x) {
 #if defined(__CUDA_ARCH__)
-  return __int_as_float(__float_as_int(x) ^ (int)0x80000000);
+  return __int_as_float(__float_as_int(x) ^ __float_as_int(c_neg_zero));
 #else
   return -x;
 #endif

@@ -1125,30 +1125,6 @@ XD bool sub_setup_lean(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR,
     resid_bad = resid_bad || fabsf(delta * door_den) > sthr_;                         \
   }
 
-// One sweep over the non-contact rows: forward on odd iterations, exact reverse on even ones.  Every row body
-// exists ONCE in the code (the kernel is instruction-fetch bound, profiles/): a warp-uniform switch picks the row and
-// the loop runs the slots [limit dof 0..N-1 | motor dof 0..N-1 | gear] up or down.  Case labels: limit i -> i,
-// motor i -> 16 + i, gear -> 32; dofs >= N of the smaller model compile to nothing.
-#define CI_(i) ((i) < N ? (i) : 0)
-#define ARM_ROW_CASE(a, i)                                                                                       \
-      case (i): if ((i) < N) { if (lim_lo[a] >> (i) & 1) UNIT_ROW(a, CI_(i), 1.f, lrhs[a][CI_(i)], 0.f, hi_lim, lapp[a][CI_(i)]) \
-                else if (lim_hi[a] >> (i) & 1) UNIT_ROW(a, CI_(i), -1.f, lrhs[a][CI_(i)], 0.f, hi_lim, lapp[a][CI_(i)]) }       \
-                break;                                                                                           \
-      case (16 + (i)): if ((i) < N) { const float hi_ = (i) < 7 ? hi_arm : hi_fin; UNIT_ROW(a, CI_(i), 1.f, mrhs[a][CI_(i)], -hi_, hi_, mapp[a][CI_(i)]) } break;
-#define ARM_ROWS_ONE(a, fwd)                                                                                     \
-  {                                                                                                              \
-    const int first_ = (lim_lo[a] | lim_hi[a]) ? 0 : N;   /* skip the limit slots when no limit is active */     \
-    for (int s_ = first_; s_ <= 2 * N; s_++) {                                                                   \
-      const int r_ = (fwd) ? s_ : 2 * N + first_ - s_;                                                           \
-      const int code_ = r_ < N ? r_ : (r_ < 2 * N ? 16 + (r_ - N) : 32);                                         \
-      switch (code_) {                                                                                           \
-        ARM_ROW_CASE(a, 0) ARM_ROW_CASE(a, 1) ARM_ROW_CASE(a, 2) ARM_ROW_CASE(a, 3) ARM_ROW_CASE(a, 4)           \
-        ARM_ROW_CASE(a, 5) ARM_ROW_CASE(a, 6) ARM_ROW_CASE(a, 7) ARM_ROW_CASE(a, 8) ARM_ROW_CASE(a, 9)           \
-        ARM_ROW_CASE(a, 10) ARM_ROW_CASE(a, 11) ARM_ROW_CASE(a, 12)                                              \
-        default: GEAR_ROW(a) break;                                                                              \
-      }                                                                                                          \
-    }                                                                                                            \
-  }
 // the motor rows of arm a, fully unrolled (no limit row active): forward = dof 0..N-1, backward = N-1..0
 #define ARM_MOTOR_ROW_(a, i) { const float hi_ = (i) < 7 ? hi_arm : hi_fin; UNIT_ROW(a, i, 1.f, mrhs[a][i], -hi_, hi_, mapp[a][i]) }
 #define ARM_MOTORS_FWD(a) { _Pragma("unroll") for (int i_ = 0; i_ < N; i_++) ARM_MOTOR_ROW_(a, i_) }
@@ -1159,72 +1135,6 @@ XD bool sub_setup_lean(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR,
     else if (lim_hi[a] >> (i) & 1) UNIT_ROW(a, i, -1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i]) }
 #define ARM_LIMITS_FWD(a) { _Pragma("unroll") for (int i_ = 0; i_ < N; i_++) ARM_LIMIT_ROW_(a, i_) }
 #define ARM_LIMITS_BWD(a) { _Pragma("unroll") for (int i_ = N - 1; i_ >= 0; i_--) ARM_LIMIT_ROW_(a, i_) }
-#define ARM_ROWS_SWEEP(it)                                                                                       \
-  if ((it) & 1) {                                                                                                \
-    _Pragma("unroll") for (int a = 0; a < NA; a++) ARM_ROWS_ONE(a, true)                                         \
-    if (T::HAS_DOOR) { DOOR_LIMIT_ROW() DOOR_MOTOR_ROW() }                                                       \
-  } else {                                                                                                       \
-    if (T::HAS_DOOR) { DOOR_MOTOR_ROW() DOOR_LIMIT_ROW() }                                                       \
-    _Pragma("unroll") for (int a = NA - 1; a >= 0; a--) ARM_ROWS_ONE(a, false)                                   \
-  }
-
-// the contact rows of one iteration: all normal rows, then the friction pairs (implicit cone).  COUPLED=false is the
-// object-only form used when no contact touches an arm link or the door (single-object tasks).
-#define CONTACT_ROWS_SWEEP(COUPLED)                                                                              \
-  for (int phase = 0; phase < 2; phase++) {                                                                      \
-    for (int c = 0; c < C.nc; c++) {                                                                             \
-      const int o1 = NOBJ <= 1 ? (C.o1[c] >= 0 ? 0 : -1) : C.o1[c];                                              \
-      const int o2 = NOBJ > 1 ? C.o2[c] : -1;                                                                    \
-      const int sl = (COUPLED) ? C.slot[c] : -1;                                                                 \
-      const float s1 = C.s1[c];                                                                                  \
-      const int arm_of = ((COUPLED) && NA > 1 && sl >= 0) ? bc_arm(bc_is_arm(C.ba[c]) ? C.ba[c] : C.bb[c]) : 0;  \
-      float delta[3] = {0.f, 0.f, 0.f};                                                                          \
-      const int k0 = phase == 0 ? 0 : 1, k1 = phase == 0 ? 1 : 3;                                                \
-      float jv[3] = {0.f, 0.f, 0.f};                                                                             \
-      for (int k = k0; k < k1; k++) {                                                                            \
-        const V3 d = C.dir[c][k];                                                                                \
-        float s_ = 0.f;                                                                                          \
-        if (o1 >= 0) s_ += s1 * dot(d, dv[NOBJ <= 1 ? 0 : o1]) + dot(C.Jo1[c][k], dw[NOBJ <= 1 ? 0 : o1]);       \
-        if (NOBJ > 1 && o2 >= 0) s_ += -dot(d, dv[o2 < 0 ? 0 : o2]) + dot(C.Jo2[NOBJ > 1 ? c : 0][k], dw[o2 < 0 ? 0 : o2]); \
-        if ((COUPLED) && sl >= 0) {                                                                              \
-          if (NA == 1 || arm_of == 0) { _Pragma("unroll") for (int i = 0; i < N; i++) s_ += C.Jarm[sl][k][i] * dqd[0][i]; } \
-          else { _Pragma("unroll") for (int i = 0; i < N; i++) s_ += C.Jarm[sl][k][i] * dqd[NA - 1][i]; }        \
-        }                                                                                                        \
-        if ((COUPLED) && T::HAS_DOOR) s_ += C.jdoor[T::HAS_DOOR ? c : 0][k] * ddoor;                             \
-        jv[k] = s_;                                                                                              \
-      }                                                                                                          \
-      if (phase == 0) {                                                                                          \
-        float d0 = C.rhs[c][0] - C.app[c][0] * C.cfmr[c] - jv[0] * C.dinv[c][0];                                 \
-        float sum = C.app[c][0] + d0;                                                                            \
-        if (sum < 0.f) { d0 = -C.app[c][0]; sum = 0.f; }                                                         \
-        else if (sum > (float)XARM_CONTACT_MAX_IMPULSE) { d0 = (float)XARM_CONTACT_MAX_IMPULSE - C.app[c][0]; sum = (float)XARM_CONTACT_MAX_IMPULSE; } \
-        C.app[c][0] = sum;                                                                                       \
-        delta[0] = d0;                                                                                           \
-        resid_bad = resid_bad || fabsf(d0) > sthr_ * C.dinv[c][0];                                               \
-      } else {                                                                                                   \
-        float lim = C.mu[c] * C.app[c][0];                                                                       \
-        float da = C.rhs[c][1] - jv[1] * C.dinv[c][1], db = C.rhs[c][2] - jv[2] * C.dinv[c][2];                  \
-        float sa = C.app[c][1] + da, sb = C.app[c][2] + db;                                                      \
-        float len = sqrtf(sa * sa + sb * sb);                                                                    \
-        if (len > lim) { float sc = len > 0.f ? lim / len : 0.f; sa *= sc; sb *= sc; da = sa - C.app[c][1]; db = sb - C.app[c][2]; } \
-        C.app[c][1] = sa; C.app[c][2] = sb;                                                                      \
-        delta[1] = da; delta[2] = db;                                                                            \
-        resid_bad = resid_bad || fabsf(da) > sthr_ * C.dinv[c][1] || fabsf(db) > sthr_ * C.dinv[c][2];           \
-      }                                                                                                          \
-      for (int k = k0; k < k1; k++) {                                                                            \
-        const V3 d = C.dir[c][k];                                                                                \
-        const float dl = delta[k];                                                                               \
-        if (o1 >= 0) { dv[NOBJ <= 1 ? 0 : o1] += (s1 * dl * inv_obj_mass) * d; dw[NOBJ <= 1 ? 0 : o1] += dl * C.dVo1[c][k]; } \
-        if (NOBJ > 1 && o2 >= 0) { dv[o2 < 0 ? 0 : o2] += (-dl * inv_obj_mass) * d; dw[o2 < 0 ? 0 : o2] += dl * C.dVo2[NOBJ > 1 ? c : 0][k]; } \
-        if ((COUPLED) && sl >= 0) {                                                                              \
-          if (NA == 1 || arm_of == 0) { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[0][i] += C.dVarm[sl][k][i] * dl; } \
-          else { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[NA - 1][i] += C.dVarm[sl][k][i] * dl; }       \
-        }                                                                                                        \
-        if ((COUPLED) && T::HAS_DOOR) ddoor += C.jdoor[T::HAS_DOOR ? c : 0][k] * dl / (float)XARM_DOOR_MASS;     \
-      }                                                                                                          \
-    }                                                                                                            \
-  }
-
 #define SOLVER_LOCALS_FROM(AR)                                                                                   \
   float Mi[NA][NT], iden[NA][N], dqd[NA][N], mrhs[NA][N], mapp[NA][N], lrhs[NA][N], lapp[NA][N];                 \
   uint32_t lim_lo[NA], lim_hi[NA];                                                                               \
@@ -1371,42 +1281,126 @@ XD void sub_solve_light(const ArmRows<T>& AR, int nc, const ManifoldIn& MI, floa
   S.dv[0] = v; S.dw[0] = w; S.ddoor = 0.f;
 }
 
-// Generic form: phase 0 = arm rows only, 1 = contact rows only (the two islands of a decoupled env), 2 = the joint
-// loop of btMultiBodyConstraintSolver::solveSingleIteration.  One expansion of each sweep serves all phases.
+// Generic form: the joint loop of btMultiBodyConstraintSolver::solveSingleIteration over ALL rows of the env -
+// non-contact rows of every arm and the door (forward on odd sweeps, backward on even ones), the normal rows of every
+// contact, then its friction pairs (implicit cone) - until no row moved more than the residual threshold.  Contact rows
+// are read from C (shared memory in the heavy kernel); the arm rows live in registers.
 template <class T>
-XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, int form) {
+XD float arm_dot(const float* J, const float* dqd) {  // three partial sums: shorter dependency chain
+  constexpr int N = T::MD::N;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; i += 3) {
+    s0 += J[i] * dqd[i];
+    if (i + 1 < N) s1 += J[i + 1] * dqd[i + 1];
+    if (i + 2 < N) s2 += J[i + 2] * dqd[i + 2];
+  }
+  return (s0 + s1) + s2;
+}
+template <class T>
+XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, int /*form*/) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1, NT = N * (N + 1) / 2;
   SOLVER_LOCALS_FROM(AR)
   V3 dv[NO], dw[NO];
 #pragma unroll
   for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
-  unsigned long long ok_arm = 0ull, ok_obj = 0ull;
-  int phase = form == SOLVE_GENERIC_DECOUPLED ? 0 : 2;
-  while (true) {
-    for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
-      bool resid_bad = false;
-      if (phase != 1) { ARM_ROWS_SWEEP(it) }
-      if (phase != 0) { CONTACT_ROWS_SWEEP(true) }
-      if (!resid_bad) {
-        if (phase == 2) break;
-        if (phase == 0) { ok_arm |= 1ull << it; if (C.nc == 0) break; } else ok_obj |= 1ull << it;
+  const int nc = C.nc;
+  for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+    bool resid_bad = false;
+    if (it & 1) {
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        if ((lim_lo[a] | lim_hi[a]) != 0u) ARM_LIMITS_FWD(a)
+        ARM_MOTORS_FWD(a) GEAR_ROW(a)
+      }
+      if (T::HAS_DOOR) { DOOR_LIMIT_ROW() DOOR_MOTOR_ROW() }
+    } else {
+      if (T::HAS_DOOR) { DOOR_MOTOR_ROW() DOOR_LIMIT_ROW() }
+#pragma unroll
+      for (int a = NA - 1; a >= 0; a--) {
+        GEAR_ROW(a) ARM_MOTORS_BWD(a)
+        if ((lim_lo[a] | lim_hi[a]) != 0u) ARM_LIMITS_BWD(a)
       }
     }
-    if (phase == 2 || C.nc == 0) break;
-    if (phase == 0) { phase = 1; continue; }
-    // both islands solved separately: would the joint loop have stopped before its last sweep?
-    if (!(ok_arm & ok_obj & ((1ull << (XARM_SOLVER_ITERATIONS - 1)) - 1ull))) break;
-#pragma unroll
-    for (int a = 0; a < NA; a++) {
-#pragma unroll
-      for (int i = 0; i < N; i++) { dqd[a][i] = 0.f; mapp[a][i] = 0.f; lapp[a][i] = 0.f; }
-      gapp[a] = 0.f;
+    // ---- normal rows
+    for (int c = 0; c < nc; c++) {
+      const int o1 = NOBJ <= 1 ? (C.o1[c] >= 0 ? 0 : -1) : C.o1[c];
+      const int o2 = NOBJ > 1 ? C.o2[c] : -1;
+      const int sl = C.slot[c];
+      const float s1 = C.s1[c];
+      const int arm_of = (NA > 1 && sl >= 0) ? bc_arm(bc_is_arm(C.ba[c]) ? C.ba[c] : C.bb[c]) : 0;
+      const V3 d = C.dir[c][0];
+      float s_ = 0.f;
+      if (o1 >= 0) s_ += s1 * dot(d, dv[NOBJ <= 1 ? 0 : o1]) + dot(C.Jo1[c][0], dw[NOBJ <= 1 ? 0 : o1]);
+      if (NOBJ > 1 && o2 >= 0) s_ += -dot(d, dv[o2 < 0 ? 0 : o2]) + dot(C.Jo2[NOBJ > 1 ? c : 0][0], dw[o2 < 0 ? 0 : o2]);
+      if (sl >= 0) {
+        if (NA == 1 || arm_of == 0) s_ += arm_dot<T>(C.Jarm[sl][0], dqd[0]);
+        else s_ += arm_dot<T>(C.Jarm[sl][0], dqd[NA - 1]);
+      }
+      if (T::HAS_DOOR) s_ += C.jdoor[T::HAS_DOOR ? c : 0][0] * ddoor;
+      const float app0 = C.app[c][0], dinv0 = C.dinv[c][0];
+      float d0 = C.rhs[c][0] - app0 * C.cfmr[c] - s_ * dinv0;
+      float sum = app0 + d0;
+      if (sum < 0.f) { d0 = -app0; sum = 0.f; }
+      else if (sum > (float)XARM_CONTACT_MAX_IMPULSE) { d0 = (float)XARM_CONTACT_MAX_IMPULSE - app0; sum = (float)XARM_CONTACT_MAX_IMPULSE; }
+      C.app[c][0] = sum;
+      resid_bad = resid_bad || fabsf(d0) > sthr_ * dinv0;
+      if (o1 >= 0) { dv[NOBJ <= 1 ? 0 : o1] += (s1 * d0 * inv_obj_mass) * d; dw[NOBJ <= 1 ? 0 : o1] += d0 * C.dVo1[c][0]; }
+      if (NOBJ > 1 && o2 >= 0) { dv[o2 < 0 ? 0 : o2] += (-d0 * inv_obj_mass) * d; dw[o2 < 0 ? 0 : o2] += d0 * C.dVo2[NOBJ > 1 ? c : 0][0]; }
+      if (sl >= 0) {
+        if (NA == 1 || arm_of == 0) { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[0][i] += C.dVarm[sl][0][i] * d0; }
+        else { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[NA - 1][i] += C.dVarm[sl][0][i] * d0; }
+      }
+      if (T::HAS_DOOR) ddoor += C.jdoor[T::HAS_DOOR ? c : 0][0] * d0 / (float)XARM_DOOR_MASS;
     }
-#pragma unroll
-    for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
-    for (int c = 0; c < C.nc; c++) { C.app[c][0] = 0.f; C.app[c][1] = 0.f; C.app[c][2] = 0.f; }
-    phase = 2;
+    // ---- friction pairs (implicit cone: the pair is scaled back onto mu * normal impulse)
+    for (int c = 0; c < nc; c++) {
+      const int o1 = NOBJ <= 1 ? (C.o1[c] >= 0 ? 0 : -1) : C.o1[c];
+      const int o2 = NOBJ > 1 ? C.o2[c] : -1;
+      const int sl = C.slot[c];
+      const float s1 = C.s1[c];
+      const int arm_of = (NA > 1 && sl >= 0) ? bc_arm(bc_is_arm(C.ba[c]) ? C.ba[c] : C.bb[c]) : 0;
+      const V3 t1 = C.dir[c][1], t2 = C.dir[c][2];
+      float ja = 0.f, jb = 0.f;
+      if (o1 >= 0) {
+        const V3 v_ = dv[NOBJ <= 1 ? 0 : o1], w_ = dw[NOBJ <= 1 ? 0 : o1];
+        ja += s1 * dot(t1, v_) + dot(C.Jo1[c][1], w_);
+        jb += s1 * dot(t2, v_) + dot(C.Jo1[c][2], w_);
+      }
+      if (NOBJ > 1 && o2 >= 0) {
+        const V3 v_ = dv[o2 < 0 ? 0 : o2], w_ = dw[o2 < 0 ? 0 : o2];
+        ja += -dot(t1, v_) + dot(C.Jo2[NOBJ > 1 ? c : 0][1], w_);
+        jb += -dot(t2, v_) + dot(C.Jo2[NOBJ > 1 ? c : 0][2], w_);
+      }
+      if (sl >= 0) {
+        if (NA == 1 || arm_of == 0) { ja += arm_dot<T>(C.Jarm[sl][1], dqd[0]); jb += arm_dot<T>(C.Jarm[sl][2], dqd[0]); }
+        else { ja += arm_dot<T>(C.Jarm[sl][1], dqd[NA - 1]); jb += arm_dot<T>(C.Jarm[sl][2], dqd[NA - 1]); }
+      }
+      if (T::HAS_DOOR) { ja += C.jdoor[T::HAS_DOOR ? c : 0][1] * ddoor; jb += C.jdoor[T::HAS_DOOR ? c : 0][2] * ddoor; }
+      const float lim = C.mu[c] * C.app[c][0];
+      const float app1 = C.app[c][1], app2 = C.app[c][2], di1 = C.dinv[c][1], di2 = C.dinv[c][2];
+      float da = C.rhs[c][1] - ja * di1, db = C.rhs[c][2] - jb * di2;
+      float sa = app1 + da, sb = app2 + db;
+      const float len = sqrtf(sa * sa + sb * sb);
+      if (len > lim) { const float sc = len > 0.f ? lim / len : 0.f; sa *= sc; sb *= sc; da = sa - app1; db = sb - app2; }
+      C.app[c][1] = sa; C.app[c][2] = sb;
+      resid_bad = resid_bad || fabsf(da) > sthr_ * di1 || fabsf(db) > sthr_ * di2;
+      if (o1 >= 0) {
+        dv[NOBJ <= 1 ? 0 : o1] += (s1 * da * inv_obj_mass) * t1; dw[NOBJ <= 1 ? 0 : o1] += da * C.dVo1[c][1];
+        dv[NOBJ <= 1 ? 0 : o1] += (s1 * db * inv_obj_mass) * t2; dw[NOBJ <= 1 ? 0 : o1] += db * C.dVo1[c][2];
+      }
+      if (NOBJ > 1 && o2 >= 0) {
+        dv[o2 < 0 ? 0 : o2] += (-da * inv_obj_mass) * t1; dw[o2 < 0 ? 0 : o2] += da * C.dVo2[NOBJ > 1 ? c : 0][1];
+        dv[o2 < 0 ? 0 : o2] += (-db * inv_obj_mass) * t2; dw[o2 < 0 ? 0 : o2] += db * C.dVo2[NOBJ > 1 ? c : 0][2];
+      }
+      if (sl >= 0) {
+        if (NA == 1 || arm_of == 0) { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[0][i] += C.dVarm[sl][1][i] * da + C.dVarm[sl][2][i] * db; }
+        else { _Pragma("unroll") for (int i = 0; i < N; i++) dqd[NA - 1][i] += C.dVarm[sl][1][i] * da + C.dVarm[sl][2][i] * db; }
+      }
+      if (T::HAS_DOOR) ddoor += (C.jdoor[T::HAS_DOOR ? c : 0][1] * da + C.jdoor[T::HAS_DOOR ? c : 0][2] * db) / (float)XARM_DOOR_MASS;
+    }
+    if (!resid_bad) break;
   }
 #pragma unroll
   for (int a = 0; a < NA; a++)
@@ -1416,17 +1410,12 @@ XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, in
   for (int o = 0; o < NO; o++) { S.dv[o] = dv[o]; S.dw[o] = dw[o]; }
   S.ddoor = ddoor;
 }
-#undef ARM_ROWS_SWEEP
 #undef ARM_MOTORS_FWD
 #undef ARM_MOTORS_BWD
 #undef ARM_MOTOR_ROW_
 #undef ARM_LIMITS_FWD
 #undef ARM_LIMITS_BWD
 #undef ARM_LIMIT_ROW_
-#undef ARM_ROWS_ONE
-#undef ARM_ROW_CASE
-#undef CI_
-#undef CONTACT_ROWS_SWEEP
 #undef UNIT_ROW
 #undef GEAR_ROW
 #undef DOOR_LIMIT_ROW
