@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "xarm_pipeline.cuh"
+#include "xarm_heavy.cuh"
 
 // ------------------------------------------------------------------------------------------------ kernels
 // One thread per env; 128-thread blocks (a warp steps 32 envs in lock-step).
@@ -61,13 +62,31 @@ __global__ void __launch_bounds__(128, 3) k_pipe_light(KArgs a) {
 // In thread-local memory the 50 sweeps stream every row from L2 again (160 KB per warp per sweep) and one heavy warp
 // needs > 1 ms per substep; the launch is persistent (grid = #SMs) and runs next to k_pipe_light.
 template <class T>
+constexpr bool task_has_heavy_rows() { return T::NARM == 1 && T::NOBJ == 1 && !T::HAS_DOOR && T::MD::N == 9; }
+template <class T>
 constexpr int heavy_stride_words() { return (int)((sizeof(Contacts<T>) + 3) / 4) | 1; }
 template <class T>
+constexpr size_t heavy_smem_bytes_of() {
+  if constexpr (task_has_heavy_rows<T>()) return HeavyLayout<T>::BYTES;
+  else return (size_t)heavy_stride_words<T>() * 32 * sizeof(float);
+}
+template <class T>
 __global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* heavy_count) {
-  extern __shared__ float heavy_smem[];
-  Contacts<T>& C = *reinterpret_cast<Contacts<T>*>(heavy_smem + (size_t)threadIdx.x * heavy_stride_words<T>());
+  extern __shared__ float4 heavy_smem4[];
+  float* heavy_smem = reinterpret_cast<float*>(heavy_smem4);
   const int count = *heavy_count;
-  for (int t = blockIdx.x * 32 + threadIdx.x; t < count; t += gridDim.x * 32) pipe_heavy<T>(a, a.heavy_list[t], sub, C);
+  for (int t = blockIdx.x * 32 + threadIdx.x; t < count; t += gridDim.x * 32) {
+    const int64_t i = a.heavy_list[t];
+    if constexpr (task_has_heavy_rows<T>()) {  // solver rows as float4 records (xarm_heavy.cuh)
+      Env<T> e;
+      env_load<T>(e, a.state, a.n, i);
+      heavy_substep<T>(e, T::DAMP_EACH || sub == 0, sub == T::NSUB - 1, heavy_smem, threadIdx.x);
+      env_store<T>(e, a.state, a.n, i);
+    } else {                                   // the generic record, one per lane at an odd word stride
+      Contacts<T>& C = *reinterpret_cast<Contacts<T>*>(heavy_smem + (size_t)threadIdx.x * heavy_stride_words<T>());
+      pipe_heavy<T>(a, i, sub, C);
+    }
+  }
 }
 // tasks without a light form (two arms / door): every env takes the generic substep (rows in thread-local memory)
 template <class T>
@@ -170,7 +189,7 @@ template <class T>
 struct OpsT {
   static constexpr bool HAS_LIGHT = task_has_light<T>();  // tasks whose envs can take the light solver form
   static dim3 grid(int64_t n) { return dim3((unsigned)((n + 127) / 128)); }
-  static size_t heavy_smem_bytes() { return (size_t)heavy_stride_words<T>() * 32 * sizeof(float); }
+  static size_t heavy_smem_bytes() { return heavy_smem_bytes_of<T>(); }
   static int prepare() {  // opt in to the large dynamic shared memory of the heavy kernel
     if constexpr (HAS_LIGHT) return (int)cudaFuncSetAttribute(k_pipe_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem_bytes());
     return 0;

@@ -1410,16 +1410,6 @@ XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, in
   for (int o = 0; o < NO; o++) { S.dv[o] = dv[o]; S.dw[o] = dw[o]; }
   S.ddoor = ddoor;
 }
-#undef ARM_MOTORS_FWD
-#undef ARM_MOTORS_BWD
-#undef ARM_MOTOR_ROW_
-#undef ARM_LIMITS_FWD
-#undef ARM_LIMITS_BWD
-#undef ARM_LIMIT_ROW_
-#undef UNIT_ROW
-#undef GEAR_ROW
-#undef DOOR_LIMIT_ROW
-#undef DOOR_MOTOR_ROW
 
 // stepPositionsMultiDof: add the solved velocity changes, integrate joints and boxes
 template <class T>
