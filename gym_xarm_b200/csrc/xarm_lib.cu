@@ -88,6 +88,29 @@ __global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* 
     }
   }
 }
+// Cooperative heavy path (tasks with HeavyRec: PickAndPlace).  k_heavy_rows: one thread per heavy env, generic setup ->
+// record in global memory.  k_heavy_solve: 16 lanes per env, 8 envs per 128-thread block, records staged in shared
+// memory (3 blocks = 24 envs = 12 warps per SM instead of the single warp of the thread-per-env form).
+#define XARM_HEAVY_ENVS_PER_BLOCK 8
+template <class T>
+__global__ void __launch_bounds__(64) k_heavy_rows(KArgs a, int sub, const int* heavy_count, float* hrec) {
+  if constexpr (task_has_heavy_rows<T>()) {
+    const int count = *heavy_count;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) heavy_rows_body<T>(a, t, sub, hrec);
+  }
+}
+template <class T>
+__global__ void __launch_bounds__(128) k_heavy_solve(KArgs a, const int* heavy_count, const float* hrec) {
+  if constexpr (task_has_heavy_rows<T>()) {
+    extern __shared__ float4 heavy_smem4[];
+    constexpr int SLOT = HeavyRec<T>::WORDS + T::MAXC * 3;
+    const int g = threadIdx.x >> 4, l = threadIdx.x & 15;
+    float* srec = reinterpret_cast<float*>(heavy_smem4) + (size_t)g * SLOT;
+    const int count = *heavy_count;
+    for (int base = blockIdx.x * XARM_HEAVY_ENVS_PER_BLOCK; base < count; base += gridDim.x * XARM_HEAVY_ENVS_PER_BLOCK)
+      heavy_solve_body<T>(a, base + g, base + g < count, hrec, srec, l);
+  }
+}
 // tasks without a light form (two arms / door): every env takes the generic substep (rows in thread-local memory)
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_heavy_all(KArgs a, int sub) {
@@ -167,7 +190,8 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // fork/join plumbing of the pipeline: a side stream for the heavy kernels and a pool of dependency events
 struct PipeCtx {
   cudaStream_t side = nullptr;
-  unsigned heavy_grid = 148;  // persistent heavy kernel: one block per SM (set from the device in xarm_create)
+  unsigned heavy_grid = 148;  // persistent heavy kernels: a few blocks per SM (set from the device in xarm_create)
+  float* hrec = nullptr;      // [N][HeavyRec::WORDS] records of the cooperative heavy solver
   std::vector<cudaEvent_t> ev;
   size_t next_ev = 0;
   cudaEvent_t next() {
@@ -182,6 +206,7 @@ struct Ops {
   void (*reset)(PipeCtx&, const KArgs&, const uint8_t*, cudaStream_t);
   void (*obs)(const KArgs&, cudaStream_t);
   int (*prepare)();
+  size_t (*hrec_words)();
   int A, O, G, S, scratch_words;
 };
 
@@ -190,8 +215,16 @@ struct OpsT {
   static constexpr bool HAS_LIGHT = task_has_light<T>();  // tasks whose envs can take the light solver form
   static dim3 grid(int64_t n) { return dim3((unsigned)((n + 127) / 128)); }
   static size_t heavy_smem_bytes() { return heavy_smem_bytes_of<T>(); }
-  static int prepare() {  // opt in to the large dynamic shared memory of the heavy kernel
-    if constexpr (HAS_LIGHT) return (int)cudaFuncSetAttribute(k_pipe_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem_bytes());
+  static size_t coop_smem_bytes() {
+    if constexpr (task_has_heavy_rows<T>()) return (size_t)XARM_HEAVY_ENVS_PER_BLOCK * (HeavyRec<T>::WORDS + T::MAXC * 3) * sizeof(float);
+    else return 0;
+  }
+  static size_t hrec_words() {  // per env: record of the cooperative heavy solver (0: task has none)
+    if constexpr (task_has_heavy_rows<T>()) return HeavyRec<T>::WORDS; else return 0;
+  }
+  static int prepare() {  // opt in to the large dynamic shared memory of the heavy kernels
+    if constexpr (task_has_heavy_rows<T>()) return (int)cudaFuncSetAttribute(k_heavy_solve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes());
+    else if constexpr (HAS_LIGHT) return (int)cudaFuncSetAttribute(k_pipe_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem_bytes());
     return 0;
   }
   static void init(const KArgs& a, cudaStream_t s) { k_init<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
@@ -208,7 +241,13 @@ struct OpsT {
         cudaEvent_t fork = c.next(), join = c.next();
         cudaEventRecord(fork, s);
         cudaStreamWaitEvent(c.side, fork, 0);
-        k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), c.side>>>(a, sub, hc);
+        if constexpr (task_has_heavy_rows<T>()) {
+          k_heavy_rows<T><<<c.heavy_grid * 4, 64, 0, c.side>>>(a, sub, hc, c.hrec);
+          k_heavy_solve<T><<<c.heavy_grid * 3, 128, coop_smem_bytes(), c.side>>>(a, hc, c.hrec);
+          g_launches++;
+        } else {
+          k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), c.side>>>(a, sub, hc);
+        }
         cudaEventRecord(join, c.side);
         k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(a);
         cudaStreamWaitEvent(s, join, 0);
@@ -256,7 +295,7 @@ struct OpsT {
     }
     reset_passes(c, a, 0, 1, s);
   }
-  static Ops make() { Ops o = {init, step, reset, obs, prepare, T::A, T::O, T::G, state_words<T>(), pipe_scratch_words<T>()}; return o; }
+  static Ops make() { Ops o = {init, step, reset, obs, prepare, hrec_words, T::A, T::O, T::G, state_words<T>(), pipe_scratch_words<T>()}; return o; }
 };
 
 // XARM_ONLY_TASK=<id> builds a single task (development builds: faster compiles); the shipped library has all five.
@@ -379,6 +418,9 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     cudaError_t ep = (cudaError_t)ops.prepare();
     if (ep != cudaSuccess) return fail(XARM_E_CUDA, std::string("cudaFuncSetAttribute(k_pipe_heavy): ") + cudaGetErrorString(ep));
   }
+  if (ops.hrec_words() > 0) {
+    if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) { cudaGetLastError(); return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed"); }
+  }
   h->k.heavy_list = h->k.reset_list + n; h->k.form = h->k.reset_list + 2 * n; h->k.rng_draw = h->k.reset_list + 3 * n;
   h->k.heavy_count = h->k.reset_list + 4 * n; h->k.reset_count = h->k.heavy_count + XARM_PIPE_COUNTERS;
   CUDA_TRY(cudaMemset(h->k.reset_list, 0, sizeof(int) * n_int));
@@ -395,6 +437,7 @@ int xarm_destroy(XarmHandle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
   cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.reset_list); cudaFree(h->k.scratch);
+  cudaFree(h->pipe.hrec);
   for (cudaEvent_t e : h->pipe.ev) cudaEventDestroy(e);
   if (h->pipe.side) cudaStreamDestroy(h->pipe.side);
   cudaFree(h->d_io); cudaFree(h->d_flags);
