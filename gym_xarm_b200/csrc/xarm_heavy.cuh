@@ -68,37 +68,51 @@ __device__ __forceinline__ void heavy_rows_fill(const Contacts<T>& C, float* sme
   }
 }
 
-// generic setup of heavy env i (thread-local Contacts record) -> record `rec` for the cooperative solver
+// generic setup of a heavy env (thread-local Contacts record; Dpre: the dynamics pass the lean setup already made) ->
+// record `rec` for the cooperative solver.  128-bit stores: every thread writes its own 7 KB record.
 template <class T>
-__device__ __forceinline__ void heavy_rows_record(Env<T>& e, bool apply_damping, bool last, float* __restrict__ rec) {
+__device__ __forceinline__ void heavy_rows_record(Env<T>& e, bool apply_damping, bool last, float* __restrict__ rec,
+                                                  const ArmDyn<typename T::MD>* Dpre) {
   using R = HeavyRec<T>;
+  static_assert(R::HDR % 4 == 0 && R::ROW % 4 == 0 && R::WORDS % 4 == 0, "records are written as float4");
   ArmRows<T> AR;
   SubBase<T> B;
   ManifoldIn MI;
   Contacts<T> C;
-  sub_setup<T>(e, apply_damping, last, AR, C, B, MI);
+  sub_setup<T>(e, apply_damping, last, AR, C, B, MI, Dpre);
+  float4* rec4 = reinterpret_cast<float4*>(rec);
+  {
+    float hd[R::HDR];
 #pragma unroll
-  for (int i = 0; i < R::NT; i++) rec[R::MI + i] = AR.Mi[0][i];
+    for (int i = 0; i < R::HDR; i++) hd[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < R::N; i++) { rec[R::MRHS + i] = AR.mrhs[0][i]; rec[R::LRHS + i] = AR.lrhs[0][i]; rec[R::QDU + i] = B.qdu[0][i]; }
-  rec[R::LIM] = (float)AR.lim_lo[0]; rec[R::LIM + 1] = (float)AR.lim_hi[0];
-  rec[R::GEAR] = AR.grhs[0]; rec[R::GEAR + 1] = AR.gdinv[0]; rec[R::GEAR + 2] = AR.gden[0];
-  rec[R::VU] = B.vu[0].x; rec[R::VU + 1] = B.vu[0].y; rec[R::VU + 2] = B.vu[0].z;
-  rec[R::WU] = B.wu[0].x; rec[R::WU + 1] = B.wu[0].y; rec[R::WU + 2] = B.wu[0].z;
-  rec[R::NC] = (float)C.nc;
+    for (int i = 0; i < R::NT; i++) hd[R::MI + i] = AR.Mi[0][i];
+#pragma unroll
+    for (int i = 0; i < R::N; i++) { hd[R::MRHS + i] = AR.mrhs[0][i]; hd[R::LRHS + i] = AR.lrhs[0][i]; hd[R::QDU + i] = B.qdu[0][i]; }
+    hd[R::LIM] = (float)AR.lim_lo[0]; hd[R::LIM + 1] = (float)AR.lim_hi[0];
+    hd[R::GEAR] = AR.grhs[0]; hd[R::GEAR + 1] = AR.gdinv[0]; hd[R::GEAR + 2] = AR.gden[0];
+    hd[R::VU] = B.vu[0].x; hd[R::VU + 1] = B.vu[0].y; hd[R::VU + 2] = B.vu[0].z;
+    hd[R::WU] = B.wu[0].x; hd[R::WU + 1] = B.wu[0].y; hd[R::WU + 2] = B.wu[0].z;
+    hd[R::NC] = (float)C.nc;
+#pragma unroll
+    for (int u = 0; u < R::HDR / 4; u++) rec4[u] = make_float4(hd[4 * u], hd[4 * u + 1], hd[4 * u + 2], hd[4 * u + 3]);
+  }
   const float inv_m = 1.f / T::OBJ_MASS;
   for (int c = 0; c < C.nc; c++) {
     const int sl = C.slot[c];
     const float s1 = C.s1[c];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      float* r = rec + R::HDR + (c * 3 + k) * R::ROW;
+      float r[R::ROW];
 #pragma unroll
       for (int i = 0; i < 9; i++) { r[i] = sl >= 0 ? C.Jarm[sl < 0 ? 0 : sl][k][i] : 0.f; r[16 + i] = sl >= 0 ? C.dVarm[sl < 0 ? 0 : sl][k][i] : 0.f; }
       const V3 d = C.dir[c][k], jo = C.Jo1[c][k], vo = C.dVo1[c][k];
       r[9] = s1 * d.x; r[10] = s1 * d.y; r[11] = s1 * d.z; r[12] = jo.x; r[13] = jo.y; r[14] = jo.z; r[15] = 0.f;
       r[25] = s1 * inv_m * d.x; r[26] = s1 * inv_m * d.y; r[27] = s1 * inv_m * d.z; r[28] = vo.x; r[29] = vo.y; r[30] = vo.z; r[31] = 0.f;
       r[32] = C.rhs[c][k]; r[33] = C.dinv[c][k]; r[34] = C.cfmr[c]; r[35] = C.mu[c];
+      float4* o = rec4 + (R::HDR + (c * 3 + k) * R::ROW) / 4;
+#pragma unroll
+      for (int u = 0; u < R::ROW / 4; u++) o[u] = make_float4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
     }
   }
 }
@@ -183,48 +197,50 @@ __device__ __forceinline__ float heavy_solve_coop(const float* srec, float* sapp
       _Pragma("unroll") for (int i = N - 1; i >= 0; i--) CO_MOTOR(i)
       if (any_lim) { _Pragma("unroll") for (int i = N - 1; i >= 0; i--) CO_LIMIT(i) }
     }
-    // ---- normal rows
+    // ---- normal rows (all loads of a row are issued before the shuffle sum)
     for (int c = 0; c < nc_max; c++) {
       const bool on = c < nc && !done;
-      const float* r = srec + R::HDR + (on ? c * 3 : 0) * R::ROW;
-      const float j = c < nc ? r[l] : 0.f;
+      const float* r = srec + R::HDR + (c < nc ? c * 3 : 0) * R::ROW;
+      const float j = c < nc ? r[l] : 0.f, vv = r[16 + l], rhs0 = r[32], dinv0 = r[33], cfmr0 = r[34];
+      const float app0 = sapp[c < nc ? c * 3 : 0];
       const float s_ = half_sum(j * u);
+      float d0 = rhs0 - app0 * cfmr0 - s_ * dinv0;
+      const float sum = app0 + d0;
+      const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
+      d0 = (sumc == sum) ? d0 : sumc - app0;
       if (on) {
-        const float app0 = sapp[c * 3], dinv0 = r[33];
-        float d0 = r[32] - app0 * r[34] - s_ * dinv0;
-        const float sum = app0 + d0;
-        const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
-        d0 = (sumc == sum) ? d0 : sumc - app0;
         if (l == 0) sapp[c * 3] = sumc;
         bad = bad || fabsf(d0) > sthr * dinv0;
-        u += r[16 + l] * d0;
+        u += vv * d0;
       }
     }
     __syncwarp();
     // ---- friction pairs (implicit cone)
     for (int c = 0; c < nc_max; c++) {
       const bool on = c < nc && !done;
-      const float* r1 = srec + R::HDR + ((on ? c * 3 : 0) + 1) * R::ROW;
+      const int cc = c < nc ? c : 0;
+      const float* r1 = srec + R::HDR + (cc * 3 + 1) * R::ROW;
       const float* r2 = r1 + R::ROW;
-      const float ja_ = c < nc ? r1[l] : 0.f, jb_ = c < nc ? r2[l] : 0.f;
+      const float ja_ = c < nc ? r1[l] : 0.f, jb_ = c < nc ? r2[l] : 0.f, va_ = r1[16 + l], vb_ = r2[16 + l];
+      const float rhs1 = r1[32], di1 = r1[33], rhs2 = r2[32], di2 = r2[33], mu_ = r1[35];
+      const float appn = sapp[cc * 3], app1 = sapp[cc * 3 + 1], app2 = sapp[cc * 3 + 2];
       float pa_ = ja_ * u, pb_ = jb_ * u;
       pa_ += __shfl_xor_sync(0xffffffffu, pa_, 8, 16); pb_ += __shfl_xor_sync(0xffffffffu, pb_, 8, 16);
       pa_ += __shfl_xor_sync(0xffffffffu, pa_, 4, 16); pb_ += __shfl_xor_sync(0xffffffffu, pb_, 4, 16);
       pa_ += __shfl_xor_sync(0xffffffffu, pa_, 2, 16); pb_ += __shfl_xor_sync(0xffffffffu, pb_, 2, 16);
       pa_ += __shfl_xor_sync(0xffffffffu, pa_, 1, 16); pb_ += __shfl_xor_sync(0xffffffffu, pb_, 1, 16);
+      const float lim = mu_ * appn;
+      float da = rhs1 - pa_ * di1, db = rhs2 - pb_ * di2;
+      float sa = app1 + da, sb = app2 + db;
+      const float l2 = sa * sa + sb * sb;
+      if (l2 > lim * lim) {
+        const float len = sqrtf(l2);
+        if (len > lim) { const float sc = len > 0.f ? lim / len : 0.f; sa *= sc; sb *= sc; da = sa - app1; db = sb - app2; }
+      }
       if (on) {
-        const float lim = r1[35] * sapp[c * 3];
-        const float app1 = sapp[c * 3 + 1], app2 = sapp[c * 3 + 2], di1 = r1[33], di2 = r2[33];
-        float da = r1[32] - pa_ * di1, db = r2[32] - pb_ * di2;
-        float sa = app1 + da, sb = app2 + db;
-        const float l2 = sa * sa + sb * sb;
-        if (l2 > lim * lim) {
-          const float len = sqrtf(l2);
-          if (len > lim) { const float sc = len > 0.f ? lim / len : 0.f; sa *= sc; sb *= sc; da = sa - app1; db = sb - app2; }
-        }
         if (l == 0) { sapp[c * 3 + 1] = sa; sapp[c * 3 + 2] = sb; }
         bad = bad || fabsf(da) > sthr * di1 || fabsf(db) > sthr * di2;
-        u += r1[16 + l] * da + r2[16 + l] * db;
+        u += va_ * da + vb_ * db;
       }
     }
     __syncwarp();
@@ -341,7 +357,9 @@ __device__ __forceinline__ void heavy_rows_body(const KArgs& a, int t, int sub, 
   Env<T> e;
   env_load<T>(e, a.state, a.n, i);
   const bool last = sub == T::NSUB - 1;
-  heavy_rows_record<T>(e, T::DAMP_EACH || sub == 0, last, hrec + (size_t)t * HeavyRec<T>::WORDS);
+  ArmDyn<typename T::MD> D[1];
+  dyn_load<T>(D[0], a.scratch, a.n, i);
+  heavy_rows_record<T>(e, T::DAMP_EACH || sub == 0, last, hrec + (size_t)t * HeavyRec<T>::WORDS, D);
   if (last) {
     const int w = state_words<T>() - 2;
     a.state[(int64_t)w * a.n + i] = e.grasp[0] ? 1.f : 0.f;

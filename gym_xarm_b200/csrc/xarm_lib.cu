@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -198,6 +199,40 @@ struct PipeCtx {
     if (next_ev == ev.size()) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); ev.push_back(e); }
     return ev[next_ev++];
   }
+  // XARM_TRACE_STAGES=1 (development): timing events around every pipeline kernel of a non-captured step, summed by
+  // kernel and by main pass / auto-reset tail, printed to stderr by xarm_step after a device synchronise
+  bool trace = false;
+  struct Mark { const char* name; int tail; cudaEvent_t a, b; };
+  std::vector<Mark> marks;
+  int cur_tail = 0;
+  void begin(const char* name, cudaStream_t s) {
+    if (!trace) return;
+    Mark m; m.name = name; m.tail = cur_tail;
+    cudaEventCreate(&m.a); cudaEventCreate(&m.b);
+    cudaEventRecord(m.a, s);
+    marks.push_back(m);
+  }
+  void end(cudaStream_t s) { if (trace) cudaEventRecord(marks.back().b, s); }
+  void report() {
+    if (!trace || marks.empty()) return;
+    cudaDeviceSynchronize();
+    struct Acc { double ms = 0; int n = 0; };
+    std::vector<std::pair<std::string, Acc>> acc;
+    for (Mark& m : marks) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, m.a, m.b);
+      std::string key = std::string(m.tail ? "tail " : "main ") + m.name;
+      size_t k = 0;
+      for (; k < acc.size(); k++) if (acc[k].first == key) break;
+      if (k == acc.size()) acc.push_back({key, Acc()});
+      acc[k].second.ms += ms; acc[k].second.n++;
+      cudaEventDestroy(m.a); cudaEventDestroy(m.b);
+    }
+    fprintf(stderr, "[xarm stages]");
+    for (auto& kv : acc) fprintf(stderr, " %s: %d x %.1f us = %.2f ms |", kv.first.c_str(), kv.second.n, 1e3 * kv.second.ms / kv.second.n, kv.second.ms);
+    fprintf(stderr, "\n");
+    marks.clear();
+  }
 };
 
 struct Ops {
@@ -237,19 +272,27 @@ struct OpsT {
         k_pipe_heavy_all<T><<<g, 128, 0, s>>>(a, sub); g_launches++;
       } else {
         int* hc = a.heavy_count + pass * XARM_MAX_SUBSTEPS + sub;
+        c.begin("setup", s);
         k_pipe_setup<T><<<g, 128, 0, s>>>(a, sub, hc);
+        c.end(s);
         cudaEvent_t fork = c.next(), join = c.next();
         cudaEventRecord(fork, s);
         cudaStreamWaitEvent(c.side, fork, 0);
         if constexpr (task_has_heavy_rows<T>()) {
+          c.begin("heavy_rows", c.side);
           k_heavy_rows<T><<<c.heavy_grid * 4, 64, 0, c.side>>>(a, sub, hc, c.hrec);
+          c.end(c.side);
+          c.begin("heavy_solve", c.side);
           k_heavy_solve<T><<<c.heavy_grid * 3, 128, coop_smem_bytes(), c.side>>>(a, hc, c.hrec);
+          c.end(c.side);
           g_launches++;
         } else {
           k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), c.side>>>(a, sub, hc);
         }
         cudaEventRecord(join, c.side);
+        c.begin("light", s);
         k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(a);
+        c.end(s);
         cudaStreamWaitEvent(s, join, 0);
         g_launches += 3;
       }
@@ -260,7 +303,9 @@ struct OpsT {
     const dim3 g = grid(r.n);
     if (reset_has_servo<T>())
       for (int rep = 0; rep < 5; rep++) {
+        c.begin("reset_stage", s);
         k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, rep, 0); g_launches++;
+        c.end(s);
         simulate(c, r, pass++, s);
       }
     k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, XARM_RESET_PLACE, 0); g_launches++;
@@ -274,9 +319,15 @@ struct OpsT {
     c.next_ev = 0;
     const dim3 g = grid(a.n);
     k_pipe_begin<<<1, XARM_PIPE_COUNTERS, 0, s>>>(a);
+    c.cur_tail = 0;
+    c.begin("action", s);
     k_pipe_action<T><<<g, 128, 0, s>>>(a);
+    c.end(s);
     simulate(c, a, 0, s);
+    c.begin("finish", s);
     k_pipe_finish<T><<<g, 128, 0, s>>>(a);
+    c.end(s);
+    c.cur_tail = 1;
     g_launches += 3;
     if (a.auto_reset) {  // VecEnv auto-reset: the finished envs (compacted list) run Env.reset() through the same pipeline
       KArgs r = a;
@@ -421,6 +472,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   if (ops.hrec_words() > 0) {
     if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) { cudaGetLastError(); return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed"); }
   }
+  h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
   h->k.heavy_list = h->k.reset_list + n; h->k.form = h->k.reset_list + 2 * n; h->k.rng_draw = h->k.reset_list + 3 * n;
   h->k.heavy_count = h->k.reset_list + 4 * n; h->k.reset_count = h->k.heavy_count + XARM_PIPE_COUNTERS;
   CUDA_TRY(cudaMemset(h->k.reset_list, 0, sizeof(int) * n_int));
@@ -484,6 +536,7 @@ int xarm_step(XarmHandle* h, void* stream) {
   } else {
     launch_step(h, s);
     CUDA_TRY(cudaGetLastError());
+    h->pipe.report();
   }
   return XARM_OK;
 }

@@ -26,7 +26,12 @@ template <class T>
 XHD int pipe_sb_words() { return T::NARM * T::MD::N + 6 * (T::NOBJ > 0 ? T::NOBJ : 1) + 1; }
 XHD int pipe_mi_words() { return 3 + 1 + 12 + 12 + 6; }
 template <class T>
-XHD int pipe_scratch_words() { return pipe_ar_words<T>() + pipe_sb_words<T>() + pipe_mi_words(); }
+XHD int pipe_dyn_words() { return T::MD::N * 6 + T::MD::N * (T::MD::N + 1) / 2 + T::MD::N + 9 + 9; }  // ArmDyn of a heavy env
+template <class T>
+XHD int pipe_scratch_words() {
+  const int light = pipe_ar_words<T>() + pipe_sb_words<T>() + pipe_mi_words(), heavy = pipe_dyn_words<T>();
+  return light > heavy ? light : heavy;
+}
 
 // ---- scratch records: word w of env i at base[w * n + i]
 template <class T>
@@ -118,6 +123,47 @@ XD void mi_load(ManifoldIn& M, const float* __restrict__ s, int64_t n, int64_t i
   M.Iinv.yy = s[(w++) * n + i]; M.Iinv.yz = s[(w++) * n + i]; M.Iinv.zz = s[(w++) * n + i];
 }
 
+// the dynamics pass of a heavy env (joint subspaces, inverse inertia, unconstrained velocities, gripper frames): the
+// heavy path reuses it instead of running arm_dynamics again
+template <class T>
+XD void dyn_store(const ArmDyn<typename T::MD>& D, float* __restrict__ s, int64_t n, int64_t i) {
+  constexpr int N = T::MD::N, NT = N * (N + 1) / 2;
+  int w = 0;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    s[(w++) * n + i] = D.S[k].a.x; s[(w++) * n + i] = D.S[k].a.y; s[(w++) * n + i] = D.S[k].a.z;
+    s[(w++) * n + i] = D.S[k].l.x; s[(w++) * n + i] = D.S[k].l.y; s[(w++) * n + i] = D.S[k].l.z;
+  }
+#pragma unroll
+  for (int k = 0; k < NT; k++) s[(w++) * n + i] = D.Minv[k];
+#pragma unroll
+  for (int k = 0; k < N; k++) s[(w++) * n + i] = D.qdu[k];
+#pragma unroll
+  for (int k = 0; k < 9; k++) s[(w++) * n + i] = D.Rh.m[k];
+  s[(w++) * n + i] = D.ph.x; s[(w++) * n + i] = D.ph.y; s[(w++) * n + i] = D.ph.z;
+  s[(w++) * n + i] = D.pf1.x; s[(w++) * n + i] = D.pf1.y; s[(w++) * n + i] = D.pf1.z;
+  s[(w++) * n + i] = D.pf2.x; s[(w++) * n + i] = D.pf2.y; s[(w++) * n + i] = D.pf2.z;
+}
+template <class T>
+XD void dyn_load(ArmDyn<typename T::MD>& D, const float* __restrict__ s, int64_t n, int64_t i) {
+  constexpr int N = T::MD::N, NT = N * (N + 1) / 2;
+  int w = 0;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    D.S[k].a.x = s[(w++) * n + i]; D.S[k].a.y = s[(w++) * n + i]; D.S[k].a.z = s[(w++) * n + i];
+    D.S[k].l.x = s[(w++) * n + i]; D.S[k].l.y = s[(w++) * n + i]; D.S[k].l.z = s[(w++) * n + i];
+  }
+#pragma unroll
+  for (int k = 0; k < NT; k++) D.Minv[k] = s[(w++) * n + i];
+#pragma unroll
+  for (int k = 0; k < N; k++) D.qdu[k] = s[(w++) * n + i];
+#pragma unroll
+  for (int k = 0; k < 9; k++) D.Rh.m[k] = s[(w++) * n + i];
+  D.ph.x = s[(w++) * n + i]; D.ph.y = s[(w++) * n + i]; D.ph.z = s[(w++) * n + i];
+  D.pf1.x = s[(w++) * n + i]; D.pf1.y = s[(w++) * n + i]; D.pf1.z = s[(w++) * n + i];
+  D.pf2.x = s[(w++) * n + i]; D.pf2.y = s[(w++) * n + i]; D.pf2.z = s[(w++) * n + i];
+}
+
 // ---- _set_action (once per env step): FK, IK, motor targets; Handover's lego clamp
 template <class T>
 XD void pipe_action(const KArgs& a, int64_t i) {
@@ -143,7 +189,12 @@ XD bool pipe_setup(const KArgs& a, int64_t i, int sub) {
   const bool last = sub == T::NSUB - 1;
   const int g0 = e.grasp[0];
   int nc = 0;
-  if (!sub_setup_lean<T>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc)) { a.form[i] = XARM_FORM_HEAVY; return true; }
+  ArmDyn<typename T::MD> D[1];
+  if (!sub_setup_lean<T>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc, D)) {
+    a.form[i] = XARM_FORM_HEAVY;
+    dyn_store<T>(D[0], a.scratch, a.n, i);  // the heavy path continues from this dynamics pass
+    return true;
+  }
   float* s = a.scratch;
   ar_store<T>(AR, s, a.n, i); s += (int64_t)pipe_ar_words<T>() * a.n;
   sb_store<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;

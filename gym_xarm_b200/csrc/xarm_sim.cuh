@@ -769,13 +769,19 @@ XD void arm_rows(const Env<T>& e, const ArmDyn<typename T::MD>* D, float door_qd
 
 // collide -> unconstrained velocities -> rows.  Returns which solver form applies.
 template <class T>
-XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Contacts<T>& C, SubBase<T>& B, ManifoldIn& MI) {
+XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Contacts<T>& C, SubBase<T>& B, ManifoldIn& MI,
+                 const ArmDyn<typename T::MD>* Dpre = nullptr) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1, NT = N * (N + 1) / 2;
   const float h = (float)T::H;
   ArmDyn<MD> D[NA];
+  if (Dpre) {  // the dynamics pass of this substep was already made (lean setup of the pipeline)
 #pragma unroll
-  for (int a = 0; a < NA; a++) arm_dynamics<T>(a, e.arm[a], apply_damping, D[a]);
+    for (int a = 0; a < NA; a++) D[a] = Dpre[a];
+  } else {
+#pragma unroll
+    for (int a = 0; a < NA; a++) arm_dynamics<T>(a, e.arm[a], apply_damping, D[a]);
+  }
 
   // ---- 1. collision detection on the current poses (fixed pair order, Appendix G)
   C.nc = 0; C.nac = 0; C.npair = 0;
@@ -985,11 +991,11 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
 // the light form (the caller then takes the generic path: sub_setup with a Contacts record); true with nc = number of
 // manifold points otherwise.  Row arithmetic = sub_setup's row loop (setupMultiBodyContactConstraint).
 template <class T>
-XD bool sub_setup_lean(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, SubBase<T>& B, ManifoldIn& MI, int& nc_out) {
+XD bool sub_setup_lean(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, SubBase<T>& B, ManifoldIn& MI, int& nc_out,
+                       ArmDyn<typename T::MD>* D) {  // D[1]: the dynamics pass, also valid when the result is false
   using MD = typename T::MD;
   static_assert(T::NARM == 1 && !T::HAS_DOOR && T::NOBJ <= 1, "lean setup: one arm, no door, at most one object");
   const float h = (float)T::H;
-  ArmDyn<MD> D[1];
   arm_dynamics<T>(0, e.arm[0], apply_damping, D[0]);
   nc_out = 0;
   if (T::NOBJ == 1) {
@@ -1461,7 +1467,8 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
   ManifoldIn MI;
   if constexpr (task_has_light<T>()) {
     int nc = 0;
-    if (sub_setup_lean<T>(e, apply_damping, last, AR, B, MI, nc)) {
+    ArmDyn<typename T::MD> D[1];
+    if (sub_setup_lean<T>(e, apply_damping, last, AR, B, MI, nc, D)) {
       float mrows[XARM_MROW_WORDS];
       sub_solve_light<T>(AR, nc, MI, mrows, 1, S);
       sub_integrate<T>(e, B, S);

@@ -5,7 +5,7 @@ usage: ncu_lines.py <report.ncu-rep> <lib.so> <kernel-substring> [launch-id]"""
 import collections, csv, os, re, subprocess, sys, tempfile
 rep, lib, pat = sys.argv[1:4]
 lid = sys.argv[4] if len(sys.argv) > 4 else "0"
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-id", f":::{lid}"] if len(sys.argv) > 4 else []), capture_output=True, text=True).stdout.splitlines()
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-id", f":::{lid}"] if lid != "0" else []), capture_output=True, text=True).stdout.splitlines()
 hdr_i = next(i for i, l in enumerate(out) if l.startswith('"Address"'))
 print(out[0][:120])
 rows = list(csv.DictReader(out[hdr_i:]))
@@ -36,5 +36,19 @@ for off, (smp, ins, src) in per_off.items():
     k = line_of.get(off, "?")
     agg[k][0] += smp; agg[k][1] += ins; tot_s += smp; tot_i += ins
 print(f"total samples {tot_s}, warp-instructions {tot_i}, matched offsets {sum(1 for o in per_off if o in line_of)}/{len(per_off)}")
+ranges = [a for a in sys.argv[5:] if ":" in a]   # file.cuh:name:lo-hi -> aggregate by source range
+if ranges:
+    tot = collections.defaultdict(lambda: [0, 0])
+    for k, (smp, ins) in agg.items():
+        f, _, ln = k.partition(":")
+        name = f
+        for r in ranges:
+            rf, rn, rr = r.split(":"); lo, hi = map(int, rr.split("-"))
+            if f == rf and ln.isdigit() and lo <= int(ln) <= hi:
+                name = rn
+        tot[name][0] += smp; tot[name][1] += ins
+    for k, (smp, ins) in sorted(tot.items(), key=lambda kv: -kv[1][0]):
+        print(f"[{k:26s}] samples {smp:7d} ({100*smp/max(tot_s,1):5.1f}%)  inst {ins:9d} ({100*ins/max(tot_i,1):5.1f}%)")
+    sys.exit(0)
 for k, (smp, ins) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
     print(f"{k:28s} samples {smp:7d} ({100*smp/max(tot_s,1):5.1f}%)  inst {ins:9d} ({100*ins/max(tot_i,1):5.1f}%)")
