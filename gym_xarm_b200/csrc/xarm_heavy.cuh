@@ -275,15 +275,12 @@ __device__ __forceinline__ void heavy_solve(const ArmRows<T>& AR, int nc, float*
   SOLVER_LOCALS_FROM(AR)
   const float4* rows4 = reinterpret_cast<const float4*>(smem);
   V3 dv = v3(0, 0, 0), dw = v3(0, 0, 0);
-  const bool any_lim = (lim_lo[0] | lim_hi[0]) != 0u;
   for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
     bool resid_bad = false;
     if (it & 1) {
-      if (any_lim) ARM_LIMITS_FWD(0)
-      ARM_MOTORS_FWD(0) GEAR_ROW(0)
+      ARM_LIMITS_FWD(0) ARM_MOTORS_FWD(0) GEAR_ROW(0)
     } else {
-      GEAR_ROW(0) ARM_MOTORS_BWD(0)
-      if (any_lim) ARM_LIMITS_BWD(0)
+      GEAR_ROW(0) ARM_MOTORS_BWD(0) ARM_LIMITS_BWD(0)
     }
     // ---- normal rows
     for (int c = 0; c < nc; c++) {
@@ -353,13 +350,13 @@ __device__ __forceinline__ void heavy_substep(Env<T>& e, bool apply_damping, boo
 // thread t of the rows kernel: generic setup of heavy env heavy_list[t] -> its record; grasp flags of the last pass
 template <class T>
 __device__ __forceinline__ void heavy_rows_body(const KArgs& a, int t, int sub, float* __restrict__ hrec) {
-  const int64_t i = a.heavy_list[t];
+  const int64_t i = a.heavy_list[a.heavy_dir * t];
   Env<T> e;
   env_load<T>(e, a.state, a.n, i);
   const bool last = sub == T::NSUB - 1;
   ArmDyn<typename T::MD> D[1];
   dyn_load<T>(D[0], a.scratch, a.n, i);
-  heavy_rows_record<T>(e, T::DAMP_EACH || sub == 0, last, hrec + (size_t)t * HeavyRec<T>::WORDS, D);
+  heavy_rows_record<T>(e, T::DAMP_EACH || sub == 0, last, hrec + (size_t)(a.heavy_dir > 0 ? t : a.n - 1 - t) * HeavyRec<T>::WORDS, D);
   if (last) {
     const int w = state_words<T>() - 2;
     a.state[(int64_t)w * a.n + i] = e.grasp[0] ? 1.f : 0.f;
@@ -373,7 +370,7 @@ __device__ __forceinline__ void heavy_solve_body(const KArgs& a, int t, bool val
   using R = HeavyRec<T>;
   float* sapp = srec + R::WORDS;
   if (valid) {
-    const float* rec = hrec + (size_t)t * R::WORDS;
+    const float* rec = hrec + (size_t)(a.heavy_dir > 0 ? t : a.n - 1 - t) * R::WORDS;
     const int words = R::HDR + (int)rec[R::NC] * 3 * R::ROW;
     for (int w = l; w < words; w += 16) srec[w] = rec[w];
   } else {
@@ -385,7 +382,7 @@ __device__ __forceinline__ void heavy_solve_body(const KArgs& a, int t, bool val
   const float dvx = __shfl_sync(0xffffffffu, u, 9, 16), dvy = __shfl_sync(0xffffffffu, u, 10, 16), dvz = __shfl_sync(0xffffffffu, u, 11, 16);
   const float dwx = __shfl_sync(0xffffffffu, u, 12, 16), dwy = __shfl_sync(0xffffffffu, u, 13, 16), dwz = __shfl_sync(0xffffffffu, u, 14, 16);
   if (valid) {
-    const int64_t i = a.heavy_list[t], n = a.n;
+    const int64_t i = a.heavy_list[a.heavy_dir * t], n = a.n;
     float* st = a.state;
     if (l < R::N) {  // joints: word l = q, word N + l = qd
       const float qd = srec[R::QDU + l] + u;

@@ -17,14 +17,15 @@ struct KArgs {
   // step pipeline (xarm_pipeline.cuh)
   float* scratch;        // [pipe_scratch_words][N] rows of the current substep
   int* form;             // [N] light / heavy classification of the current substep (+ manifold point count)
-  int* heavy_list;       // [N] envs the setup kernel classified as heavy
+  int* heavy_list;       // [N] envs the setup kernel classified as heavy: entry t at heavy_list[heavy_dir * t]
+  int heavy_dir;         // +1: the list grows up from heavy_list; -1: down from it (the two concurrent branches of a step share one array)
   int* heavy_count;      // [XARM_PIPE_COUNTERS] one counter per simulate() pass and substep (zeroed by k_pipe_begin)
   int* rng_draw;         // [N] Philox draw counter carried from the placement stage of a reset to its goal stage
   const int* list;       // optional: thread t works on env list[t] (auto-reset tail); NULL = identity
   const int* list_count;
 };
 #define XARM_MAX_SUBSTEPS 32
-#define XARM_PIPE_PASSES 8   /* simulate() passes of one xarm_step: the step itself + up to 6 of the auto-reset tail */
+#define XARM_PIPE_PASSES 16  /* simulate() passes of one xarm_step: per branch the step itself + up to 6 of the auto-reset tail */
 #define XARM_PIPE_COUNTERS (XARM_PIPE_PASSES * XARM_MAX_SUBSTEPS)
 struct StepStats {
   float eps, ret, len, suc, div;

@@ -28,14 +28,14 @@ __device__ __forceinline__ int64_t pipe_env(const KArgs& a, int64_t t) {
   return t < a.n ? t : -1;
 }
 // warp-aggregated append of the flagged lanes' env ids to a list
-__device__ __forceinline__ void list_append(bool flag, int64_t i, int* list, int* count) {
+__device__ __forceinline__ void list_append(bool flag, int64_t i, int* list, int* count, int dir = 1) {
   const unsigned m = __ballot_sync(0xffffffffu, flag);
   if (!m) return;
   const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
   int base = 0;
   if (lane == leader) base = atomicAdd(count, __popc(m));
   base = __shfl_sync(0xffffffffu, base, leader);
-  if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = (int)i;
+  if (flag) list[dir * (base + __popc(m & ((1u << lane) - 1u)))] = (int)i;
 }
 
 template <class T>
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(128, 4) k_pipe_setup(KArgs a, int sub, int* he
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = pipe_env(a, t);
   const bool heavy = i >= 0 && pipe_setup<T>(a, i, sub);
-  list_append(heavy, i, a.heavy_list, heavy_count);
+  list_append(heavy, i, a.heavy_list, heavy_count, a.heavy_dir);
 }
 template <class T>
 __global__ void __launch_bounds__(128, 3) k_pipe_light(KArgs a) {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* 
   float* heavy_smem = reinterpret_cast<float*>(heavy_smem4);
   const int count = *heavy_count;
   for (int t = blockIdx.x * 32 + threadIdx.x; t < count; t += gridDim.x * 32) {
-    const int64_t i = a.heavy_list[t];
+    const int64_t i = a.heavy_list[a.heavy_dir * t];
     if constexpr (task_has_heavy_rows<T>()) {  // solver rows as float4 records (xarm_heavy.cuh)
       Env<T> e;
       env_load<T>(e, a.state, a.n, i);
@@ -152,11 +152,18 @@ __global__ void __launch_bounds__(128) k_pipe_reset_stage(KArgs a, int stage, in
   const int64_t i = pipe_env(a, t);
   if (i >= 0) pipe_reset_stage<T>(a, i, stage, clear_return != 0);
 }
-// zero the per-launch counters of one env step (heavy lists of every pass and substep, the reset list)
-__global__ void k_pipe_begin(KArgs a) {
-  const int t = threadIdx.x;
-  if (t < XARM_PIPE_COUNTERS) a.heavy_count[t] = 0;
-  if (t == 0) *a.reset_count = 0;
+// zero the per-launch counters of one env step (heavy lists of every pass and substep, the reset / branch lists)
+__global__ void k_pipe_begin(KArgs a, int* counters, int n_counters) {
+  for (int t = threadIdx.x; t < n_counters; t += blockDim.x) counters[t] = 0;
+}
+// envs that may finish in the coming step -> early list, the others -> main list (order-preserving per warp)
+template <class T>
+__global__ void __launch_bounds__(128) k_pipe_split(KArgs a, int* list_e, int* count_e, int* list_m, int* count_m) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < a.n;
+  const bool early = valid && pipe_may_finish<T>(a, i);
+  list_append(early, i, list_e, count_e);
+  list_append(valid && !early, i, list_m, count_m);
 }
 // list = the envs selected by a mask (xarm_reset)
 __global__ void __launch_bounds__(128) k_mask_to_list(KArgs a, const uint8_t* mask) {
@@ -190,7 +197,12 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 // fork/join plumbing of the pipeline: a side stream for the heavy kernels and a pool of dependency events
 struct PipeCtx {
-  cudaStream_t side = nullptr;
+  cudaStream_t side = nullptr;          // heavy kernels of the main branch
+  cudaStream_t e_main = nullptr, e_side = nullptr;  // the early branch (high priority): envs that may finish this step
+  int *list_e = nullptr, *list_m = nullptr, *reset_list_e = nullptr;   // [N] each
+  int *count_e = nullptr, *count_m = nullptr, *reset_count_e = nullptr, *counters = nullptr;
+  int n_counters = 0;
+  bool split = true;                    // XARM_NO_SPLIT=1: one branch (development A/B)
   unsigned heavy_grid = 148;  // persistent heavy kernels: a few blocks per SM (set from the device in xarm_create)
   float* hrec = nullptr;      // [N][HeavyRec::WORDS] records of the cooperative heavy solver
   std::vector<cudaEvent_t> ev;
@@ -265,7 +277,7 @@ struct OpsT {
   static void init(const KArgs& a, cudaStream_t s) { k_init<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
   static void obs(const KArgs& a, cudaStream_t s) { k_obs<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
   // p.stepSimulation(): NSUB x { setup -> light || heavy }
-  static void simulate(PipeCtx& c, const KArgs& a, int pass, cudaStream_t s) {
+  static void simulate(PipeCtx& c, const KArgs& a, int pass, cudaStream_t s, cudaStream_t sh) {
     const dim3 g = grid(a.n);
     for (int sub = 0; sub < T::NSUB; sub++) {
       if constexpr (!HAS_LIGHT) {
@@ -277,19 +289,19 @@ struct OpsT {
         c.end(s);
         cudaEvent_t fork = c.next(), join = c.next();
         cudaEventRecord(fork, s);
-        cudaStreamWaitEvent(c.side, fork, 0);
+        cudaStreamWaitEvent(sh, fork, 0);
         if constexpr (task_has_heavy_rows<T>()) {
-          c.begin("heavy_rows", c.side);
-          k_heavy_rows<T><<<c.heavy_grid * 4, 64, 0, c.side>>>(a, sub, hc, c.hrec);
-          c.end(c.side);
-          c.begin("heavy_solve", c.side);
-          k_heavy_solve<T><<<c.heavy_grid * 3, 128, coop_smem_bytes(), c.side>>>(a, hc, c.hrec);
-          c.end(c.side);
+          c.begin("heavy_rows", sh);
+          k_heavy_rows<T><<<c.heavy_grid * 4, 64, 0, sh>>>(a, sub, hc, c.hrec);
+          c.end(sh);
+          c.begin("heavy_solve", sh);
+          k_heavy_solve<T><<<c.heavy_grid * 3, 128, coop_smem_bytes(), sh>>>(a, hc, c.hrec);
+          c.end(sh);
           g_launches++;
         } else {
-          k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), c.side>>>(a, sub, hc);
+          k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), sh>>>(a, sub, hc);
         }
-        cudaEventRecord(join, c.side);
+        cudaEventRecord(join, sh);
         c.begin("light", s);
         k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(a);
         c.end(s);
@@ -299,52 +311,82 @@ struct OpsT {
     }
   }
   // Env.reset() of the envs in r.list (all envs when r.list is NULL)
-  static void reset_passes(PipeCtx& c, const KArgs& r, int pass, int clear_return, cudaStream_t s) {
+  static void reset_passes(PipeCtx& c, const KArgs& r, int pass, int clear_return, cudaStream_t s, cudaStream_t sh) {
     const dim3 g = grid(r.n);
     if (reset_has_servo<T>())
       for (int rep = 0; rep < 5; rep++) {
         c.begin("reset_stage", s);
         k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, rep, 0); g_launches++;
         c.end(s);
-        simulate(c, r, pass++, s);
+        simulate(c, r, pass++, s, sh);
       }
     k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, XARM_RESET_PLACE, 0); g_launches++;
-    simulate(c, r, pass++, s);
+    simulate(c, r, pass++, s, sh);
     k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, XARM_RESET_FINISH, clear_return); g_launches++;
+  }
+  // one branch of a step: _set_action, stepSimulation, outputs for the envs of a.list (all envs when NULL), then
+  // Env.reset() of the envs that finished (VecEnv auto-reset) through the same pipeline
+  static void step_branch(PipeCtx& c, const KArgs& a, int pass, bool tail, cudaStream_t s, cudaStream_t sh) {
+    const dim3 g = grid(a.n);
+    c.cur_tail = tail ? 1 : 0;
+    c.begin("action", s);
+    k_pipe_action<T><<<g, 128, 0, s>>>(a);
+    c.end(s);
+    simulate(c, a, pass, s, sh);
+    c.begin("finish", s);
+    k_pipe_finish<T><<<g, 128, 0, s>>>(a);
+    c.end(s);
+    g_launches += 2;
+    if (a.auto_reset && tail) {
+      c.cur_tail = 1;
+      KArgs r = a;
+      r.list = a.reset_list; r.list_count = a.reset_count;
+      reset_passes(c, r, pass + 1, 0, s, sh);
+    }
   }
   static void step(PipeCtx& c, const KArgs& a0, cudaStream_t s) {
     static_assert(T::NSUB <= XARM_MAX_SUBSTEPS, "substep counters");
     KArgs a = a0;
-    a.list = nullptr; a.list_count = nullptr;
+    a.list = nullptr; a.list_count = nullptr; a.heavy_dir = 1;
     c.next_ev = 0;
-    const dim3 g = grid(a.n);
-    k_pipe_begin<<<1, XARM_PIPE_COUNTERS, 0, s>>>(a);
-    c.cur_tail = 0;
-    c.begin("action", s);
-    k_pipe_action<T><<<g, 128, 0, s>>>(a);
-    c.end(s);
-    simulate(c, a, 0, s);
-    c.begin("finish", s);
-    k_pipe_finish<T><<<g, 128, 0, s>>>(a);
-    c.end(s);
-    c.cur_tail = 1;
-    g_launches += 3;
-    if (a.auto_reset) {  // VecEnv auto-reset: the finished envs (compacted list) run Env.reset() through the same pipeline
-      KArgs r = a;
-      r.list = a.reset_list; r.list_count = a.reset_count;
-      reset_passes(c, r, 1, 0, s);
+    k_pipe_begin<<<1, 256, 0, s>>>(a, c.counters, c.n_counters); g_launches++;
+    if (!a.auto_reset || !c.split) {  // one branch: every env, then the auto-reset tail
+      step_branch(c, a, 0, true, s, c.side);
+      return;
     }
+    // Two concurrent branches.  Early: the envs that may finish in this step (time limit, success within reach) and
+    // their auto-reset passes - few envs, latency bound (6 more stepSimulation passes), high-priority streams.  Main:
+    // all the other envs - throughput bound.  The early branch hides the reset latency behind the main branch.
+    k_pipe_split<T><<<grid(a.n), 128, 0, s>>>(a, c.list_e, c.count_e, c.list_m, c.count_m); g_launches++;
+    cudaEvent_t fork = c.next(), join = c.next();
+    cudaEventRecord(fork, s);
+    cudaStreamWaitEvent(c.e_main, fork, 0);
+    KArgs e = a;
+    e.list = c.list_e; e.list_count = c.count_e;
+    e.heavy_list = a.heavy_list + (a.n - 1); e.heavy_dir = -1;
+    e.reset_list = c.reset_list_e; e.reset_count = c.reset_count_e;
+    step_branch(c, e, XARM_PIPE_PASSES / 2, true, c.e_main, c.e_side);
+    cudaEventRecord(join, c.e_main);
+    KArgs m = a;
+    m.list = c.list_m; m.list_count = c.count_m;
+    step_branch(c, m, 0, false, s, c.side);
+    cudaStreamWaitEvent(s, join, 0);
+    // late tail: envs of the main branch that finished although the predictor said no (normally none)
+    c.cur_tail = 1;
+    KArgs r = a;
+    r.list = a.reset_list; r.list_count = a.reset_count;
+    reset_passes(c, r, 1, 0, s, c.side);
   }
   static void reset(PipeCtx& c, const KArgs& a0, const uint8_t* mask, cudaStream_t s) {
     KArgs a = a0;
-    a.list = nullptr; a.list_count = nullptr;
+    a.list = nullptr; a.list_count = nullptr; a.heavy_dir = 1;
     c.next_ev = 0;
-    k_pipe_begin<<<1, XARM_PIPE_COUNTERS, 0, s>>>(a); g_launches++;
+    k_pipe_begin<<<1, 256, 0, s>>>(a, c.counters, c.n_counters); g_launches++;
     if (mask) {
       k_mask_to_list<<<grid(a.n), 128, 0, s>>>(a, mask); g_launches++;
       a.list = a.reset_list; a.list_count = a.reset_count;
     }
-    reset_passes(c, a, 0, 1, s);
+    reset_passes(c, a, 0, 1, s, c.side);
   }
   static Ops make() { Ops o = {init, step, reset, obs, prepare, hrec_words, T::A, T::O, T::G, state_words<T>(), pipe_scratch_words<T>()}; return o; }
 };
@@ -448,7 +490,11 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   h->k.rc.seed = c.seed; h->k.rc.env_index_base = c.env_index_base; h->k.rc.reward_type = c.reward_type;
   h->k.rc.goal_shape = c.goal_shape; h->k.rc.max_episode_steps = c.max_episode_steps;
   h->k.rc.init_grasp_rate = c.init_grasp_rate; h->k.rc.goal_ground_rate = c.goal_ground_rate; h->k.rc.same_side_rate = c.same_side_rate;
-  const size_t n_int = (size_t)4 * n + XARM_PIPE_COUNTERS + 1;
+  // int scratch: reset list | heavy list | form | rng draw | early list | main list | early reset list | counters
+  const int n_counters = XARM_PIPE_COUNTERS + 4;
+  const size_t n_int = (size_t)7 * n + n_counters;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   cudaError_t e1 = cudaMalloc(&h->k.state, sizeof(float) * ops.S * n);
   cudaError_t e2 = cudaMalloc(&h->k.ep_return, sizeof(float) * n);
   cudaError_t e3 = cudaMalloc(&h->k.need_reset, n);
@@ -456,9 +502,13 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   cudaError_t e5 = cudaMalloc(&h->k.reset_list, sizeof(int) * n_int);
   cudaError_t e6 = cudaMalloc(&h->k.scratch, sizeof(float) * ops.scratch_words * n);
   cudaError_t e7 = cudaStreamCreateWithFlags(&h->pipe.side, cudaStreamNonBlocking);
+  if (e7 == cudaSuccess) e7 = cudaStreamCreateWithPriority(&h->pipe.e_main, cudaStreamNonBlocking, prio_hi);
+  if (e7 == cudaSuccess) e7 = cudaStreamCreateWithPriority(&h->pipe.e_side, cudaStreamNonBlocking, prio_hi);
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
     cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.reset_list); cudaFree(h->k.scratch);
     if (h->pipe.side) cudaStreamDestroy(h->pipe.side);
+    if (h->pipe.e_main) cudaStreamDestroy(h->pipe.e_main);
+    if (h->pipe.e_side) cudaStreamDestroy(h->pipe.e_side);
     delete h; cudaGetLastError();
     return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc failed");
   }
@@ -473,8 +523,13 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) { cudaGetLastError(); return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed"); }
   }
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
+  h->pipe.split = getenv("XARM_NO_SPLIT") == nullptr;
   h->k.heavy_list = h->k.reset_list + n; h->k.form = h->k.reset_list + 2 * n; h->k.rng_draw = h->k.reset_list + 3 * n;
-  h->k.heavy_count = h->k.reset_list + 4 * n; h->k.reset_count = h->k.heavy_count + XARM_PIPE_COUNTERS;
+  h->pipe.list_e = h->k.reset_list + 4 * n; h->pipe.list_m = h->k.reset_list + 5 * n; h->pipe.reset_list_e = h->k.reset_list + 6 * n;
+  h->pipe.counters = h->k.reset_list + 7 * n; h->pipe.n_counters = n_counters;
+  h->k.heavy_count = h->pipe.counters; h->k.reset_count = h->pipe.counters + XARM_PIPE_COUNTERS;
+  h->pipe.reset_count_e = h->k.reset_count + 1; h->pipe.count_e = h->k.reset_count + 2; h->pipe.count_m = h->k.reset_count + 3;
+  h->k.heavy_dir = 1;
   CUDA_TRY(cudaMemset(h->k.reset_list, 0, sizeof(int) * n_int));
   CUDA_TRY(cudaMemset(h->k.stats, 0, sizeof(double) * 5));
   ops.init(h->k, 0);
@@ -492,6 +547,8 @@ int xarm_destroy(XarmHandle* h) {
   cudaFree(h->pipe.hrec);
   for (cudaEvent_t e : h->pipe.ev) cudaEventDestroy(e);
   if (h->pipe.side) cudaStreamDestroy(h->pipe.side);
+  if (h->pipe.e_main) cudaStreamDestroy(h->pipe.e_main);
+  if (h->pipe.e_side) cudaStreamDestroy(h->pipe.e_side);
   cudaFree(h->d_io); cudaFree(h->d_flags);
   if (h->h_io) cudaFreeHost(h->h_io);
   if (h->h_flags) cudaFreeHost(h->h_flags);

@@ -277,6 +277,37 @@ XD bool pipe_finish(const KArgs& a, int64_t i, StepStats& st) {
   return so.done && a.auto_reset;
 }
 
+// ---- which envs may finish in the coming step (time limit reached, or success within reach): the "early" branch of
+// xarm_step runs them first, so that their auto-reset passes overlap the step of all the other envs.  A wrong "no"
+// is only slower (the env is reset by the late tail after both branches), never wrong.
+template <class T>
+XD bool pipe_may_finish(const KArgs& a, int64_t i) {
+  if (!a.auto_reset) return false;
+  const int64_t n = a.n;
+  const int w_goal = state_words<T>() - 5 - T::G;
+  const int step_count = (int)a.state[(int64_t)(w_goal + T::G) * n + i];
+  const int limit = a.rc.max_episode_steps > 0 ? a.rc.max_episode_steps : T::MAX_STEPS;
+  if (step_count + 1 >= limit) return true;
+  if (T::TASK == XARM_TASK_PICK_AND_PLACE || T::TASK == XARM_TASK_HANDOVER) {  // success ends the episode
+    const int w_obj = T::NARM * 3 * T::MD::N;
+    bool all_near = true;
+    for (int o = 0; o < T::NOBJ; o++) {
+      float d2 = 0.f, v2 = 0.f;
+      for (int c = 0; c < 3; c++) {
+        const float d = a.state[(int64_t)(w_obj + 13 * o + c) * n + i] - a.state[(int64_t)(w_goal + 3 * o + c) * n + i];
+        const float v = a.state[(int64_t)(w_obj + 13 * o + 7 + c) * n + i];
+        d2 += d * d; v2 += v * v;
+      }
+      // an object at rest that no gripper touches stays where it is; otherwise it can travel with the gripper
+      const bool moving = v2 > 1e-4f || (a.form[i] & 0xff) != XARM_FORM_LIGHT;
+      const float reach = T::THRESHOLD + (moving ? 0.15f : 0.02f);
+      all_near = all_near && d2 < reach * reach;
+    }
+    return all_near;
+  }
+  return false;
+}
+
 // ---- Env.reset() through the same pipeline (auto-reset tail and xarm_reset): env_reset() cut at its stepSimulation
 // calls.  Stages: 0..4 = the five servo repetitions of PickAndPlace / Handover (IK to the start pose, finger command;
 // stage 0 also opens the episode), XARM_RESET_PLACE = object placement (teleport tasks: also joint teleport and episode

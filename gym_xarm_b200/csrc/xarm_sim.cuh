@@ -1135,12 +1135,32 @@ XD bool sub_setup_lean(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR,
 #define ARM_MOTOR_ROW_(a, i) { const float hi_ = (i) < 7 ? hi_arm : hi_fin; UNIT_ROW(a, i, 1.f, mrhs[a][i], -hi_, hi_, mapp[a][i]) }
 #define ARM_MOTORS_FWD(a) { _Pragma("unroll") for (int i_ = 0; i_ < N; i_++) ARM_MOTOR_ROW_(a, i_) }
 #define ARM_MOTORS_BWD(a) { _Pragma("unroll") for (int i_ = N - 1; i_ >= 0; i_--) ARM_MOTOR_ROW_(a, i_) }
-// the joint-limit rows of arm a (only the violated limits have a row)
+// the joint-limit rows of arm a (only the violated limits have a row).  Arm joints (dof < 7) rarely sit on a limit:
+// their rows are behind a branch.  Gripper dofs often do (a finger driven to its stop, Reach's knuckles): their rows are
+// always executed, with a zero impulse when the limit is not violated - no warp divergence in the batched kernels.
 #define ARM_LIMIT_ROW_(a, i)                                                                                     \
   { if (lim_lo[a] >> (i) & 1) UNIT_ROW(a, i, 1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i])                           \
     else if (lim_hi[a] >> (i) & 1) UNIT_ROW(a, i, -1.f, lrhs[a][i], 0.f, hi_lim, lapp[a][i]) }
-#define ARM_LIMITS_FWD(a) { _Pragma("unroll") for (int i_ = 0; i_ < N; i_++) ARM_LIMIT_ROW_(a, i_) }
-#define ARM_LIMITS_BWD(a) { _Pragma("unroll") for (int i_ = N - 1; i_ >= 0; i_--) ARM_LIMIT_ROW_(a, i_) }
+#define ARM_LIMIT_ROW_PRED_(a, i)                                                                                \
+  {                                                                                                              \
+    const bool act_ = ((lim_lo[a] | lim_hi[a]) >> (i) & 1) != 0;                                                 \
+    const float sg_ = (lim_hi[a] >> (i) & 1) ? -1.f : 1.f;                                                       \
+    float delta = lrhs[a][i] - sg_ * dqd[a][i] * iden[a][i];                                                     \
+    const float sum = lapp[a][i] + delta;                                                                        \
+    const float sumc = fminf(fmaxf(sum, 0.f), hi_lim);                                                           \
+    delta = (sumc == sum) ? delta : sumc - lapp[a][i];                                                           \
+    delta = act_ ? delta : 0.f;                                                                                  \
+    lapp[a][i] = act_ ? sumc : lapp[a][i];                                                                       \
+    const float sd = sg_ * delta;                                                                                \
+    _Pragma("unroll") for (int k_ = 0; k_ < N; k_++) dqd[a][k_] += Mi[a][tri(k_, i)] * sd;                       \
+    resid_bad = resid_bad || fabsf(delta) > sthr_ * iden[a][i];                                                  \
+  }
+#define ARM_LIMITS_FWD(a)                                                                                        \
+  { if (((lim_lo[a] | lim_hi[a]) & 0x7fu) != 0u) { _Pragma("unroll") for (int i_ = 0; i_ < 7; i_++) ARM_LIMIT_ROW_(a, i_) } \
+    _Pragma("unroll") for (int i_ = 7; i_ < N; i_++) ARM_LIMIT_ROW_PRED_(a, i_) }
+#define ARM_LIMITS_BWD(a)                                                                                        \
+  { _Pragma("unroll") for (int i_ = N - 1; i_ >= 7; i_--) ARM_LIMIT_ROW_PRED_(a, i_)                             \
+    if (((lim_lo[a] | lim_hi[a]) & 0x7fu) != 0u) { _Pragma("unroll") for (int i_ = 6; i_ >= 0; i_--) ARM_LIMIT_ROW_(a, i_) } }
 #define SOLVER_LOCALS_FROM(AR)                                                                                   \
   float Mi[NA][NT], iden[NA][N], dqd[NA][N], mrhs[NA][N], mapp[NA][N], lrhs[NA][N], lapp[NA][N];                 \
   uint32_t lim_lo[NA], lim_hi[NA];                                                                               \
@@ -1237,17 +1257,14 @@ XD void sub_solve_light(const ArmRows<T>& AR, int nc, const ManifoldIn& MI, floa
 #pragma unroll
   for (int c = 0; c < 4; c++) { an[c] = 0.f; a1[c] = 0.f; a2[c] = 0.f; }
   V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
-  const bool any_lim = (lim_lo[0] | lim_hi[0]) != 0u;
 #define MR(c, k) mrows[(size_t)(24 * (c) + (k)) * stride]
 #define MRV(c, k) v3(MR(c, k), MR(c, (k) + 1), MR(c, (k) + 2))
   for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
     bool resid_bad = false;
     if (it & 1) {
-      if (any_lim) ARM_LIMITS_FWD(0)
-      ARM_MOTORS_FWD(0) GEAR_ROW(0)
+      ARM_LIMITS_FWD(0) ARM_MOTORS_FWD(0) GEAR_ROW(0)
     } else {
-      GEAR_ROW(0) ARM_MOTORS_BWD(0)
-      if (any_lim) ARM_LIMITS_BWD(0)
+      GEAR_ROW(0) ARM_MOTORS_BWD(0) ARM_LIMITS_BWD(0)
     }
     if (nc > 0) {
 #pragma unroll
@@ -1317,16 +1334,14 @@ XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, in
     if (it & 1) {
 #pragma unroll
       for (int a = 0; a < NA; a++) {
-        if ((lim_lo[a] | lim_hi[a]) != 0u) ARM_LIMITS_FWD(a)
-        ARM_MOTORS_FWD(a) GEAR_ROW(a)
+        ARM_LIMITS_FWD(a) ARM_MOTORS_FWD(a) GEAR_ROW(a)
       }
       if (T::HAS_DOOR) { DOOR_LIMIT_ROW() DOOR_MOTOR_ROW() }
     } else {
       if (T::HAS_DOOR) { DOOR_MOTOR_ROW() DOOR_LIMIT_ROW() }
 #pragma unroll
       for (int a = NA - 1; a >= 0; a--) {
-        GEAR_ROW(a) ARM_MOTORS_BWD(a)
-        if ((lim_lo[a] | lim_hi[a]) != 0u) ARM_LIMITS_BWD(a)
+        GEAR_ROW(a) ARM_MOTORS_BWD(a) ARM_LIMITS_BWD(a)
       }
     }
     // ---- normal rows

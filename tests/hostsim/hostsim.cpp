@@ -127,8 +127,8 @@ HS* hs_create(int task, int reward_type, int num_obj, int goal_shape, double ini
   memset(h->stats, 0, sizeof(h->stats));
   KArgs& k = h->k; memset(&k, 0, sizeof(k));
   k.state = h->state.data(); k.ep_return = h->ep_return.data(); k.need_reset = h->need_reset.data(); k.stats = h->stats;
-  k.n = n; k.auto_reset = cfg->auto_reset;
-  h->scratch.assign((size_t)n * o.scratch_words, 0.f); h->ints.assign((size_t)4 * n + XARM_PIPE_COUNTERS + 1, 0);
+  k.n = n; k.auto_reset = cfg->auto_reset; k.heavy_dir = 1;
+  h->scratch.assign((size_t)n * o.scratch_words, 0.f); h->ints.assign((size_t)4 * n + XARM_PIPE_COUNTERS + 4, 0);
   k.scratch = h->scratch.data(); k.reset_list = h->ints.data(); k.heavy_list = k.reset_list + n; k.form = k.reset_list + 2 * n;
   k.rng_draw = k.reset_list + 3 * n; k.heavy_count = k.reset_list + 4 * n; k.reset_count = k.heavy_count + XARM_PIPE_COUNTERS;
   k.rc.seed = cfg->seed; k.rc.env_index_base = cfg->env_index_base; k.rc.reward_type = cfg->reward_type;
