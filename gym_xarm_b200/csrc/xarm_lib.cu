@@ -27,6 +27,15 @@ __device__ __forceinline__ int64_t pipe_env(const KArgs& a, int64_t t) {
   if (a.list) return t < (int64_t)*a.list_count ? (int64_t)a.list[t] : -1;
   return t < a.n ? t : -1;
 }
+// Launches are persistent-style: the grid may be smaller than the work (xarm_step keeps a few block slots per SM free
+// for its latency-bound early branch), so every kernel walks its envs with a block-stride loop.  Trip counts are
+// uniform per block (the bodies use warp-wide ballots).
+#define PIPE_FOR_EACH(a, t, i)                                                                                   \
+  for (int64_t bound_ = (a).list ? (int64_t)*(a).list_count : (a).n, base_ = (int64_t)blockIdx.x * blockDim.x;  \
+       base_ < bound_; base_ += (int64_t)gridDim.x * blockDim.x)                                                 \
+    if (const int64_t t = base_ + threadIdx.x; true)                                                             \
+      if (const int64_t i = pipe_env(a, t); true)
+
 // warp-aggregated append of the flagged lanes' env ids to a list
 __device__ __forceinline__ void list_append(bool flag, int64_t i, int* list, int* count, int dir = 1) {
   const unsigned m = __ballot_sync(0xffffffffu, flag);
@@ -40,23 +49,19 @@ __device__ __forceinline__ void list_append(bool flag, int64_t i, int* list, int
 
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_action(KArgs a) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = pipe_env(a, t);
-  if (i >= 0) pipe_action<T>(a, i);
+  PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_action<T>(a, i); }
 }
 template <class T>
 __global__ void __launch_bounds__(128, 4) k_pipe_setup(KArgs a, int sub, int* heavy_count) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = pipe_env(a, t);
-  const bool heavy = i >= 0 && pipe_setup<T>(a, i, sub);
-  list_append(heavy, i, a.heavy_list, heavy_count, a.heavy_dir);
+  PIPE_FOR_EACH(a, t, i) {
+    const bool heavy = i >= 0 && pipe_setup<T>(a, i, sub);
+    list_append(heavy, i, a.heavy_list, heavy_count, a.heavy_dir);
+  }
 }
 template <class T>
-__global__ void __launch_bounds__(128, 3) k_pipe_light(KArgs a) {
+__global__ void __launch_bounds__(128, 4) k_pipe_light(KArgs a) {
   extern __shared__ float light_mrows[];  // [XARM_MROW_WORDS][128]: the manifold rows of this block's envs
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = pipe_env(a, t);
-  if (i >= 0) pipe_light<T>(a, i, light_mrows + threadIdx.x, 128);
+  PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_light<T>(a, i, light_mrows + threadIdx.x, 128); }
 }
 // Heavy envs of this substep.  One warp per block, a few blocks per SM at most: the contact rows of the generic solver
 // (Contacts<T>, ~6 KB per env) live in SHARED memory, one record per lane at an odd word stride (bank-conflict free).
@@ -115,42 +120,38 @@ __global__ void __launch_bounds__(128) k_heavy_solve(KArgs a, const int* heavy_c
 // tasks without a light form (two arms / door): every env takes the generic substep (rows in thread-local memory)
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_heavy_all(KArgs a, int sub) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = pipe_env(a, t);
-  if (i < 0) return;
-  Contacts<T> C;
-  pipe_heavy<T>(a, i, sub, C);
+  PIPE_FOR_EACH(a, t, i) {
+    if (i >= 0) { Contacts<T> C; pipe_heavy<T>(a, i, sub, C); }
+  }
 }
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_finish(KArgs a) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = pipe_env(a, t);
-  StepStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
-  const bool fin = i >= 0 && pipe_finish<T>(a, i, st);
-  list_append(fin, i, a.reset_list, a.reset_count);
-  // episode statistics (K8): warp-aggregate, one atomic per warp and counter
-  unsigned any = __ballot_sync(0xffffffffu, st.eps != 0.f || st.div != 0.f);
-  if (any) {
+  PIPE_FOR_EACH(a, t, i) {
+    StepStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool fin = i >= 0 && pipe_finish<T>(a, i, st);
+    list_append(fin, i, a.reset_list, a.reset_count);
+    // episode statistics (K8): warp-aggregate, one atomic per warp and counter
+    unsigned any = __ballot_sync(0xffffffffu, st.eps != 0.f || st.div != 0.f);
+    if (any) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      st.eps += __shfl_down_sync(0xffffffffu, st.eps, off);
-      st.ret += __shfl_down_sync(0xffffffffu, st.ret, off);
-      st.len += __shfl_down_sync(0xffffffffu, st.len, off);
-      st.suc += __shfl_down_sync(0xffffffffu, st.suc, off);
-      st.div += __shfl_down_sync(0xffffffffu, st.div, off);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&a.stats[0], (double)st.eps); atomicAdd(&a.stats[1], (double)st.ret); atomicAdd(&a.stats[2], (double)st.len);
-      atomicAdd(&a.stats[3], (double)st.suc);
-      if (st.div != 0.f) atomicAdd(&a.stats[4], (double)st.div);
+      for (int off = 16; off > 0; off >>= 1) {
+        st.eps += __shfl_down_sync(0xffffffffu, st.eps, off);
+        st.ret += __shfl_down_sync(0xffffffffu, st.ret, off);
+        st.len += __shfl_down_sync(0xffffffffu, st.len, off);
+        st.suc += __shfl_down_sync(0xffffffffu, st.suc, off);
+        st.div += __shfl_down_sync(0xffffffffu, st.div, off);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&a.stats[0], (double)st.eps); atomicAdd(&a.stats[1], (double)st.ret); atomicAdd(&a.stats[2], (double)st.len);
+        atomicAdd(&a.stats[3], (double)st.suc);
+        if (st.div != 0.f) atomicAdd(&a.stats[4], (double)st.div);
+      }
     }
   }
 }
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_reset_stage(KArgs a, int stage, int clear_return) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = pipe_env(a, t);
-  if (i >= 0) pipe_reset_stage<T>(a, i, stage, clear_return != 0);
+  PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_reset_stage<T>(a, i, stage, clear_return != 0); }
 }
 // zero the per-launch counters of one env step (heavy lists of every pass and substep, the reset / branch lists)
 __global__ void k_pipe_begin(KArgs a, int* counters, int n_counters) {
@@ -203,6 +204,7 @@ struct PipeCtx {
   int *count_e = nullptr, *count_m = nullptr, *reset_count_e = nullptr, *counters = nullptr;
   int n_counters = 0;
   bool split = true;                    // XARM_NO_SPLIT=1: one branch (development A/B)
+  int64_t max_blocks = 4 * 148 - 32;
   unsigned heavy_grid = 148;  // persistent heavy kernels: a few blocks per SM (set from the device in xarm_create)
   float* hrec = nullptr;      // [N][HeavyRec::WORDS] records of the cooperative heavy solver
   std::vector<cudaEvent_t> ev;
@@ -261,6 +263,9 @@ template <class T>
 struct OpsT {
   static constexpr bool HAS_LIGHT = task_has_light<T>();  // tasks whose envs can take the light solver form
   static dim3 grid(int64_t n) { return dim3((unsigned)((n + 127) / 128)); }
+  // persistent-style grid of the pipeline kernels: at most c.max_blocks (4 blocks of 128 threads x 128 registers fit an SM;
+  // a few slots per SM stay free so that the early branch never waits for a block slot)
+  static dim3 pgrid(const PipeCtx& c, int64_t n) { const int64_t b = (n + 127) / 128; return dim3((unsigned)(b < c.max_blocks ? b : c.max_blocks)); }
   static size_t heavy_smem_bytes() { return heavy_smem_bytes_of<T>(); }
   static size_t coop_smem_bytes() {
     if constexpr (task_has_heavy_rows<T>()) return (size_t)XARM_HEAVY_ENVS_PER_BLOCK * (HeavyRec<T>::WORDS + T::MAXC * 3) * sizeof(float);
@@ -277,8 +282,14 @@ struct OpsT {
   static void init(const KArgs& a, cudaStream_t s) { k_init<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
   static void obs(const KArgs& a, cudaStream_t s) { k_obs<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
   // p.stepSimulation(): NSUB x { setup -> light || heavy }
+  // sh != s: the heavy kernels run on sh next to k_pipe_light (fork / join); sh == s: one stream, heavy kernels first.
+  // The main branch of a split step uses one stream: its kernels fill the GPU anyway, and with a single kernel in
+  // flight at a time the block slots that pgrid() leaves free really stay free for the early branch.
   static void simulate(PipeCtx& c, const KArgs& a, int pass, cudaStream_t s, cudaStream_t sh) {
-    const dim3 g = grid(a.n);
+    const dim3 g = pgrid(c, a.n);
+    const bool fork_heavy = sh != s;
+    const unsigned rows_grid = fork_heavy ? c.heavy_grid * 4 : (unsigned)c.max_blocks;
+    const unsigned solve_grid = fork_heavy ? c.heavy_grid * 3 : (unsigned)(c.max_blocks * 3 / 4);
     for (int sub = 0; sub < T::NSUB; sub++) {
       if constexpr (!HAS_LIGHT) {
         k_pipe_heavy_all<T><<<g, 128, 0, s>>>(a, sub); g_launches++;
@@ -287,32 +298,36 @@ struct OpsT {
         c.begin("setup", s);
         k_pipe_setup<T><<<g, 128, 0, s>>>(a, sub, hc);
         c.end(s);
-        cudaEvent_t fork = c.next(), join = c.next();
-        cudaEventRecord(fork, s);
-        cudaStreamWaitEvent(sh, fork, 0);
+        cudaEvent_t join = nullptr;
+        if (fork_heavy) {
+          cudaEvent_t fork = c.next();
+          join = c.next();
+          cudaEventRecord(fork, s);
+          cudaStreamWaitEvent(sh, fork, 0);
+        }
         if constexpr (task_has_heavy_rows<T>()) {
           c.begin("heavy_rows", sh);
-          k_heavy_rows<T><<<c.heavy_grid * 4, 64, 0, sh>>>(a, sub, hc, c.hrec);
+          k_heavy_rows<T><<<rows_grid, 64, 0, sh>>>(a, sub, hc, c.hrec);
           c.end(sh);
           c.begin("heavy_solve", sh);
-          k_heavy_solve<T><<<c.heavy_grid * 3, 128, coop_smem_bytes(), sh>>>(a, hc, c.hrec);
+          k_heavy_solve<T><<<solve_grid, 128, coop_smem_bytes(), sh>>>(a, hc, c.hrec);
           c.end(sh);
           g_launches++;
         } else {
           k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), sh>>>(a, sub, hc);
         }
-        cudaEventRecord(join, sh);
+        if (fork_heavy) cudaEventRecord(join, sh);
         c.begin("light", s);
         k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(a);
         c.end(s);
-        cudaStreamWaitEvent(s, join, 0);
+        if (fork_heavy) cudaStreamWaitEvent(s, join, 0);
         g_launches += 3;
       }
     }
   }
   // Env.reset() of the envs in r.list (all envs when r.list is NULL)
   static void reset_passes(PipeCtx& c, const KArgs& r, int pass, int clear_return, cudaStream_t s, cudaStream_t sh) {
-    const dim3 g = grid(r.n);
+    const dim3 g = pgrid(c, r.n);
     if (reset_has_servo<T>())
       for (int rep = 0; rep < 5; rep++) {
         c.begin("reset_stage", s);
@@ -327,7 +342,7 @@ struct OpsT {
   // one branch of a step: _set_action, stepSimulation, outputs for the envs of a.list (all envs when NULL), then
   // Env.reset() of the envs that finished (VecEnv auto-reset) through the same pipeline
   static void step_branch(PipeCtx& c, const KArgs& a, int pass, bool tail, cudaStream_t s, cudaStream_t sh) {
-    const dim3 g = grid(a.n);
+    const dim3 g = pgrid(c, a.n);
     c.cur_tail = tail ? 1 : 0;
     c.begin("action", s);
     k_pipe_action<T><<<g, 128, 0, s>>>(a);
@@ -369,7 +384,7 @@ struct OpsT {
     cudaEventRecord(join, c.e_main);
     KArgs m = a;
     m.list = c.list_m; m.list_count = c.count_m;
-    step_branch(c, m, 0, false, s, c.side);
+    step_branch(c, m, 0, false, s, s);
     cudaStreamWaitEvent(s, join, 0);
     // late tail: envs of the main branch that finished although the predictor said no (normally none)
     c.cur_tail = 1;
@@ -516,6 +531,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     int sms = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
     h->pipe.heavy_grid = (unsigned)(sms > 0 ? sms : 148);
+    h->pipe.max_blocks = (int64_t)h->pipe.heavy_grid * 4 - (getenv("XARM_RESERVE_BLOCKS") ? atoi(getenv("XARM_RESERVE_BLOCKS")) : 32);
     cudaError_t ep = (cudaError_t)ops.prepare();
     if (ep != cudaSuccess) return fail(XARM_E_CUDA, std::string("cudaFuncSetAttribute(k_pipe_heavy): ") + cudaGetErrorString(ep));
   }
