@@ -242,6 +242,11 @@ struct PipeCtx {
       acc[k].second.ms += ms; acc[k].second.n++;
       cudaEventDestroy(m.a); cudaEventDestroy(m.b);
     }
+    if (counters) {
+      int cnt[4] = {0, 0, 0, 0};
+      cudaMemcpy(cnt, counters + (n_counters - 4), sizeof(cnt), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[xarm lists] late-tail finishers %d | early finishers %d | early branch %d envs | main branch %d envs\n", cnt[0], cnt[1], cnt[2], cnt[3]);
+    }
     fprintf(stderr, "[xarm stages]");
     for (auto& kv : acc) fprintf(stderr, " %s: %d x %.1f us = %.2f ms |", kv.first.c_str(), kv.second.n, 1e3 * kv.second.ms / kv.second.n, kv.second.ms);
     fprintf(stderr, "\n");

@@ -298,9 +298,14 @@ XD bool pipe_may_finish(const KArgs& a, int64_t i) {
         const float v = a.state[(int64_t)(w_obj + 13 * o + 7 + c) * n + i];
         d2 += d * d; v2 += v * v;
       }
-      // an object at rest that no gripper touches stays where it is; otherwise it can travel with the gripper
-      const bool moving = v2 > 1e-4f || (a.form[i] & 0xff) != XARM_FORM_LIGHT;
-      const float reach = T::THRESHOLD + (moving ? 0.15f : 0.02f);
+      // an object no gripper touches travels |v| dt (+ what gravity adds while it falls); one in the gripper travels with it:
+      // at most max_vel * dt per axis and step
+      const bool held = (a.form[i] & 0xff) != XARM_FORM_LIGHT;
+      const float dt_step = (float)(T::TIME_STEP * (T::TASK == XARM_TASK_HANDOVER ? T::NSUB : 1));
+      // (generous factors: a wrong "no" costs a whole serial reset tail after both branches)
+      const float free_travel = 3.f * sqrtf(v2) * dt_step + (float)XARM_GRAVITY * dt_step * dt_step + 0.02f;
+      const float held_travel = 3.f * (float)(T::MAX_VEL * T::DT_CMD) + 0.02f;
+      const float reach = T::THRESHOLD + (held ? held_travel : fminf(free_travel, held_travel));
       all_near = all_near && d2 < reach * reach;
     }
     return all_near;
