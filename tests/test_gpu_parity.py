@@ -213,3 +213,73 @@ def test_full_size_properties():
     st = env.episode_stats()
     assert st["episodes"] == ndone and st["diverged"] == 0
     env.close()
+
+
+def test_two_branch_step_equals_single_branch():
+    """xarm_step runs the envs that may finish (time limit, success within reach) as an early branch whose auto-reset passes
+    overlap the main branch; XARM_NO_SPLIT=1 runs one branch + tail.  Envs are independent, so both must give the same bits."""
+    import os
+    import torch
+    from gym_xarm_b200 import XarmVecEnv
+    n = 4096
+    a_env = XarmVecEnv("pick_and_place", n, device="cuda:0", seed=5, max_episode_steps=20)
+    os.environ["XARM_NO_SPLIT"] = "1"
+    try:
+        b_env = XarmVecEnv("pick_and_place", n, device="cuda:0", seed=5, max_episode_steps=20)
+    finally:
+        del os.environ["XARM_NO_SPLIT"]
+    a_env.capture_graph()
+    a_env.reset()
+    b_env.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ndone = 0
+    for t in range(45):
+        a = torch.rand(n, 4, generator=g, device="cuda") * 2 - 1
+        oa, ra, da, _ = a_env.step(a)
+        ob, rb, db, _ = b_env.step(a)
+        assert torch.equal(oa["observation"], ob["observation"]), t
+        assert torch.equal(oa["desired_goal"], ob["desired_goal"]) and torch.equal(ra, rb) and torch.equal(da, db), t
+        ndone += int(da.sum())
+    assert ndone >= 2 * n
+    assert np.array_equal(a_env.get_state(), b_env.get_state())
+    sa, sb = a_env.episode_stats(), b_env.episode_stats()
+    assert sa["episodes"] == sb["episodes"] == ndone
+    a_env.close()
+    b_env.close()
+
+
+def test_contact_statistics_scripted_grasp():
+    """Contact tasks (north_star): success rate of a scripted policy, CUDA path vs oracle.  PickAndPlace with the lego spawned
+    under the gripper (init_grasp_rate=1), the script of the reference's _run_demo [REF xarm_pick_and_place.py:310-349]:
+    close the fingers for 3 steps, then carry the lego up and back for 10 steps; per-env gripper commands and lateral drift
+    spread the outcomes (the oracle lifts ~80 %).
+    Gripper contacts amplify float32 rounding, so trajectories are not compared - the fraction of lifted legos is."""
+    import torch
+    n = 384
+    cfg = {"init_grasp_rate": 1.0, "goal_shape": "air"}
+    env = _mk("pick_and_place", n, seed=17, auto_reset=False, config=cfg)
+    ref = [orc.OracleEnv("pick_and_place", env_index=i, seed=17, auto_reset=0, goal_shape="air", init_grasp_rate=1.0) for i in range(n)]
+    env.reset()
+    for r in ref:
+        r.reset()
+    rng = np.random.default_rng(2)
+    grip = np.where(rng.random(n) < 0.5, -1.0, rng.uniform(-1, 1, n)).astype(np.float32)  # half close fully, half anything
+    off = rng.normal(0, 0.5, (n, 2)).astype(np.float32)                                    # lateral drift while closing
+    z_gpu = z_ref = None
+    for t in range(13):
+        a = np.zeros((n, 4), np.float32)
+        if t < 3:
+            a[:, :2] = 0.5 * off
+        else:
+            a[:, 0], a[:, 2] = -0.4, 1.0
+        a[:, 3] = grip
+        a = np.clip(a, -1, 1)
+        obs, rew, done, infos = env.step(torch.from_numpy(a).cuda())
+        res = [r.step(a[i]) for i, r in enumerate(ref)]
+        z_gpu = obs["achieved_goal"].cpu().numpy()[:, 2]
+        z_ref = np.array([r[0]["achieved_goal"][2] for r in res])
+        assert np.isfinite(z_gpu).all()
+    lifted_gpu, lifted_ref = float((z_gpu > 0.1).mean()), float((z_ref > 0.1).mean())
+    print(f"scripted grasp: lifted fraction CUDA {lifted_gpu:.3f} vs oracle {lifted_ref:.3f} ({n} envs)")
+    assert 0.3 < lifted_ref < 0.97 and abs(lifted_gpu - lifted_ref) < 0.06, (lifted_gpu, lifted_ref)
+    env.close()
