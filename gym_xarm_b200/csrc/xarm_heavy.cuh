@@ -254,6 +254,235 @@ __device__ __forceinline__ float heavy_solve_coop(const float* srec, float* sapp
   return u;
 }
 
+// ---- Low-latency cooperative joint loop in IMPULSE space (Delassus form), 16 lanes per env.
+// The velocity form above pays a 4-level shuffle sum (J_r . u) on the critical path of EVERY row: ~250 cycles per row,
+// ~10 k cycles per sweep, 250 us per substep for a warp that runs alone - and the auto-reset tail of a step is a chain
+// of 105 such substeps (profiles/).  Here every lane OWNS rows and keeps s_r = J_r . u of its rows up to date instead:
+//   lane c < nc : the three rows of contact c (normal, friction 1, friction 2)
+//   lane i < 9  : also motor i and the limit row of dof i (J = +-e_i, so s_limit = sign * s_motor: no extra storage)
+//   lane 9      : also the gear row
+// Processing row k = the owner computes delta_k from its own s_k (registers only), ONE shuffle broadcasts it, and every
+// lane adds A[r][k] * delta_k to its <= 4 sums (A = J M^-1 J^T, built once per substep in shared memory, layout
+// A[(k * 4 + slot) * 16 + lane]: conflict-free, and the loads do not depend on the solve so they are issued ahead).
+// Critical path per row: delta (~7 dependent FP ops) + shuffle + FMA ~ 60 cycles.  Same row order, clamps, cone and exit
+// test as sub_solve_generic / btMultiBodyConstraintSolver::solveSingleIteration; rounding differs from the
+// velocity form (sums are accumulated per row, u is formed once at the end from the accumulated impulses).
+// Row numbering k: 0..8 motors, 9 gear, 10 + 3 c + j contact rows.  nc <= XARM_DELA_MAXC = T::MAXC (one lane per contact).
+// Validation: tools/_emul_pgs.py replays dumped records in both forms, float32 against float64 - both forms sit at
+// 5e-5..2e-4 of the float64 sweep on ordinary grasps, and both lose all digits on the same (diverging) records.
+#define XARM_DELA_MAXC 16
+template <class T>
+struct DelaLayout {
+  static constexpr int NU = 10;                                  // unit columns: 9 motors + gear
+  static constexpr int RMAX = NU + 3 * XARM_DELA_MAXC;           // 58
+  static constexpr int A_WORDS = RMAX * 4 * 16;                  // 3712
+  static constexpr int VU = A_WORDS;                             // M^-1 J^T of the unit rows [NU][16]
+  static constexpr int LAM = VU + NU * 16;                       // accumulated impulses [RMAX] (+ pad)
+  static constexpr int WORDS_ = LAM + 64;
+  static constexpr int W0 = WORDS_;
+  static constexpr int SLOT = ((W0 + 31) / 32) * 32 + 16;        // = 16 mod 32: the two envs of a warp use different banks
+};
+
+// reads of the record (written by k_heavy_rows in the previous launch): XARM_DELA_LDCG routes them past L1
+#ifdef XARM_DELA_LDCG
+#define RL(p) __ldcg(p)
+#define RL4(p) __ldcg(p)
+#else
+#define RL(p) (*(p))
+#define RL4(p) (*(p))
+#endif
+template <class T>
+__device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec, float* sm, int l, bool valid) {
+  using R = HeavyRec<T>;
+  using D = DelaLayout<T>;
+  using MD = typename T::MD;
+  constexpr int N = R::N;
+  constexpr unsigned FULL = 0xffffffffu;
+  float* A = sm;
+  float* Vu = sm + D::VU;
+  float* lam = sm + D::LAM;
+  const float gr = (float)XARM_GEAR_RATIO;
+  const int nc = valid ? (int)RL(rec + R::NC) : 0;
+  const int Rn = D::NU + 3 * nc;
+  const bool own_c = l < nc;
+  // ---- unit columns: M^-1 e_k (motors), M^-1 (e_F1 + gr e_F2) (gear); the object part is zero
+#pragma unroll
+  for (int k = 0; k < D::NU; k++) {
+    float v = 0.f;
+    if (valid && l < N) v = k < N ? RL(rec + R::MI + tri(l, k)) : RL(rec + R::MI + tri(l, MD::F1)) + gr * RL(rec + R::MI + tri(l, MD::F2));
+    Vu[k * 16 + l] = v;
+  }
+  // ---- this lane's contact rows (J) and row constants
+  float Jn[16], Ja[16], Jb[16];
+  float rhs0 = 0.f, dinv0 = 1.f, cfmr0 = 0.f, rhs1 = 0.f, di1 = 1.f, rhs2 = 0.f, di2 = 1.f, mu = 0.f;
+  {
+    const float4* r4 = reinterpret_cast<const float4*>(rec + R::HDR + (own_c ? l * 3 : 0) * R::ROW);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const float4 a = own_c ? RL4(r4 + u) : make_float4(0, 0, 0, 0);
+      const float4 b = own_c ? RL4(r4 + R::ROW / 4 + u) : make_float4(0, 0, 0, 0);
+      const float4 c = own_c ? RL4(r4 + 2 * (R::ROW / 4) + u) : make_float4(0, 0, 0, 0);
+      Jn[4 * u] = a.x; Jn[4 * u + 1] = a.y; Jn[4 * u + 2] = a.z; Jn[4 * u + 3] = a.w;
+      Ja[4 * u] = b.x; Ja[4 * u + 1] = b.y; Ja[4 * u + 2] = b.z; Ja[4 * u + 3] = b.w;
+      Jb[4 * u] = c.x; Jb[4 * u + 1] = c.y; Jb[4 * u + 2] = c.z; Jb[4 * u + 3] = c.w;
+    }
+    if (own_c) {
+      const float4 k0 = RL4(r4 + 8), k1 = RL4(r4 + R::ROW / 4 + 8), k2 = RL4(r4 + 2 * (R::ROW / 4) + 8);
+      rhs0 = k0.x; dinv0 = k0.y; cfmr0 = k0.z; mu = k0.w;
+      rhs1 = k1.x; di1 = k1.y; rhs2 = k2.x; di2 = k2.y;
+    }
+  }
+  // unit row of this lane: motor l (l < 9) or the gear (l == 9); limit row of dof l
+  float urhs = 0.f, uden = 1.f, uhi = 0.f, lrhs = 0.f, lsign = 0.f;
+  if (valid && l < N) {
+    urhs = RL(rec + R::MRHS + l); uden = 1.f / RL(rec + R::MI + tri(l, l));
+    uhi = l < 7 ? (float)(T::ARM_FORCE * T::TIME_STEP) : (float)(T::FINGER_FORCE * T::TIME_STEP);
+    lrhs = RL(rec + R::LRHS + l);
+    const uint32_t lo = (uint32_t)RL(rec + R::LIM), hi = (uint32_t)RL(rec + R::LIM + 1);
+    lsign = (lo >> l & 1u) ? 1.f : ((hi >> l & 1u) ? -1.f : 0.f);
+  } else if (valid && l == N) {
+    urhs = RL(rec + R::GEAR); uden = RL(rec + R::GEAR + 1); uhi = (float)(XARM_GEAR_MAX_FORCE * T::TIME_STEP);
+  }
+  const float hi_lim = (float)XARM_LIMIT_MAX_IMPULSE;
+  const float sthr = sqrtf((float)XARM_RESIDUAL_THRESHOLD);
+  __syncwarp();
+  // ---- A = J M^-1 J^T: column k against this lane's rows
+#define DELA_COLUMN(k_, V0, V1, V2, V3, vl_)                                                                      \
+  {                                                                                                               \
+    const float vv_[16] = {V0.x, V0.y, V0.z, V0.w, V1.x, V1.y, V1.z, V1.w, V2.x, V2.y, V2.z, V2.w, V3.x, V3.y, V3.z, V3.w}; \
+    float an_ = 0.f, aa_ = 0.f, ab_ = 0.f;                                                                        \
+    _Pragma("unroll") for (int q_ = 0; q_ < 15; q_++) { an_ += Jn[q_] * vv_[q_]; aa_ += Ja[q_] * vv_[q_]; ab_ += Jb[q_] * vv_[q_]; } \
+    float* o_ = A + (k_) * 64 + l;                                                                                \
+    o_[0] = an_; o_[16] = aa_; o_[32] = ab_; o_[48] = (vl_);                                                      \
+  }
+  for (int k = 0; k < D::NU; k++) {
+    const float4* v4 = reinterpret_cast<const float4*>(Vu + k * 16);
+    const float4 V0 = v4[0], V1 = v4[1], V2 = v4[2], V3 = v4[3];
+    // unit slot: e_l . V_k (motor), (e_F1 + gr e_F2) . V_k (gear)
+    const float vl = l < N ? Vu[k * 16 + l] : (l == N ? Vu[k * 16 + MD::F1] + gr * Vu[k * 16 + MD::F2] : 0.f);
+    DELA_COLUMN(k, V0, V1, V2, V3, vl)
+  }
+#pragma unroll 4
+  for (int k = D::NU; k < Rn; k++) {
+    const float* row = rec + R::HDR + (k - D::NU) * R::ROW + 16;
+    const float4* v4 = reinterpret_cast<const float4*>(row);
+    const float4 V0 = RL4(v4), V1 = RL4(v4 + 1), V2 = RL4(v4 + 2), V3 = RL4(v4 + 3);
+    const float vl = l < N ? RL(row + l) : (l == N ? RL(row + MD::F1) + gr * RL(row + MD::F2) : 0.f);
+    DELA_COLUMN(k, V0, V1, V2, V3, vl)
+  }
+#undef DELA_COLUMN
+  __syncwarp();
+  // ---- sweeps.  Row update in its short-chain form: with c = app + rhs - app * cfm kept ready (it only changes in the
+  // row's own step), x = c - s * dinv, app' = clamp(x), delta = app' - app: on the critical path of a row remain
+  // FFMA (s) -> FFMA (x) -> FMNMX -> FMNMX -> FADD -> SHFL.  (Same fixed point and clamps as the textbook form
+  // delta = rhs - app cfm - s dinv, app' = clamp(app + delta); tools/_emul_pgs.py: same float32 error against float64.)
+  // Limit rows carry the SIGNED impulse q = sign * app in sign * [0, hi]: x = q + sign * rhs - s3 * den, and the
+  // broadcast delta is already the joint-space one.  A finished env (exit test) has its rows switched off: dinv = 0,
+  // c = app, so every delta is exactly zero.
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float appn = 0.f, app1 = 0.f, app2 = 0.f, mapp = 0.f, q = 0.f;
+  const int nc_max = max(nc, __shfl_xor_sync(FULL, nc, 16));
+  const uint32_t lim_bits = __ballot_sync(FULL, lsign != 0.f);
+  const uint32_t lim_any = (lim_bits | (lim_bits >> 16)) & 0x1ffu;  // dofs with a limit row in either env of the warp
+  bool done = !valid;
+  const float llo = lsign < 0.f ? -hi_lim : 0.f, lhi = lsign > 0.f ? hi_lim : 0.f;
+  float lrs = lsign * lrhs;
+  if (!own_c) { dinv0 = 0.f; di1 = 0.f; di2 = 0.f; }
+  const float dinv_t = dinv0, di1_t = di1, di2_t = di2;
+  if (done) { uden = 0.f; urhs = 0.f; }
+  float uden_t = uden;              // residual test scale (kept when the rows are switched off)
+  float cu = urhs, cl = lrs, cn = rhs0, ca = rhs1, cb = rhs2;
+#define DELA_APPLY(k_, d_)                                                                                        \
+  { const float* c_ = A + (k_) * 64 + l; s0 += c_[0] * (d_); s1 += c_[16] * (d_); s2 += c_[32] * (d_); s3 += c_[48] * (d_); }
+#define DELA_UNIT(o_)                                                                                             \
+  {                                                                                                               \
+    const float x_ = fmaf(-s3, uden, cu);                                                                         \
+    const float xn_ = fminf(fmaxf(x_, -uhi), uhi);                                                                \
+    const float delta = xn_ - mapp;                                                                               \
+    const float d_ = __shfl_sync(FULL, delta, (o_), 16);                                                          \
+    const bool own_ = l == (o_);                                                                                  \
+    mapp = own_ ? xn_ : mapp; cu = mapp + urhs;                                                                   \
+    bad = bad || (own_ && fabsf(delta) > sthr * uden_t);                                                          \
+    DELA_APPLY((o_), d_)                                                                                          \
+  }
+#define DELA_LIMIT(o_)                                                                                            \
+  if (lim_any >> (o_) & 1u) {                                                                                     \
+    const float x_ = fmaf(-s3, uden, cl);                                                                         \
+    const float xn_ = fminf(fmaxf(x_, llo), lhi);                                                                 \
+    const float delta = xn_ - q;                                                                                  \
+    const float d_ = __shfl_sync(FULL, delta, (o_), 16);                                                          \
+    const bool own_ = l == (o_);                                                                                  \
+    q = own_ ? xn_ : q; cl = q + lrs;                                                                             \
+    bad = bad || (own_ && fabsf(delta) > sthr * uden_t);                                                          \
+    DELA_APPLY((o_), d_)                                                                                          \
+  }
+  for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+    bool bad = false;
+    if (it & 1) {
+      if (lim_any) { _Pragma("unroll") for (int i = 0; i < N; i++) DELA_LIMIT(i) }
+      _Pragma("unroll") for (int i = 0; i < N; i++) DELA_UNIT(i)
+      DELA_UNIT(N)
+    } else {
+      DELA_UNIT(N)
+      _Pragma("unroll") for (int i = N - 1; i >= 0; i--) DELA_UNIT(i)
+      if (lim_any) { _Pragma("unroll") for (int i = N - 1; i >= 0; i--) DELA_LIMIT(i) }
+    }
+    // ---- normal rows
+    for (int c = 0; c < nc_max; c++) {
+      const float x_ = fmaf(-s0, dinv0, cn);
+      const float xn_ = fminf(fmaxf(x_, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
+      const float d0 = xn_ - appn;
+      const float d_ = __shfl_sync(FULL, d0, c, 16);
+      const bool own_ = l == c;
+      appn = own_ ? xn_ : appn; cn = fmaf(-appn, cfmr0, appn + rhs0);
+      bad = bad || (own_ && fabsf(d0) > sthr * dinv_t);
+      if (c < nc) DELA_APPLY(D::NU + 3 * c, d_)  // (columns past this env's rows were never built)
+    }
+    // ---- friction pairs (implicit cone)
+    const float lim = mu * appn, lim2 = lim * lim;
+    for (int c = 0; c < nc_max; c++) {
+      float xa = fmaf(-s1, di1, ca), xb = fmaf(-s2, di2, cb);
+      const float l2 = xa * xa + xb * xb;
+      const float sc = l2 > lim2 ? lim * rsqrtf(l2) : 1.f;
+      xa *= sc; xb *= sc;
+      const float da = xa - app1, db = xb - app2;
+      const float da_ = __shfl_sync(FULL, da, c, 16), db_ = __shfl_sync(FULL, db, c, 16);
+      const bool own_ = l == c;
+      app1 = own_ ? xa : app1; app2 = own_ ? xb : app2; ca = app1 + rhs1; cb = app2 + rhs2;
+      bad = bad || (own_ && (fabsf(da) > sthr * di1_t || fabsf(db) > sthr * di2_t));
+      if (c < nc) {
+        const float* c_ = A + (D::NU + 3 * c + 1) * 64 + l;
+        s0 += c_[0] * da_ + c_[64] * db_; s1 += c_[16] * da_ + c_[80] * db_;
+        s2 += c_[32] * da_ + c_[96] * db_; s3 += c_[48] * da_ + c_[112] * db_;
+      }
+    }
+    const uint32_t bb = __ballot_sync(FULL, bad);
+    if (!done && ((bb >> (threadIdx.x & 16)) & 0xffffu) == 0u) {  // this env is finished: switch its rows off
+      done = true;
+      uden = 0.f; urhs = 0.f; cu = mapp; lrs = 0.f; cl = q;
+      dinv0 = 0.f; cfmr0 = 0.f; rhs0 = 0.f; cn = appn;
+      di1 = 0.f; di2 = 0.f; rhs1 = 0.f; rhs2 = 0.f; ca = app1; cb = app2; mu = 1e30f;   // (cone never bites: impulses stay)
+    }
+    if (__all_sync(FULL, done)) break;
+  }
+#undef DELA_APPLY
+#undef DELA_UNIT
+#undef DELA_LIMIT
+  // ---- u = M^-1 J^T lambda, component l (lane 15 idle)
+  if (l < N) lam[l] = mapp + q; else if (l == N) lam[N] = mapp;
+  if (own_c) { lam[D::NU + 3 * l] = appn; lam[D::NU + 3 * l + 1] = app1; lam[D::NU + 3 * l + 2] = app2; }
+  __syncwarp();
+  float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < D::NU; k++) u0 += Vu[k * 16 + l] * lam[k];
+  for (int k = D::NU; k < Rn; k += 2) {
+    u0 += RL(rec + R::HDR + (k - D::NU) * R::ROW + 16 + l) * lam[k];
+    if (k + 1 < Rn) u1 += RL(rec + R::HDR + (k + 1 - D::NU) * R::ROW + 16 + l) * lam[k + 1];
+  }
+  __syncwarp();
+  return u0 + u1;
+}
+
 #define HV_DOT(j0, j1, j2, j3)                                                                                   \
   (((j0.x * dqd[0][0] + j0.y * dqd[0][1]) + (j0.z * dqd[0][2] + j0.w * dqd[0][3])) +                             \
    ((j1.x * dqd[0][4] + j1.y * dqd[0][5]) + (j1.z * dqd[0][6] + j1.w * dqd[0][7])) +                             \
@@ -364,20 +593,10 @@ __device__ __forceinline__ void heavy_rows_body(const KArgs& a, int t, int sub, 
   }
 }
 
-// 16 lanes of the solve kernel: record -> shared memory, joint loop, stepPositionsMultiDof, state
+// stepPositionsMultiDof of a heavy env by its 16 lanes: u = velocity change of component l; hdr = the record's header
 template <class T>
-__device__ __forceinline__ void heavy_solve_body(const KArgs& a, int t, bool valid, const float* __restrict__ hrec, float* srec, int l) {
+__device__ __forceinline__ void heavy_integrate_coop(const KArgs& a, int t, bool valid, const float* hdr, float u, int l) {
   using R = HeavyRec<T>;
-  float* sapp = srec + R::WORDS;
-  if (valid) {
-    const float* rec = hrec + (size_t)(a.heavy_dir > 0 ? t : a.n - 1 - t) * R::WORDS;
-    const int words = R::HDR + (int)rec[R::NC] * 3 * R::ROW;
-    for (int w = l; w < words; w += 16) srec[w] = rec[w];
-  } else {
-    for (int w = l; w < R::HDR; w += 16) srec[w] = w < R::NT ? 1.f : 0.f;  // a harmless empty env for the idle half
-  }
-  __syncwarp();
-  const float u = heavy_solve_coop<T>(srec, sapp, l);
   const float h = (float)T::H;
   const float dvx = __shfl_sync(0xffffffffu, u, 9, 16), dvy = __shfl_sync(0xffffffffu, u, 10, 16), dvz = __shfl_sync(0xffffffffu, u, 11, 16);
   const float dwx = __shfl_sync(0xffffffffu, u, 12, 16), dwy = __shfl_sync(0xffffffffu, u, 13, 16), dwz = __shfl_sync(0xffffffffu, u, 14, 16);
@@ -385,7 +604,7 @@ __device__ __forceinline__ void heavy_solve_body(const KArgs& a, int t, bool val
     const int64_t i = a.heavy_list[a.heavy_dir * t], n = a.n;
     float* st = a.state;
     if (l < R::N) {  // joints: word l = q, word N + l = qd
-      const float qd = srec[R::QDU + l] + u;
+      const float qd = hdr[R::QDU + l] + u;
       st[(int64_t)(R::N + l) * n + i] = qd;
       st[(int64_t)l * n + i] += qd * h;
     } else if (l == R::N) {  // the object (words 3N .. 3N + 12: pos, quat, v, w), as in sub_integrate
@@ -393,8 +612,8 @@ __device__ __forceinline__ void heavy_solve_body(const KArgs& a, int t, bool val
       ObjState b;
       b.pos = v3(st[(int64_t)w0 * n + i], st[(int64_t)(w0 + 1) * n + i], st[(int64_t)(w0 + 2) * n + i]);
       b.quat.x = st[(int64_t)(w0 + 3) * n + i]; b.quat.y = st[(int64_t)(w0 + 4) * n + i]; b.quat.z = st[(int64_t)(w0 + 5) * n + i]; b.quat.w = st[(int64_t)(w0 + 6) * n + i];
-      b.v = v3(srec[R::VU] + dvx, srec[R::VU + 1] + dvy, srec[R::VU + 2] + dvz);
-      b.w = v3(srec[R::WU] + dwx, srec[R::WU + 1] + dwy, srec[R::WU + 2] + dwz);
+      b.v = v3(hdr[R::VU] + dvx, hdr[R::VU + 1] + dvy, hdr[R::VU + 2] + dvz);
+      b.w = v3(hdr[R::WU] + dwx, hdr[R::WU + 1] + dwy, hdr[R::WU + 2] + dwz);
       b.pos += h * b.v;
       float ang = norm(b.w);
       if (ang * h > (float)XARM_ANGULAR_MOTION_THRESHOLD) ang = (float)XARM_ANGULAR_MOTION_THRESHOLD / h;
@@ -410,6 +629,34 @@ __device__ __forceinline__ void heavy_solve_body(const KArgs& a, int t, bool val
       st[(int64_t)(w0 + 10) * n + i] = b.w.x; st[(int64_t)(w0 + 11) * n + i] = b.w.y; st[(int64_t)(w0 + 12) * n + i] = b.w.z;
     }
   }
+}
+
+// 16 lanes of the solve kernel: record -> shared memory, joint loop, stepPositionsMultiDof, state
+template <class T>
+__device__ __forceinline__ void heavy_solve_body(const KArgs& a, int t, bool valid, const float* __restrict__ hrec, float* srec, int l) {
+  using R = HeavyRec<T>;
+  float* sapp = srec + R::WORDS;
+  if (valid) {
+    const float* rec = hrec + (size_t)(a.heavy_dir > 0 ? t : a.n - 1 - t) * R::WORDS;
+    const int words = R::HDR + (int)rec[R::NC] * 3 * R::ROW;
+    for (int w = l; w < words; w += 16) srec[w] = rec[w];
+  } else {
+    for (int w = l; w < R::HDR; w += 16) srec[w] = w < R::NT ? 1.f : 0.f;  // a harmless empty env for the idle half
+  }
+  __syncwarp();
+  const float u = heavy_solve_coop<T>(srec, sapp, l);
+  heavy_integrate_coop<T>(a, t, valid, srec, u, l);
+  __syncwarp();
+}
+// 16 lanes of the low-latency solve kernel: impulse-space joint loop straight from the record in global memory (L2)
+template <class T>
+__device__ __forceinline__ void heavy_solve2_body(const KArgs& a, int t, bool valid, const float* __restrict__ hrec, float* sm, int l) {
+  using R = HeavyRec<T>;
+  static_assert(T::MAXC <= XARM_DELA_MAXC && XARM_DELA_MAXC <= 16, "one lane per contact");
+  const int tt = valid ? t : 0;
+  const float* rec = hrec + (size_t)(a.heavy_dir > 0 ? tt : a.n - 1 - tt) * R::WORDS;
+  const float u = heavy_solve_dela<T>(rec, sm, l, valid);
+  heavy_integrate_coop<T>(a, t, valid, rec, u, l);
   __syncwarp();
 }
 #endif

@@ -23,7 +23,15 @@ struct KArgs {
   int* rng_draw;         // [N] Philox draw counter carried from the placement stage of a reset to its goal stage
   const int* list;       // optional: thread t works on env list[t] (auto-reset tail); NULL = identity
   const int* list_count;
+  // development timeline (XARM_TIMELINE=1): first block start / last block end of every pipeline launch, %globaltimer ns
+  unsigned long long* tl;  // [2 * XARM_TL_SLOTS] or NULL
+  int tl_slot;
+  // SM partition of a split step (xarm_lib.cu): launches of the main branch carry a work counter (blocks claim their
+  // chunks dynamically) and leave at once when they land on an SM of sm_mask - those SMs belong to the early branch
+  int* work;                       // NULL: static block-stride loop, every SM
+  unsigned long long sm_mask[4];   // bit smid set: reserved for the early branch
 };
+#define XARM_TL_SLOTS 4096
 #define XARM_MAX_SUBSTEPS 32
 #define XARM_PIPE_PASSES 16  /* simulate() passes of one xarm_step: per branch the step itself + up to 6 of the auto-reset tail */
 #define XARM_PIPE_COUNTERS (XARM_PIPE_PASSES * XARM_MAX_SUBSTEPS)

@@ -30,12 +30,37 @@ __device__ __forceinline__ int64_t pipe_env(const KArgs& a, int64_t t) {
 // Launches are persistent-style: the grid may be smaller than the work (xarm_step keeps a few block slots per SM free
 // for its latency-bound early branch), so every kernel walks its envs with a block-stride loop.  Trip counts are
 // uniform per block (the bodies use warp-wide ballots).
+// Main-branch launches of a split step (a.work != NULL) claim their chunks from a counter instead: the blocks that land
+// on the SMs reserved for the early branch leave at once (PIPE_LEAVE_RESERVED), the others share all the work.
+__device__ __forceinline__ bool on_reserved_sm(const KArgs& a) {
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  return (a.sm_mask[(smid >> 6) & 3u] >> (smid & 63u)) & 1ull;
+}
+#define PIPE_LEAVE_RESERVED(a) if ((a).work && on_reserved_sm(a)) return;
+// next chunk (of `chunk` work items) of this block: static stride or claimed from a.work; uniform over the block
+__device__ __forceinline__ int64_t pipe_next(const KArgs& a, int64_t prev, int chunk) {
+  if (!a.work) return prev < 0 ? (int64_t)blockIdx.x * chunk : prev + (int64_t)gridDim.x * chunk;
+  __shared__ int claim_;
+  __syncthreads();   // (everyone has read the previous claim)
+  if (threadIdx.x == 0) claim_ = atomicAdd(a.work, 1);
+  __syncthreads();
+  return (int64_t)claim_ * chunk;
+}
 #define PIPE_FOR_EACH(a, t, i)                                                                                   \
-  for (int64_t bound_ = (a).list ? (int64_t)*(a).list_count : (a).n, base_ = (int64_t)blockIdx.x * blockDim.x;  \
-       base_ < bound_; base_ += (int64_t)gridDim.x * blockDim.x)                                                 \
+  for (int64_t bound_ = (a).list ? (int64_t)*(a).list_count : (a).n, base_ = pipe_next(a, -1, blockDim.x);      \
+       base_ < bound_; base_ = pipe_next(a, base_, blockDim.x))                                                  \
     if (const int64_t t = base_ + threadIdx.x; true)                                                             \
       if (const int64_t i = pipe_env(a, t); true)
 
+// development timeline: thread 0 of every block stamps the launch's slot (min of starts, max of ends)
+__device__ __forceinline__ void tl_mark(const KArgs& a, int end) {
+  if (a.tl && threadIdx.x == 0 && a.tl_slot >= 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (end) atomicMax(a.tl + 2 * a.tl_slot + 1, t); else atomicMin(a.tl + 2 * a.tl_slot, t);
+  }
+}
 // warp-aggregated append of the flagged lanes' env ids to a list
 __device__ __forceinline__ void list_append(bool flag, int64_t i, int* list, int* count, int dir = 1) {
   const unsigned m = __ballot_sync(0xffffffffu, flag);
@@ -49,19 +74,28 @@ __device__ __forceinline__ void list_append(bool flag, int64_t i, int* list, int
 
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_action(KArgs a) {
+  PIPE_LEAVE_RESERVED(a)
+  tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_action<T>(a, i); }
+  tl_mark(a, 1);
 }
 template <class T>
 __global__ void __launch_bounds__(128, 4) k_pipe_setup(KArgs a, int sub, int* heavy_count) {
+  PIPE_LEAVE_RESERVED(a)
+  tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) {
     const bool heavy = i >= 0 && pipe_setup<T>(a, i, sub);
     list_append(heavy, i, a.heavy_list, heavy_count, a.heavy_dir);
   }
+  tl_mark(a, 1);
 }
 template <class T>
 __global__ void __launch_bounds__(128, 4) k_pipe_light(KArgs a) {
   extern __shared__ float light_mrows[];  // [XARM_MROW_WORDS][128]: the manifold rows of this block's envs
+  PIPE_LEAVE_RESERVED(a)
+  tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_light<T>(a, i, light_mrows + threadIdx.x, 128); }
+  tl_mark(a, 1);
 }
 // Heavy envs of this substep.  One warp per block, a few blocks per SM at most: the contact rows of the generic solver
 // (Contacts<T>, ~6 KB per env) live in SHARED memory, one record per lane at an odd word stride (bank-conflict free).
@@ -101,8 +135,14 @@ __global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* 
 template <class T>
 __global__ void __launch_bounds__(64) k_heavy_rows(KArgs a, int sub, const int* heavy_count, float* hrec) {
   if constexpr (task_has_heavy_rows<T>()) {
+    PIPE_LEAVE_RESERVED(a)
     const int count = *heavy_count;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) heavy_rows_body<T>(a, t, sub, hrec);
+    bool any = false;
+    for (int64_t base = pipe_next(a, -1, blockDim.x); base < count; base = pipe_next(a, base, blockDim.x)) {
+      if (!any) { tl_mark(a, 0); any = true; }
+      if (base + threadIdx.x < count) heavy_rows_body<T>(a, (int)base + threadIdx.x, sub, hrec);
+    }
+    if (any) tl_mark(a, 1);
   }
 }
 template <class T>
@@ -117,6 +157,28 @@ __global__ void __launch_bounds__(128) k_heavy_solve(KArgs a, const int* heavy_c
       heavy_solve_body<T>(a, base + g, base + g < count, hrec, srec, l);
   }
 }
+// Low-latency form (heavy_solve_dela: impulse-space joint loop, ~4x shorter dependency chain per row): one warp = 2 envs
+// per block, 15.8 KB of shared memory per env (the Delassus matrix of up to 58 rows), 7 blocks per SM.
+#ifndef XARM_HEAVY2_ENVS_PER_BLOCK
+#define XARM_HEAVY2_ENVS_PER_BLOCK 2
+#endif
+#define XARM_HEAVY2_BLOCKS_PER_SM 7
+template <class T>
+__global__ void __launch_bounds__(16 * XARM_HEAVY2_ENVS_PER_BLOCK) k_heavy_solve2(KArgs a, const int* heavy_count, const float* hrec) {
+  if constexpr (task_has_heavy_rows<T>()) {
+    extern __shared__ float4 heavy_smem4[];
+    const int g = threadIdx.x >> 4, l = threadIdx.x & 15;
+    float* sm = reinterpret_cast<float*>(heavy_smem4) + (size_t)g * DelaLayout<T>::SLOT;
+    PIPE_LEAVE_RESERVED(a)
+    const int count = *heavy_count;
+    bool any = false;
+    for (int64_t base = pipe_next(a, -1, XARM_HEAVY2_ENVS_PER_BLOCK); base < count; base = pipe_next(a, base, XARM_HEAVY2_ENVS_PER_BLOCK)) {
+      if (!any) { tl_mark(a, 0); any = true; }
+      heavy_solve2_body<T>(a, (int)base + g, base + g < count, hrec, sm, l);
+    }
+    if (any) tl_mark(a, 1);
+  }
+}
 // tasks without a light form (two arms / door): every env takes the generic substep (rows in thread-local memory)
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_heavy_all(KArgs a, int sub) {
@@ -126,6 +188,8 @@ __global__ void __launch_bounds__(128) k_pipe_heavy_all(KArgs a, int sub) {
 }
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_finish(KArgs a) {
+  PIPE_LEAVE_RESERVED(a)
+  tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) {
     StepStats st = {0.f, 0.f, 0.f, 0.f, 0.f};
     const bool fin = i >= 0 && pipe_finish<T>(a, i, st);
@@ -148,14 +212,27 @@ __global__ void __launch_bounds__(128) k_pipe_finish(KArgs a) {
       }
     }
   }
+  tl_mark(a, 1);
 }
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_reset_stage(KArgs a, int stage, int clear_return) {
+  tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_reset_stage<T>(a, i, stage, clear_return != 0); }
+  tl_mark(a, 1);
+}
+// which SM ids exist on this device (ids need not be contiguous): every block reports its %smid and lingers a little so
+// that the grid spreads over all SMs
+__global__ void k_probe_smid(unsigned* seen) {
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (threadIdx.x == 0 && smid < 256u) atomicOr(&seen[smid >> 5], 1u << (smid & 31u));
+  const long long t0 = clock64();
+  while (clock64() - t0 < 20000) {}
 }
 // zero the per-launch counters of one env step (heavy lists of every pass and substep, the reset / branch lists)
 __global__ void k_pipe_begin(KArgs a, int* counters, int n_counters) {
   for (int t = threadIdx.x; t < n_counters; t += blockDim.x) counters[t] = 0;
+  if (a.tl) for (int t = threadIdx.x; t < 2 * XARM_TL_SLOTS; t += blockDim.x) a.tl[t] = (t & 1) ? 0ull : ~0ull;
 }
 // envs that may finish in the coming step -> early list, the others -> main list (order-preserving per warp)
 template <class T>
@@ -204,6 +281,7 @@ struct PipeCtx {
   int *count_e = nullptr, *count_m = nullptr, *reset_count_e = nullptr, *counters = nullptr;
   int n_counters = 0;
   bool split = true;                    // XARM_NO_SPLIT=1: one branch (development A/B)
+  bool dela = true;                     // XARM_HEAVY_SOLVER=coop: the velocity-form cooperative solver (A/B, parity tests)
   int64_t max_blocks = 4 * 148 - 32;
   unsigned heavy_grid = 148;  // persistent heavy kernels: a few blocks per SM (set from the device in xarm_create)
   float* hrec = nullptr;      // [N][HeavyRec::WORDS] records of the cooperative heavy solver
@@ -219,7 +297,33 @@ struct PipeCtx {
   struct Mark { const char* name; int tail; cudaEvent_t a, b; };
   std::vector<Mark> marks;
   int cur_tail = 0;
+  // XARM_TIMELINE=1 (development): %globaltimer stamps of every pipeline launch of the last step, also inside a graph
+  bool timeline = false;
+  unsigned long long* tl_dev = nullptr;
+  std::vector<std::string> tl_names;
+  int cur_slot = -1;
+  char cur_branch = 'M';
+  // SM partition (XARM_RESERVE_SMS, default 12; 0 = off): while `dyn` is set (main branch of a split step) every launch
+  // gets a work counter and the mask of the SMs it must leave to the early branch
+  bool dyn = false;
+  int reserve_sms = 0, n_work = 0, next_work = 0;
+  int* work_base = nullptr;
+  unsigned long long sm_mask[4] = {0, 0, 0, 0};
+  KArgs tl(const KArgs& a) {
+    KArgs b = a;
+    b.tl = timeline ? tl_dev : nullptr; b.tl_slot = cur_slot;
+    b.work = nullptr;
+    if (dyn && reserve_sms > 0 && next_work < n_work) {
+      b.work = work_base + next_work++;
+      for (int k = 0; k < 4; k++) b.sm_mask[k] = sm_mask[k];
+    }
+    return b;
+  }
   void begin(const char* name, cudaStream_t s) {
+    if (timeline) {
+      cur_slot = (int)tl_names.size() < XARM_TL_SLOTS ? (int)tl_names.size() : -1;
+      if (cur_slot >= 0) tl_names.push_back(std::string(1, cur_branch) + " " + name);
+    }
     if (!trace) return;
     Mark m; m.name = name; m.tail = cur_tail;
     cudaEventCreate(&m.a); cudaEventCreate(&m.b);
@@ -279,8 +383,20 @@ struct OpsT {
   static size_t hrec_words() {  // per env: record of the cooperative heavy solver (0: task has none)
     if constexpr (task_has_heavy_rows<T>()) return HeavyRec<T>::WORDS; else return 0;
   }
+  static size_t dela_smem_bytes() {
+    if constexpr (task_has_heavy_rows<T>()) return (size_t)XARM_HEAVY2_ENVS_PER_BLOCK * DelaLayout<T>::SLOT * sizeof(float);
+    else return 0;
+  }
   static int prepare() {  // opt in to the large dynamic shared memory of the heavy kernels
-    if constexpr (task_has_heavy_rows<T>()) return (int)cudaFuncSetAttribute(k_heavy_solve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes());
+    if constexpr (HAS_LIGHT) {  // 48 KB of manifold rows + the static chunk-claim word of pipe_next
+      int rc = (int)cudaFuncSetAttribute(k_pipe_light<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XARM_MROW_WORDS * 128 * sizeof(float)));
+      if (rc) return rc;
+    }
+    if constexpr (task_has_heavy_rows<T>()) {
+      int rc = (int)cudaFuncSetAttribute(k_heavy_solve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes());
+      if (rc) return rc;
+      return (int)cudaFuncSetAttribute(k_heavy_solve2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dela_smem_bytes());
+    }
     else if constexpr (HAS_LIGHT) return (int)cudaFuncSetAttribute(k_pipe_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem_bytes());
     return 0;
   }
@@ -291,17 +407,18 @@ struct OpsT {
   // The main branch of a split step uses one stream: its kernels fill the GPU anyway, and with a single kernel in
   // flight at a time the block slots that pgrid() leaves free really stay free for the early branch.
   static void simulate(PipeCtx& c, const KArgs& a, int pass, cudaStream_t s, cudaStream_t sh) {
-    const dim3 g = pgrid(c, a.n);
+    const bool part = c.dyn && c.reserve_sms > 0;   // partitioned main branch: full grids, dynamic chunks
+    const dim3 g = part ? dim3(c.heavy_grid * 4) : pgrid(c, a.n);
     const bool fork_heavy = sh != s;
-    const unsigned rows_grid = fork_heavy ? c.heavy_grid * 4 : (unsigned)c.max_blocks;
-    const unsigned solve_grid = fork_heavy ? c.heavy_grid * 3 : (unsigned)(c.max_blocks * 3 / 4);
+    const unsigned rows_grid = fork_heavy || part ? c.heavy_grid * 4 : (unsigned)c.max_blocks;
+    const unsigned solve_grid = fork_heavy || part ? c.heavy_grid * 3 : (unsigned)(c.max_blocks * 3 / 4);
     for (int sub = 0; sub < T::NSUB; sub++) {
       if constexpr (!HAS_LIGHT) {
         k_pipe_heavy_all<T><<<g, 128, 0, s>>>(a, sub); g_launches++;
       } else {
         int* hc = a.heavy_count + pass * XARM_MAX_SUBSTEPS + sub;
         c.begin("setup", s);
-        k_pipe_setup<T><<<g, 128, 0, s>>>(a, sub, hc);
+        k_pipe_setup<T><<<g, 128, 0, s>>>(c.tl(a), sub, hc);
         c.end(s);
         cudaEvent_t join = nullptr;
         if (fork_heavy) {
@@ -312,10 +429,11 @@ struct OpsT {
         }
         if constexpr (task_has_heavy_rows<T>()) {
           c.begin("heavy_rows", sh);
-          k_heavy_rows<T><<<rows_grid, 64, 0, sh>>>(a, sub, hc, c.hrec);
+          k_heavy_rows<T><<<rows_grid, 64, 0, sh>>>(c.tl(a), sub, hc, c.hrec);
           c.end(sh);
           c.begin("heavy_solve", sh);
-          k_heavy_solve<T><<<solve_grid, 128, coop_smem_bytes(), sh>>>(a, hc, c.hrec);
+          if (c.dela) k_heavy_solve2<T><<<solve_grid / 3 * XARM_HEAVY2_BLOCKS_PER_SM, 16 * XARM_HEAVY2_ENVS_PER_BLOCK, dela_smem_bytes(), sh>>>(c.tl(a), hc, c.hrec);
+          else k_heavy_solve<T><<<solve_grid, 128, coop_smem_bytes(), sh>>>(c.tl(a), hc, c.hrec);
           c.end(sh);
           g_launches++;
         } else {
@@ -323,7 +441,7 @@ struct OpsT {
         }
         if (fork_heavy) cudaEventRecord(join, sh);
         c.begin("light", s);
-        k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(a);
+        k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(c.tl(a));
         c.end(s);
         if (fork_heavy) cudaStreamWaitEvent(s, join, 0);
         g_launches += 3;
@@ -336,7 +454,7 @@ struct OpsT {
     if (reset_has_servo<T>())
       for (int rep = 0; rep < 5; rep++) {
         c.begin("reset_stage", s);
-        k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, rep, 0); g_launches++;
+        k_pipe_reset_stage<T><<<g, 128, 0, s>>>(c.tl(r), rep, 0); g_launches++;
         c.end(s);
         simulate(c, r, pass++, s, sh);
       }
@@ -347,14 +465,14 @@ struct OpsT {
   // one branch of a step: _set_action, stepSimulation, outputs for the envs of a.list (all envs when NULL), then
   // Env.reset() of the envs that finished (VecEnv auto-reset) through the same pipeline
   static void step_branch(PipeCtx& c, const KArgs& a, int pass, bool tail, cudaStream_t s, cudaStream_t sh) {
-    const dim3 g = pgrid(c, a.n);
+    const dim3 g = c.dyn && c.reserve_sms > 0 ? dim3(c.heavy_grid * 4) : pgrid(c, a.n);
     c.cur_tail = tail ? 1 : 0;
     c.begin("action", s);
-    k_pipe_action<T><<<g, 128, 0, s>>>(a);
+    k_pipe_action<T><<<g, 128, 0, s>>>(c.tl(a));
     c.end(s);
     simulate(c, a, pass, s, sh);
     c.begin("finish", s);
-    k_pipe_finish<T><<<g, 128, 0, s>>>(a);
+    k_pipe_finish<T><<<g, 128, 0, s>>>(c.tl(a));
     c.end(s);
     g_launches += 2;
     if (a.auto_reset && tail) {
@@ -369,7 +487,8 @@ struct OpsT {
     KArgs a = a0;
     a.list = nullptr; a.list_count = nullptr; a.heavy_dir = 1;
     c.next_ev = 0;
-    k_pipe_begin<<<1, 256, 0, s>>>(a, c.counters, c.n_counters); g_launches++;
+    c.cur_slot = -1; c.tl_names.clear(); k_pipe_begin<<<1, 256, 0, s>>>(c.tl(a), c.counters, c.n_counters); g_launches++;
+    c.cur_branch = 'M';
     if (!a.auto_reset || !c.split) {  // one branch: every env, then the auto-reset tail
       step_branch(c, a, 0, true, s, c.side);
       return;
@@ -385,14 +504,18 @@ struct OpsT {
     e.list = c.list_e; e.list_count = c.count_e;
     e.heavy_list = a.heavy_list + (a.n - 1); e.heavy_dir = -1;
     e.reset_list = c.reset_list_e; e.reset_count = c.reset_count_e;
+    c.cur_branch = 'E';
     step_branch(c, e, XARM_PIPE_PASSES / 2, true, c.e_main, c.e_side);
     cudaEventRecord(join, c.e_main);
     KArgs m = a;
     m.list = c.list_m; m.list_count = c.count_m;
+    c.cur_branch = 'M';
+    c.dyn = true; c.next_work = 0;
     step_branch(c, m, 0, false, s, s);
+    c.dyn = false;
     cudaStreamWaitEvent(s, join, 0);
     // late tail: envs of the main branch that finished although the predictor said no (normally none)
-    c.cur_tail = 1;
+    c.cur_tail = 1; c.cur_branch = 'L';
     KArgs r = a;
     r.list = a.reset_list; r.list_count = a.reset_count;
     reset_passes(c, r, 1, 0, s, c.side);
@@ -401,7 +524,7 @@ struct OpsT {
     KArgs a = a0;
     a.list = nullptr; a.list_count = nullptr; a.heavy_dir = 1;
     c.next_ev = 0;
-    k_pipe_begin<<<1, 256, 0, s>>>(a, c.counters, c.n_counters); g_launches++;
+    c.cur_slot = -1; c.tl_names.clear(); k_pipe_begin<<<1, 256, 0, s>>>(c.tl(a), c.counters, c.n_counters); g_launches++;
     if (mask) {
       k_mask_to_list<<<grid(a.n), 128, 0, s>>>(a, mask); g_launches++;
       a.list = a.reset_list; a.list_count = a.reset_count;
@@ -511,7 +634,8 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   h->k.rc.goal_shape = c.goal_shape; h->k.rc.max_episode_steps = c.max_episode_steps;
   h->k.rc.init_grasp_rate = c.init_grasp_rate; h->k.rc.goal_ground_rate = c.goal_ground_rate; h->k.rc.same_side_rate = c.same_side_rate;
   // int scratch: reset list | heavy list | form | rng draw | early list | main list | early reset list | counters
-  const int n_counters = XARM_PIPE_COUNTERS + 4;
+  const int n_work = 128;  // work counters of the partitioned main branch (one per launch: 2 + 4 per substep)
+  const int n_counters = XARM_PIPE_COUNTERS + n_work + 4;
   const size_t n_int = (size_t)7 * n + n_counters;
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -543,12 +667,36 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   if (ops.hrec_words() > 0) {
     if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) { cudaGetLastError(); return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed"); }
   }
+  {  // SMs reserved for the early branch of a split step
+    const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 12;
+    if (want > 0 && ops.hrec_words() > 0) {
+      unsigned* d_seen = nullptr;
+      unsigned seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (cudaMalloc(&d_seen, sizeof(seen)) == cudaSuccess) {
+        cudaMemset(d_seen, 0, sizeof(seen));
+        k_probe_smid<<<h->pipe.heavy_grid * 16, 32>>>(d_seen);
+        cudaMemcpy(seen, d_seen, sizeof(seen), cudaMemcpyDeviceToHost);
+        cudaFree(d_seen);
+        int total = 0, taken = 0;
+        for (int id = 0; id < 256; id++) total += (seen[id >> 5] >> (id & 31)) & 1u;
+        if (total >= 4 * want)
+          for (int id = 0; id < 256 && taken < want; id++)
+            if ((seen[id >> 5] >> (id & 31)) & 1u) { h->pipe.sm_mask[id >> 6] |= 1ull << (id & 63); taken++; }
+        h->pipe.reserve_sms = taken;
+      }
+      cudaGetLastError();
+    }
+  }
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
+  h->pipe.timeline = getenv("XARM_TIMELINE") != nullptr;
+  if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 2 * XARM_TL_SLOTS) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }
   h->pipe.split = getenv("XARM_NO_SPLIT") == nullptr;
+  h->pipe.dela = !(getenv("XARM_HEAVY_SOLVER") && strcmp(getenv("XARM_HEAVY_SOLVER"), "coop") == 0);
   h->k.heavy_list = h->k.reset_list + n; h->k.form = h->k.reset_list + 2 * n; h->k.rng_draw = h->k.reset_list + 3 * n;
   h->pipe.list_e = h->k.reset_list + 4 * n; h->pipe.list_m = h->k.reset_list + 5 * n; h->pipe.reset_list_e = h->k.reset_list + 6 * n;
   h->pipe.counters = h->k.reset_list + 7 * n; h->pipe.n_counters = n_counters;
-  h->k.heavy_count = h->pipe.counters; h->k.reset_count = h->pipe.counters + XARM_PIPE_COUNTERS;
+  h->k.heavy_count = h->pipe.counters; h->k.reset_count = h->pipe.counters + XARM_PIPE_COUNTERS + n_work;
+  h->pipe.work_base = h->pipe.counters + XARM_PIPE_COUNTERS; h->pipe.n_work = n_work;
   h->pipe.reset_count_e = h->k.reset_count + 1; h->pipe.count_e = h->k.reset_count + 2; h->pipe.count_m = h->k.reset_count + 3;
   h->k.heavy_dir = 1;
   CUDA_TRY(cudaMemset(h->k.reset_list, 0, sizeof(int) * n_int));
@@ -565,7 +713,7 @@ int xarm_destroy(XarmHandle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
   cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.reset_list); cudaFree(h->k.scratch);
-  cudaFree(h->pipe.hrec);
+  cudaFree(h->pipe.hrec); cudaFree(h->pipe.tl_dev);
   for (cudaEvent_t e : h->pipe.ev) cudaEventDestroy(e);
   if (h->pipe.side) cudaStreamDestroy(h->pipe.side);
   if (h->pipe.e_main) cudaStreamDestroy(h->pipe.e_main);
@@ -773,6 +921,38 @@ int xarm_get_obs(XarmHandle* h, void* stream) {
   h->ops.obs(h->k, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return XARM_OK;
+}
+
+// development aid (not part of include/xarm_abi.h): timeline of the last step as text lines "branch kernel start_us end_us"
+int xarm_debug_timeline(XarmHandle* h, char* out, int64_t cap) {
+  if (!h || !out || !h->pipe.timeline) return -1;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  const size_t nslot = h->pipe.tl_names.size();
+  std::vector<unsigned long long> t(2 * XARM_TL_SLOTS);
+  cudaMemcpy(t.data(), h->pipe.tl_dev, sizeof(unsigned long long) * 2 * XARM_TL_SLOTS, cudaMemcpyDeviceToHost);
+  unsigned long long t0 = ~0ull;
+  for (size_t k = 0; k < nslot; k++) if (t[2 * k] < t0) t0 = t[2 * k];
+  std::string txt;
+  char line[160];
+  for (size_t k = 0; k < nslot; k++) {
+    if (t[2 * k] == ~0ull) continue;  // launch had no work
+    snprintf(line, sizeof(line), "%s %.1f %.1f\n", h->pipe.tl_names[k].c_str(), (t[2 * k] - t0) * 1e-3, (t[2 * k + 1] - t0) * 1e-3);
+    txt += line;
+  }
+  if ((int64_t)txt.size() + 1 > cap) txt.resize(cap - 1);
+  memcpy(out, txt.c_str(), txt.size() + 1);
+  return (int)nslot;
+}
+
+// development aid (not part of include/xarm_abi.h): the heavy-solver records of the last substep, [N][HeavyRec::WORDS]
+int xarm_debug_hrec(XarmHandle* h, float* host_out, int64_t max_words) {
+  if (!h || !host_out || !h->pipe.hrec) return -1;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  const int64_t words = (int64_t)h->ops.hrec_words() * h->cfg.num_envs;
+  cudaMemcpy(host_out, h->pipe.hrec, sizeof(float) * (words < max_words ? words : max_words), cudaMemcpyDeviceToHost);
+  return (int)h->ops.hrec_words();
 }
 
 int xarm_episode_stats(XarmHandle* h, double out[5], void* stream) {
