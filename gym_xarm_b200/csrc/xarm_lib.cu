@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(64) k_heavy_rows(KArgs a, int sub, const int* 
   if constexpr (task_has_heavy_rows<T>()) {
     PIPE_LEAVE_RESERVED(a)
     const int count = *heavy_count;
+    if (a.tl && a.tl_slot >= 0 && threadIdx.x == 0) a.tl[2 * XARM_TL_SLOTS + a.tl_slot] = (unsigned long long)count;
     bool any = false;
     for (int64_t base = pipe_next(a, -1, blockDim.x); base < count; base = pipe_next(a, base, blockDim.x)) {
       if (!any) { tl_mark(a, 0); any = true; }
@@ -689,7 +690,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   }
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
   h->pipe.timeline = getenv("XARM_TIMELINE") != nullptr;
-  if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 2 * XARM_TL_SLOTS) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }
+  if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 3 * XARM_TL_SLOTS) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }
   h->pipe.split = getenv("XARM_NO_SPLIT") == nullptr;
   h->pipe.dela = !(getenv("XARM_HEAVY_SOLVER") && strcmp(getenv("XARM_HEAVY_SOLVER"), "coop") == 0);
   h->k.heavy_list = h->k.reset_list + n; h->k.form = h->k.reset_list + 2 * n; h->k.rng_draw = h->k.reset_list + 3 * n;
@@ -929,15 +930,15 @@ int xarm_debug_timeline(XarmHandle* h, char* out, int64_t cap) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   const size_t nslot = h->pipe.tl_names.size();
-  std::vector<unsigned long long> t(2 * XARM_TL_SLOTS);
-  cudaMemcpy(t.data(), h->pipe.tl_dev, sizeof(unsigned long long) * 2 * XARM_TL_SLOTS, cudaMemcpyDeviceToHost);
+  std::vector<unsigned long long> t(3 * XARM_TL_SLOTS);
+  cudaMemcpy(t.data(), h->pipe.tl_dev, sizeof(unsigned long long) * 3 * XARM_TL_SLOTS, cudaMemcpyDeviceToHost);
   unsigned long long t0 = ~0ull;
   for (size_t k = 0; k < nslot; k++) if (t[2 * k] < t0) t0 = t[2 * k];
   std::string txt;
   char line[160];
   for (size_t k = 0; k < nslot; k++) {
     if (t[2 * k] == ~0ull) continue;  // launch had no work
-    snprintf(line, sizeof(line), "%s %.1f %.1f\n", h->pipe.tl_names[k].c_str(), (t[2 * k] - t0) * 1e-3, (t[2 * k + 1] - t0) * 1e-3);
+    snprintf(line, sizeof(line), "%s %.1f %.1f %llu\n", h->pipe.tl_names[k].c_str(), (t[2 * k] - t0) * 1e-3, (t[2 * k + 1] - t0) * 1e-3, t[2 * XARM_TL_SLOTS + k]);
     txt += line;
   }
   if ((int64_t)txt.size() + 1 > cap) txt.resize(cap - 1);

@@ -22,7 +22,7 @@ for t in range(steps):
         torch.cuda.synchronize()
         L.xarm_debug_timeline(env._h, buf, len(buf))
         rows = [l.split() for l in buf.value.decode().splitlines()]
-        rows = [(r[0], r[1], float(r[2]), float(r[3])) for r in rows]
+        rows = [(r[0], r[1], float(r[2]), float(r[3]), int(r[4]) if len(r) > 4 else 0) for r in rows]
         print(f"== step {t}: {len(rows)} launches with work")
         for br in "EML":
             rb = [r for r in rows if r[0] == br]
@@ -33,10 +33,14 @@ for t in range(steps):
                 acc[r[1]][0] += 1; acc[r[1]][1] += r[3] - r[2]
             print(f" branch {br}: {t0/1e3:.2f} .. {t1/1e3:.2f} ms | " + " | ".join(f"{k}: {v[0]} x {v[1]/v[0]:.0f} us = {v[1]/1e3:.2f} ms" for k, v in acc.items()))
         if os.environ.get("PASSES"):
-            for name in ("setup", "heavy_rows", "heavy_solve", "light"):
+            for name in ("setup", "heavy_rows", "heavy_solve", "heavy_solve16", "light"):
                 rb = sorted([r for r in rows if r[0] == "E" and r[1] == name], key=lambda r: r[2])
                 per = [rb[k:k + 15] for k in range(0, len(rb), 15)]
                 print(f"  E {name:12s} per pass avg us: " + " ".join(f"{sum(r[3]-r[2] for r in p_)/len(p_):.0f}" for p_ in per) + "   max: " + " ".join(f"{max(r[3]-r[2] for r in p_):.0f}" for p_ in per))
+            for br in "EM":
+                rb = sorted([r for r in rows if r[0] == br and r[1] == "heavy_rows"], key=lambda r: r[2])
+                per = [rb[k:k + 15] for k in range(0, len(rb), 15)]
+                print(f"  {br} heavy env count per pass (avg): " + " ".join(f"{sum(r[4] for r in p_)/len(p_):.0f}" for p_ in per))
             rb = sorted([r for r in rows if r[0] == "E"], key=lambda r: r[2])
             st = [r for r in rb if r[1] == "setup"]
             print("  E pass durations ms: " + " ".join(f"{(st[min(k+15, len(st)-1)][2]-st[k][2])/1e3:.2f}" for k in range(0, len(st), 15)))
