@@ -28,7 +28,7 @@ class XarmBuffers(C.Structure):
 ABI_SYMBOLS = [
     "xarm_task_dims", "xarm_create", "xarm_destroy", "xarm_bind", "xarm_reset", "xarm_step", "xarm_step_host",
     "xarm_reset_host", "xarm_compute_reward", "xarm_get_state", "xarm_set_state", "xarm_get_obs", "xarm_graph_capture",
-    "xarm_episode_stats", "xarm_launch_count", "xarm_last_error", "xarm_abi_version",
+    "xarm_episode_stats", "xarm_launch_count", "xarm_last_error", "xarm_abi_version", "xarm_set_profiling", "xarm_kernel_times",
 ]
 
 _lib = None
@@ -70,6 +70,8 @@ def load():
     L.xarm_get_obs.argtypes = [vp, vp]
     L.xarm_graph_capture.argtypes = [vp, vp]
     L.xarm_episode_stats.argtypes = [vp, C.POINTER(C.c_double), vp]
+    L.xarm_set_profiling.argtypes = [vp, C.c_int32]
+    L.xarm_kernel_times.argtypes = [vp, C.c_char_p, C.c_int64]
     L.xarm_launch_count.restype = C.c_int64
     L.xarm_last_error.restype = C.c_char_p
     _lib = L

@@ -233,7 +233,13 @@ __global__ void k_probe_smid(unsigned* seen) {
 // zero the per-launch counters of one env step (heavy lists of every pass and substep, the reset / branch lists)
 __global__ void k_pipe_begin(KArgs a, int* counters, int n_counters) {
   for (int t = threadIdx.x; t < n_counters; t += blockDim.x) counters[t] = 0;
-  if (a.tl) for (int t = threadIdx.x; t < 2 * XARM_TL_SLOTS; t += blockDim.x) a.tl[t] = (t & 1) ? 0ull : ~0ull;
+  if (a.tl) {  // fold the previous step's stamps into the per-launch accumulators, then re-arm
+    for (int t = threadIdx.x; t < XARM_TL_SLOTS; t += blockDim.x) {
+      const unsigned long long t0 = a.tl[2 * t], t1 = a.tl[2 * t + 1];
+      if (t0 != ~0ull && t1 >= t0) { a.tl[3 * XARM_TL_SLOTS + t] += t1 - t0; a.tl[4 * XARM_TL_SLOTS + t] += 1ull; }
+      a.tl[2 * t] = ~0ull; a.tl[2 * t + 1] = 0ull;
+    }
+  }
 }
 // envs that may finish in the coming step -> early list, the others -> main list (order-preserving per warp)
 template <class T>
@@ -690,7 +696,8 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   }
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
   h->pipe.timeline = getenv("XARM_TIMELINE") != nullptr;
-  if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 3 * XARM_TL_SLOTS) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }
+  if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }
+  if (h->pipe.timeline) cudaMemset(h->pipe.tl_dev, 0, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS);
   h->pipe.split = getenv("XARM_NO_SPLIT") == nullptr;
   h->pipe.dela = !(getenv("XARM_HEAVY_SOLVER") && strcmp(getenv("XARM_HEAVY_SOLVER"), "coop") == 0);
   h->k.heavy_list = h->k.reset_list + n; h->k.form = h->k.reset_list + 2 * n; h->k.rng_draw = h->k.reset_list + 3 * n;
@@ -922,6 +929,50 @@ int xarm_get_obs(XarmHandle* h, void* stream) {
   h->ops.obs(h->k, (cudaStream_t)stream);
   CUDA_TRY(cudaGetLastError());
   return XARM_OK;
+}
+
+// Profiling aid of bench.py: %globaltimer stamps around every pipeline launch (first block start .. last block end),
+// accumulated on the device per launch slot - it works inside the captured graph and in the real concurrent schedule.
+int xarm_set_profiling(XarmHandle* h, int32_t on) {
+  if (!h) return fail(XARM_E_INVALID, "xarm_set_profiling: null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (on && !h->pipe.tl_dev) CUDA_TRY(cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS));
+  if (h->pipe.tl_dev) CUDA_TRY(cudaMemset(h->pipe.tl_dev, 0, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const bool was = h->pipe.timeline;
+  h->pipe.timeline = on != 0;   // (calling it again while on just clears the accumulators)
+  if (was != h->pipe.timeline && h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }  // the launches carry the buffer: recapture
+  return XARM_OK;
+}
+
+// text lines "branch kernel launches total_us" summed over the steps since xarm_set_profiling (branch: M main, E early
+// = envs that may finish + their auto-reset passes, L late tail); returns the number of lines, < 0 on error
+int xarm_kernel_times(XarmHandle* h, char* out, int64_t cap) {
+  if (!h || !out || cap < 1) return fail(XARM_E_INVALID, "xarm_kernel_times: null argument");
+  if (!h->pipe.timeline || !h->pipe.tl_dev) return fail(XARM_E_STATE, "xarm_kernel_times: call xarm_set_profiling(h, 1) first");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t nslot = h->pipe.tl_names.size();
+  std::vector<unsigned long long> t(5 * XARM_TL_SLOTS);
+  CUDA_TRY(cudaMemcpy(t.data(), h->pipe.tl_dev, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS, cudaMemcpyDeviceToHost));
+  std::vector<std::pair<std::string, std::pair<unsigned long long, unsigned long long>>> acc;
+  for (size_t k = 0; k < nslot; k++) {
+    unsigned long long ns = t[3 * XARM_TL_SLOTS + k], cnt = t[4 * XARM_TL_SLOTS + k];
+    if (t[2 * k] != ~0ull && t[2 * k + 1] >= t[2 * k]) { ns += t[2 * k + 1] - t[2 * k]; cnt += 1; }  // the last step
+    size_t j = 0;
+    for (; j < acc.size(); j++) if (acc[j].first == h->pipe.tl_names[k]) break;
+    if (j == acc.size()) acc.push_back({h->pipe.tl_names[k], {0ull, 0ull}});
+    acc[j].second.first += cnt; acc[j].second.second += ns;
+  }
+  std::string txt;
+  char line[160];
+  for (auto& kv : acc) {
+    snprintf(line, sizeof(line), "%s %llu %.1f\n", kv.first.c_str(), kv.second.first, kv.second.second * 1e-3);
+    txt += line;
+  }
+  if ((int64_t)txt.size() + 1 > cap) txt.resize(cap - 1);
+  memcpy(out, txt.c_str(), txt.size() + 1);
+  return (int)acc.size();
 }
 
 // development aid (not part of include/xarm_abi.h): timeline of the last step as text lines "branch kernel start_us end_us"

@@ -146,6 +146,26 @@ class XarmVecEnv:
         _native.check(self._lib.xarm_graph_capture(self._h, C.c_void_p(self._stream.cuda_stream)), "xarm_graph_capture")
         self._graph_ok = True
 
+    def set_profiling(self, on=True):
+        """Device-side per-kernel timers of the step pipeline (xarm_set_profiling).  Turning them on or off drops a captured
+        graph (capture again); calling it again while on clears the accumulators."""
+        _native.check(self._lib.xarm_set_profiling(self._h, 1 if on else 0), "xarm_set_profiling")
+        if bool(on) != getattr(self, "_profiling", False):
+            self._graph_ok = False
+        self._profiling = bool(on)
+
+    def kernel_times(self):
+        """{(branch, kernel): (launches, total_us)} accumulated since set_profiling (xarm_kernel_times)."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self._lib.xarm_kernel_times(self._h, buf, len(buf))
+        if n < 0:
+            _native.check(n, "xarm_kernel_times")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            br, name, cnt, us = line.split()
+            out[(br, name)] = (int(cnt), float(us))
+        return out
+
     # ------------------------------------------------------------------ gym / VecEnv surface
     def seed(self, seed=None):
         return [seed]  # D11: RNG streams are fixed at construction (seed, global env index, episode)

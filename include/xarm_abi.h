@@ -132,6 +132,12 @@ int xarm_graph_capture(XarmHandle* h, void* stream);
 int xarm_episode_stats(XarmHandle* h, double out[5], void* stream);
 
 /* kernels launched by this library since load (claim for bench.py's gpu_launches) */
+/* Profiling aid (bench.py): device-side %globaltimer stamps around every launch of the step pipeline, accumulated per
+ * kernel.  xarm_set_profiling invalidates a captured graph (capture again).  xarm_kernel_times writes text lines
+ * "branch kernel launches total_us" (branch M = main, E = early branch + its auto-reset passes, L = late tail) into
+ * out[cap] and returns the number of lines.  [no reference counterpart: PyBullet has no per-stage timers] */
+int xarm_set_profiling(XarmHandle* h, int32_t on);
+int xarm_kernel_times(XarmHandle* h, char* out, int64_t cap);
 int64_t xarm_launch_count(void);
 const char* xarm_last_error(void);
 int xarm_abi_version(void);

@@ -2,7 +2,7 @@
 """Print the kernel sequence of an ncu launch list (gpu__time_duration csv): tag + microseconds, and per-kernel totals."""
 import collections, csv, sys
 rows = list(csv.DictReader(l for l in open(sys.argv[1]) if l.startswith('"')))
-tag = {'k_pipe_heavy_all': 'HA', 'k_pipe_heavy': 'H', 'k_pipe_setup': 'S', 'k_pipe_light': 'L', 'k_pipe_reset': 'R', 'k_pipe_action': 'A',
+tag = {'k_heavy_solve2': 'Z', 'k_heavy_solve': 'Y', 'k_heavy_rows': 'W', 'k_pipe_heavy_all': 'HA', 'k_pipe_heavy': 'H', 'k_pipe_setup': 'S', 'k_pipe_light': 'L', 'k_pipe_reset': 'R', 'k_pipe_action': 'A',
        'k_pipe_finish': 'F', 'k_pipe_begin': 'B', 'k_pipe_split': 'P'}
 out, agg = [], collections.defaultdict(lambda: [0, 0.0])
 for r in rows:
