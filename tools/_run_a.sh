@@ -1,4 +1,8 @@
 cd $GRAFT_REPO_ROOT
-python bench.py --steps 2 --warmup 47 --no-graph --no-cpu-baseline --e2e-steps 1 > gpurun_out/r1z_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'k_heavy_solve2|k_heavy_rows' -s 20960 -c 4 -o gpurun_out/r1z_wave python bench.py --steps 2 --warmup 47 --no-graph --no-cpu-baseline --e2e-steps 1 > gpurun_out/r1z_ncu.log 2>&1
-echo "ncu rc=$?"; tail -2 gpurun_out/r1z_ncu.log | cut -c1-200
+python bench.py --steps 110 --warmup 5 --no-cpu-baseline > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err
+python -c "
+import json
+d=json.load(open('gpurun_out/r2a_bench.json')); print(round(d['value']), d['step_ms_quantiles'], d['e2e']['value'], d['episode_stats']); print(d['step_ms_first_60'])
+"
+XARM_TRACE_STAGES=1 python bench.py --steps 40 --warmup 3 --no-graph --no-cpu-baseline --e2e-steps 1 2>&1 | grep "xarm lists" | tail -12
+PASSES=1 LAST=1 python tools/timeline.py 30 2>&1 | grep -v "branch L" | tail -9
