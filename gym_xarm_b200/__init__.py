@@ -8,6 +8,7 @@ from .vec_env import XarmVecEnv, InfoList  # noqa: F401
 from .envs import XarmReachEnv, XarmPickAndPlace, XarmStackTowerEnv, XarmPushWithDoorEnv, XarmHandover  # noqa: F401
 from .registration import REGISTRY, make, make_vec, register_with_gym  # noqa: F401
 from . import distributed  # noqa: F401
+from .policies import ezpolicy  # noqa: F401
 
 register_with_gym()
 __version__ = "0.1.0"

@@ -313,6 +313,7 @@ struct PipeCtx {
   // SM partition (XARM_RESERVE_SMS, default 12; 0 = off): while `dyn` is set (main branch of a split step) every launch
   // gets a work counter and the mask of the SMs it must leave to the early branch
   bool dyn = false;
+  int setup_bps = 4;   // resident blocks per SM of the partitioned main branch's setup kernel (XARM_SETUP_BPS)
   int reserve_sms = 0, n_work = 0, next_work = 0;
   int* work_base = nullptr;
   unsigned long long sm_mask[4] = {0, 0, 0, 0};
@@ -425,7 +426,7 @@ struct OpsT {
       } else {
         int* hc = a.heavy_count + pass * XARM_MAX_SUBSTEPS + sub;
         c.begin("setup", s);
-        k_pipe_setup<T><<<g, 128, 0, s>>>(c.tl(a), sub, hc);
+        k_pipe_setup<T><<<part ? dim3(c.heavy_grid * c.setup_bps) : g, 128, 0, s>>>(c.tl(a), sub, hc);
         c.end(s);
         cudaEvent_t join = nullptr;
         if (fork_heavy) {
@@ -675,7 +676,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) { cudaGetLastError(); return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed"); }
   }
   {  // SMs reserved for the early branch of a split step
-    const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 12;
+    const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 20;
     if (want > 0 && ops.hrec_words() > 0) {
       unsigned* d_seen = nullptr;
       unsigned seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -694,6 +695,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
       cudaGetLastError();
     }
   }
+  if (getenv("XARM_SETUP_BPS")) h->pipe.setup_bps = atoi(getenv("XARM_SETUP_BPS"));
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
   h->pipe.timeline = getenv("XARM_TIMELINE") != nullptr;
   if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }

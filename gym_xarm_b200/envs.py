@@ -81,5 +81,9 @@ class XarmPushWithDoorEnv(_SingleEnv):   # [REF gym_xarm/envs/xarm_push_with_doo
 class XarmHandover(_SingleEnv):          # [REF gym_xarm/envs/xarm_handover.py:19]
     _task = "handover"
 
+    def ezpolicy(self, obs):             # [REF gym_xarm/envs/xarm_handover.py:404-446] the reference's scripted handover
+        from .policies import ezpolicy
+        return ezpolicy(obs)
+
 
 ENV_CLASSES = {c._task: c for c in (XarmReachEnv, XarmPickAndPlace, XarmStackTowerEnv, XarmPushWithDoorEnv, XarmHandover)}

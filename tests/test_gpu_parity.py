@@ -332,3 +332,32 @@ def test_heavy_solver_impulse_form_matches_velocity_form():
     assert abs(la - lb) < 0.03, (la, lb)
     a_env.close()
     b_env.close()
+
+
+def test_handover_ezpolicy_statistics():
+    """Contact task under the reference's own scripted policy (XarmHandover.ezpolicy [REF xarm_handover.py:404-446]): the CUDA
+    path and the oracle run the same closed loop (each on its own observations) for 40 steps from the same seeded resets.
+    Gripper contacts amplify float32 rounding, so outcomes are compared as statistics: how far arm 1 carried the lego and the
+    fraction of envs in which a gripper closed on it."""
+    import torch
+    from gym_xarm_b200.policies import ezpolicy
+    n = 192
+    env = _mk("handover", n, seed=29, auto_reset=False)
+    ref = [orc.OracleEnv("handover", env_index=i, seed=29, auto_reset=0, goal_shape="ground") for i in range(n)]
+    obs = env.reset()
+    robs = [r.reset() for r in ref]
+    o_gpu = obs["observation"]
+    for t in range(40):
+        a_gpu = ezpolicy(o_gpu).clamp(-1, 1).float()
+        o_gpu = env.step(a_gpu)[0]["observation"]
+        a_ref = [np.clip(ezpolicy(ro["observation"]), -1, 1).astype(np.float32) for ro in robs]
+        robs = [r.step(a)[0] for r, a in zip(ref, a_ref)]
+        assert torch.isfinite(o_gpu).all()
+    og = o_gpu.cpu().numpy()
+    orf = np.stack([ro["observation"] for ro in robs])
+    near_gpu = float((np.linalg.norm(og[:, 0:3] - og[:, 13:16], axis=1) < 0.1).mean())
+    near_ref = float((np.linalg.norm(orf[:, 0:3] - orf[:, 13:16], axis=1) < 0.1).mean())
+    z_gpu, z_ref = float(np.median(og[:, 2])), float(np.median(orf[:, 2]))
+    print(f"ezpolicy after 40 steps: gripper-1 within 10 cm of the lego CUDA {near_gpu:.3f} vs oracle {near_ref:.3f}; median lego z {z_gpu:.4f} vs {z_ref:.4f}")
+    assert abs(near_gpu - near_ref) < 0.06 and abs(z_gpu - z_ref) < 0.01
+    env.close()
