@@ -361,3 +361,51 @@ def test_handover_ezpolicy_statistics():
     print(f"ezpolicy after 40 steps: gripper-1 within 10 cm of the lego CUDA {near_gpu:.3f} vs oracle {near_ref:.3f}; median lego z {z_gpu:.4f} vs {z_ref:.4f}")
     assert abs(near_gpu - near_ref) < 0.06 and abs(z_gpu - z_ref) < 0.01
     env.close()
+
+
+@pytest.mark.parametrize("task", ["stack_tower", "push_with_door"])
+def test_two_arm_contact_statistics_scripted_push(task):
+    """Two-arm contact tasks under a scripted push (each arm servoes its open gripper, as low as its workspace allows, at the
+    nearest cube): the CUDA path and the oracle run the same closed loop, each on its own observations.  Gripper contacts
+    amplify float32 rounding, so the outcome is compared as statistics over the envs: the fraction of envs whose cube was
+    pushed more than 1 cm and the mean push distance (PushWithDoor: also the mean door travel)."""
+    import torch
+    n, steps = 64, 30
+    env = _mk(task, n, seed=41, auto_reset=False)
+    ref = [orc.OracleEnv(task, env_index=i, seed=41, auto_reset=0) for i in range(n)]
+    obs = env.reset()["observation"].cpu().numpy()
+    robs = np.stack([r.reset()["observation"] for r in ref])
+    nobj = 3 if task == "stack_tower" else 1
+    h1 = 13 * nobj                                # hand-1 position; hand-2 follows 8 (StackTower: pos, vel, finger) or 6 words later
+    h2 = h1 + (8 if task == "stack_tower" else 6)
+    adim = env.act_dim
+
+    def policy(o):
+        a = np.zeros((len(o), adim), np.float32)
+        cubes = o[:, :3 * nobj].reshape(len(o), nobj, 3)
+        for arm, hp in enumerate((h1, h2)):
+            hand = o[:, hp:hp + 3]
+            d = np.linalg.norm(cubes[:, :, :2] - hand[:, None, :2], axis=2)
+            tgt = cubes[np.arange(len(o)), d.argmin(1)]
+            delta = tgt - hand
+            delta[:, 2] = -1.0                    # stay as low as the eef clip allows
+            k = 4 if task == "stack_tower" else 3
+            a[:, k * arm:k * arm + 3] = np.clip(8.0 * delta, -1, 1)
+            if task == "stack_tower":
+                a[:, 4 * arm + 3] = 1.0           # fingers open
+        return a
+
+    p0_gpu, p0_ref = obs[:, :3 * nobj].copy(), robs[:, :3 * nobj].copy()
+    for t in range(steps):
+        obs = env.step(torch.from_numpy(policy(obs)).cuda())[0]["observation"].cpu().numpy()
+        ar = policy(robs)
+        robs = np.stack([r.step(ar[i])[0]["observation"] for i, r in enumerate(ref)])
+        assert np.isfinite(obs).all()
+    push_gpu = np.linalg.norm((obs[:, :3 * nobj] - p0_gpu).reshape(n, nobj, 3)[:, :, :2], axis=2).max(1)
+    push_ref = np.linalg.norm((robs[:, :3 * nobj] - p0_ref).reshape(n, nobj, 3)[:, :, :2], axis=2).max(1)
+    f_gpu, f_ref = float((push_gpu > 0.01).mean()), float((push_ref > 0.01).mean())
+    m_gpu, m_ref = float(push_gpu.mean()), float(push_ref.mean())
+    print(f"{task} scripted push: pushed > 1 cm CUDA {f_gpu:.3f} vs oracle {f_ref:.3f}; mean push {m_gpu:.4f} vs {m_ref:.4f} m")
+    assert f_ref > 0.1, "the script must reach the cubes"
+    assert abs(f_gpu - f_ref) < 0.08 and abs(m_gpu - m_ref) < 0.25 * max(m_ref, 0.02)
+    env.close()
