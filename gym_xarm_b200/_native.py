@@ -24,11 +24,21 @@ class XarmBuffers(C.Structure):
     ]
 
 
+class XarmVecNormConfig(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int64), ("obs_dim", C.c_int32), ("device", C.c_int32),
+        ("gamma", C.c_float), ("clip_obs", C.c_float), ("clip_reward", C.c_float), ("epsilon", C.c_float),
+        ("norm_obs", C.c_int32), ("norm_reward", C.c_int32), ("training", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 # every symbol include/xarm_abi.h declares
 ABI_SYMBOLS = [
     "xarm_task_dims", "xarm_create", "xarm_destroy", "xarm_bind", "xarm_reset", "xarm_step", "xarm_step_host",
     "xarm_reset_host", "xarm_compute_reward", "xarm_get_state", "xarm_set_state", "xarm_get_obs", "xarm_graph_capture",
     "xarm_episode_stats", "xarm_launch_count", "xarm_last_error", "xarm_abi_version", "xarm_set_profiling", "xarm_kernel_times",
+    "xarm_vecnorm_create", "xarm_vecnorm_destroy", "xarm_vecnorm_reset", "xarm_vecnorm_step", "xarm_vecnorm_set_training",
+    "xarm_vecnorm_get_stats", "xarm_vecnorm_set_stats",
 ]
 
 _lib = None
@@ -72,6 +82,14 @@ def load():
     L.xarm_episode_stats.argtypes = [vp, C.POINTER(C.c_double), vp]
     L.xarm_set_profiling.argtypes = [vp, C.c_int32]
     L.xarm_kernel_times.argtypes = [vp, C.c_char_p, C.c_int64]
+    dp = C.POINTER(C.c_double)
+    L.xarm_vecnorm_create.argtypes = [C.POINTER(XarmVecNormConfig), C.POINTER(vp)]
+    L.xarm_vecnorm_destroy.argtypes = [vp]
+    L.xarm_vecnorm_reset.argtypes = [vp, vp, vp, vp]
+    L.xarm_vecnorm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.xarm_vecnorm_set_training.argtypes = [vp, C.c_int32]
+    L.xarm_vecnorm_get_stats.argtypes = [vp, dp, dp, dp, dp]
+    L.xarm_vecnorm_set_stats.argtypes = [vp, dp, dp, C.c_double, dp]
     L.xarm_launch_count.restype = C.c_int64
     L.xarm_last_error.restype = C.c_char_p
     _lib = L

@@ -12,6 +12,7 @@
 
 #include "xarm_pipeline.cuh"
 #include "xarm_heavy.cuh"
+#include "xarm_vecnorm.cuh"
 
 // ------------------------------------------------------------------------------------------------ kernels
 // One thread per env; 128-thread blocks (a warp steps 32 envs in lock-step).
@@ -1016,6 +1017,119 @@ int xarm_episode_stats(XarmHandle* h, double out[5], void* stream) {
   CUDA_TRY(cudaMemcpyAsync(out, h->k.stats, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemsetAsync(h->k.stats, 0, sizeof(double) * 5, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  return XARM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ VecNormalize
+struct XarmVecNorm {
+  XarmVecNormConfig cfg;
+  VnStats* st = nullptr;     // device
+  float* ret = nullptr;      // [N] discounted returns
+  unsigned grid = 0;         // grid * 256 threads: a multiple of obs_dim
+};
+
+static int vn_gcd(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+int xarm_vecnorm_create(const XarmVecNormConfig* cfg, XarmVecNorm** out) {
+  if (!cfg || !out) return fail(XARM_E_INVALID, "xarm_vecnorm_create: null argument");
+  if (cfg->num_envs <= 0 || cfg->obs_dim <= 0 || cfg->obs_dim > XARM_VN_MAX_OBS) return fail(XARM_E_INVALID, "xarm_vecnorm_create: num_envs > 0 and 0 < obs_dim <= 128 required");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(XARM_E_INVALID, "xarm_vecnorm_create: bad device ordinal");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  XarmVecNorm* v = new (std::nothrow) XarmVecNorm();
+  if (!v) return fail(XARM_E_NOMEM, "xarm_vecnorm_create: out of host memory");
+  v->cfg = *cfg;
+  if (cudaMalloc(&v->st, sizeof(VnStats)) != cudaSuccess || cudaMalloc(&v->ret, sizeof(float) * cfg->num_envs) != cudaSuccess) {
+    cudaFree(v->st); cudaFree(v->ret); delete v; cudaGetLastError();
+    return fail(XARM_E_NOMEM, "xarm_vecnorm_create: cudaMalloc failed");
+  }
+  VnStats h;
+  memset(&h, 0, sizeof(h));
+  for (int k = 0; k < XARM_VN_MAX_OBS; k++) h.var[k] = 1.0;     // RunningMeanStd(): mean 0, var 1, count 1e-4
+  h.count = 1e-4; h.rvar = 1.0; h.rcount = 1e-4;
+  CUDA_TRY(cudaMemcpy(v->st, &h, sizeof(h), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemset(v->ret, 0, sizeof(float) * cfg->num_envs));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  const int unit = cfg->obs_dim / vn_gcd(cfg->obs_dim, 256);     // grid must be a multiple of this
+  int64_t want = (cfg->num_envs * cfg->obs_dim + 256 * 8 - 1) / (256 * 8);   // ~8 elements per thread
+  if (want > (int64_t)sms * 8) want = (int64_t)sms * 8;
+  if (want < 1) want = 1;
+  v->grid = (unsigned)((want + unit - 1) / unit * unit);
+  k_vn_finalize<<<1, XARM_VN_MAX_OBS>>>(v->st, 1, cfg->obs_dim, cfg->epsilon, 0, 0);  // fmean / finv / rinv of the initial statistics
+  g_launches++;
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = v;
+  return XARM_OK;
+}
+
+int xarm_vecnorm_destroy(XarmVecNorm* v) {
+  if (!v) return XARM_OK;
+  cudaSetDevice(v->cfg.device);
+  cudaFree(v->st); cudaFree(v->ret);
+  delete v;
+  return XARM_OK;
+}
+
+int xarm_vecnorm_set_training(XarmVecNorm* v, int32_t training) {
+  if (!v) return fail(XARM_E_INVALID, "xarm_vecnorm_set_training: null handle");
+  v->cfg.training = training;
+  return XARM_OK;
+}
+
+int xarm_vecnorm_reset(XarmVecNorm* v, const float* obs, float* obs_out, void* stream) {
+  if (!v || !obs || !obs_out) return fail(XARM_E_INVALID, "xarm_vecnorm_reset: null argument");
+  CUDA_TRY(cudaSetDevice(v->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const XarmVecNormConfig& c = v->cfg;
+  // returns := 0; ret_rms.update(returns) when training (stable-baselines3 1.x); obs_rms is not touched
+  k_vn_moments<<<v->grid, 256, 0, s>>>(v->st, obs, c.num_envs, c.obs_dim, v->ret, nullptr, c.gamma, 0, 2);
+  k_vn_finalize<<<1, XARM_VN_MAX_OBS, 0, s>>>(v->st, c.num_envs, c.obs_dim, c.epsilon, 0, c.training != 0);
+  k_vn_apply<<<v->grid, 256, 0, s>>>(v->st, obs, obs_out, c.num_envs, c.obs_dim, nullptr, nullptr, nullptr, v->ret, c.clip_obs, c.clip_reward, c.norm_obs, c.norm_reward);
+  g_launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_vecnorm_step(XarmVecNorm* v, const float* obs, const float* reward, const uint8_t* done, float* obs_out, float* reward_out, void* stream) {
+  if (!v || !obs || !reward || !done || !obs_out || !reward_out) return fail(XARM_E_INVALID, "xarm_vecnorm_step: null argument");
+  CUDA_TRY(cudaSetDevice(v->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const XarmVecNormConfig& c = v->cfg;
+  const int tr = c.training != 0;
+  if (tr) { k_vn_moments<<<v->grid, 256, 0, s>>>(v->st, obs, c.num_envs, c.obs_dim, v->ret, reward, c.gamma, c.norm_obs != 0, 1); g_launches++; }
+  k_vn_finalize<<<1, XARM_VN_MAX_OBS, 0, s>>>(v->st, c.num_envs, c.obs_dim, c.epsilon, tr && c.norm_obs, tr);
+  k_vn_apply<<<v->grid, 256, 0, s>>>(v->st, obs, obs_out, c.num_envs, c.obs_dim, reward, reward_out, done, v->ret, c.clip_obs, c.clip_reward, c.norm_obs, c.norm_reward);
+  g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_vecnorm_get_stats(XarmVecNorm* v, double* obs_mean, double* obs_var, double* obs_count, double* ret_stats3) {
+  if (!v) return fail(XARM_E_INVALID, "xarm_vecnorm_get_stats: null handle");
+  CUDA_TRY(cudaSetDevice(v->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  VnStats h;
+  CUDA_TRY(cudaMemcpy(&h, v->st, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < v->cfg.obs_dim; k++) { if (obs_mean) obs_mean[k] = h.mean[k]; if (obs_var) obs_var[k] = h.var[k]; }
+  if (obs_count) *obs_count = h.count;
+  if (ret_stats3) { ret_stats3[0] = h.rmean; ret_stats3[1] = h.rvar; ret_stats3[2] = h.rcount; }
+  return XARM_OK;
+}
+
+int xarm_vecnorm_set_stats(XarmVecNorm* v, const double* obs_mean, const double* obs_var, double obs_count, const double* ret_stats3) {
+  if (!v || !obs_mean || !obs_var || !ret_stats3) return fail(XARM_E_INVALID, "xarm_vecnorm_set_stats: null argument");
+  CUDA_TRY(cudaSetDevice(v->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  VnStats h;
+  CUDA_TRY(cudaMemcpy(&h, v->st, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < v->cfg.obs_dim; k++) { h.mean[k] = obs_mean[k]; h.var[k] = obs_var[k]; }
+  h.count = obs_count; h.rmean = ret_stats3[0]; h.rvar = ret_stats3[1]; h.rcount = ret_stats3[2];
+  CUDA_TRY(cudaMemcpy(v->st, &h, sizeof(h), cudaMemcpyHostToDevice));
+  k_vn_finalize<<<1, XARM_VN_MAX_OBS>>>(v->st, 1, v->cfg.obs_dim, v->cfg.epsilon, 0, 0);
+  g_launches++;
+  CUDA_TRY(cudaDeviceSynchronize());
   return XARM_OK;
 }
 

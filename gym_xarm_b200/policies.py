@@ -7,8 +7,8 @@ Handover observation (num_obj = 1): lego pos 0:3, quat 3:7, linvel 7:10, angvel 
 finger-1 joint 19, its velocity 20, hand-2 pos 21:24, vel 24:27, finger-2 joint 27, its velocity 28.
 
 Works on one observation ([29] numpy, as the reference) or on a batch ([N, 29] numpy array or torch tensor on any
-device); the arithmetic is the reference's, in the array's own dtype.  tests/test_oracle_golden.py checks it bit for bit
-against vectors produced by the reference's own function (tests/golden/make_golden_ezpolicy.py).
+device); the arithmetic is the reference's, in the array's own dtype.  The CPU test suite checks it bit for bit against
+vectors produced by the reference's own function (tests/golden/make_golden_ezpolicy.py).
 """
 import numpy as np
 

@@ -131,13 +131,44 @@ int xarm_graph_capture(XarmHandle* h, void* stream);
  * out[0]=episodes, out[1]=sum return, out[2]=sum length, out[3]=sum success, out[4]=diverged (NaN-guard resets). */
 int xarm_episode_stats(XarmHandle* h, double out[5], void* stream);
 
-/* kernels launched by this library since load (claim for bench.py's gpu_launches) */
 /* Profiling aid (bench.py): device-side %globaltimer stamps around every launch of the step pipeline, accumulated per
  * kernel.  xarm_set_profiling invalidates a captured graph (capture again).  xarm_kernel_times writes text lines
  * "branch kernel launches total_us" (branch M = main, E = early branch + its auto-reset passes, L = late tail) into
  * out[cap] and returns the number of lines.  [no reference counterpart: PyBullet has no per-stage timers] */
 int xarm_set_profiling(XarmHandle* h, int32_t on);
 int xarm_kernel_times(XarmHandle* h, char* out, int64_t cap);
+/* ---- caller side of the path: SB3 VecExtractDictObs + VecNormalize on the device
+ * [REF benchmark/train.py:44-62,74-75: make_vec_env -> VecNormalize(env, norm_obs=True, norm_reward=True, clip_obs=10.)].
+ * Semantics of stable-baselines3 1.x VecNormalize, pinned by the reference's saved benchmark/saved_data/
+ * XarmPDHandoverNoGoal-v1/vec_normalize.pkl (epsilon 1e-8, gamma 0.99, clip 10/10, RunningMeanStd count 1e-4 at start;
+ * after 6250 steps of 4 envs obs_rms.count = 25000.0001 and ret_rms.count = 25004.0001: reset() feeds the zeroed
+ * returns to ret_rms and does not touch obs_rms).  Running statistics are float64 on the device. */
+typedef struct XarmVecNormConfig {
+  int64_t num_envs;
+  int32_t obs_dim;        /* flat observation (obs['observation']) */
+  int32_t device;
+  float gamma;            /* 0.99 */
+  float clip_obs;         /* 10 */
+  float clip_reward;      /* 10 */
+  float epsilon;          /* 1e-8 */
+  int32_t norm_obs, norm_reward, training, reserved;
+} XarmVecNormConfig;
+typedef struct XarmVecNorm XarmVecNorm;
+int xarm_vecnorm_create(const XarmVecNormConfig* cfg, XarmVecNorm** out);
+int xarm_vecnorm_destroy(XarmVecNorm* v);
+/* VecNormalize.reset(): returns := 0, ret_rms.update(returns) when training, obs_out = normalize_obs(obs).  Device pointers. */
+int xarm_vecnorm_reset(XarmVecNorm* v, const float* obs, float* obs_out, void* stream);
+/* VecNormalize.step_wait() after the env step: obs_rms.update(obs), obs_out = clip((obs - mean) / sqrt(var + eps)),
+ * returns = returns * gamma + reward, ret_rms.update(returns), reward_out = clip(reward / sqrt(ret var + eps)),
+ * returns[done] = 0.  obs [N, obs_dim], reward [N], done uint8 [N]: device pointers; outputs may alias the inputs. */
+int xarm_vecnorm_step(XarmVecNorm* v, const float* obs, const float* reward, const uint8_t* done, float* obs_out,
+                      float* reward_out, void* stream);
+int xarm_vecnorm_set_training(XarmVecNorm* v, int32_t training);
+/* obs_rms / ret_rms (HOST float64: mean[obs_dim], var[obs_dim], count; mean, var, count) - VecNormalize.save / load */
+int xarm_vecnorm_get_stats(XarmVecNorm* v, double* obs_mean, double* obs_var, double* obs_count, double* ret_stats3);
+int xarm_vecnorm_set_stats(XarmVecNorm* v, const double* obs_mean, const double* obs_var, double obs_count, const double* ret_stats3);
+
+/* kernels launched by this library since load (claim for bench.py's gpu_launches) */
 int64_t xarm_launch_count(void);
 const char* xarm_last_error(void);
 int xarm_abi_version(void);

@@ -409,3 +409,54 @@ def test_two_arm_contact_statistics_scripted_push(task):
     assert f_ref > 0.1, "the script must reach the cubes"
     assert abs(f_gpu - f_ref) < 0.08 and abs(m_gpu - m_ref) < 0.25 * max(m_ref, 0.02)
     env.close()
+
+
+def test_vecnormalize_matches_sb3_restatement():
+    """xarm_vecnorm_* (VecExtractDictObs + VecNormalize on the device) against the numpy float64 restatement
+    of stable-baselines3 1.x (oracle/vecnorm_oracle.py, pinned by the reference's saved vec_normalize.pkl): 60 steps of a real
+    Handover env under random actions - normalised observation / reward to 1e-4 (float32 arithmetic on float64 statistics),
+    running statistics to 1e-6 relative, the counts exactly; then evaluation mode and a save / load round trip."""
+    import os
+    import tempfile
+    import torch
+    from gym_xarm_b200.vec_normalize import XarmVecNormalize
+    from oracle.vecnorm_oracle import VecNormalizeOracle
+    n = 512
+    env = _mk("handover", n, seed=7, auto_reset=True, config={"reward_type": "dense"})
+    vn = XarmVecNormalize(env)
+    ref = VecNormalizeOracle(n, vn.obs_dim)
+    o = vn.reset()
+    np.testing.assert_allclose(o.cpu().numpy(), ref.reset(env.obs_buf["observation"].cpu().numpy().astype(np.float64)), atol=1e-4)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(60):
+        a = torch.rand(n, env.act_dim, generator=g, device="cuda") * 2 - 1
+        o, r, d, _ = vn.step(a)
+        raw_o = vn.get_original_obs().cpu().numpy().astype(np.float64)
+        raw_r = vn.get_original_reward().cpu().numpy().astype(np.float64)
+        ro, rr = ref.step(raw_o, raw_r, d.cpu().numpy())
+        np.testing.assert_allclose(o.cpu().numpy(), ro, atol=2e-4, err_msg=f"obs step {t}")
+        np.testing.assert_allclose(r.cpu().numpy(), rr, atol=2e-4, rtol=1e-4, err_msg=f"reward step {t}")
+    om, rm = vn.obs_rms, vn.ret_rms
+    assert om.count == ref.obs_rms.count == 1e-4 + 60 * n and rm.count == ref.ret_rms.count == 1e-4 + 61 * n
+    np.testing.assert_allclose(om.mean, ref.obs_rms.mean, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(om.var, ref.obs_rms.var, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose([rm.mean, rm.var], [ref.ret_rms.mean, ref.ret_rms.var], rtol=1e-5, atol=1e-9)
+    # evaluation mode: statistics frozen
+    vn.training = False
+    ref.training = False
+    a = torch.rand(n, env.act_dim, generator=g, device="cuda") * 2 - 1
+    o, r, d, _ = vn.step(a)
+    ro, rr = ref.step(vn.get_original_obs().cpu().numpy().astype(np.float64), vn.get_original_reward().cpu().numpy().astype(np.float64), d.cpu().numpy())
+    np.testing.assert_allclose(o.cpu().numpy(), ro, atol=2e-4)
+    assert vn.obs_rms.count == om.count
+    # save / load (VecNormalize.save / load of the training script)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "vec_normalize.npz")
+        vn.save(path)
+        vn2 = XarmVecNormalize(env, training=False)
+        vn2.load(path)
+        np.testing.assert_array_equal(vn2.obs_rms.mean, vn.obs_rms.mean)
+        assert vn2.ret_rms == vn.ret_rms
+        vn2.close()
+    vn.close()
+    env.close()
