@@ -15,18 +15,59 @@ struct VnStats {          // device, float64
 
 // batch moments of obs (per column) and, for step, of the updated returns.  The launch uses a thread count that is a
 // multiple of obs_dim, so a thread's column is fixed over its grid-stride loop and its two sums stay in registers.
-__global__ void __launch_bounds__(256) k_vn_moments(VnStats* st, const float* __restrict__ obs, int64_t n, int O, float* __restrict__ ret,
+__global__ void __launch_bounds__(256, 6) k_vn_moments(VnStats* st, const float* __restrict__ obs, int64_t n, int O, float* __restrict__ ret,
                                                     const float* __restrict__ reward, float gamma, int do_obs, int ret_mode) {
-  __shared__ double sh[2 * XARM_VN_MAX_OBS + 2];
-  for (int k = threadIdx.x; k < 2 * O + 2; k += blockDim.x) sh[k] = 0.0;
+  // per-warp accumulators (shared-memory double atomics are CAS loops: keep the contention to the <= 5 lanes of a warp that
+  // share a column), combined by the first 2 O + 2 threads
+  constexpr int SW = 2 * XARM_VN_MAX_OBS + 2;
+  __shared__ double shw[8][SW];
+  double* sh = shw[threadIdx.x >> 5];
+  for (int k = threadIdx.x; k < 8 * SW; k += blockDim.x) (&shw[0][0])[k] = 0.0;
   __syncthreads();
   const int64_t T = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (do_obs) {
-    const int col = (int)(t0 % O);
-    const double m0 = st->mean[col];
-    double s1 = 0.0, s2 = 0.0;
-    for (int64_t e = t0; e < n * O; e += T) { const double d = (double)obs[e] - m0; s1 += d; s2 += d * d; }
-    atomicAdd(&sh[col], s1); atomicAdd(&sh[O + col], s2);
+    // 4 consecutive elements per thread and iteration (one 128-bit load); T * 4 is a multiple of O, so the four columns
+    // of a thread are fixed.  float partial sums over chunks of 8 iterations, folded into doubles (shifted data: small)
+    const int64_t total = n * O, q0 = t0 * 4;
+    int col[4];
+    float m0[4];
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) { col[k] = (int)((q0 + k) % O); m0[k] = (float)st->mean[col[k]]; }
+    float p1[4] = {0, 0, 0, 0}, p2[4] = {0, 0, 0, 0};
+    int it = 0, cnt[4] = {0, 0, 0, 0};
+    const int64_t step = T * 4;
+    int64_t e = q0;
+    // main part: two 128-bit loads in flight per thread
+    for (; e + step + 3 < total; e += 2 * step) {
+      const float4 va = *reinterpret_cast<const float4*>(obs + e);
+      const float4 vb = *reinterpret_cast<const float4*>(obs + e + step);
+      const float xa[4] = {va.x, va.y, va.z, va.w}, xb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float da = xa[k] - m0[k], db = xb[k] - m0[k];
+        p1[k] += da + db; p2[k] += da * da + db * db;
+        cnt[k] += 2;
+      }
+      if ((++it & 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { s1[k] += (double)p1[k]; s2[k] += (double)p2[k]; p1[k] = 0.f; p2[k] = 0.f; }
+      }
+    }
+    for (; e < total; e += step) {   // tail
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (e + k < total) { const float d = obs[e + k] - m0[k]; p1[k] += d; p2[k] += d * d; cnt[k] += 1; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      s1[k] += (double)p1[k]; s2[k] += (double)p2[k];
+      // the data were shifted by float(mean): move the sums to the double mean the finalize pass assumes
+      const double c = (double)m0[k] - st->mean[col[k]];
+      const double t1 = s1[k] + (double)cnt[k] * c, t2 = s2[k] + 2.0 * c * s1[k] + (double)cnt[k] * c * c;
+      atomicAdd(&sh[col[k]], t1); atomicAdd(&sh[O + col[k]], t2);
+    }
   }
   if (ret_mode) {  // 1: returns = returns * gamma + reward (step); 2: returns = 0 (reset)
     double s1 = 0.0, s2 = 0.0;
@@ -40,7 +81,12 @@ __global__ void __launch_bounds__(256) k_vn_moments(VnStats* st, const float* __
     if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[2 * O], s1); atomicAdd(&sh[2 * O + 1], s2); }
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < 2 * O + 2; k += blockDim.x) if (sh[k] != 0.0) atomicAdd(&st->acc[k], sh[k]);
+  for (int k = threadIdx.x; k < 2 * O + 2; k += blockDim.x) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) v += shw[w][k];
+    if (v != 0.0) atomicAdd(&st->acc[k], v);
+  }
 }
 
 // RunningMeanStd.update_from_moments for every column and for the returns; refresh what the apply pass reads
@@ -83,12 +129,36 @@ __global__ void __launch_bounds__(256) k_vn_apply(const VnStats* __restrict__ st
   __syncthreads();
   const int64_t T = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (obs_out) {
-    const int col = (int)(t0 % O);   // fixed per thread: T is a multiple of O
-    const float m = sm[col], iv = sm[O + col];
-    for (int64_t e = t0; e < n * O; e += T) {
-      const float x = obs[e];
-      obs_out[e] = norm_obs ? fminf(fmaxf((x - m) * iv, -clip_obs), clip_obs) : x;
+    const int64_t total = n * O, q0 = t0 * 4;   // four fixed columns per thread: T * 4 is a multiple of O
+    float m[4], iv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int col = (int)((q0 + k) % O); m[k] = sm[col]; iv[k] = sm[O + col]; }
+    const int64_t step = T * 4;
+    int64_t e = q0;
+#define VN_NORM4(v, o)                                                                                            \
+    if (norm_obs) {                                                                                               \
+      o.x = fminf(fmaxf((v.x - m[0]) * iv[0], -clip_obs), clip_obs); o.y = fminf(fmaxf((v.y - m[1]) * iv[1], -clip_obs), clip_obs); \
+      o.z = fminf(fmaxf((v.z - m[2]) * iv[2], -clip_obs), clip_obs); o.w = fminf(fmaxf((v.w - m[3]) * iv[3], -clip_obs), clip_obs); \
     }
+    for (; e + step + 3 < total; e += 2 * step) {   // two 128-bit loads in flight per thread
+      const float4 va = *reinterpret_cast<const float4*>(obs + e);
+      const float4 vb = *reinterpret_cast<const float4*>(obs + e + step);
+      float4 oa = va, ob = vb;
+      VN_NORM4(va, oa) VN_NORM4(vb, ob)
+      *reinterpret_cast<float4*>(obs_out + e) = oa;
+      *reinterpret_cast<float4*>(obs_out + e + step) = ob;
+    }
+    for (; e < total; e += step) {
+      if (e + 3 < total) {
+        const float4 v = *reinterpret_cast<const float4*>(obs + e);
+        float4 o = v;
+        VN_NORM4(v, o)
+        *reinterpret_cast<float4*>(obs_out + e) = o;
+      } else {
+        for (int k = 0; k < 4 && e + k < total; k++) { const float x = obs[e + k]; obs_out[e + k] = norm_obs ? fminf(fmaxf((x - m[k]) * iv[k], -clip_obs), clip_obs) : x; }
+      }
+    }
+#undef VN_NORM4
   }
   if (reward_out) {
     const float rinv = st->rinv;
