@@ -557,6 +557,8 @@ static bool get_ops(int task, int num_obj, Ops* out) {
 #if XARM_HAS_TASK(1)
     case XARM_TASK_PICK_AND_PLACE:
       if (num_obj == 1) { *out = OpsT<TaskT<XARM_TASK_PICK_AND_PLACE, 1>>::make(); return true; }
+      if (num_obj == 2) { *out = OpsT<TaskT<XARM_TASK_PICK_AND_PLACE, 2>>::make(); return true; }
+      if (num_obj == 3) { *out = OpsT<TaskT<XARM_TASK_PICK_AND_PLACE, 3>>::make(); return true; }
       return false;
 #endif
 #if XARM_HAS_TASK(2)
@@ -568,6 +570,7 @@ static bool get_ops(int task, int num_obj, Ops* out) {
 #if XARM_HAS_TASK(4)
     case XARM_TASK_HANDOVER:
       if (num_obj == 1) { *out = OpsT<TaskT<XARM_TASK_HANDOVER, 1>>::make(); return true; }
+      if (num_obj == 2) { *out = OpsT<TaskT<XARM_TASK_HANDOVER, 2>>::make(); return true; }
       return false;
 #endif
   }
@@ -621,7 +624,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   XarmConfig c = *cfg;
   c.num_obj = norm_num_obj(c.task, c.num_obj);
   Ops ops;
-  if (!get_ops(c.task, c.num_obj, &ops)) return fail(XARM_E_INVALID, "xarm_create: unsupported task / num_obj (built: num_obj=1 for PickAndPlace and Handover)");
+  if (!get_ops(c.task, c.num_obj, &ops)) return fail(XARM_E_INVALID, "xarm_create: unsupported task / num_obj (built: num_obj 1..3 for PickAndPlace, 1..2 for Handover)");
   // reward types the reference defines per task (others raise NotImplementedError there, D6)
   bool ok_reward = c.reward_type == XARM_REWARD_SPARSE || c.reward_type == XARM_REWARD_DENSE ||
                    (c.task == XARM_TASK_PICK_AND_PLACE && c.reward_type == XARM_REWARD_DENSE_O2G) ||

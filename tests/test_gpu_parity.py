@@ -460,3 +460,53 @@ def test_vecnormalize_matches_sb3_restatement():
         vn2.close()
     vn.close()
     env.close()
+
+
+@pytest.mark.parametrize("task,num_obj", [("pick_and_place", 2), ("pick_and_place", 3), ("handover", 2)])
+def test_multi_object_parity(task, num_obj):
+    """config['num_obj'] > 1 [REF xarm_pick_and_place.py:50,71-74,220-248,271-287; xarm_handover.py:57,89-92,299-336,370-393]:
+    observation / goal dimensions, bit-exact goal sampling (incl. the pairwise rejection loops) and 25 steps of contact-free
+    parity (1e-3) against the oracle for the envs whose grippers touch nothing; the others must stay finite."""
+    import torch
+    n = 24
+    gs = "air" if task == "pick_and_place" else "ground"
+    cfg = {"num_obj": num_obj, "goal_shape": gs}
+    env = _mk(task, n, seed=13, auto_reset=False, config=cfg)
+    ref = [orc.OracleEnv(task, env_index=i, seed=13, auto_reset=0, goal_shape=gs, num_obj=num_obj) for i in range(n)]
+    assert env.obs_dim == (8 + 16 * num_obj if task == "pick_and_place" else 13 * num_obj + 16) and env.goal_dim == 3 * num_obj
+    obs = env.reset()
+    robs = [r.reset() for r in ref]
+    assert np.array_equal(obs["desired_goal"].cpu().numpy(), np.stack([o["desired_goal"] for o in robs]))
+    clean = np.array([r.arm_contacts() == 0 for r in ref])
+    st0 = np.stack([r.get_state() for r in ref])
+    narm = 1 if task == "pick_and_place" else 2
+    nq = 3 * 9 * narm
+    if task == "pick_and_place":
+        # park the legos of half the envs on the table outside the gripper's workspace (x <= 0.5, |y| <= 0.3): their tape is
+        # gripper-contact-free while the lego-table contact rows stay active (Handover clamps its legos into the workspace)
+        for o in range(num_obj):
+            st0[::2, nq + 13 * o:nq + 13 * o + 3] = [0.65, 0.42 - 0.14 * o, 0.04]
+            st0[::2, nq + 13 * o + 3:nq + 13 * o + 13] = [0, 0, 0, 1, 0, 0, 0, 0, 0, 0]
+    env.set_state(st0)                    # identical start (resets with gripper contacts differ by float32 rounding)
+    for r, s_ in zip(ref, st0):
+        r.set_state(s_)
+    clean[:] = True
+    rng = np.random.default_rng(9)
+    for t in range(25):
+        a = _actions(rng, task, n, env.act_dim)
+        obs, rew, done, _ = env.step(torch.from_numpy(a).cuda())
+        res = [r.step(a[i]) for i, r in enumerate(ref)]
+        clean &= np.array([r.arm_contacts() == 0 for r in ref])
+        st, rst = env.get_state(), np.stack([r.get_state() for r in ref])
+        assert np.isfinite(st).all()
+        for arm in range(narm):
+            sl = slice(arm * 27, arm * 27 + 9)
+            np.testing.assert_allclose(st[clean][:, sl], rst[clean][:, sl], atol=TOL, err_msg=f"{task} N={num_obj} step {t} arm {arm}")
+        for o in range(num_obj):
+            sl = slice(nq + 13 * o, nq + 13 * o + 7)
+            np.testing.assert_allclose(st[clean][:, sl], rst[clean][:, sl], atol=TOL, err_msg=f"{task} N={num_obj} step {t} obj {o}")
+        ag, dg = obs["achieved_goal"].cpu().numpy(), obs["desired_goal"].cpu().numpy()
+        want = orc.compute_reward(task, "sparse", num_obj, ag, dg)
+        assert np.array_equal(rew.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    assert clean.sum() >= (n // 4 if task == "pick_and_place" else 1), f"only {clean.sum()} contact-free envs"
+    env.close()
