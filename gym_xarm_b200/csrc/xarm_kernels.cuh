@@ -28,6 +28,7 @@ struct KArgs {
   int tl_slot;
   // SM partition of a split step (xarm_lib.cu): launches of the main branch carry a work counter (blocks claim their
   // chunks dynamically) and leave at once when they land on an SM of sm_mask - those SMs belong to the early branch
+  int light_dual;                  // list launches of the light kernel come in two register budgets (xarm_lib.cu)
   int* work;                       // NULL: static block-stride loop, every SM
   unsigned long long sm_mask[4];   // bit smid set: reserved for the early branch
 };

@@ -80,8 +80,14 @@ __global__ void __launch_bounds__(128) k_pipe_action(KArgs a) {
   PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_action<T>(a, i); }
   tl_mark(a, 1);
 }
+#ifndef XARM_SETUP_MINB
+#define XARM_SETUP_MINB 4
+#endif
+#ifndef XARM_LIGHT_MINB
+#define XARM_LIGHT_MINB 4
+#endif
 template <class T>
-__global__ void __launch_bounds__(128, 4) k_pipe_setup(KArgs a, int sub, int* heavy_count) {
+__global__ void __launch_bounds__(128, XARM_SETUP_MINB) k_pipe_setup(KArgs a, int sub, int* heavy_count) {
   PIPE_LEAVE_RESERVED(a)
   tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) {
@@ -90,14 +96,25 @@ __global__ void __launch_bounds__(128, 4) k_pipe_setup(KArgs a, int sub, int* he
   }
   tl_mark(a, 1);
 }
-template <class T>
-__global__ void __launch_bounds__(128, 4) k_pipe_light(KArgs a) {
+// Two register budgets of the same light kernel.  LAT = false: 128 registers (some spills), 4 blocks per SM - the
+// throughput form (main branch, reset waves).  LAT = true: 160 registers (no hot spills: 86 instead of 121 us per warp) -
+// the latency form for SHORT lists (the auto-reset tail of an ordinary step).  A list launch carries both; each looks at
+// the list size and one of them leaves at once (the register budget is fixed per launch, the list size is not known on
+// the host).
+#define XARM_LIGHT_LAT_MAX 4096
+template <class T, bool LAT>
+__device__ __forceinline__ void light_body(const KArgs& a) {
   extern __shared__ float light_mrows[];  // [XARM_MROW_WORDS][128]: the manifold rows of this block's envs
   PIPE_LEAVE_RESERVED(a)
+  if (a.list && a.light_dual && LAT != (*a.list_count <= XARM_LIGHT_LAT_MAX)) return;
   tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_light<T>(a, i, light_mrows + threadIdx.x, 128); }
   tl_mark(a, 1);
 }
+template <class T>
+__global__ void __launch_bounds__(128, 4) k_pipe_light(KArgs a) { light_body<T, false>(a); }
+template <class T>
+__global__ void __maxnreg__(160) k_pipe_light_lat(KArgs a) { light_body<T, true>(a); }
 // Heavy envs of this substep.  One warp per block, a few blocks per SM at most: the contact rows of the generic solver
 // (Contacts<T>, ~6 KB per env) live in SHARED memory, one record per lane at an odd word stride (bank-conflict free).
 // In thread-local memory the 50 sweeps stream every row from L2 again (160 KB per warp per sweep) and one heavy warp
@@ -314,6 +331,7 @@ struct PipeCtx {
   // SM partition (XARM_RESERVE_SMS, default 12; 0 = off): while `dyn` is set (main branch of a split step) every launch
   // gets a work counter and the mask of the SMs it must leave to the early branch
   bool dyn = false;
+  bool light_dual = true;   // XARM_LIGHT_DUAL=0: one light kernel form everywhere
   int setup_bps = 4;   // resident blocks per SM of the partitioned main branch's setup kernel (XARM_SETUP_BPS)
   int reserve_sms = 0, n_work = 0, next_work = 0;
   int* work_base = nullptr;
@@ -400,6 +418,8 @@ struct OpsT {
     if constexpr (HAS_LIGHT) {  // 48 KB of manifold rows + the static chunk-claim word of pipe_next
       int rc = (int)cudaFuncSetAttribute(k_pipe_light<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XARM_MROW_WORDS * 128 * sizeof(float)));
       if (rc) return rc;
+      rc = (int)cudaFuncSetAttribute(k_pipe_light_lat<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(XARM_MROW_WORDS * 128 * sizeof(float)));
+      if (rc) return rc;
     }
     if constexpr (task_has_heavy_rows<T>()) {
       int rc = (int)cudaFuncSetAttribute(k_heavy_solve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes());
@@ -450,7 +470,15 @@ struct OpsT {
         }
         if (fork_heavy) cudaEventRecord(join, sh);
         c.begin("light", s);
-        k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(c.tl(a));
+        if (c.cur_branch == 'E' && c.light_dual) {   // short list -> latency form, long list -> throughput form
+          KArgs al = c.tl(a);
+          al.light_dual = 1;
+          k_pipe_light_lat<T><<<XARM_LIGHT_LAT_MAX / 128, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(al);
+          k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(al);
+          g_launches++;
+        } else {
+          k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(c.tl(a));
+        }
         c.end(s);
         if (fork_heavy) cudaStreamWaitEvent(s, join, 0);
         g_launches += 3;
@@ -700,6 +728,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     }
   }
   if (getenv("XARM_SETUP_BPS")) h->pipe.setup_bps = atoi(getenv("XARM_SETUP_BPS"));
+  h->pipe.light_dual = !(getenv("XARM_LIGHT_DUAL") && atoi(getenv("XARM_LIGHT_DUAL")) == 0);
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
   h->pipe.timeline = getenv("XARM_TIMELINE") != nullptr;
   if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }
