@@ -332,6 +332,7 @@ struct PipeCtx {
   // gets a work counter and the mask of the SMs it must leave to the early branch
   bool dyn = false;
   bool light_dual = true;   // XARM_LIGHT_DUAL=0: one light kernel form everywhere
+  bool light_main_lat = true;    // XARM_LIGHT_MAIN_LAT=0: the partitioned main branch keeps the 128-register form (A/B)
   int setup_bps = 4;   // resident blocks per SM of the partitioned main branch's setup kernel (XARM_SETUP_BPS)
   int reserve_sms = 0, n_work = 0, next_work = 0;
   int* work_base = nullptr;
@@ -476,6 +477,8 @@ struct OpsT {
           k_pipe_light_lat<T><<<XARM_LIGHT_LAT_MAX / 128, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(al);
           k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(al);
           g_launches++;
+        } else if (part && c.light_main_lat) {   // partitioned main branch: nothing runs next to it on its SMs - 3 blocks of the 160-register form
+          k_pipe_light_lat<T><<<c.heavy_grid * 3, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(c.tl(a));
         } else {
           k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(c.tl(a));
         }
@@ -729,6 +732,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   }
   if (getenv("XARM_SETUP_BPS")) h->pipe.setup_bps = atoi(getenv("XARM_SETUP_BPS"));
   h->pipe.light_dual = !(getenv("XARM_LIGHT_DUAL") && atoi(getenv("XARM_LIGHT_DUAL")) == 0);
+  h->pipe.light_main_lat = !(getenv("XARM_LIGHT_MAIN_LAT") && atoi(getenv("XARM_LIGHT_MAIN_LAT")) == 0);
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
   h->pipe.timeline = getenv("XARM_TIMELINE") != nullptr;
   if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }
