@@ -137,6 +137,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: park fd 1 on stderr while libraries run (NCCL prints its version banner to
+    # stdout at init) and restore it for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import numpy as np
     import torch
     from gym_xarm_b200 import XarmVecEnv, _native, distributed as xd
@@ -283,7 +289,10 @@ def main():
                                   "p90": sorted(per_step_ms)[(9 * len(per_step_ms)) // 10], "max": max(per_step_ms)},
             "step_ms_first_60": [round(x, 2) for x in per_step_ms[:60]],
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     env.close()
     if world > 1:
         import torch.distributed as dist
