@@ -251,7 +251,7 @@ def main():
                         "fraction is ~1e-4 by construction; see fp32 (oracle-counted FLOPs against the nominal FP32 peak) and the per-kernel "
                         "list (profiles/ holds the ncu captures of the same kernels)"}
         cb = None
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:   # the CPU arm is timed beside the GPU arm at N=1 only
             try:
                 cb = cpu_baseline(task, os.cpu_count() or 1, 300000)
             except Exception as e:  # noqa: BLE001
