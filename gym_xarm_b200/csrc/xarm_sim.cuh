@@ -209,12 +209,15 @@ XD void arm_fk7(int a, const float* q, M3& Re, V3& pe, V3* org, V3* axs) {
 // calculateInverseKinematics (N9): n_ik damped-least-squares iterations on the 7 arm joints
 template <class T>
 NOINL void arm_ik(int a, const float* q_in, V3 target, float* q_out) {
+  // (1) one FK per iteration - the FK that checks the residual at the end
+  // of an iteration IS the FK the next iteration starts from - and (2) the 7 x 7 normal equations and their Cholesky solve
+  // unrolled, so that A and b live in registers.
   float q[7];
 #pragma unroll
   for (int i = 0; i < 7; i++) q[i] = q_in[i];
+  M3 Re; V3 pe, org[7], axs[7];
+  arm_fk7<T>(a, q, Re, pe, org, axs);
   for (int it = 0; it < T::NIK; it++) {
-    M3 Re; V3 pe, org[7], axs[7];
-    arm_fk7<T>(a, q, Re, pe, org, axs);
     float e[6];
     e[0] = target.x - pe.x; e[1] = target.y - pe.y; e[2] = target.z - pe.z;
     Q4 qc = m3_to_quat(Re);
@@ -228,16 +231,15 @@ NOINL void arm_ik(int a, const float* q_in, V3 target, float* q_out) {
     float an = vn > 1e-30f ? angle / vn : 0.f;
     e[3] = an * dq.x; e[4] = an * dq.y; e[5] = an * dq.z;
     float J[6][7];
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < 7; j++) {
       V3 lin = cross(axs[j], pe - org[j]);
       J[0][j] = lin.x; J[1][j] = lin.y; J[2][j] = lin.z; J[3][j] = axs[j].x; J[4][j] = axs[j].y; J[5][j] = axs[j].z;
     }
-    // A = J^T J + 0.5 I (packed lower), b = J^T e; Cholesky solve (A is SPD).  Rolled loops: small code, see arm_dynamics.
     float A[28], b[7];
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 7; i++) {
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j <= i; j++) {
         float s = (i == j) ? (float)XARM_IK_DAMPING : 0.f;
 #pragma unroll
@@ -249,28 +251,32 @@ NOINL void arm_ik(int a, const float* q_in, V3 target, float* q_out) {
       for (int r = 0; r < 6; r++) s += J[r][i] * e[r];
       b[i] = s;
     }
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < 7; j++) {
       float s = A[tri(j, j)];
+#pragma unroll
       for (int k = 0; k < j; k++) s -= A[tri(j, k)] * A[tri(j, k)];
       float d = sqrtf(s), di = 1.f / d;
-      A[tri(j, j)] = di;  // store the reciprocal of the diagonal
-#pragma unroll 1
+      A[tri(j, j)] = di;
+#pragma unroll
       for (int i = j + 1; i < 7; i++) {
         float t = A[tri(i, j)];
+#pragma unroll
         for (int k = 0; k < j; k++) t -= A[tri(i, k)] * A[tri(j, k)];
         A[tri(i, j)] = t * di;
       }
     }
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 7; i++) {
       float s = b[i];
+#pragma unroll
       for (int k = 0; k < i; k++) s -= A[tri(i, k)] * b[k];
       b[i] = s * A[tri(i, i)];
     }
-#pragma unroll 1
+#pragma unroll
     for (int i = 6; i >= 0; i--) {
       float s = b[i];
+#pragma unroll
       for (int k = i + 1; k < 7; k++) s -= A[tri(k, i)] * b[k];
       b[i] = s * A[tri(i, i)];
     }
@@ -290,9 +296,10 @@ NOINL void arm_ik(int a, const float* q_in, V3 target, float* q_out) {
 // Full-arm pass: FK, spatial velocities, bias forces (world-frame RNEA), joint-space inertia (CRBA), its inverse
 // (Cholesky) and the unconstrained velocity update qdu = qd + h * Minv (tau - bias).  Equivalent to the ABA +
 // calcAccelerationDeltas pair Bullet runs per substep (N3).
-// Written as ROLLED loops over links with thread-local arrays: this pass runs once per substep, and a fully
-// unrolled version (~10k straight-line instructions) is instruction-fetch bound on the SM (profiles/: every
-// 128-byte line costs an L2 round trip), while the rolled form stays in the instruction cache.
+// The link passes are ROLLED loops over thread-local arrays: a fully unrolled version (~10k straight-line instructions) is
+// instruction-fetch bound on the SM (profiles/: every 128-byte line costs an L2 round trip).  The Cholesky factorisation,
+// its inverse and Minv (static triangular indices, ~1.1 k FMAs) ARE unrolled: their arrays then live in registers instead of
+// thread-local memory - the setup kernel went from 63 to 48 us per launch on average.
 template <class T>
 NOINL void arm_dynamics(int a, const ArmState<typename T::MD>& st, bool apply_damping, ArmDyn<typename T::MD>& D) {
   using MD = typename T::MD;
@@ -380,46 +387,58 @@ NOINL void arm_dynamics(int a, const ArmState<typename T::MD>& st, bool apply_da
     for (int j = 0; j <= i; j++) M[tri(i, j)] = (anc >> j & 1u) ? dot(D.S[j], F) : 0.f;
     if (pi >= 0) { f[pi] += fi; I[pi] = I[pi] + Ii; }
   }
-  // Cholesky M = L L^T in place (reciprocal diagonal)
-#pragma unroll 1
+  // Cholesky / inverse / Minv fully unrolled: M, Li and Minv live in registers (static indices), ~1.1 k straight-line FMAs
+  float Mr[NT];
+#pragma unroll
+  for (int k = 0; k < NT; k++) Mr[k] = M[k];
+#pragma unroll
   for (int j = 0; j < N; j++) {
-    float s = M[tri(j, j)];
-    for (int k = 0; k < j; k++) s -= M[tri(j, k)] * M[tri(j, k)];
+    float s = Mr[tri(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) s -= Mr[tri(j, k)] * Mr[tri(j, k)];
     float di = rsqrtf(s);
-    di = di * (1.5f - 0.5f * s * di * di);  // one Newton step: full float accuracy
-    M[tri(j, j)] = di;
-#pragma unroll 1
+    di = di * (1.5f - 0.5f * s * di * di);
+    Mr[tri(j, j)] = di;
+#pragma unroll
     for (int i = j + 1; i < N; i++) {
-      float t = M[tri(i, j)];
-      for (int k = 0; k < j; k++) t -= M[tri(i, k)] * M[tri(j, k)];
-      M[tri(i, j)] = t * di;
+      float t = Mr[tri(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= Mr[tri(i, k)] * Mr[tri(j, k)];
+      Mr[tri(i, j)] = t * di;
     }
   }
-  // Linv (lower): Linv[j][j] = 1/L[j][j]; Linv[i][j] = -sum_{k=j}^{i-1} L[i][k] Linv[k][j] / L[i][i]
   float Li[NT];
-#pragma unroll 1
+#pragma unroll
   for (int j = 0; j < N; j++) {
-    Li[tri(j, j)] = M[tri(j, j)];
-#pragma unroll 1
+    Li[tri(j, j)] = Mr[tri(j, j)];
+#pragma unroll
     for (int i = j + 1; i < N; i++) {
       float s = 0.f;
-      for (int k = j; k < i; k++) s += M[tri(i, k)] * Li[tri(k, j)];
-      Li[tri(i, j)] = -s * M[tri(i, i)];
+#pragma unroll
+      for (int k = j; k < i; k++) s += Mr[tri(i, k)] * Li[tri(k, j)];
+      Li[tri(i, j)] = -s * Mr[tri(i, i)];
     }
   }
-  // Minv = Linv^T Linv
-#pragma unroll 1
+  float Mv[NT];
+#pragma unroll
   for (int i = 0; i < N; i++)
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j <= i; j++) {
       float s = 0.f;
+#pragma unroll
       for (int k = i; k < N; k++) s += Li[tri(k, i)] * Li[tri(k, j)];
-      D.Minv[tri(i, j)] = s;
+      Mv[tri(i, j)] = s;
     }
-#pragma unroll 1
+#pragma unroll
+  for (int k = 0; k < NT; k++) D.Minv[k] = Mv[k];
+  float rr[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) rr[i] = rhs[i];
+#pragma unroll
   for (int i = 0; i < N; i++) {
     float s = 0.f;
-    for (int j = 0; j < N; j++) s += D.Minv[tri(i, j)] * rhs[j];
+#pragma unroll
+    for (int j = 0; j < N; j++) s += Mv[tri(i, j)] * rr[j];
     D.qdu[i] = st.qd[i] + h * s;
   }
 }
