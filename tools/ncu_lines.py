@@ -8,7 +8,8 @@ lid = sys.argv[4] if len(sys.argv) > 4 else "0"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-id", f":::{lid}"] if lid != "0" else []), capture_output=True, text=True).stdout.splitlines()
 hdr_i = next(i for i, l in enumerate(out) if l.startswith('"Address"'))
 print(out[0][:120])
-rows = list(csv.DictReader(out[hdr_i:]))
+end_i = next((i for i in range(hdr_i + 1, len(out)) if out[i].startswith('"Kernel Name"')), len(out))   # first kernel of the report only
+rows = list(csv.DictReader(out[hdr_i:end_i]))
 base = int(rows[0]["Address"], 16)
 per_off = {int(r["Address"], 16) - base: (int(r["# Samples"] or 0), int(r["Instructions Executed"] or 0), r["Source"]) for r in rows}
 # line info
