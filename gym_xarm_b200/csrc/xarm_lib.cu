@@ -113,8 +113,11 @@ __device__ __forceinline__ void light_body(const KArgs& a) {
 }
 template <class T>
 __global__ void __launch_bounds__(128, 4) k_pipe_light(KArgs a) { light_body<T, false>(a); }
+#ifndef XARM_LIGHT_LAT_REGS
+#define XARM_LIGHT_LAT_REGS 160
+#endif
 template <class T>
-__global__ void __maxnreg__(160) k_pipe_light_lat(KArgs a) { light_body<T, true>(a); }
+__global__ void __maxnreg__(XARM_LIGHT_LAT_REGS) k_pipe_light_lat(KArgs a) { light_body<T, true>(a); }
 // Heavy envs of this substep.  One warp per block, a few blocks per SM at most: the contact rows of the generic solver
 // (Contacts<T>, ~6 KB per env) live in SHARED memory, one record per lane at an odd word stride (bank-conflict free).
 // In thread-local memory the 50 sweeps stream every row from L2 again (160 KB per warp per sweep) and one heavy warp
