@@ -48,11 +48,21 @@ __device__ __forceinline__ int64_t pipe_next(const KArgs& a, int64_t prev, int c
   __syncthreads();
   return (int64_t)claim_ * chunk;
 }
+// Short lists (the auto-reset tail of an ordinary step: a handful of envs) are SPREAD over the lanes - one env per 32 or 8
+// lanes - so that a warp does not serialise the different code paths of its envs (near / far from the lego, resting /
+// airborne lego, contact cases); those launches are latency bound and the idle lanes cost nothing.
+__device__ __forceinline__ int pipe_spread(const KArgs& a) {
+  if (!a.list) return 1;
+  const int c = *a.list_count;
+  return c <= 64 ? 32 : (c <= 256 ? 8 : 1);
+}
 #define PIPE_FOR_EACH(a, t, i)                                                                                   \
-  for (int64_t bound_ = (a).list ? (int64_t)*(a).list_count : (a).n, base_ = pipe_next(a, -1, blockDim.x);      \
+  for (int64_t sp_ = pipe_spread(a), bound_ = ((a).list ? (int64_t)*(a).list_count : (a).n) * sp_,              \
+               base_ = pipe_next(a, -1, blockDim.x);                                                            \
        base_ < bound_; base_ = pipe_next(a, base_, blockDim.x))                                                  \
-    if (const int64_t t = base_ + threadIdx.x; true)                                                             \
-      if (const int64_t i = pipe_env(a, t); true)
+    if (const int64_t tv_ = base_ + threadIdx.x; true)                                                           \
+      if (const int64_t t = tv_ / sp_; true)                                                                     \
+        if (const int64_t i = (tv_ % sp_ == 0) ? pipe_env(a, t) : -1; true)
 
 // development timeline: thread 0 of every block stamps the launch's slot (min of starts, max of ends)
 __device__ __forceinline__ void tl_mark(const KArgs& a, int end) {
@@ -159,10 +169,16 @@ __global__ void __launch_bounds__(64) k_heavy_rows(KArgs a, int sub, const int* 
     PIPE_LEAVE_RESERVED(a)
     const int count = *heavy_count;
     if (a.tl && a.tl_slot >= 0 && threadIdx.x == 0) a.tl[2 * XARM_TL_SLOTS + a.tl_slot] = (unsigned long long)count;
+    // Short lists (the auto-reset tail, the candidates of the early branch) are spread over the lanes: with one env per
+    // 8 or 32 lanes the warp no longer serialises the different collision cases (face / edge contacts, 1..4 manifolds) of
+    // 32 envs - the kernel is latency bound there and the idle lanes cost nothing.
+    const int spread = count <= 256 ? 32 : (count <= 1024 ? 8 : 1);
+    const int64_t vcount = (int64_t)count * spread;
     bool any = false;
-    for (int64_t base = pipe_next(a, -1, blockDim.x); base < count; base = pipe_next(a, base, blockDim.x)) {
+    for (int64_t base = pipe_next(a, -1, blockDim.x); base < vcount; base = pipe_next(a, base, blockDim.x)) {
       if (!any) { tl_mark(a, 0); any = true; }
-      if (base + threadIdx.x < count) heavy_rows_body<T>(a, (int)base + threadIdx.x, sub, hrec);
+      const int64_t g = base + threadIdx.x;
+      if (g < vcount && g % spread == 0) heavy_rows_body<T>(a, (int)(g / spread), sub, hrec);
     }
     if (any) tl_mark(a, 1);
   }
