@@ -190,7 +190,8 @@ XD bool pipe_setup(const KArgs& a, int64_t i, int sub) {
   const int g0 = e.grasp[0];
   int nc = 0;
   ArmDyn<typename T::MD> D[1];
-  if (!sub_setup_lean<T>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc, D)) {
+  // heavy: a gripper link touches the object - or (rare) an arm joint sits on a limit: the light solver keeps no rows for those
+  if (!sub_setup_lean<T>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc, D) || ((AR.lim_lo[0] | AR.lim_hi[0]) & 0x7fu) != 0u) {
     a.form[i] = XARM_FORM_HEAVY;
     dyn_store<T>(D[0], a.scratch, a.n, i);  // the heavy path continues from this dynamics pass
     return true;

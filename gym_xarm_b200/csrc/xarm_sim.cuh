@@ -1242,6 +1242,10 @@ XD bool sub_setup_lean(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR,
 #define ARM_LIMITS_BWD(a)                                                                                        \
   { _Pragma("unroll") for (int i_ = N - 1; i_ >= 7; i_--) ARM_LIMIT_ROW_PRED_(a, i_)                             \
     if (((lim_lo[a] | lim_hi[a]) & 0x7fu) != 0u) { _Pragma("unroll") for (int i_ = 6; i_ >= 0; i_--) ARM_LIMIT_ROW_(a, i_) } }
+// light solver form: an env whose ARM joints (dof < 7) sit on a limit is sent through the heavy path by the setup kernel
+// (rare: the IK keeps the arm inside its range), so only the gripper dofs' limit rows remain - 14 registers less
+#define ARM_LIMITS_FWD_GRIPPER(a) { _Pragma("unroll") for (int i_ = 7; i_ < N; i_++) ARM_LIMIT_ROW_PRED_(a, i_) }
+#define ARM_LIMITS_BWD_GRIPPER(a) { _Pragma("unroll") for (int i_ = N - 1; i_ >= 7; i_--) ARM_LIMIT_ROW_PRED_(a, i_) }
 #define SOLVER_LOCALS_FROM(AR)                                                                                   \
   float Mi[NA][NT], iden[NA][N], dqd[NA][N], mrhs[NA][N], mapp[NA][N], lrhs[NA][N], lapp[NA][N];                 \
   uint32_t lim_lo[NA], lim_hi[NA];                                                                               \
@@ -1343,9 +1347,9 @@ XD void sub_solve_light(const ArmRows<T>& AR, int nc, const ManifoldIn& MI, floa
   for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
     bool resid_bad = false;
     if (it & 1) {
-      ARM_LIMITS_FWD(0) ARM_MOTORS_FWD(0) GEAR_ROW(0)
+      ARM_LIMITS_FWD_GRIPPER(0) ARM_MOTORS_FWD(0) GEAR_ROW(0)
     } else {
-      GEAR_ROW(0) ARM_MOTORS_BWD(0) ARM_LIMITS_BWD(0)
+      GEAR_ROW(0) ARM_MOTORS_BWD(0) ARM_LIMITS_BWD_GRIPPER(0)
     }
     if (nc > 0) {
 #pragma unroll
@@ -1564,7 +1568,7 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
   if constexpr (task_has_light<T>()) {
     int nc = 0;
     ArmDyn<typename T::MD> D[1];
-    if (sub_setup_lean<T>(e, apply_damping, last, AR, B, MI, nc, D)) {
+    if (sub_setup_lean<T>(e, apply_damping, last, AR, B, MI, nc, D) && ((AR.lim_lo[0] | AR.lim_hi[0]) & 0x7fu) == 0u) {  // (arm-joint limits: generic form)
       float mrows[XARM_MROW_WORDS];
       sub_solve_light<T>(AR, nc, MI, mrows, 1, S);
       sub_integrate<T>(e, B, S);
