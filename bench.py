@@ -279,7 +279,7 @@ def main():
                                    f"U(-1,1) actions from a 64-batch device ring", "env_id": ENV_ID[task], "envs_per_gpu": n,
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
                        "timing": "CUDA events on the launching stream around every step, summed; max over ranks",
-                       "cuda_graph": not args.no_graph, "mapping": "one thread per env (16 lanes per env in the coupled contact solver); step = kernel pipeline action -> 15 x {setup -> light | heavy_rows -> heavy_solve} -> finish -> auto-reset passes; envs that may finish run as an early branch on 12 reserved SMs"},
+                       "cuda_graph": not args.no_graph, "mapping": "one thread per env (16 lanes per env in the coupled contact solver); step = kernel pipeline action -> 15 x {setup -> light | heavy_rows -> heavy_solve} -> finish -> auto-reset passes; envs that may finish run as an early branch on 32 reserved SMs"},
             "clocks": clocks, "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                       "steps": args.e2e_steps, "path": "XarmVecEnv(output='numpy').step -> xarm_step_host (pinned staging)"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb,

@@ -347,7 +347,7 @@ struct PipeCtx {
   std::vector<std::string> tl_names;
   int cur_slot = -1;
   char cur_branch = 'M';
-  // SM partition (XARM_RESERVE_SMS, default 12; 0 = off): while `dyn` is set (main branch of a split step) every launch
+  // SM partition (XARM_RESERVE_SMS, default 32; 0 = off): while `dyn` is set (main branch of a split step) every launch
   // gets a work counter and the mask of the SMs it must leave to the early branch
   bool dyn = false;
   bool light_dual = true;   // XARM_LIGHT_DUAL=0: one light kernel form everywhere
@@ -730,7 +730,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) { cudaGetLastError(); return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed"); }
   }
   {  // SMs reserved for the early branch of a split step
-    const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 20;
+    const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 32;  // of 148: main branch (116 SMs) and early branch then take about equally long
     if (want > 0 && ops.hrec_words() > 0) {
       unsigned* d_seen = nullptr;
       unsigned seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
