@@ -32,6 +32,15 @@ class XarmVecNormConfig(C.Structure):
     ]
 
 
+class XarmHerConfig(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int64), ("episodes_per_env", C.c_int32), ("max_episode_length", C.c_int32),
+        ("obs_dim", C.c_int32), ("goal_dim", C.c_int32), ("action_dim", C.c_int32),
+        ("task", C.c_int32), ("reward_type", C.c_int32), ("num_obj", C.c_int32),
+        ("n_sampled_goal", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint64),
+    ]
+
+
 # every symbol include/xarm_abi.h declares
 ABI_SYMBOLS = [
     "xarm_task_dims", "xarm_create", "xarm_destroy", "xarm_bind", "xarm_reset", "xarm_step", "xarm_step_host",
@@ -39,6 +48,7 @@ ABI_SYMBOLS = [
     "xarm_episode_stats", "xarm_launch_count", "xarm_last_error", "xarm_abi_version", "xarm_set_profiling", "xarm_kernel_times",
     "xarm_vecnorm_create", "xarm_vecnorm_destroy", "xarm_vecnorm_reset", "xarm_vecnorm_step", "xarm_vecnorm_set_training",
     "xarm_vecnorm_get_stats", "xarm_vecnorm_set_stats",
+    "xarm_her_create", "xarm_her_destroy", "xarm_her_begin", "xarm_her_add", "xarm_her_sample", "xarm_her_stats",
 ]
 
 _lib = None
@@ -90,6 +100,12 @@ def load():
     L.xarm_vecnorm_set_training.argtypes = [vp, C.c_int32]
     L.xarm_vecnorm_get_stats.argtypes = [vp, dp, dp, dp, dp]
     L.xarm_vecnorm_set_stats.argtypes = [vp, dp, dp, C.c_double, dp]
+    L.xarm_her_create.argtypes = [C.POINTER(XarmHerConfig), C.POINTER(vp)]
+    L.xarm_her_destroy.argtypes = [vp]
+    L.xarm_her_begin.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.xarm_her_add.argtypes = [vp] + [vp] * 8 + [vp]
+    L.xarm_her_sample.argtypes = [vp, C.c_int64] + [vp] * 9 + [vp]
+    L.xarm_her_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     L.xarm_launch_count.restype = C.c_int64
     L.xarm_last_error.restype = C.c_char_p
     _lib = L

@@ -13,6 +13,7 @@
 #include "xarm_pipeline.cuh"
 #include "xarm_heavy.cuh"
 #include "xarm_vecnorm.cuh"
+#include "xarm_her.cuh"
 
 // ------------------------------------------------------------------------------------------------ kernels
 // One thread per env; 128-thread blocks (a warp steps 32 envs in lock-step).
@@ -1185,6 +1186,133 @@ int xarm_vecnorm_set_stats(XarmVecNorm* v, const double* obs_mean, const double*
   k_vn_finalize<<<1, XARM_VN_MAX_OBS>>>(v->st, 1, v->cfg.obs_dim, v->cfg.epsilon, 0, 0);
   g_launches++;
   CUDA_TRY(cudaDeviceSynchronize());
+  return XARM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ hindsight experience replay
+struct XarmHer {
+  XarmHerConfig cfg;
+  HerBuf b;
+  int4* index = nullptr;        // scratch of the last sample call
+  int64_t index_cap = 0;
+  uint32_t calls = 0;
+};
+
+static void her_free(XarmHer* h) {
+  cudaFree(h->b.obs); cudaFree(h->b.ag); cudaFree(h->b.dg); cudaFree(h->b.act); cudaFree(h->b.rew); cudaFree(h->b.done);
+  cudaFree(h->b.ep_len); cudaFree(h->b.cur_k); cudaFree(h->b.cur_t); cudaFree(h->b.counters); cudaFree(h->index);
+  cudaGetLastError();
+}
+
+int xarm_her_create(const XarmHerConfig* cfg, XarmHer** out) {
+  if (!cfg || !out) return fail(XARM_E_INVALID, "xarm_her_create: null argument");
+  if (cfg->num_envs <= 0 || cfg->num_envs > 0x7fffffffLL) return fail(XARM_E_INVALID, "xarm_her_create: 0 < num_envs < 2^31 required");
+  if (cfg->episodes_per_env < 2) return fail(XARM_E_INVALID, "xarm_her_create: episodes_per_env >= 2 required (one slot is always being written)");
+  if (cfg->max_episode_length < 1) return fail(XARM_E_INVALID, "xarm_her_create: max_episode_length >= 1 required");
+  if (cfg->obs_dim < 1 || cfg->obs_dim > XARM_HER_MAX_OBS || cfg->action_dim < 1 || cfg->action_dim > 32 || cfg->goal_dim < 1 || cfg->goal_dim > 9)
+    return fail(XARM_E_INVALID, "xarm_her_create: 1 <= obs_dim <= 128, 1 <= action_dim <= 32 and 1 <= goal_dim <= 9 required");
+  if (cfg->n_sampled_goal < 0) return fail(XARM_E_INVALID, "xarm_her_create: n_sampled_goal >= 0 required");
+  if (cfg->task < 0 || cfg->task >= XARM_NUM_TASKS) return fail(XARM_E_INVALID, "xarm_her_create: bad task");
+  {
+    const int rt = cfg->reward_type;   // the same gate as xarm_compute_reward: relabelling needs a state-free reward
+    const bool ok = rt == XARM_REWARD_SPARSE || (rt == XARM_REWARD_DENSE && cfg->task != XARM_TASK_PICK_AND_PLACE && cfg->task != XARM_TASK_HANDOVER) ||
+                    (rt == XARM_REWARD_DENSE_O2G && cfg->task == XARM_TASK_PICK_AND_PLACE);
+    if (!ok) return fail(XARM_E_INVALID, "xarm_her_create: this reward type reads simulator state (not batch-safe in the reference either)");
+  }
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(XARM_E_INVALID, "xarm_her_create: bad device ordinal");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  XarmHer* h = new (std::nothrow) XarmHer();
+  if (!h) return fail(XARM_E_NOMEM, "xarm_her_create: out of host memory");
+  h->cfg = *cfg;
+  HerBuf& b = h->b;
+  memset(&b, 0, sizeof(b));
+  b.N = cfg->num_envs; b.K = cfg->episodes_per_env; b.T = cfg->max_episode_length;
+  b.O = cfg->obs_dim; b.G = cfg->goal_dim; b.A = cfg->action_dim;
+  const size_t rows = (size_t)b.K * (b.T + 1) * b.N, trs = (size_t)b.K * b.T * b.N, eps = (size_t)b.K * b.N;
+  bool ok = cudaMalloc(&b.obs, rows * b.O * 4) == cudaSuccess && cudaMalloc(&b.ag, rows * b.G * 4) == cudaSuccess &&
+            cudaMalloc(&b.dg, eps * b.G * 4) == cudaSuccess && cudaMalloc(&b.act, trs * b.A * 4) == cudaSuccess &&
+            cudaMalloc(&b.rew, trs * 4) == cudaSuccess && cudaMalloc(&b.done, trs) == cudaSuccess &&
+            cudaMalloc(&b.ep_len, eps * 4) == cudaSuccess && cudaMalloc(&b.cur_k, b.N * 4) == cudaSuccess &&
+            cudaMalloc(&b.cur_t, b.N * 4) == cudaSuccess && cudaMalloc(&b.counters, 4 * sizeof(unsigned long long)) == cudaSuccess;
+  if (!ok) { her_free(h); delete h; return fail(XARM_E_NOMEM, "xarm_her_create: cudaMalloc failed (K x (T+1) x N x (O + G) floats)"); }
+  // rows are zero until written: a gather never reads uninitialised memory even if begin() was skipped
+  cudaMemset(b.obs, 0, rows * b.O * 4); cudaMemset(b.ag, 0, rows * b.G * 4); cudaMemset(b.dg, 0, eps * b.G * 4);
+  cudaMemset(b.ep_len, 0, eps * 4); cudaMemset(b.cur_k, 0, b.N * 4); cudaMemset(b.cur_t, 0, b.N * 4);
+  cudaMemset(b.counters, 0, 4 * sizeof(unsigned long long));
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = h;
+  return XARM_OK;
+}
+
+int xarm_her_destroy(XarmHer* h) {
+  if (!h) return XARM_OK;
+  cudaSetDevice(h->cfg.device);
+  her_free(h);
+  delete h;
+  return XARM_OK;
+}
+
+int xarm_her_begin(XarmHer* h, const float* obs, const float* ag, const float* dg, const uint8_t* mask, void* stream) {
+  if (!h || !obs || !ag || !dg) return fail(XARM_E_INVALID, "xarm_her_begin: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  k_her_begin<<<(unsigned)((h->b.N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(h->b, obs, ag, dg, mask);   // one warp per env
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_her_add(XarmHer* h, const float* obs, const float* ag, const float* dg, const float* terminal, const float* action,
+                 const float* reward, const uint8_t* done, const uint8_t* truncated, void* stream) {
+  if (!h || !obs || !ag || !dg || !action || !reward || !done) return fail(XARM_E_INVALID, "xarm_her_add: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const HerBuf& b = h->b;
+  cudaStream_t s = (cudaStream_t)stream;
+  k_her_store<<<(unsigned)((b.N + 7) / 8), 256, 0, s>>>(b, obs, ag, dg, terminal, action, reward, done, truncated);
+  k_her_advance<<<(unsigned)((b.N + 255) / 256), 256, 0, s>>>(b, done);
+  g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_her_sample(XarmHer* h, int64_t batch, float* obs, float* ag, float* dg, float* action, float* next_obs, float* next_ag,
+                    float* reward, uint8_t* done, int32_t* index, void* stream) {
+  if (!h || !obs || !ag || !dg || !action || !next_obs || !next_ag || !reward || !done) return fail(XARM_E_INVALID, "xarm_her_sample: null argument");
+  if (batch <= 0) return fail(XARM_E_INVALID, "xarm_her_sample: batch > 0 required");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int4* idx = reinterpret_cast<int4*>(index);
+  if (!idx) {
+    if (batch > h->index_cap) {
+      CUDA_TRY(cudaStreamSynchronize(s));
+      cudaFree(h->index); h->index = nullptr; h->index_cap = 0;
+      if (cudaMalloc(&h->index, sizeof(int4) * batch) != cudaSuccess) { cudaGetLastError(); return fail(XARM_E_NOMEM, "xarm_her_sample: cudaMalloc failed"); }
+      h->index_cap = batch;
+    }
+    idx = h->index;
+  } else if ((reinterpret_cast<uintptr_t>(index) & 15) != 0) {
+    return fail(XARM_E_INVALID, "xarm_her_sample: index must be 16-byte aligned");
+  }
+  const HerBuf& b = h->b;
+  const int64_t n_her = (int64_t)((1.0 - 1.0 / (double)(h->cfg.n_sampled_goal + 1)) * (double)batch);   // int(her_ratio * batch_size)
+  k_her_index<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(b, batch, n_her, h->cfg.seed, h->calls, idx);
+  k_her_gather<<<(unsigned)((batch + 7) / 8), 256, 0, s>>>(b, batch, idx, h->cfg.task, h->cfg.reward_type, h->cfg.num_obj, obs, ag, dg,
+                                                         action, next_obs, next_ag, reward, done);
+  h->calls++;
+  g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_her_stats(XarmHer* h, int64_t out[4]) {
+  if (!h || !out) return fail(XARM_E_INVALID, "xarm_her_stats: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  unsigned long long c[4];
+  CUDA_TRY(cudaMemcpy(c, h->b.counters, sizeof(c), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemset(h->b.counters, 0, sizeof(unsigned long long)));   // invalid-sample counter resets on read
+  out[0] = (int64_t)c[0]; out[1] = (int64_t)c[1]; out[2] = (int64_t)c[2]; out[3] = (int64_t)h->calls;
   return XARM_OK;
 }
 

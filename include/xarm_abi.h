@@ -168,6 +168,47 @@ int xarm_vecnorm_set_training(XarmVecNorm* v, int32_t training);
 int xarm_vecnorm_get_stats(XarmVecNorm* v, double* obs_mean, double* obs_var, double* obs_count, double* ret_stats3);
 int xarm_vecnorm_set_stats(XarmVecNorm* v, const double* obs_mean, const double* obs_var, double obs_count, const double* ret_stats3);
 
+/* ---- caller side of the path: hindsight experience replay on the device
+ * [REF benchmark/train.py:81-97: HerReplayBuffer(n_sampled_goal=4, goal_selection_strategy="future",
+ *  max_episode_length=100, online_sampling=True), whose relabelling calls env.compute_reward on batches].
+ * Semantics of stable-baselines3 1.x HerReplayBuffer ('future' strategy, online sampling), with three stated differences:
+ * (1) every env owns a ring of `episodes_per_env` episode slots (SB3: one global ring; it supports a single env only);
+ * (2) indices come from Philox4x32-10 keyed by (seed; sample, call, try) instead of np.random, so a batch is a pure function
+ *     of the buffer and the call number (oracle/her_oracle.py restates it);
+ * (3) the desired goal is kept once per episode (the reference's envs draw it in reset() only).
+ * All data pointers are DEVICE pointers. */
+typedef struct XarmHerConfig {
+  int64_t num_envs;
+  int32_t episodes_per_env;     /* ring slots per env (>= 2: one is always being written) */
+  int32_t max_episode_length;   /* T: longer episodes are closed at T transitions */
+  int32_t obs_dim, goal_dim, action_dim;
+  int32_t task, reward_type, num_obj;   /* for compute_reward: state-free reward types only (as xarm_compute_reward) */
+  int32_t n_sampled_goal;       /* her_ratio = 1 - 1 / (n_sampled_goal + 1) */
+  int32_t device;
+  uint64_t seed;
+} XarmHerConfig;
+typedef struct XarmHer XarmHer;
+int xarm_her_create(const XarmHerConfig* cfg, XarmHer** out);
+int xarm_her_destroy(XarmHer* h);
+/* after Env.reset(): first row and goal of the episode each (masked) env starts; an unfinished episode is dropped */
+int xarm_her_begin(XarmHer* h, const float* observation, const float* achieved_goal, const float* desired_goal,
+                   const uint8_t* mask_or_null, void* stream);
+/* HerReplayBuffer.add after Env.step: observation / achieved_goal / desired_goal [N, O | G | G] as the step left them (after
+ * the auto-reset where done), terminal [N, O + 2 G] = the finishing step's [obs | ag | dg] (XarmBuffers.terminal_observation;
+ * NULL without auto-reset), action [N, A], reward [N], done [N] u8, truncated [N] u8 or NULL (stored done = done & !truncated). */
+int xarm_her_add(XarmHer* h, const float* observation, const float* achieved_goal, const float* desired_goal,
+                 const float* terminal, const float* action, const float* reward, const uint8_t* done,
+                 const uint8_t* truncated, void* stream);
+/* HerReplayBuffer.sample(batch): observation, next_observation [B, O]; achieved_goal, next_achieved_goal, desired_goal [B, G];
+ * action [B, A]; reward [B]; done [B] u8; index_or_null [B, 4] int32 = (env, ring slot, transition, future transition or -1).
+ * Samples that found no finished episode in 64 draws are zero-filled with env = -1 and counted (xarm_her_stats). */
+int xarm_her_sample(XarmHer* h, int64_t batch, float* observation, float* achieved_goal, float* desired_goal, float* action,
+                    float* next_observation, float* next_achieved_goal, float* reward, uint8_t* done, int32_t* index_or_null,
+                    void* stream);
+/* out[0] = invalid samples since the last call, out[1] = finished episodes stored so far, out[2] = transitions added,
+ * out[3] = sample calls so far.  Synchronises the device. */
+int xarm_her_stats(XarmHer* h, int64_t out[4]);
+
 /* kernels launched by this library since load (claim for bench.py's gpu_launches) */
 int64_t xarm_launch_count(void);
 const char* xarm_last_error(void);

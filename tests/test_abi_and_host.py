@@ -36,8 +36,29 @@ def test_struct_layouts_match_header():
     from gym_xarm_b200 import _native
     assert C.sizeof(_native.XarmConfig) == 72 and _native.XarmConfig.num_envs.offset == 48 and _native.XarmConfig.seed.offset == 64
     assert C.sizeof(_native.XarmBuffers) == 9 * 8
+    assert C.sizeof(_native.XarmHerConfig) == 56 and _native.XarmHerConfig.seed.offset == 48 and _native.XarmHerConfig.device.offset == 44
     from oracle import oracle as orc
     assert C.sizeof(orc.XarmConfig) == C.sizeof(_native.XarmConfig)
+
+
+def test_her_create_rejects_bad_configs_without_gpu():
+    """argument errors of xarm_her_create surface as ValueError / NotImplementedError before any CUDA call"""
+    import pytest
+    from gym_xarm_b200 import _native
+    L = _native.load()
+    base = dict(num_envs=8, episodes_per_env=4, max_episode_length=50, obs_dim=24, goal_dim=3, action_dim=4, task=1, reward_type=0,
+                num_obj=1, n_sampled_goal=4, device=0, seed=0)
+    for bad, exc in [(dict(episodes_per_env=1), ValueError), (dict(goal_dim=10), ValueError), (dict(num_envs=0), ValueError),
+                     (dict(task=9), ValueError), (dict(reward_type=1), NotImplementedError), (dict(n_sampled_goal=-1), ValueError)]:
+        cfg = _native.XarmHerConfig(**{**base, **bad})
+        h = C.c_void_p()
+        rc = L.xarm_her_create(C.byref(cfg), C.byref(h))
+        assert rc == -1
+        with pytest.raises(exc):
+            _native.check(rc, "xarm_her_create")
+    from gym_xarm_b200.her import XarmHerReplayBuffer
+    with pytest.raises(NotImplementedError):
+        XarmHerReplayBuffer(num_envs=8, obs_dim=24, goal_dim=3, action_dim=4, task=1, max_episode_length=50, goal_selection_strategy="final")
 
 
 def test_task_dims_without_gpu():

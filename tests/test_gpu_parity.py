@@ -510,3 +510,124 @@ def test_multi_object_parity(task, num_obj):
         assert np.array_equal(rew.cpu().numpy().view(np.uint32), want.view(np.uint32))
     assert clean.sum() >= (n // 4 if task == "pick_and_place" else 1), f"only {clean.sum()} contact-free envs"
     env.close()
+
+
+@pytest.mark.parametrize("task,num_obj,reward_type", [("pick_and_place", 1, "sparse"), ("stack_tower", 3, "dense"), ("handover", 2, "sparse")])
+def test_her_buffer_matches_oracle_bit_exact(task, num_obj, reward_type):
+    """xarm_her_* (hindsight relabelling on the device) against oracle/her_oracle.py on the same random
+    transition tape: episode bookkeeping, sampled indices, gathered rows, relabelled goals and recomputed rewards are all
+    bit-exact (integer / copy work + the bit-exact compute_reward), over several sample calls interleaved with adds."""
+    import torch
+    from gym_xarm_b200.her import XarmHerReplayBuffer
+    from oracle.her_oracle import HerOracle
+    from tests.test_oracle_golden import _her_fill
+    A, O, G, _ = orc.dims(orc.TASKS[task], num_obj)
+    N, K, T = 96, 3, 12
+    cr = lambda ag, dg: orc.compute_reward(task, reward_type, num_obj, ag, dg)
+    ref = HerOracle(N, K, T, O, G, A, cr, n_sampled_goal=4, seed=0xC0FFEE1234)
+    buf = XarmHerReplayBuffer(num_envs=N, obs_dim=O, goal_dim=G, action_dim=A, task=orc.TASKS[task], reward_type=orc.REWARDS[reward_type],
+                              num_obj=num_obj, episodes_per_env=K, max_episode_length=T, n_sampled_goal=4, seed=0xC0FFEE1234, device="cuda:0")
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+    class Tee:   # HerOracle surface that forwards every call to the device buffer too
+        N, O, G, A = ref.N, ref.O, ref.G, ref.A
+
+        def begin(self, o, a, d):
+            ref.begin(o, a, d)
+            buf.begin({"observation": dev(o), "achieved_goal": dev(a), "desired_goal": dev(d)})
+
+        def add(self, o, a, d, term, act, rew, done, trunc):
+            ref.add(o, a, d, term, act, rew, done, trunc)
+            buf.add({"observation": dev(o), "achieved_goal": dev(a), "desired_goal": dev(d)}, dev(act), dev(rew), dev(done), dev(trunc), dev(term))
+
+    def compare(B):
+        want = ref.sample(B)
+        got, index = buf.sample(B, return_index=True)
+        assert np.array_equal(index.cpu().numpy(), want["index"])
+        pairs = [(got.observations["observation"], "observation"), (got.observations["achieved_goal"], "achieved_goal"),
+                 (got.observations["desired_goal"], "desired_goal"), (got.actions, "action"), (got.next_observations["observation"], "next_observation"),
+                 (got.next_observations["achieved_goal"], "next_achieved_goal")]
+        for t, name in pairs:
+            assert np.array_equal(t.cpu().numpy(), want[name]), name
+        assert np.array_equal(got.rewards[:, 0].cpu().numpy().view(np.uint32), want["reward"].view(np.uint32))   # bit-exact incl. -0.0
+        assert np.array_equal(got.dones[:, 0].cpu().numpy(), want["done"])
+        return want
+
+    got, index = buf.sample(64, return_index=True)     # nothing finished yet: every sample invalid, zero-filled, counted
+    ref.sample(64)
+    assert (index.cpu().numpy() == -1).all() and float(got.rewards.abs().sum()) == 0.0 and buf.stats()["invalid_samples"] == 64
+    rng = np.random.default_rng(17)
+    tee = Tee()
+    _her_fill(tee, rng, 9, p_done=0.15)
+    compare(1000)                                      # rings partly filled: rejection of unfinished slots is exercised
+    _her_fill(tee, rng, 40, p_done=0.1)
+    w = compare(4096)
+    compare(257)
+    st = buf.stats()
+    assert st["episodes"] == ref.episodes and st["transitions"] == ref.transitions and st["sample_calls"] == ref.calls and st["invalid_samples"] == 0
+    her = w["index"][:, 3] >= 0
+    assert her.sum() > 0.7 * 4096 and len(np.unique(w["reward"][her])) >= 2
+    buf.close()
+
+
+def test_her_on_env_rollout_pick_and_place():
+    """XarmHerReplayBuffer fed by a real XarmVecEnv rollout (auto-reset on): stored rows equal what the env returned
+    (terminal observation where done), relabelled rewards equal env.compute_reward on the sampled goals, a relabelled
+    transition whose future step is the next one is always a success (sparse reward 1), and size-independent properties at
+    a large batch."""
+    import torch
+    from gym_xarm_b200.her import XarmHerReplayBuffer
+    n = 2048
+    env = _mk("pick_and_place", n, seed=3, auto_reset=True, max_episode_steps=8)
+    buf = XarmHerReplayBuffer(env, episodes_per_env=3, n_sampled_goal=4, seed=9)
+    env.reset()
+    buf.begin()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    hist = []
+    for t in range(20):
+        a = torch.rand(n, env.act_dim, generator=g, device="cuda") * 2 - 1
+        obs, rew, done, infos = env.step(a)
+        buf.add()
+        term = env.terminal_buf.clone()
+        nxt = torch.where(done[:, None], term[:, :env.obs_dim], obs["observation"])
+        hist.append((nxt.clone(), rew.clone(), done.clone(), a.clone()))
+    st = buf.stats()
+    assert st["transitions"] == 20 * n and st["episodes"] >= 2 * n
+    B = 1 << 16
+    s, index = buf.sample(B, return_index=True)
+    idx = index.cpu().numpy()
+    assert (idx[:, 0] >= 0).all()
+    her = idx[:, 3] >= 0
+    n_her = int(0.8 * B)     # relabelled: the first int(her_ratio * B) samples, except those of one-transition episodes (solved at the first step)
+    assert not her[n_her:].any() and (idx[:n_her][~her[:n_her], 2] == 0).all() and 0.7 < her.mean() <= 0.8
+    # relabelled reward == compute_reward(next_achieved_goal, desired_goal); others keep a stored env reward
+    r = env.compute_reward(s.next_observations["achieved_goal"], s.observations["desired_goal"]).cpu().numpy()
+    got = s.rewards[:, 0].cpu().numpy()
+    assert np.array_equal(got[her], r[her])
+    nxt1 = her & (idx[:, 3] == idx[:, 2] + 1)
+    assert nxt1.any() and (got[nxt1] == 1.0).all()     # the goal is the next achieved goal itself: distance 0 < 0.05
+    # episodes are 8 steps here (TimeLimit) unless solved early: every env's ring was filled in lock-step, so slot k of env e
+    # holds steps 8k .. 8k+7 of the rollout while no early success shifted it; check those rows against the rollout
+    L = 8
+    e, k, t = idx[:, 0], idx[:, 1], idx[:, 2]
+    all_done = torch.stack([h[2] for h in hist]).cpu().numpy()            # [20, n]
+    early = np.zeros(n, bool)
+    for j in range(20):
+        if (j + 1) % L:
+            early |= all_done[j]
+    pick = ~early[e] & (k < 2)
+    assert pick.sum() > 1000
+    step = k[pick] * L + t[pick]
+    H_next = torch.stack([h[0] for h in hist]).cpu().numpy()
+    H_act = torch.stack([h[3] for h in hist]).cpu().numpy()
+    H_rew = torch.stack([h[1] for h in hist]).cpu().numpy()
+    assert np.array_equal(s.next_observations["observation"].cpu().numpy()[pick], H_next[step, e[pick]])
+    assert np.array_equal(s.actions.cpu().numpy()[pick], H_act[step, e[pick]])
+    keep = pick & ~her
+    assert np.array_equal(got[keep], H_rew[k[keep] * L + t[keep], e[keep]])
+    dn = s.dones[:, 0].cpu().numpy()[pick]
+    assert (dn[t[pick] < L - 1] == 0).all()                              # done only on a last transition, and there only when the
+    last = step[t[pick] == L - 1]                                        # episode was solved at that step: time-limit endings are timeouts
+    assert dn[t[pick] == L - 1].mean() < 0.2 and len(last) > 0
+    buf.close()
+    env.close()
