@@ -9,7 +9,7 @@ from .envs import XarmReachEnv, XarmPickAndPlace, XarmStackTowerEnv, XarmPushWit
 from .registration import REGISTRY, make, make_vec, register_with_gym  # noqa: F401
 from . import distributed  # noqa: F401
 from .policies import ezpolicy  # noqa: F401
-from .vec_normalize import XarmVecNormalize  # noqa: F401
+from .vec_normalize import XarmVecNormalize, XarmVecExtractDictObs  # noqa: F401
 from .her import XarmHerReplayBuffer  # noqa: F401
 
 register_with_gym()

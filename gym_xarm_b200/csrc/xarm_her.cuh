@@ -32,8 +32,10 @@ XD int64_t her_tr(const HerBuf& h, int k, int t, int64_t i) { return ((int64_t)k
 // One warp per env, lanes over the words of a row (no index arithmetic beyond the row base; cur_k / cur_t / done are
 // warp-uniform loads); every load of the row is issued before the first store.  The bookkeeping is k_her_advance's (a second
 // launch: every warp reads cur_k / cur_t).
+// HER_OBS_REGS = ceil(O / 32) rounded up to 1, 2 or 4: observation words a lane carries (template: the row loops unroll to
+// exactly that many predicated loads; the first version unrolled 4 for every O and was issue bound at 195 instructions per warp).
 #define XARM_HER_MAX_OBS 128
-#define HER_OBS_REGS (XARM_HER_MAX_OBS / 32)
+template <int HER_OBS_REGS>
 __global__ void __launch_bounds__(256) k_her_store(HerBuf h, const float* __restrict__ obs, const float* __restrict__ ag,
                                                    const float* __restrict__ dg, const float* __restrict__ terminal,
                                                    const float* __restrict__ action, const float* __restrict__ reward,
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(256) k_her_index(HerBuf h, int64_t batch, int6
 
 // gather + relabel + reward: one warp per sample, lanes over the words of a row; the eight row segments are loaded before the
 // first store (eight independent gathers in flight per warp).  Outputs are SB3's DictReplayBufferSamples fields.
+template <int HER_OBS_REGS>
 __global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, const int4* __restrict__ index, int task, int reward_type,
                                                     int num_obj, float* __restrict__ o_obs, float* __restrict__ o_ag,
                                                     float* __restrict__ o_dg, float* __restrict__ o_act, float* __restrict__ o_nobs,
@@ -191,7 +194,8 @@ __global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, con
   if (her) {   // env.compute_reward(next_achieved_goal, new desired_goal, info): lane 0 collects the goals (warp-uniform branch)
     float a[9], d[9];
 #pragma unroll
-    for (int g = 0; g < 9; g++) { a[g] = __shfl_sync(0xffffffffu, vna, g); d[g] = __shfl_sync(0xffffffffu, vd, g); }
+    for (int g = 0; g < 9; g++)
+      if (g < G) { a[g] = __shfl_sync(0xffffffffu, vna, g); d[g] = __shfl_sync(0xffffffffu, vd, g); }
     if (lane == 0) vr = reward_stateless(task, reward_type, num_obj, task_threshold(task), a, d, G);
   }
 #pragma unroll

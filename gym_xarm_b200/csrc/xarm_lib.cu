@@ -1269,7 +1269,10 @@ int xarm_her_add(XarmHer* h, const float* obs, const float* ag, const float* dg,
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   const HerBuf& b = h->b;
   cudaStream_t s = (cudaStream_t)stream;
-  k_her_store<<<(unsigned)((b.N + 7) / 8), 256, 0, s>>>(b, obs, ag, dg, terminal, action, reward, done, truncated);
+  const unsigned grid = (unsigned)((b.N + 7) / 8);   // one warp per env
+  if (b.O <= 32) k_her_store<1><<<grid, 256, 0, s>>>(b, obs, ag, dg, terminal, action, reward, done, truncated);
+  else if (b.O <= 64) k_her_store<2><<<grid, 256, 0, s>>>(b, obs, ag, dg, terminal, action, reward, done, truncated);
+  else k_her_store<4><<<grid, 256, 0, s>>>(b, obs, ag, dg, terminal, action, reward, done, truncated);
   k_her_advance<<<(unsigned)((b.N + 255) / 256), 256, 0, s>>>(b, done);
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
@@ -1297,8 +1300,10 @@ int xarm_her_sample(XarmHer* h, int64_t batch, float* obs, float* ag, float* dg,
   const HerBuf& b = h->b;
   const int64_t n_her = (int64_t)((1.0 - 1.0 / (double)(h->cfg.n_sampled_goal + 1)) * (double)batch);   // int(her_ratio * batch_size)
   k_her_index<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(b, batch, n_her, h->cfg.seed, h->calls, idx);
-  k_her_gather<<<(unsigned)((batch + 7) / 8), 256, 0, s>>>(b, batch, idx, h->cfg.task, h->cfg.reward_type, h->cfg.num_obj, obs, ag, dg,
-                                                         action, next_obs, next_ag, reward, done);
+  const unsigned grid = (unsigned)((batch + 7) / 8);   // one warp per sample
+#define HER_GATHER(R) k_her_gather<R><<<grid, 256, 0, s>>>(b, batch, idx, h->cfg.task, h->cfg.reward_type, h->cfg.num_obj, obs, ag, dg, action, next_obs, next_ag, reward, done)
+  if (b.O <= 32) HER_GATHER(1); else if (b.O <= 64) HER_GATHER(2); else HER_GATHER(4);
+#undef HER_GATHER
   h->calls++;
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());

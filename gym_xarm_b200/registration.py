@@ -17,6 +17,11 @@ REGISTRY = {
     "XarmPDHandover-v1": ("handover", {"reward_type": "dense"}),
 }
 
+# flat-observation ids: id -> (dict-observation id, key).  The reference trains on 'XarmPDHandoverNoGoal-v1'
+# [REF benchmark/train.py:66,74] (the Handover env behind VecExtractDictObs [REF benchmark/train.py:44-62]); its snapshot
+# does not register the id, so it exists here for make_vec only.
+FLAT_IDS = {"XarmPDHandoverNoGoal-v1": ("XarmPDHandover-v1", "observation")}
+
 
 class TimeLimit:
     """gym.wrappers.TimeLimit stand-in (a20): sets done and info['TimeLimit.truncated'] at max_episode_steps."""
@@ -53,6 +58,10 @@ def make(env_id, config=None, **kwargs):
 
 def make_vec(env_id, num_envs, config=None, **kwargs):
     """Batched counterpart of SB3's make_vec_env(env_id, n_envs=...) [REF benchmark/train.py:74]."""
+    if env_id in FLAT_IDS:
+        from .vec_normalize import XarmVecExtractDictObs
+        base, key = FLAT_IDS[env_id]
+        return XarmVecExtractDictObs(make_vec(base, num_envs, config=config, **kwargs), key)
     task, defaults = REGISTRY[env_id]
     cfg = dict(defaults)
     cfg.update(config or {})

@@ -18,9 +18,34 @@ from . import _native
 RunningMeanStd = namedtuple("RunningMeanStd", "mean var count")
 
 
+class XarmVecExtractDictObs:
+    """The reference's VecExtractDictObs(venv, key) [REF benchmark/train.py:44-62]: a VecEnv whose observation is
+    `obs[key]` (the flat Box the 'NoGoal' env id exposes).  No copy: the env's own device buffer is returned."""
+
+    def __init__(self, venv, key="observation"):
+        self.venv, self.key = venv, key
+        self.observation_space = venv.observation_space.spaces[key]
+
+    def __getattr__(self, name):
+        return getattr(self.venv, name)
+
+    def reset(self, *a, **k):
+        return self.venv.reset(*a, **k)[self.key]
+
+    def step_wait(self):
+        obs, reward, done, info = self.venv.step_wait()
+        return obs[self.key], reward, done, info
+
+    def step(self, actions):
+        obs, reward, done, info = self.venv.step(actions)
+        return obs[self.key], reward, done, info
+
+
 class XarmVecNormalize:
     def __init__(self, venv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0, clip_reward=10.0, gamma=0.99,
                  epsilon=1e-8, key="observation"):
+        if isinstance(venv, XarmVecExtractDictObs):   # make_vec('XarmPDHandoverNoGoal-v1'): normalise the key it extracts
+            venv, key = venv.venv, venv.key
         self.venv, self.key = venv, key
         self.num_envs, self.device = venv.num_envs, venv.device
         self.obs_dim = int(venv.obs_buf[key].shape[1])

@@ -512,8 +512,9 @@ def test_multi_object_parity(task, num_obj):
     env.close()
 
 
-@pytest.mark.parametrize("task,num_obj,reward_type", [("pick_and_place", 1, "sparse"), ("stack_tower", 3, "dense"), ("handover", 2, "sparse")])
-def test_her_buffer_matches_oracle_bit_exact(task, num_obj, reward_type):
+@pytest.mark.parametrize("task,num_obj,reward_type,obs_dim", [("pick_and_place", 1, "sparse", None), ("stack_tower", 3, "dense", None),
+                                                              ("handover", 2, "sparse", None), ("pick_and_place", 1, "dense_o2g", 100)])
+def test_her_buffer_matches_oracle_bit_exact(task, num_obj, reward_type, obs_dim):
     """xarm_her_* (hindsight relabelling on the device) against oracle/her_oracle.py on the same random
     transition tape: episode bookkeeping, sampled indices, gathered rows, relabelled goals and recomputed rewards are all
     bit-exact (integer / copy work + the bit-exact compute_reward), over several sample calls interleaved with adds."""
@@ -522,6 +523,7 @@ def test_her_buffer_matches_oracle_bit_exact(task, num_obj, reward_type):
     from oracle.her_oracle import HerOracle
     from tests.test_oracle_golden import _her_fill
     A, O, G, _ = orc.dims(orc.TASKS[task], num_obj)
+    O = obs_dim or O          # the kernels come in three row widths (O <= 32, <= 64, <= 128): 24, 55 / 42 and 100 cover them
     N, K, T = 96, 3, 12
     cr = lambda ag, dg: orc.compute_reward(task, reward_type, num_obj, ag, dg)
     ref = HerOracle(N, K, T, O, G, A, cr, n_sampled_goal=4, seed=0xC0FFEE1234)
@@ -630,4 +632,26 @@ def test_her_on_env_rollout_pick_and_place():
     last = step[t[pick] == L - 1]                                        # episode was solved at that step: time-limit endings are timeouts
     assert dn[t[pick] == L - 1].mean() < 0.2 and len(last) > 0
     buf.close()
+    env.close()
+
+
+def test_nogoal_flat_obs_id_with_vecnormalize():
+    """make_vec('XarmPDHandoverNoGoal-v1') - the id the reference's training script uses [REF benchmark/train.py:66,74] - is the
+    dense-reward Handover env behind VecExtractDictObs: flat [N, 29] observations (the same device buffer, no copy), and
+    XarmVecNormalize wraps it like VecNormalize wraps it in the script."""
+    import gym_xarm_b200 as gx
+    env = gx.make_vec("XarmPDHandoverNoGoal-v1", 64, device="cuda:0", seed=2)
+    assert env.observation_space.shape == (29,) and env.reward_type == "dense"
+    o = env.reset()
+    assert tuple(o.shape) == (64, 29) and o.data_ptr() == env.venv.obs_buf["observation"].data_ptr()
+    import torch
+    a = torch.zeros(64, 8, device="cuda")
+    o2, r, d, info = env.step(a)
+    assert tuple(o2.shape) == (64, 29) and tuple(r.shape) == (64,) and bool(torch.isfinite(o2).all())
+    vn = gx.XarmVecNormalize(env)
+    on = vn.reset()
+    assert tuple(on.shape) == (64, 29) and vn.key == "observation" and vn.venv is env.venv
+    on, rn, d, _ = vn.step(a)
+    assert float(on.abs().max()) <= 10.0 and vn.obs_rms.count == 64 + 1e-4
+    vn.close()
     env.close()
