@@ -24,8 +24,10 @@ struct HerBuf {
   int K, T, O, G, A;
 };
 
-XD int64_t her_row(const HerBuf& h, int k, int t, int64_t i) { return ((int64_t)k * (h.T + 1) + t) * h.N + i; }   // obs / ag rows
-XD int64_t her_tr(const HerBuf& h, int k, int t, int64_t i) { return ((int64_t)k * h.T + t) * h.N + i; }          // act / rew / done rows
+// Row numbers are 32-bit (xarm_her_create checks K (T+1) N < 2^32): one 32-bit multiply-add per row and one widening multiply per
+// array instead of chains of 64-bit multiplies - the kernels are issue bound on exactly this arithmetic.
+XD size_t her_row(const HerBuf& h, int k, int t, int64_t i) { return (uint32_t)(k * (h.T + 1) + t) * (uint32_t)h.N + (uint32_t)i; }   // obs / ag rows
+XD size_t her_tr(const HerBuf& h, int k, int t, int64_t i) { return (uint32_t)(k * h.T + t) * (uint32_t)h.N + (uint32_t)i; }          // act / rew / done rows
 
 // HerReplayBuffer.add for one transition of every env.  Inputs are the buffers an env step leaves behind: obs / ag / dg
 // AFTER the step (after the auto-reset where done), terminal = [obs | ag | dg] of the finishing step (or null: no auto-reset).
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(256) k_her_store(HerBuf h, const float* __rest
                                                    const uint8_t* __restrict__ done, const uint8_t* __restrict__ truncated) {
   const int O = h.O, G = h.G, A = h.A;
   const int lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t i = (int64_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));   // 32-bit arithmetic: N < 2^31
   if (i >= h.N) return;
   const int k = h.cur_k[i], t = h.cur_t[i];
   const bool d = done[i] != 0;
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(256) k_her_store(HerBuf h, const float* __rest
   const float vd2 = (close && lane < G) ? dg[i * G + lane] : 0.f;
   const float vr = reward[i];
   const bool tr = truncated && truncated[i];
-  const int64_t r1 = her_row(h, k, t + 1, i), r0 = her_tr(h, k, t, i);
+  const size_t r1 = her_row(h, k, t + 1, i), r0 = her_tr(h, k, t, i);
 #pragma unroll
   for (int j = 0; j < HER_OBS_REGS; j++) {
     const int w = lane + 32 * j;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256) k_her_store(HerBuf h, const float* __rest
   }
   if (!close) return;                   // the episode goes on: nothing else to store
   const int k2 = (k + 1 == h.K) ? 0 : k + 1;  // first row of the next episode = the observation after the auto-reset
-  const int64_t r2 = her_row(h, k2, 0, i);
+  const size_t r2 = her_row(h, k2, 0, i);
 #pragma unroll
   for (int j = 0; j < HER_OBS_REGS; j++) {
     const int w = lane + 32 * j;
@@ -118,12 +120,12 @@ __global__ void __launch_bounds__(256) k_her_begin(HerBuf h, const float* __rest
                                                    const float* __restrict__ dg, const uint8_t* __restrict__ mask) {
   const int O = h.O, G = h.G;
   const int lane = threadIdx.x & 31;
-  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t i = (int64_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));   // 32-bit arithmetic: N < 2^31
   if (i >= h.N) return;
   if (mask && !mask[i]) return;
   const int k = h.cur_k[i];
   if (lane == 0) h.cur_t[i] = 0;            // a partial episode is dropped
-  const int64_t r = her_row(h, k, 0, i);
+  const size_t r = her_row(h, k, 0, i);
   for (int w = lane; w < O; w += 32) h.obs[r * O + w] = obs[i * O + w];
   if (lane < G) {
     h.ag[r * G + lane] = ag[i * G + lane];
@@ -169,13 +171,13 @@ __global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, con
                                                     float* __restrict__ o_nag, float* __restrict__ o_rew, uint8_t* __restrict__ o_done) {
   const int O = h.O, G = h.G, A = h.A;
   const int lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t b = (int64_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));   // 32-bit arithmetic: batch < 2^31
   if (b >= batch) return;
   const int4 s = index[b];
   const bool ok = s.x >= 0, her = ok && s.w >= 0;
-  const int64_t i = ok ? s.x : 0;
+  const int64_t i = ok ? (int64_t)(uint32_t)s.x : 0;
   const int k = ok ? s.y : 0, t = ok ? s.z : 0;
-  const int64_t r0 = her_row(h, k, t, i), r1 = her_row(h, k, t + 1, i), q = her_tr(h, k, t, i);
+  const size_t r0 = her_row(h, k, t, i), r1 = her_row(h, k, t + 1, i), q = her_tr(h, k, t, i);
   float vo[HER_OBS_REGS], vn[HER_OBS_REGS];
 #pragma unroll
   for (int j = 0; j < HER_OBS_REGS; j++) {
@@ -196,7 +198,13 @@ __global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, con
 #pragma unroll
     for (int g = 0; g < 9; g++)
       if (g < G) { a[g] = __shfl_sync(0xffffffffu, vna, g); d[g] = __shfl_sync(0xffffffffu, vd, g); }
-    if (lane == 0) vr = reward_stateless(task, reward_type, num_obj, task_threshold(task), a, d, G);
+    if (lane == 0) {   // constant G at the call sites: the goal arrays stay in registers and the distance loops unroll
+      const float thr = task_threshold(task);
+      if (G == 3) vr = reward_stateless(task, reward_type, num_obj, thr, a, d, 3);
+      else if (G == 6) vr = reward_stateless(task, reward_type, num_obj, thr, a, d, 6);
+      else if (G == 9) vr = reward_stateless(task, reward_type, num_obj, thr, a, d, 9);
+      else vr = reward_stateless(task, reward_type, num_obj, thr, a, d, G);
+    }
   }
 #pragma unroll
   for (int j = 0; j < HER_OBS_REGS; j++) {

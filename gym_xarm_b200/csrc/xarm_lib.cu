@@ -1212,6 +1212,8 @@ int xarm_her_create(const XarmHerConfig* cfg, XarmHer** out) {
   if (cfg->obs_dim < 1 || cfg->obs_dim > XARM_HER_MAX_OBS || cfg->action_dim < 1 || cfg->action_dim > 32 || cfg->goal_dim < 1 || cfg->goal_dim > 9)
     return fail(XARM_E_INVALID, "xarm_her_create: 1 <= obs_dim <= 128, 1 <= action_dim <= 32 and 1 <= goal_dim <= 9 required");
   if (cfg->n_sampled_goal < 0) return fail(XARM_E_INVALID, "xarm_her_create: n_sampled_goal >= 0 required");
+  if ((double)cfg->episodes_per_env * ((double)cfg->max_episode_length + 1.0) * (double)cfg->num_envs >= 4294967296.0)
+    return fail(XARM_E_INVALID, "xarm_her_create: episodes_per_env x (max_episode_length + 1) x num_envs must stay below 2^32 rows");
   if (cfg->task < 0 || cfg->task >= XARM_NUM_TASKS) return fail(XARM_E_INVALID, "xarm_her_create: bad task");
   {
     const int rt = cfg->reward_type;   // the same gate as xarm_compute_reward: relabelling needs a state-free reward
@@ -1282,7 +1284,7 @@ int xarm_her_add(XarmHer* h, const float* obs, const float* ag, const float* dg,
 int xarm_her_sample(XarmHer* h, int64_t batch, float* obs, float* ag, float* dg, float* action, float* next_obs, float* next_ag,
                     float* reward, uint8_t* done, int32_t* index, void* stream) {
   if (!h || !obs || !ag || !dg || !action || !next_obs || !next_ag || !reward || !done) return fail(XARM_E_INVALID, "xarm_her_sample: null argument");
-  if (batch <= 0) return fail(XARM_E_INVALID, "xarm_her_sample: batch > 0 required");
+  if (batch <= 0 || batch > 0x7fffffffLL) return fail(XARM_E_INVALID, "xarm_her_sample: 0 < batch < 2^31 required");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   int4* idx = reinterpret_cast<int4*>(index);
