@@ -1,12 +1,16 @@
 // xarm_her.cuh - hindsight-experience-replay episode store and 'future' relabelling on the device
 // [REF benchmark/train.py:81-97: HerReplayBuffer(n_sampled_goal=4, goal_selection_strategy="future",
 //  max_episode_length=100, online_sampling=True)], semantics of stable-baselines3 1.x HerReplayBuffer (include/xarm_abi.h).
-// HBM bound: add = one read of the step's outputs + one write of the same words; sample = gathered rows -> dense batch.
+// HBM bound: add = one read of the step's outputs + one write of the same words; sample = gathered records -> dense batch.
 //
-// Layout (time-major, so that the envs of a slab, which step together, write neighbouring addresses):
-//   obs [K][T+1][N][O]   row t = observation before transition t; row t+1 = observation after it (next_obs of t)
-//   ag  [K][T+1][N][G]   achieved goals, same indexing
-//   act [K][T][N][A], rew [K][T][N], done [K][T][N] (uint8)
+// Layout: an array of step records, an episode contiguous, an env's ring of K episodes contiguous:
+//   rec [N][K][T+1][RW]  RW = O + G + A + 2 words: [ obs_t (O) | achieved_goal_t (G) | action_t (A) | reward_t | done_t (0.f / 1.f) ]
+//                        record t+1 starts with next_obs / next_achieved_goal of transition t (nothing is stored twice), so
+//                        * add writes ONE contiguous run of RW words per env: the tail of record t (action, reward, done) and the
+//                          head of record t+1 (obs, achieved goal);
+//                        * a sample reads ONE contiguous run of RW + O + G words (record t and the head of record t+1) plus the
+//                          future step's achieved goal - two scattered accesses instead of the eight of a structure of arrays
+//                          (the first version of this file: 1.0 GB of DRAM reads per 1 M samples for 0.28 GB algorithmic).
 //   dg  [K][N][G]        desired goal, one per episode: the reference's envs draw the goal in reset() only
 //                        [REF xarm_pick_and_place.py:121-127; xarm_reach.py:96-102; xarm_handover.py:141-151]
 //   ep_len [K][N]        transitions of a finished episode; 0 = empty or being written
@@ -16,33 +20,32 @@
 #include <stdint.h>
 
 struct HerBuf {
-  float *obs, *ag, *dg, *act, *rew;
-  uint8_t* done;
+  float *rec, *dg;
   int *ep_len, *cur_k, *cur_t;
   unsigned long long* counters;   // [0] invalid samples since the last read, [1] finished episodes stored, [2] transitions added
   int64_t N;
   int K, T, O, G, A;
 };
+#define XARM_HER_MAX_OBS 128
+#define XARM_HER_MAX_ACT 32
 
-// Row numbers are 32-bit (xarm_her_create checks K (T+1) N < 2^32): one 32-bit multiply-add per row and one widening multiply per
-// array instead of chains of 64-bit multiplies - the kernels are issue bound on exactly this arithmetic.
-XD size_t her_row(const HerBuf& h, int k, int t, int64_t i) { return (uint32_t)(k * (h.T + 1) + t) * (uint32_t)h.N + (uint32_t)i; }   // obs / ag rows
-XD size_t her_tr(const HerBuf& h, int k, int t, int64_t i) { return (uint32_t)(k * h.T + t) * (uint32_t)h.N + (uint32_t)i; }          // act / rew / done rows
+// Record numbers are 32-bit (xarm_her_create checks N K (T+1) < 2^32): one 32-bit multiply-add and one widening multiply per
+// record instead of chains of 64-bit multiplies - these kernels are issue bound on exactly that arithmetic.
+XD size_t her_rec(const HerBuf& h, int k, int t, int64_t i, int RW) {
+  return (size_t)(((uint32_t)i * (uint32_t)h.K + (uint32_t)k) * (uint32_t)(h.T + 1) + (uint32_t)t) * (uint32_t)RW;
+}
 
 // HerReplayBuffer.add for one transition of every env.  Inputs are the buffers an env step leaves behind: obs / ag / dg
 // AFTER the step (after the auto-reset where done), terminal = [obs | ag | dg] of the finishing step (or null: no auto-reset).
-// One warp per env, lanes over the words of a row (no index arithmetic beyond the row base; cur_k / cur_t / done are
-// warp-uniform loads); every load of the row is issued before the first store.  The bookkeeping is k_her_advance's (a second
-// launch: every warp reads cur_k / cur_t).
-// HER_OBS_REGS = ceil(O / 32) rounded up to 1, 2 or 4: observation words a lane carries (template: the row loops unroll to
-// exactly that many predicated loads; the first version unrolled 4 for every O and was issue bound at 195 instructions per warp).
-#define XARM_HER_MAX_OBS 128
-template <int HER_OBS_REGS>
+// One warp per env, lanes over the RW words of the run [action | reward | done | next_obs | next_ag]; cur_k / cur_t / done are
+// warp-uniform loads; every load is issued before the first store.  NR = ceil(RW / 32) (template: the loops unroll to predicated
+// loads).  The bookkeeping is k_her_advance's (a second launch: every warp reads cur_k / cur_t).
+template <int NR>
 __global__ void __launch_bounds__(256) k_her_store(HerBuf h, const float* __restrict__ obs, const float* __restrict__ ag,
                                                    const float* __restrict__ dg, const float* __restrict__ terminal,
                                                    const float* __restrict__ action, const float* __restrict__ reward,
                                                    const uint8_t* __restrict__ done, const uint8_t* __restrict__ truncated) {
-  const int O = h.O, G = h.G, A = h.A;
+  const int O = h.O, G = h.G, A = h.A, RW = O + G + A + 2;
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));   // 32-bit arithmetic: N < 2^31
   if (i >= h.N) return;
@@ -53,43 +56,37 @@ __global__ void __launch_bounds__(256) k_her_store(HerBuf h, const float* __rest
   const float* trow = terminal + i * (O + 2 * G);
   const float* src_o = term ? trow : obs + i * O;
   const float* src_g = term ? trow + O : ag + i * G;
-  float vo[HER_OBS_REGS], vo2[HER_OBS_REGS];
-#pragma unroll
-  for (int j = 0; j < HER_OBS_REGS; j++) {
-    const int w = lane + 32 * j;
-    vo[j] = w < O ? src_o[w] : 0.f;
-    vo2[j] = (close && w < O) ? obs[i * O + w] : 0.f;
-  }
-  const float vg = lane < G ? src_g[lane] : 0.f;
-  const float va = lane < A ? action[i * A + lane] : 0.f;
-  const float vg2 = (close && lane < G) ? ag[i * G + lane] : 0.f;
-  const float vd2 = (close && lane < G) ? dg[i * G + lane] : 0.f;
-  const float vr = reward[i];
   const bool tr = truncated && truncated[i];
-  const size_t r1 = her_row(h, k, t + 1, i), r0 = her_tr(h, k, t, i);
+  float v[NR], v2[NR];
 #pragma unroll
-  for (int j = 0; j < HER_OBS_REGS; j++) {
+  for (int j = 0; j < NR; j++) {
     const int w = lane + 32 * j;
-    if (w < O) h.obs[r1 * O + w] = vo[j];
+    float x = 0.f;
+    if (w < A) x = action[i * A + w];
+    else if (w == A) x = reward[i];
+    else if (w == A + 1) x = (d && !tr) ? 1.f : 0.f;   // SB3 handle_timeout_termination: done * (1 - timeout)
+    else if (w < A + 2 + O) x = src_o[w - A - 2];
+    else if (w < RW) x = src_g[w - A - 2 - O];
+    v[j] = x;
+    // first record of the next episode = the observation after the auto-reset
+    v2[j] = (close && w < O + G) ? (w < O ? obs[i * O + w] : ag[i * G + w - O]) : 0.f;
   }
-  if (lane < G) h.ag[r1 * G + lane] = vg;
-  if (lane < A) h.act[r0 * A + lane] = va;
-  if (lane == 0) {
-    h.rew[r0] = vr;
-    h.done[r0] = (uint8_t)(d && !tr);   // SB3 handle_timeout_termination: done * (1 - timeout)
+  const float vd2 = (close && lane < G) ? dg[i * G + lane] : 0.f;
+  float* run = h.rec + her_rec(h, k, t, i, RW) + (O + G);   // tail of record t, then the head of record t+1
+#pragma unroll
+  for (int j = 0; j < NR; j++) {
+    const int w = lane + 32 * j;
+    if (w < RW) run[w] = v[j];
   }
   if (!close) return;                   // the episode goes on: nothing else to store
-  const int k2 = (k + 1 == h.K) ? 0 : k + 1;  // first row of the next episode = the observation after the auto-reset
-  const size_t r2 = her_row(h, k2, 0, i);
+  const int k2 = (k + 1 == h.K) ? 0 : k + 1;
+  float* head = h.rec + her_rec(h, k2, 0, i, RW);
 #pragma unroll
-  for (int j = 0; j < HER_OBS_REGS; j++) {
+  for (int j = 0; j < NR; j++) {
     const int w = lane + 32 * j;
-    if (w < O) h.obs[r2 * O + w] = vo2[j];
+    if (w < O + G) head[w] = v2[j];
   }
-  if (lane < G) {
-    h.ag[r2 * G + lane] = vg2;
-    h.dg[((int64_t)k2 * h.N + i) * G + lane] = vd2;
-  }
+  if (lane < G) h.dg[((int64_t)k2 * h.N + i) * G + lane] = vd2;
 }
 
 __global__ void __launch_bounds__(256) k_her_advance(HerBuf h, const uint8_t* __restrict__ done) {
@@ -115,22 +112,19 @@ __global__ void __launch_bounds__(256) k_her_advance(HerBuf h, const uint8_t* __
   }
 }
 
-// start of an episode outside the auto-reset path (after Env.reset()): row 0 and the goal of the episode being written
+// start of an episode outside the auto-reset path (after Env.reset()): head of record 0 and the goal of the episode being written
 __global__ void __launch_bounds__(256) k_her_begin(HerBuf h, const float* __restrict__ obs, const float* __restrict__ ag,
                                                    const float* __restrict__ dg, const uint8_t* __restrict__ mask) {
-  const int O = h.O, G = h.G;
+  const int O = h.O, G = h.G, RW = O + G + h.A + 2;
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));   // 32-bit arithmetic: N < 2^31
   if (i >= h.N) return;
   if (mask && !mask[i]) return;
   const int k = h.cur_k[i];
   if (lane == 0) h.cur_t[i] = 0;            // a partial episode is dropped
-  const size_t r = her_row(h, k, 0, i);
-  for (int w = lane; w < O; w += 32) h.obs[r * O + w] = obs[i * O + w];
-  if (lane < G) {
-    h.ag[r * G + lane] = ag[i * G + lane];
-    h.dg[((int64_t)k * h.N + i) * G + lane] = dg[i * G + lane];
-  }
+  float* head = h.rec + her_rec(h, k, 0, i, RW);
+  for (int w = lane; w < O + G; w += 32) head[w] = w < O ? obs[i * O + w] : ag[i * G + w - O];
+  if (lane < G) h.dg[((int64_t)k * h.N + i) * G + lane] = dg[i * G + lane];
 }
 
 // ---- sampling.  Sample b of call c draws Philox4x32-10 blocks with counter (b lo, b hi, c, try) and key = seed: word 0 -> env,
@@ -162,14 +156,15 @@ __global__ void __launch_bounds__(256) k_her_index(HerBuf h, int64_t batch, int6
   index[b] = r;
 }
 
-// gather + relabel + reward: one warp per sample, lanes over the words of a row; the eight row segments are loaded before the
-// first store (eight independent gathers in flight per warp).  Outputs are SB3's DictReplayBufferSamples fields.
-template <int HER_OBS_REGS>
+// gather + relabel + reward: one warp per sample, lanes over the RW + O + G words of the run [record t | head of record t+1];
+// the run, the future goal and the episode goal are loaded before the first store.  NR = ceil((RW + O + G) / 32).  Outputs are SB3's
+// DictReplayBufferSamples fields.
+template <int NR>
 __global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, const int4* __restrict__ index, int task, int reward_type,
                                                     int num_obj, float* __restrict__ o_obs, float* __restrict__ o_ag,
                                                     float* __restrict__ o_dg, float* __restrict__ o_act, float* __restrict__ o_nobs,
                                                     float* __restrict__ o_nag, float* __restrict__ o_rew, uint8_t* __restrict__ o_done) {
-  const int O = h.O, G = h.G, A = h.A;
+  const int O = h.O, G = h.G, A = h.A, RW = O + G + A + 2, RL = RW + O + G;
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));   // 32-bit arithmetic: batch < 2^31
   if (b >= batch) return;
@@ -177,22 +172,18 @@ __global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, con
   const bool ok = s.x >= 0, her = ok && s.w >= 0;
   const int64_t i = ok ? (int64_t)(uint32_t)s.x : 0;
   const int k = ok ? s.y : 0, t = ok ? s.z : 0;
-  const size_t r0 = her_row(h, k, t, i), r1 = her_row(h, k, t + 1, i), q = her_tr(h, k, t, i);
-  float vo[HER_OBS_REGS], vn[HER_OBS_REGS];
+  const float* run = h.rec + her_rec(h, k, t, i, RW);
+  float v[NR];
 #pragma unroll
-  for (int j = 0; j < HER_OBS_REGS; j++) {
+  for (int j = 0; j < NR; j++) {
     const int w = lane + 32 * j;
-    vo[j] = (ok && w < O) ? h.obs[r0 * O + w] : 0.f;
-    vn[j] = (ok && w < O) ? h.obs[r1 * O + w] : 0.f;
+    v[j] = (ok && w < RL) ? run[w] : 0.f;
   }
   const bool lg = ok && lane < G;
-  const float va = lg ? h.ag[r0 * G + lane] : 0.f;
-  const float vna = lg ? h.ag[r1 * G + lane] : 0.f;
+  const float vna = lg ? run[RW + O + lane] : 0.f;   // next achieved goal again, in the low lanes (an L1 hit) for the reward
   // desired goal: the achieved goal of the future step for a relabelled sample
-  const float vd = lg ? (her ? h.ag[her_row(h, k, s.w, i) * G + lane] : h.dg[((int64_t)k * h.N + i) * G + lane]) : 0.f;
-  const float vact = (ok && lane < A) ? h.act[q * A + lane] : 0.f;
-  float vr = ok ? h.rew[q] : 0.f;
-  const uint8_t vdone = ok ? h.done[q] : (uint8_t)0;
+  const float vd = lg ? (her ? h.rec[her_rec(h, k, s.w, i, RW) + O + lane] : h.dg[((int64_t)k * h.N + i) * G + lane]) : 0.f;
+  float vr = 0.f;
   if (her) {   // env.compute_reward(next_achieved_goal, new desired_goal, info): lane 0 collects the goals (warp-uniform branch)
     float a[9], d[9];
 #pragma unroll
@@ -205,13 +196,19 @@ __global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, con
       else if (G == 9) vr = reward_stateless(task, reward_type, num_obj, thr, a, d, 9);
       else vr = reward_stateless(task, reward_type, num_obj, thr, a, d, G);
     }
+    vr = __shfl_sync(0xffffffffu, vr, 0);
   }
 #pragma unroll
-  for (int j = 0; j < HER_OBS_REGS; j++) {
+  for (int j = 0; j < NR; j++) {
     const int w = lane + 32 * j;
-    if (w < O) { o_obs[b * O + w] = vo[j]; o_nobs[b * O + w] = vn[j]; }
+    const float x = v[j];
+    if (w < O) o_obs[b * O + w] = x;
+    else if (w < O + G) o_ag[b * G + w - O] = x;
+    else if (w < O + G + A) o_act[b * A + w - O - G] = x;
+    else if (w == O + G + A) o_rew[b] = her ? vr : x;
+    else if (w == O + G + A + 1) o_done[b] = (uint8_t)(x != 0.f);
+    else if (w < RW + O) o_nobs[b * O + w - RW] = x;
+    else if (w < RL) o_nag[b * G + w - RW - O] = x;
   }
-  if (lane < G) { o_ag[b * G + lane] = va; o_nag[b * G + lane] = vna; o_dg[b * G + lane] = vd; }
-  if (lane < A) o_act[b * A + lane] = vact;
-  if (lane == 0) { o_rew[b] = vr; o_done[b] = vdone; }
+  if (lane < G) o_dg[b * G + lane] = vd;
 }

@@ -1199,8 +1199,8 @@ struct XarmHer {
 };
 
 static void her_free(XarmHer* h) {
-  cudaFree(h->b.obs); cudaFree(h->b.ag); cudaFree(h->b.dg); cudaFree(h->b.act); cudaFree(h->b.rew); cudaFree(h->b.done);
-  cudaFree(h->b.ep_len); cudaFree(h->b.cur_k); cudaFree(h->b.cur_t); cudaFree(h->b.counters); cudaFree(h->index);
+  cudaFree(h->b.rec); cudaFree(h->b.dg); cudaFree(h->b.ep_len); cudaFree(h->b.cur_k); cudaFree(h->b.cur_t); cudaFree(h->b.counters);
+  cudaFree(h->index);
   cudaGetLastError();
 }
 
@@ -1209,7 +1209,7 @@ int xarm_her_create(const XarmHerConfig* cfg, XarmHer** out) {
   if (cfg->num_envs <= 0 || cfg->num_envs > 0x7fffffffLL) return fail(XARM_E_INVALID, "xarm_her_create: 0 < num_envs < 2^31 required");
   if (cfg->episodes_per_env < 2) return fail(XARM_E_INVALID, "xarm_her_create: episodes_per_env >= 2 required (one slot is always being written)");
   if (cfg->max_episode_length < 1) return fail(XARM_E_INVALID, "xarm_her_create: max_episode_length >= 1 required");
-  if (cfg->obs_dim < 1 || cfg->obs_dim > XARM_HER_MAX_OBS || cfg->action_dim < 1 || cfg->action_dim > 32 || cfg->goal_dim < 1 || cfg->goal_dim > 9)
+  if (cfg->obs_dim < 1 || cfg->obs_dim > XARM_HER_MAX_OBS || cfg->action_dim < 1 || cfg->action_dim > XARM_HER_MAX_ACT || cfg->goal_dim < 1 || cfg->goal_dim > 9)
     return fail(XARM_E_INVALID, "xarm_her_create: 1 <= obs_dim <= 128, 1 <= action_dim <= 32 and 1 <= goal_dim <= 9 required");
   if (cfg->n_sampled_goal < 0) return fail(XARM_E_INVALID, "xarm_her_create: n_sampled_goal >= 0 required");
   if ((double)cfg->episodes_per_env * ((double)cfg->max_episode_length + 1.0) * (double)cfg->num_envs >= 4294967296.0)
@@ -1232,15 +1232,13 @@ int xarm_her_create(const XarmHerConfig* cfg, XarmHer** out) {
   memset(&b, 0, sizeof(b));
   b.N = cfg->num_envs; b.K = cfg->episodes_per_env; b.T = cfg->max_episode_length;
   b.O = cfg->obs_dim; b.G = cfg->goal_dim; b.A = cfg->action_dim;
-  const size_t rows = (size_t)b.K * (b.T + 1) * b.N, trs = (size_t)b.K * b.T * b.N, eps = (size_t)b.K * b.N;
-  bool ok = cudaMalloc(&b.obs, rows * b.O * 4) == cudaSuccess && cudaMalloc(&b.ag, rows * b.G * 4) == cudaSuccess &&
-            cudaMalloc(&b.dg, eps * b.G * 4) == cudaSuccess && cudaMalloc(&b.act, trs * b.A * 4) == cudaSuccess &&
-            cudaMalloc(&b.rew, trs * 4) == cudaSuccess && cudaMalloc(&b.done, trs) == cudaSuccess &&
+  const size_t recs = (size_t)b.K * (b.T + 1) * b.N, eps = (size_t)b.K * b.N, rw = (size_t)(b.O + b.G + b.A + 2);
+  bool ok = cudaMalloc(&b.rec, recs * rw * 4) == cudaSuccess && cudaMalloc(&b.dg, eps * b.G * 4) == cudaSuccess &&
             cudaMalloc(&b.ep_len, eps * 4) == cudaSuccess && cudaMalloc(&b.cur_k, b.N * 4) == cudaSuccess &&
             cudaMalloc(&b.cur_t, b.N * 4) == cudaSuccess && cudaMalloc(&b.counters, 4 * sizeof(unsigned long long)) == cudaSuccess;
-  if (!ok) { her_free(h); delete h; return fail(XARM_E_NOMEM, "xarm_her_create: cudaMalloc failed (K x (T+1) x N x (O + G) floats)"); }
-  // rows are zero until written: a gather never reads uninitialised memory even if begin() was skipped
-  cudaMemset(b.obs, 0, rows * b.O * 4); cudaMemset(b.ag, 0, rows * b.G * 4); cudaMemset(b.dg, 0, eps * b.G * 4);
+  if (!ok) { her_free(h); delete h; return fail(XARM_E_NOMEM, "xarm_her_create: cudaMalloc failed (N x K x (T+1) x (O + G + A + 2) floats)"); }
+  // records are zero until written: a gather never reads uninitialised memory even if begin() was skipped
+  cudaMemset(b.rec, 0, recs * rw * 4); cudaMemset(b.dg, 0, eps * b.G * 4);
   cudaMemset(b.ep_len, 0, eps * 4); cudaMemset(b.cur_k, 0, b.N * 4); cudaMemset(b.cur_t, 0, b.N * 4);
   cudaMemset(b.counters, 0, 4 * sizeof(unsigned long long));
   CUDA_TRY(cudaDeviceSynchronize());
@@ -1272,9 +1270,10 @@ int xarm_her_add(XarmHer* h, const float* obs, const float* ag, const float* dg,
   const HerBuf& b = h->b;
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned grid = (unsigned)((b.N + 7) / 8);   // one warp per env
-  if (b.O <= 32) k_her_store<1><<<grid, 256, 0, s>>>(b, obs, ag, dg, terminal, action, reward, done, truncated);
-  else if (b.O <= 64) k_her_store<2><<<grid, 256, 0, s>>>(b, obs, ag, dg, terminal, action, reward, done, truncated);
-  else k_her_store<4><<<grid, 256, 0, s>>>(b, obs, ag, dg, terminal, action, reward, done, truncated);
+  const int nr = (b.O + b.G + b.A + 2 + 31) / 32;    // registers per lane for the run (<= 6: O <= 128, G <= 9, A <= 32)
+#define HER_STORE(R) k_her_store<R><<<grid, 256, 0, s>>>(b, obs, ag, dg, terminal, action, reward, done, truncated)
+  if (nr <= 1) HER_STORE(1); else if (nr == 2) HER_STORE(2); else if (nr == 3) HER_STORE(3); else if (nr == 4) HER_STORE(4); else HER_STORE(6);
+#undef HER_STORE
   k_her_advance<<<(unsigned)((b.N + 255) / 256), 256, 0, s>>>(b, done);
   g_launches += 2;
   CUDA_TRY(cudaGetLastError());
@@ -1303,8 +1302,10 @@ int xarm_her_sample(XarmHer* h, int64_t batch, float* obs, float* ag, float* dg,
   const int64_t n_her = (int64_t)((1.0 - 1.0 / (double)(h->cfg.n_sampled_goal + 1)) * (double)batch);   // int(her_ratio * batch_size)
   k_her_index<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(b, batch, n_her, h->cfg.seed, h->calls, idx);
   const unsigned grid = (unsigned)((batch + 7) / 8);   // one warp per sample
+  const int nr = (2 * (b.O + b.G) + b.A + 2 + 31) / 32;   // registers per lane for the run (<= 10)
 #define HER_GATHER(R) k_her_gather<R><<<grid, 256, 0, s>>>(b, batch, idx, h->cfg.task, h->cfg.reward_type, h->cfg.num_obj, obs, ag, dg, action, next_obs, next_ag, reward, done)
-  if (b.O <= 32) HER_GATHER(1); else if (b.O <= 64) HER_GATHER(2); else HER_GATHER(4);
+  if (nr <= 2) HER_GATHER(2); else if (nr == 3) HER_GATHER(3); else if (nr == 4) HER_GATHER(4); else if (nr == 5) HER_GATHER(5);
+  else if (nr <= 7) HER_GATHER(7); else HER_GATHER(10);
 #undef HER_GATHER
   h->calls++;
   g_launches += 2;
