@@ -11,6 +11,7 @@ episode statistics.  Prints ONE JSON line from rank 0.
 """
 import argparse
 import json
+import re
 import os
 import statistics
 import subprocess
@@ -120,6 +121,33 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+
+def ncu_traffic_per_step(task, n):
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of one env step, from the committed `ncu --set full` capture of
+    the four substep kernels of a full-size main pass (profiles/r1c_ncu_full_main_pass_kernels_summary.txt: one launch each of
+    setup / heavy_rows / heavy_solve2 / light at 131 072 PickAndPlace envs) x the 15 substeps of a step.  None when the capture
+    does not describe this workload.  It is implementation traffic (thread-local link arrays and solver records that spill
+    through L2), not the 445 algorithmic bytes per env-step."""
+    try:
+        if task != "pick_and_place" or n != 131072:
+            return None, "no ncu capture for this workload"
+        path = os.path.join(ROOT, "profiles", "r1c_ncu_full_main_pass_kernels_summary.txt")
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total, launches = 0.0, 0
+        for line in open(path):
+            got = re.findall(r"dram_(?:rd|wr)=([0-9.]+)([KMG]?byte)", line)
+            if got:
+                total += sum(float(v) * unit[u] for v, u in got)
+                launches += 1
+        if launches != 4:
+            return None, "capture not understood"
+        return 15.0 * total, ("15 substeps x one ncu --set full launch each of k_pipe_setup, k_heavy_rows, k_heavy_solve2, k_pipe_light "
+                              "(profiles/r1c_ncu_full_main_pass_kernels_summary.txt, 131 072 envs, two steps after a reset); implementation "
+                              "traffic per step, to compare with algorithmic_bytes_per_env_step x envs")
+    except Exception as e:  # noqa: BLE001
+        return None, f"unavailable: {e}"
 
 
 def main():
@@ -243,7 +271,8 @@ def main():
         branch_ms = {br: sum(us for (b_, _), (_, us) in ktimes.items() if b_ == br) / 1e3 / K for br in "MEL"}
         dom = kernels[0] if kernels else {"kernel": "xarm_step", "avg_us": k_ms * 1e3}
         achieved = ALGO_BYTES[task] * n / (k_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+        traffic, traffic_note = ncu_traffic_per_step(task, n)
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_note": traffic_note,
                 "kernel": "xarm_step pipeline (dominant kernel: %s)" % dom["kernel"], "kernel_ms": k_ms,
                 "algorithmic_bytes_per_env_step": ALGO_BYTES[task], "peak_source": peak_src,
                 "dominant_kernel": dom, "kernels": kernels[:8], "kernel_ms_per_step_by_branch": branch_ms,
