@@ -134,11 +134,8 @@ __global__ void __launch_bounds__(256) k_her_begin(HerBuf h, const float* __rest
 // her_ratio = 1 - 1 / (n_sampled_goal + 1)) of an episode longer than one transition draw t in [0, L-1) and the future index
 // in [t+1, L); the others - and HER samples of one-transition episodes - draw t in [0, L) and keep goal and reward.
 #define XARM_HER_MAX_TRIES 64
-__global__ void __launch_bounds__(256) k_her_index(HerBuf h, int64_t batch, int64_t n_her, uint64_t seed, uint32_t call,
-                                                   int4* __restrict__ index) {
-  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
-  int4 r = make_int4(-1, -1, -1, -1);
+#define XARM_HER_FUSED_MAX_BATCH 2048   // up to here one fused launch draws and gathers (xarm_her_sample)
+XD int4 her_draw(const HerBuf& h, int64_t b, int64_t n_her, uint64_t seed, uint32_t call) {
   for (uint32_t tr = 0; tr < XARM_HER_MAX_TRIES; tr++) {
     uint32_t c[4] = {(uint32_t)b, (uint32_t)((uint64_t)b >> 32), call, tr};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -149,18 +146,26 @@ __global__ void __launch_bounds__(256) k_her_index(HerBuf h, int64_t batch, int6
     const bool her = b < n_her && L > 1;
     const int t = (int)__umulhi(c[2], (uint32_t)(her ? L - 1 : L));
     const int tf = her ? t + 1 + (int)__umulhi(c[3], (uint32_t)(L - 1 - t)) : -1;
-    r = make_int4(env, k, t, tf);
-    break;
+    return make_int4(env, k, t, tf);
   }
-  if (r.x < 0) atomicAdd(&h.counters[0], 1ull);
-  index[b] = r;
+  atomicAdd(&h.counters[0], 1ull);
+  return make_int4(-1, -1, -1, -1);
+}
+__global__ void __launch_bounds__(256) k_her_index(HerBuf h, int64_t batch, int64_t n_her, uint64_t seed, uint32_t call,
+                                                   int4* __restrict__ index) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  index[b] = her_draw(h, b, n_her, seed, call);
 }
 
 // gather + relabel + reward: one warp per sample, lanes over the RW + O + G words of the run [record t | head of record t+1];
 // the run, the future goal and the episode goal are loaded before the first store.  NR = ceil((RW + O + G) / 32).  Outputs are SB3's
-// DictReplayBufferSamples fields.
-template <int NR>
-__global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, const int4* __restrict__ index, int task, int reward_type,
+// DictReplayBufferSamples fields.  FUSED (small batches, which are launch bound: SB3 trains on 256): lane 0 draws the index itself
+// (same her_draw, same result) and no index kernel is launched; large batches keep the separate index pass, where 32 samples
+// share a warp's Philox instructions.
+template <int NR, bool FUSED>
+__global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, int4* __restrict__ index, int64_t n_her, uint64_t seed,
+                                                    uint32_t call, int task, int reward_type,
                                                     int num_obj, float* __restrict__ o_obs, float* __restrict__ o_ag,
                                                     float* __restrict__ o_dg, float* __restrict__ o_act, float* __restrict__ o_nobs,
                                                     float* __restrict__ o_nag, float* __restrict__ o_rew, uint8_t* __restrict__ o_done) {
@@ -168,7 +173,17 @@ __global__ void __launch_bounds__(256) k_her_gather(HerBuf h, int64_t batch, con
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));   // 32-bit arithmetic: batch < 2^31
   if (b >= batch) return;
-  const int4 s = index[b];
+  int4 s = make_int4(-1, -1, -1, -1);
+  if (FUSED) {
+    if (lane == 0) {
+      s = her_draw(h, b, n_her, seed, call);
+      if (index) index[b] = s;
+    }
+    s.x = __shfl_sync(0xffffffffu, s.x, 0); s.y = __shfl_sync(0xffffffffu, s.y, 0);
+    s.z = __shfl_sync(0xffffffffu, s.z, 0); s.w = __shfl_sync(0xffffffffu, s.w, 0);
+  } else {
+    s = index[b];
+  }
   const bool ok = s.x >= 0, her = ok && s.w >= 0;
   const int64_t i = ok ? (int64_t)(uint32_t)s.x : 0;
   const int k = ok ? s.y : 0, t = ok ? s.z : 0;

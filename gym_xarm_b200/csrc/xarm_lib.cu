@@ -1287,7 +1287,11 @@ int xarm_her_sample(XarmHer* h, int64_t batch, float* obs, float* ag, float* dg,
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   int4* idx = reinterpret_cast<int4*>(index);
-  if (!idx) {
+  if (idx && (reinterpret_cast<uintptr_t>(index) & 15) != 0) return fail(XARM_E_INVALID, "xarm_her_sample: index must be 16-byte aligned");
+  const HerBuf& b = h->b;
+  const int64_t n_her = (int64_t)((1.0 - 1.0 / (double)(h->cfg.n_sampled_goal + 1)) * (double)batch);   // int(her_ratio * batch_size)
+  const bool fused = batch <= XARM_HER_FUSED_MAX_BATCH;   // launch-bound sizes: one kernel, lane 0 of each warp draws its own index
+  if (!fused && !idx) {
     if (batch > h->index_cap) {
       CUDA_TRY(cudaStreamSynchronize(s));
       cudaFree(h->index); h->index = nullptr; h->index_cap = 0;
@@ -1295,20 +1299,18 @@ int xarm_her_sample(XarmHer* h, int64_t batch, float* obs, float* ag, float* dg,
       h->index_cap = batch;
     }
     idx = h->index;
-  } else if ((reinterpret_cast<uintptr_t>(index) & 15) != 0) {
-    return fail(XARM_E_INVALID, "xarm_her_sample: index must be 16-byte aligned");
   }
-  const HerBuf& b = h->b;
-  const int64_t n_her = (int64_t)((1.0 - 1.0 / (double)(h->cfg.n_sampled_goal + 1)) * (double)batch);   // int(her_ratio * batch_size)
-  k_her_index<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(b, batch, n_her, h->cfg.seed, h->calls, idx);
+  if (!fused) { k_her_index<<<(unsigned)((batch + 255) / 256), 256, 0, s>>>(b, batch, n_her, h->cfg.seed, h->calls, idx); g_launches++; }
   const unsigned grid = (unsigned)((batch + 7) / 8);   // one warp per sample
   const int nr = (2 * (b.O + b.G) + b.A + 2 + 31) / 32;   // registers per lane for the run (<= 10)
-#define HER_GATHER(R) k_her_gather<R><<<grid, 256, 0, s>>>(b, batch, idx, h->cfg.task, h->cfg.reward_type, h->cfg.num_obj, obs, ag, dg, action, next_obs, next_ag, reward, done)
+#define HER_GATHER_F(R, F) k_her_gather<R, F><<<grid, 256, 0, s>>>(b, batch, idx, n_her, h->cfg.seed, h->calls, h->cfg.task, h->cfg.reward_type, h->cfg.num_obj, obs, ag, dg, action, next_obs, next_ag, reward, done)
+#define HER_GATHER(R) do { if (fused) HER_GATHER_F(R, true); else HER_GATHER_F(R, false); } while (0)
   if (nr <= 2) HER_GATHER(2); else if (nr == 3) HER_GATHER(3); else if (nr == 4) HER_GATHER(4); else if (nr == 5) HER_GATHER(5);
   else if (nr <= 7) HER_GATHER(7); else HER_GATHER(10);
 #undef HER_GATHER
+#undef HER_GATHER_F
+  g_launches++;
   h->calls++;
-  g_launches += 2;
   CUDA_TRY(cudaGetLastError());
   return XARM_OK;
 }
