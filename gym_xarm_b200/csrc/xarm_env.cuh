@@ -139,7 +139,9 @@ XD float reward_dense_staged(const Env<T>& e, const Obs<T>& o) {
   float p1[3] = {o.obs[n0] - o.ag[0] + 0.06f, o.obs[n0 + 1] - o.ag[1], o.obs[n0 + 2] - o.ag[2]};
   float p2[3] = {o.obs[n0 + 8] - o.ag[0] - 0.06f, o.obs[n0 + 9] - o.ag[1], o.obs[n0 + 10] - o.ag[2]};
   float d1 = np_dist(p1, z3, 3), d2 = np_dist(p2, z3, 3);
-  const bool g1 = e.grasp[0], g2 = e.grasp[1];
+  // if_xarm1_grasp / if_xarm2_grasp are set by _set_action, BEFORE the 15 stepSimulation calls, and compute_reward reads
+  // those values [REF xarm_handover.py:262-263, 185-199] (PickAndPlace above queries getContactPoints afresh)
+  const bool g1 = e.grasp_cmd[0], g2 = e.grasp_cmd[1];
   if (!g1 && !g2) return 0.25f * (1.f - tanhf(d1)) / 2.25f;
   if (g1 && !g2) return o.ag[2] > 0.05f ? (1.0f + 0.25f * (1.f - tanhf(d2))) / 2.25f : 0.5f / 2.25f;
   if (g1 && g2) return 1.5f / 2.25f;
@@ -153,6 +155,7 @@ XD void set_action(Env<T>& e, const float* act_in) {
   float act[T::A];
 #pragma unroll
   for (int i = 0; i < T::A; i++) act[i] = fminf(1.f, fmaxf(-1.f, act_in[i]));  // np.clip(action, -1, 1)
+  e.grasp_cmd[0] = e.grasp[0]; e.grasp_cmd[1] = e.grasp[1];  // the contact flags _set_action reads (friction switch, Handover's reward stages)
 #pragma unroll
   for (int a = 0; a < T::NARM; a++) {
     const float* u = T::TASK == XARM_TASK_PUSH_WITH_DOOR ? act + 3 * a : act + 4 * a;
@@ -299,7 +302,7 @@ template <class T>
 XD void env_construct(Env<T>& e, const ResetCfg& cfg, int64_t genv) {
   using MD = typename T::MD;
   Rng rng = {cfg.seed, (uint64_t)genv, 0u, 0u};
-  e.episode = 0; e.step_count = 0; e.d_old = 0.f; e.grasp[0] = 0; e.grasp[1] = 0; e.door_q = 0.f; e.door_qd = 0.f;
+  e.episode = 0; e.step_count = 0; e.d_old = 0.f; e.grasp[0] = 0; e.grasp[1] = 0; e.grasp_cmd[0] = 0; e.grasp_cmd[1] = 0; e.door_q = 0.f; e.door_qd = 0.f;
 #pragma unroll
   for (int a = 0; a < T::NARM; a++) {
     if (T::TASK == XARM_TASK_PICK_AND_PLACE) {  // its ctor never calls resetJointState [REF xarm_pick_and_place.py:76-79]

@@ -588,8 +588,8 @@ __device__ __forceinline__ void heavy_rows_body(const KArgs& a, int t, int sub, 
   heavy_rows_record<T>(e, T::DAMP_EACH || sub == 0, last, hrec + (size_t)(a.heavy_dir > 0 ? t : a.n - 1 - t) * HeavyRec<T>::WORDS, D);
   if (last) {
     const int w = state_words<T>() - 2;
-    a.state[(int64_t)w * a.n + i] = e.grasp[0] ? 1.f : 0.f;
-    a.state[(int64_t)(w + 1) * a.n + i] = e.grasp[1] ? 1.f : 0.f;
+    a.state[(int64_t)w * a.n + i] = grasp_word(e.grasp[0], e.grasp_cmd[0]);
+    a.state[(int64_t)(w + 1) * a.n + i] = grasp_word(e.grasp[1], e.grasp_cmd[1]);
   }
 }
 

@@ -201,7 +201,7 @@ XD bool pipe_setup(const KArgs& a, int64_t i, int sub) {
   sb_store<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
   if (nc > 0) mi_store(MI, s, a.n, i);
   a.form[i] = XARM_FORM_LIGHT | (nc << 8);
-  if (last && e.grasp[0] != g0) a.state[(int64_t)(state_words<T>() - 2) * a.n + i] = e.grasp[0] ? 1.f : 0.f;  // grasp flag of the last collision pass
+  if (last && e.grasp[0] != g0) a.state[(int64_t)(state_words<T>() - 2) * a.n + i] = grasp_word(e.grasp[0], e.grasp_cmd[0]);  // grasp flag of the last collision pass
   return false;
 }
 

@@ -28,8 +28,11 @@ struct Env {
   int step_count;
   uint32_t episode;
   float d_old;
-  int grasp[2];
+  int grasp[2];      // both fingers of arm a touch lego 0 in the LAST collision pass (what getContactPoints would report now)
+  int grasp_cmd[2];  // the same flags as _set_action read them at the start of the current step [REF xarm_handover.py:262-263]
 };
+// the two grasp words of the state slab carry (live flag) | (flag snapshot of _set_action) << 1
+XD float grasp_word(int live, int cmd) { return (float)((live ? 1 : 0) | (cmd ? 2 : 0)); }
 
 // SoA slab: word w of env e lives at state[w * n + e] (coalesced when consecutive threads own consecutive envs)
 template <class T>
@@ -59,8 +62,11 @@ XD void env_load(Env<T>& e, const float* __restrict__ s, int64_t n, int64_t i) {
   e.step_count = (int)s[(w++) * n + i];
   e.episode = (uint32_t)s[(w++) * n + i];
   e.d_old = s[(w++) * n + i];
-  e.grasp[0] = s[(w++) * n + i] != 0.f;
-  e.grasp[1] = s[(w++) * n + i] != 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    const int g = (int)s[(w++) * n + i];
+    e.grasp[a] = g & 1; e.grasp_cmd[a] = (g >> 1) & 1;
+  }
 }
 template <class T>
 XD void env_store(const Env<T>& e, float* __restrict__ s, int64_t n, int64_t i) {
@@ -89,8 +95,8 @@ XD void env_store(const Env<T>& e, float* __restrict__ s, int64_t n, int64_t i) 
   s[(w++) * n + i] = (float)e.step_count;
   s[(w++) * n + i] = (float)e.episode;
   s[(w++) * n + i] = e.d_old;
-  s[(w++) * n + i] = e.grasp[0] ? 1.f : 0.f;
-  s[(w++) * n + i] = e.grasp[1] ? 1.f : 0.f;
+  s[(w++) * n + i] = grasp_word(e.grasp[0], e.grasp_cmd[0]);
+  s[(w++) * n + i] = grasp_word(e.grasp[1], e.grasp_cmd[1]);
 }
 
 // the dynamic part only (what a substep changes): joint positions / velocities, object poses / velocities, the door.
@@ -893,7 +899,7 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
     int gcount[2][2][NO];
     if (MD::HAS_BOXES) {
       for (int a = 0; a < NA; a++) {
-        const float ff = (T::FRICTION_SWITCH && e.grasp[a]) ? (float)XARM_FINGER_FRICTION_GRASP : (float)XARM_FINGER_FRICTION_FREE;
+        const float ff = (T::FRICTION_SWITCH && e.grasp_cmd[a]) ? (float)XARM_FINGER_FRICTION_GRASP : (float)XARM_FINGER_FRICTION_FREE;
         Box f1 = arm_box<T>(D[a], 1), f2 = arm_box<T>(D[a], 2), hd = arm_box<T>(D[a], 0);
         const int c0 = a == 0 ? BC_ARM0_HAND : BC_ARM1_HAND;
         for (int o = 0; o < NOBJ; o++) {
@@ -926,7 +932,7 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
     }
     if (T::FINGER_TABLE) {
       for (int a = 0; a < NA; a++) {
-        const float ff = (T::FRICTION_SWITCH && e.grasp[a]) ? (float)XARM_FINGER_FRICTION_GRASP : (float)XARM_FINGER_FRICTION_FREE;
+        const float ff = (T::FRICTION_SWITCH && e.grasp_cmd[a]) ? (float)XARM_FINGER_FRICTION_GRASP : (float)XARM_FINGER_FRICTION_FREE;
         Box f1 = arm_box<T>(D[a], 1), f2 = arm_box<T>(D[a], 2);
         const int c0 = a == 0 ? BC_ARM0_HAND : BC_ARM1_HAND;
         for (int k = 0; k < T::NTABLE; k++) {

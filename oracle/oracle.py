@@ -67,6 +67,9 @@ def lib():
         L.or_debug_assemble_obs.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, fp, fp, fp, fp]
         L.or_debug_command.argtypes = [C.c_int32, C.c_int, fp, dp, C.c_double, dp, C.POINTER(C.c_double)]
         L.or_debug_lego_clamp.argtypes = [dp, dp]
+        L.or_debug_dense_reward.restype = C.c_float
+        L.or_debug_dense_reward.argtypes = [C.c_int32, C.c_int32, dp, fp, fp, C.POINTER(C.c_int32)]
+        L.or_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int64, C.c_int, fp, fp, fp, fp, fp, u8p, fp, u8p, C.c_int]
         L.or_bench.restype = C.c_double
         L.or_bench.argtypes = [C.POINTER(XarmConfig), C.c_int64, C.c_int, C.c_int, dp]
         _lib = L
@@ -171,6 +174,50 @@ class OracleEnv:
         return self.L.or_flops(self.h, int(reset))
 
 
+class OracleBatch:
+    """n independent oracle envs (global env indices env_index_base .. +n) stepped by all host threads; same call shapes as
+    the CUDA library wrapper.  For the statistics tests at >= 32 768 envs."""
+
+    def __init__(self, task, n, env_index_base=0, threads=None, **kw):
+        self.envs = [OracleEnv(task, env_index=env_index_base + i, **kw) for i in range(n)]
+        self.n, self.L = n, lib()
+        self.threads = threads or os.cpu_count() or 1
+        e0 = self.envs[0]
+        self.act_dim, self.obs_dim, self.goal_dim, self.state_words = e0.act_dim, e0.obs_dim, e0.goal_dim, e0.state_words
+        self._h = (C.c_void_p * n)(*[e.h for e in self.envs])
+
+    def _run(self, op, actions=None):
+        n = self.n
+        o, a, d = np.zeros((n, self.obs_dim), np.float32), np.zeros((n, self.goal_dim), np.float32), np.zeros((n, self.goal_dim), np.float32)
+        r, s = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        dn, tr = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        u8 = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint8))
+        act = _f(actions) if actions is not None else None
+        self.L.or_batch(self._h, n, op, act, _f(o), _f(a), _f(d), _f(r), u8(dn), _f(s), u8(tr), self.threads)
+        return {"observation": o, "achieved_goal": a, "desired_goal": d}, r, dn.astype(bool), s, tr.astype(bool)
+
+    def reset(self):
+        return self._run(0)[0]
+
+    def get_obs(self):
+        return self._run(2)[0]
+
+    def step(self, actions):
+        actions = np.ascontiguousarray(actions, np.float32)
+        assert actions.shape == (self.n, self.act_dim), "action shape error"
+        return self._run(1, actions)
+
+    def get_state(self):
+        return np.stack([e.get_state() for e in self.envs])
+
+    def set_state(self, st):
+        for e, s in zip(self.envs, st):
+            e.set_state(s)
+
+    def arm_contacts(self):
+        return np.array([e.arm_contacts() for e in self.envs])
+
+
 def compute_reward(task, reward_type, num_obj, ag, dg):
     t = TASKS[task] if isinstance(task, str) else int(task)
     ag = np.ascontiguousarray(ag, np.float32)
@@ -239,6 +286,15 @@ def lego_clamp(pos, quat):
     pos, quat = np.array(pos, np.float64), np.array(quat, np.float64)
     lib().or_debug_lego_clamp(_d(pos), _d(quat))
     return pos, quat
+
+
+def dense_reward(task, num_obj, hand, ag, dg, grasp):
+    """the staged dense reward of PickAndPlace / Handover from what the reference reads: link-9 COM position per arm,
+    achieved / desired goal, grasp flags (PickAndPlace: after the step; Handover: as _set_action stored them)"""
+    hand = np.ascontiguousarray(hand, np.float64).reshape(-1)
+    ag, dg = np.ascontiguousarray(ag, np.float32), np.ascontiguousarray(dg, np.float32)
+    g = (C.c_int32 * 2)(*[int(x) for x in list(grasp) + [0] * (2 - len(grasp))])
+    return lib().or_debug_dense_reward(TASKS[task], num_obj, _d(hand), _f(ag), _f(dg), g)
 
 
 def philox(seed, env, episode, block):

@@ -306,7 +306,9 @@ typedef struct OrEnv {
   int step_count;
   uint32_t episode;
   float d_old;
-  int grasp[MAXARM];
+  int grasp[MAXARM];     /* both fingers of arm a hold manifold points with lego 0 after the LAST collision pass */
+  int grasp_cmd[MAXARM]; /* those flags as _set_action read them: the friction switch and Handover's if_xarm*_grasp
+                            [REF xarm_pick_and_place.py:212-218, xarm_handover.py:262-280]; they persist through reset() */
   uint32_t rng_draw; /* draws consumed in the current episode */
   double flops;      /* instrumented flop counter (FMA=2) over PGS/ABA inner loops: see or_flops() */
   long st_substeps, st_iters, st_rows, st_contacts; /* solver statistics (or_solver_stats) */
@@ -862,7 +864,7 @@ static void world_build(OrEnv* e, World* w) {
   if (m->has_gripper_boxes)
     for (int a = 0; a < t->n_arms; a++) {
       const Kin* k = &w->kin[a];
-      double ff = (t->friction_switch && e->grasp[a]) ? XARM_FINGER_FRICTION_GRASP : XARM_FINGER_FRICTION_FREE;
+      double ff = (t->friction_switch && e->grasp_cmd[a]) ? XARM_FINGER_FRICTION_GRASP : XARM_FINGER_FRICTION_FREE;
       v3 c;
       w->col_f1[a] = w->ncol;
       link_point(k, m->finger1, m->f1c, c);
@@ -1347,31 +1349,47 @@ static void get_obs(const OrEnv* e, ObsOut* o) {
   assemble_obs(t, &in, o);
 }
 
-/* staged dense rewards that read the live simulator (not batch-safe in the reference either) */
-static float reward_dense_staged(const OrEnv* e, const ObsOut* o) {
-  const Task* t = &e->t;
-  if (t->task == XARM_TASK_PICK_AND_PLACE) { /* [REF xarm_pick_and_place.py:166-175] */
-    v3 hp, hv; hand_state(e, 0, hp, hv);
-    float g[3] = {(float)hp[0], (float)hp[1], (float)(hp[2] - (0.088 - 0.021))};
+/* staged dense rewards that read the live simulator (not batch-safe in the reference either).  Pure function of what
+ * the reference reads: hand-link COM positions (getLinkState(arm, 9)[0]), the achieved / desired goal, the grasp flags.
+ * PickAndPlace queries getContactPoints inside compute_reward (flags AFTER the step) [REF xarm_pick_and_place.py:166-175];
+ * Handover reads self.if_xarm*_grasp, which _set_action stored BEFORE the step's 15 stepSimulation calls
+ * [REF xarm_handover.py:185-199, 262-263].  D2: Handover's last branch uses d = ||ag - goal||. */
+static float dense_staged_core(int task, int goal_dim, const double hand[MAXARM][3], const float* ag, const float* dg, const int* grasp) {
+  float z[3] = {0, 0, 0};
+  if (task == XARM_TASK_PICK_AND_PLACE) {
+    float g[3] = {(float)hand[0][0], (float)hand[0][1], (float)(hand[0][2] - (0.088 - 0.021))};
     float off[3] = {0.06f, 0, 0}, d3[3];
-    for (int c = 0; c < 3; c++) d3[c] = g[c] - o->ag[c] + off[c];
-    float z[3] = {0, 0, 0};
-    float d_ao = np_norm_f32(d3, z, 3), d_og = np_norm_f32(o->ag, o->dg, t->goal_dim);
-    if (!e->grasp[0]) return 0.25f * (1 - tanhf(d_ao));
-    if (o->ag[2] > 0.05f) return 1.0f + 0.25f * (1 - tanhf(d_og));
+    for (int c = 0; c < 3; c++) d3[c] = g[c] - ag[c] + off[c];
+    float d_ao = np_norm_f32(d3, z, 3), d_og = np_norm_f32(ag, dg, goal_dim);
+    if (!grasp[0]) return 0.25f * (1 - tanhf(d_ao));
+    if (ag[2] > 0.05f) return 1.0f + 0.25f * (1 - tanhf(d_og));
     return 0.5f;
   }
-  /* Handover [REF xarm_handover.py:185-199], D2: final branch uses d = ||ag - goal|| */
-  float p1[3], p2[3], z[3] = {0, 0, 0};
-  int n0 = 13 * t->n_obj;
-  for (int c = 0; c < 3; c++) { p1[c] = o->obs[n0 + c] - o->ag[c]; p2[c] = o->obs[n0 + 8 + c] - o->ag[c]; }
+  float p1[3], p2[3];
+  for (int c = 0; c < 3; c++) {
+    const double off = c == 2 ? 0.088 - 0.021 : 0.0;
+    float h1 = (float)(hand[0][c] - off), h2 = (float)(hand[1][c] - off); /* the float32 words of _get_obs */
+    p1[c] = h1 - ag[c]; p2[c] = h2 - ag[c];
+  }
   p1[0] += 0.06f; p2[0] -= 0.06f;
   float d1 = np_norm_f32(p1, z, 3), d2 = np_norm_f32(p2, z, 3);
-  int g1 = e->grasp[0], g2 = e->grasp[1];
+  int g1 = grasp[0], g2 = grasp[1];
   if (!g1 && !g2) return 0.25f * (1 - tanhf(d1)) / 2.25f;
-  if (g1 && !g2) return o->ag[2] > 0.05f ? (1.0f + 0.25f * (1 - tanhf(d2))) / 2.25f : 0.5f / 2.25f;
+  if (g1 && !g2) return ag[2] > 0.05f ? (1.0f + 0.25f * (1 - tanhf(d2))) / 2.25f : 0.5f / 2.25f;
   if (g1 && g2) return 1.5f / 2.25f;
-  return (2.0f + 0.25f * (1 - tanhf(np_norm_f32(o->ag, o->dg, t->goal_dim)))) / 2.25f;
+  return (2.0f + 0.25f * (1 - tanhf(np_norm_f32(ag, dg, goal_dim)))) / 2.25f;
+}
+static float reward_dense_staged(const OrEnv* e, const ObsOut* o) {
+  const Task* t = &e->t;
+  double hand[MAXARM][3]; v3 hv;
+  for (int a = 0; a < t->n_arms; a++) hand_state(e, a, hand[a], hv);
+  return dense_staged_core(t->task, t->goal_dim, hand, o->ag, o->dg, t->task == XARM_TASK_PICK_AND_PLACE ? e->grasp : e->grasp_cmd);
+}
+float or_debug_dense_reward(int32_t task, int32_t num_obj, const double* hand /* [n_arms][3] link-9 COM */, const float* ag, const float* dg, const int32_t* grasp) {
+  double h[MAXARM][3] = {{0}}; int g[MAXARM] = {0};
+  int na = task == XARM_TASK_PICK_AND_PLACE ? 1 : 2;
+  for (int a = 0; a < na; a++) { for (int c = 0; c < 3; c++) h[a][c] = hand[3 * a + c]; g[a] = grasp[a]; }
+  return dense_staged_core(task, 3 * num_obj, h, ag, dg, g);
 }
 
 /* ------------------------------------------------------------------------------------------------ reset / goals */
@@ -1568,6 +1586,7 @@ static void set_action(OrEnv* e, const float* act_in) {
   const Model* m = t->model;
   float act[8];
   for (int i = 0; i < t->act_dim; i++) act[i] = act_in[i] < -1 ? -1 : (act_in[i] > 1 ? 1 : act_in[i]);
+  for (int a = 0; a < MAXARM; a++) e->grasp_cmd[a] = e->grasp[a]; /* getContactPoints as _set_action sees them */
   for (int a = 0; a < t->n_arms; a++) {
     const float* u = t->task == XARM_TASK_PUSH_WITH_DOOR ? act + 3 * a : act + 4 * a;
     Kin k;
@@ -1693,8 +1712,10 @@ static int state_io(OrEnv* e, double* buf, int write_env) {
   }
   if (t->has_door) { IO(e->door_q); IO(e->door_qd); }
   for (int c = 0; c < t->goal_dim; c++) { if (write_env) e->goal[c] = (float)buf[n]; else buf[n] = e->goal[c]; n++; }
-  if (write_env) { e->step_count = (int)buf[n]; e->episode = (uint32_t)buf[n + 1]; e->d_old = (float)buf[n + 2]; e->grasp[0] = buf[n + 3] != 0; e->grasp[1] = buf[n + 4] != 0; }
-  else { buf[n] = e->step_count; buf[n + 1] = e->episode; buf[n + 2] = e->d_old; buf[n + 3] = e->grasp[0]; buf[n + 4] = e->grasp[1]; }
+  if (write_env) { e->step_count = (int)buf[n]; e->episode = (uint32_t)buf[n + 1]; e->d_old = (float)buf[n + 2];
+    for (int a = 0; a < 2; a++) { int g = (int)buf[n + 3 + a]; e->grasp[a] = g & 1; e->grasp_cmd[a] = (g >> 1) & 1; } } /* live | snapshot << 1 */
+  else { buf[n] = e->step_count; buf[n + 1] = e->episode; buf[n + 2] = e->d_old;
+    for (int a = 0; a < 2; a++) buf[n + 3 + a] = (e->grasp[a] ? 1 : 0) | (e->grasp_cmd[a] ? 2 : 0); }
   n += 5;
 #undef IO
   return n;
@@ -1835,4 +1856,40 @@ double or_bench(const XarmConfig* cfg, int64_t n_envs, int steps, int n_threads,
   clock_gettime(CLOCK_MONOTONIC, &t1);
   *env_steps_out = total;
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ------------------------------------------------------------------------------------------------ batch stepping (tests)
+ * n independent oracle envs stepped by n_threads host threads: what the statistics tests at >= 32 768 envs need (a
+ * Python loop over single-env calls does ~2 k env-steps/s).  op 0: reset, 1: step, 2: get_obs. */
+typedef struct {
+  OrEnv** envs; int64_t first, count; int op, A, O, G;
+  const float* actions; float *obs, *ag, *dg, *reward, *success; uint8_t *done, *truncated;
+} BatchArg;
+static void* batch_thread(void* p) {
+  BatchArg* b = (BatchArg*)p;
+  for (int64_t i = b->first; i < b->first + b->count; i++) {
+    OrEnv* e = b->envs[i];
+    float* o = b->obs ? b->obs + i * b->O : NULL; float* a = b->ag ? b->ag + i * b->G : NULL; float* d = b->dg ? b->dg + i * b->G : NULL;
+    if (b->op == 0) or_reset(e, o, a, d);
+    else if (b->op == 2) or_get_obs(e, o, a, d);
+    else or_step(e, b->actions + i * b->A, o, a, d, b->reward ? b->reward + i : NULL, b->done ? b->done + i : NULL,
+                 b->success ? b->success + i : NULL, b->truncated ? b->truncated + i : NULL);
+  }
+  return NULL;
+}
+void or_batch(OrEnv** envs, int64_t n, int op, const float* actions, float* obs, float* ag, float* dg, float* reward, uint8_t* done,
+              float* success, uint8_t* truncated, int n_threads) {
+  if (n <= 0) return;
+  pthread_t th[256]; BatchArg arg[256];
+  if (n_threads > 256) n_threads = 256;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n) n_threads = (int)n;
+  const Task* t = &envs[0]->t;
+  for (int i = 0; i < n_threads; i++) {
+    BatchArg b = {envs, n * i / n_threads, 0, op, t->act_dim, t->obs_dim, t->goal_dim, actions, obs, ag, dg, reward, success, done, truncated};
+    b.count = n * (i + 1) / n_threads - b.first;
+    arg[i] = b;
+    pthread_create(&th[i], NULL, batch_thread, &arg[i]);
+  }
+  for (int i = 0; i < n_threads; i++) pthread_join(th[i], NULL);
 }

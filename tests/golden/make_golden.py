@@ -320,6 +320,75 @@ def main():
         out[f"act_handover{trial}_lego_pos"] = fb.reset_calls[0][1]
         out[f"act_handover{trial}_lego_quat"] = fb.reset_calls[0][2]
         out[f"act_handover{trial}_grasp"] = np.array([s.if_xarm1_grasp, s.if_xarm2_grasp])
+
+    # ---------------- staged dense rewards (the reference's training path: benchmark/train.py sets reward_type='dense' on
+    # XarmPDHandoverNoGoal-v1) [REF xarm_pick_and_place.py:166-175; xarm_handover.py:185-199].  Every stage is visited:
+    # grasp flags x lego height around the 0.05 lift test x random hand / goal positions.  Timing of the contact query:
+    # PickAndPlace asks getContactPoints INSIDE compute_reward (contacts as they are after the step); Handover reads
+    # self.if_xarm*_grasp, which _set_action stored BEFORE the step's stepSimulation calls - the fake client's contacts are
+    # switched between the two calls to pin exactly that.
+    def set_contacts(fb, arm_body, lego, on):
+        fb.contacts.pop((arm_body, lego, 10), None); fb.contacts.pop((arm_body, lego, 11), None)
+        if on:
+            fb.contacts[(arm_body, lego, 10)] = [1]; fb.contacts[(arm_body, lego, 11)] = [1]
+
+    KD = 96
+    rec = {k: [] for k in ("hand", "ag", "dg", "g_set", "g_rew", "reward")}
+    for trial in range(KD):
+        fb = FakeBullet(rng, [1], [5])
+        fb.arms[1]["eef"] = rng.uniform([0.3, -0.3, 0.15], [0.5, 0.3, 0.4])
+        fb.arms[1]["hand"] = rng.uniform([0.3, -0.3, 0.1], [0.5, 0.3, 0.45])
+        pap.p = fb
+        s = fake_self(xarm=1, arm_eef_index=8, finger1_index=10, finger2_index=11, gripper_base_index=9, legos=[5], max_vel=0.25,
+                      max_gripper_vel=0.08, dt=0.25, n_substeps=15, action_space=Box(-1., 1., shape=(4,), dtype="float32"),
+                      pos_space=Box(low=np.array([0.3, -0.3, 0.15]), high=np.array([0.5, 0.3, 0.4])), gripper_space=Box(low=0.01, high=0.04, shape=[1]),
+                      config={"reward_type": "dense", "num_obj": 1}, distance_threshold=0.05, eef2grip_offset=[0, 0, 0.088 - 0.021])
+        s._subgoal_distances = lambda a, b, s=s: pap.XarmPickAndPlace._subgoal_distances(s, a, b)
+        g_set, g_rew = bool(trial & 1), bool(trial & 2)
+        set_contacts(fb, 1, 5, g_set)
+        pap.XarmPickAndPlace._set_action(s, rng.uniform(-1, 1, 4).astype(np.float32))
+        set_contacts(fb, 1, 5, g_rew)   # ... the step happens here ...
+        ag = rng.uniform([0.3, -0.3, 0.02], [0.5, 0.3, 0.045 if trial & 4 else 0.3])   # lego position as _get_obs returns it (float64)
+        if trial < 8:
+            ag = fb.arms[1]["hand"] - np.array([0, 0, 0.088 - 0.021]) + np.array([0.06, 0, 0]) + (0 if trial < 4 else 1e-4)  # d_ao = 0 / tiny
+        dg = (ag + rng.normal(0, 0.05, 3)).astype(np.float32)
+        r = pap.XarmPickAndPlace.compute_reward(s, ag, dg, {})
+        for k, v in (("hand", fb.arms[1]["hand"]), ("ag", ag), ("dg", dg), ("g_set", g_set), ("g_rew", g_rew), ("reward", float(r))):
+            rec[k].append(np.asarray(v))
+    for k, v in rec.items():
+        out[f"dense_pap_{k}"] = np.stack(v)
+
+    rec = {k: [] for k in ("hand1", "hand2", "ag", "dg", "g_set", "g_rew", "reward", "raised")}
+    for trial in range(KD):
+        fb = FakeBullet(rng, [1, 2], [5])
+        for b in (1, 2):
+            fb.arms[b]["eef"] = rng.uniform([-0.35, -0.25, 0.05], [0.35, 0.25, 0.3])
+            fb.arms[b]["hand"] = rng.uniform([-0.35, -0.25, 0.05], [0.35, 0.25, 0.3])
+        fb.legos[5]["pos"] = rng.uniform([-0.3, -0.2, 0.0], [0.3, 0.2, 0.2])
+        s = fake_self(_p=fb, xarm_1=1, xarm_2=2, arm_eef_index=8, finger1_index=10, finger2_index=11, gripper_base_index=9, legos=[5],
+                      config={"num_obj": 1}, max_vel=1.8, max_gripper_vel=1, dt=15 / 240., n_substeps=15, reward_type="dense",
+                      distance_threshold=0.05, eef2grip_offset=[0, 0, 0.088 - 0.021],
+                      pos_space_1=Box(low=np.array([-0.3, -0.2, 0.1]), high=np.array([0.0, 0.2, 0.22])),
+                      pos_space_2=Box(low=np.array([0.0, -0.2, 0.1]), high=np.array([0.3, 0.2, 0.22])),
+                      gripper_space=Box(low=0.020, high=0.04, shape=[1]), obj_space=Box(low=np.array([0.11, -0.18]), high=np.array([0.28, 0.2])))
+        g_set = (bool(trial & 1), bool(trial & 2))
+        g_rew = (bool(trial & 4), bool(trial & 8))
+        set_contacts(fb, 1, 5, g_set[0]); set_contacts(fb, 2, 5, g_set[1])
+        hand.XarmHandover._set_action(s, rng.uniform(-1, 1, 8).astype(np.float32))
+        assert (s.if_xarm1_grasp, s.if_xarm2_grasp) == g_set
+        set_contacts(fb, 1, 5, g_rew[0]); set_contacts(fb, 2, 5, g_rew[1])   # ... the step happens here ...
+        ag = rng.uniform([-0.3, -0.2, 0.02], [0.3, 0.2, 0.045 if trial & 16 else 0.25])
+        dg = (ag + rng.normal(0, 0.05, 3)).astype(np.float32)
+        raised = 0
+        try:
+            r = float(hand.XarmHandover.compute_reward(s, ag, dg, {}))
+        except NameError:   # D2: the (not grasp 1, grasp 2) branch reads an undefined `d` [REF xarm_handover.py:199]
+            r, raised = np.nan, 1
+        for k, v in (("hand1", fb.arms[1]["hand"]), ("hand2", fb.arms[2]["hand"]), ("ag", ag), ("dg", dg), ("g_set", g_set), ("g_rew", g_rew),
+                     ("reward", r), ("raised", raised)):
+            rec[k].append(np.asarray(v))
+    for k, v in rec.items():
+        out[f"dense_handover_{k}"] = np.stack(v)
     out["n_trials"] = np.array(K)
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, len(out), "arrays", os.path.getsize(OUT), "bytes")

@@ -6,11 +6,19 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
+from tests.parity_util import Worst, compare_full
 
 pytestmark = pytest.mark.gpu
 
 TASKS = ["reach", "pick_and_place", "stack_tower", "push_with_door", "handover"]
 TOL = 1e-3
+# Contact-task statistics (north_star: success rates of a scripted policy within 1 %): a proportion over n envs has a standard
+# error of sqrt(p (1 - p) / n) - 2.5 % at n = 384 but 0.28 % at n = 32 768, so a 1 % bias is a > 3 sigma event there.  Both
+# sides run THE SAME n seeded envs, so most of the sampling noise is common to both and cancels.  XARM_STATS_ENVS shrinks the
+# batch for development runs; the tolerance is 1 % only at the full size.
+import os as _os
+STATS_ENVS = int(_os.environ.get("XARM_STATS_ENVS", "32768"))
+STATS_TOL = 0.01 if STATS_ENVS >= 32768 else 0.01 + 2.0 / np.sqrt(STATS_ENVS)
 
 
 def _mk(task, n, **kw):
@@ -63,11 +71,9 @@ def test_step_parity_50_steps(task):
         r.set_state(s)
     clean[:] = True
     rng = np.random.default_rng(5)
-    ndof = 13 if task == "reach" else 9
-    narm = 1 if task in ("reach", "pick_and_place") else 2
-    nq = 3 * ndof * narm
     nobj = {"reach": 0, "pick_and_place": 1, "stack_tower": 3, "push_with_door": 1, "handover": 1}[task]
     steps = 50 if task != "reach" else 25
+    worst = Worst()
     for t in range(steps):
         a = _actions(rng, task, n, env.act_dim)
         obs, rew, done, infos = env.step(torch.from_numpy(a).cuda())
@@ -77,21 +83,20 @@ def test_step_parity_50_steps(task):
         rst = np.stack([r.get_state() for r in ref])
         assert np.isfinite(st).all()
         c = clean
-        for arm in range(narm):
-            sl = slice(arm * 3 * ndof, arm * 3 * ndof + (9 if ndof == 9 else 7))  # Reach: the 7 arm joints (DESIGN.md on its gripper)
-            np.testing.assert_allclose(st[c][:, sl], rst[c][:, sl], atol=TOL, err_msg=f"{task} step {t} arm {arm} q")
-        if task == "reach":  # hand position within 1e-3 m; the xArm-gripper knuckles (driven through their limits) only loosely
-            np.testing.assert_allclose(obs["observation"].cpu().numpy()[:, :3], np.stack([r[0]["observation"][:3] for r in res]), atol=TOL)
-            assert np.abs(st[:, 7:13]).max() < 20.0   # chaotic in float32: bounded, not compared
-        for o in range(nobj):
-            sl = slice(nq + 13 * o, nq + 13 * o + 7)
-            np.testing.assert_allclose(st[c][:, sl], rst[c][:, sl], atol=TOL, err_msg=f"{task} step {t} obj {o} pose")
+        # the WHOLE state record (q, qd, motor targets, object pose and velocities, door) and the WHOLE observation dict
+        # (hand COM position / velocity, finger q / qd, relative terms, quaternions) - tolerances in tests/parity_util.py
+        gobs = {k: v.cpu().numpy() for k, v in obs.items()}
+        robs_t = {k: np.stack([r[0][k] for r in res]) for k in gobs}
+        compare_full(task, nobj, st, rst, gobs, robs_t, c, worst, msg=f"step {t}")
+        if task == "reach":
+            assert np.abs(st[:, 7:13]).max() < 20.0   # the knuckle joints: chaotic in float32 when driven through their limits
         np.testing.assert_array_equal(done.cpu().numpy()[c], np.array([r[2] for r in res])[c])
         np.testing.assert_array_equal(env.success_buf.cpu().numpy()[c], np.array([r[3]["is_success"] for r in res], np.float32)[c])
         # the in-step reward is the batch compute_reward of the step's own float32 goals, bit for bit
         ag, dg = obs["achieved_goal"].cpu().numpy(), obs["desired_goal"].cpu().numpy()
         want = orc.compute_reward(task, "sparse", max(nobj, 1), ag, dg)
         assert np.array_equal(rew.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    print(f"{task}: worst |CUDA - oracle| over {steps} steps, {int(clean.sum())} contact-free envs: {worst}")
     assert clean.sum() >= n // 4, f"only {clean.sum()} contact-free envs"
     env.close()
 
@@ -255,13 +260,12 @@ def test_contact_statistics_scripted_grasp():
     spread the outcomes (the oracle lifts ~80 %).
     Gripper contacts amplify float32 rounding, so trajectories are not compared - the fraction of lifted legos is."""
     import torch
-    n = 384
+    n = STATS_ENVS
     cfg = {"init_grasp_rate": 1.0, "goal_shape": "air"}
     env = _mk("pick_and_place", n, seed=17, auto_reset=False, config=cfg)
-    ref = [orc.OracleEnv("pick_and_place", env_index=i, seed=17, auto_reset=0, goal_shape="air", init_grasp_rate=1.0) for i in range(n)]
+    ref = orc.OracleBatch("pick_and_place", n, seed=17, auto_reset=0, goal_shape="air", init_grasp_rate=1.0)
     env.reset()
-    for r in ref:
-        r.reset()
+    ref.reset()
     rng = np.random.default_rng(2)
     grip = np.where(rng.random(n) < 0.5, -1.0, rng.uniform(-1, 1, n)).astype(np.float32)  # half close fully, half anything
     off = rng.normal(0, 0.5, (n, 2)).astype(np.float32)                                    # lateral drift while closing
@@ -275,14 +279,44 @@ def test_contact_statistics_scripted_grasp():
         a[:, 3] = grip
         a = np.clip(a, -1, 1)
         obs, rew, done, infos = env.step(torch.from_numpy(a).cuda())
-        res = [r.step(a[i]) for i, r in enumerate(ref)]
+        robs = ref.step(a)[0]
         z_gpu = obs["achieved_goal"].cpu().numpy()[:, 2]
-        z_ref = np.array([r[0]["achieved_goal"][2] for r in res])
+        z_ref = robs["achieved_goal"][:, 2]
         assert np.isfinite(z_gpu).all()
     lifted_gpu, lifted_ref = float((z_gpu > 0.1).mean()), float((z_ref > 0.1).mean())
-    print(f"scripted grasp: lifted fraction CUDA {lifted_gpu:.3f} vs oracle {lifted_ref:.3f} ({n} envs)")
-    assert 0.3 < lifted_ref < 0.97 and abs(lifted_gpu - lifted_ref) < 0.06, (lifted_gpu, lifted_ref)
+    agree = float(((z_gpu > 0.1) == (z_ref > 0.1)).mean())
+    print(f"scripted grasp: lifted fraction CUDA {lifted_gpu:.4f} vs oracle {lifted_ref:.4f} (gap {abs(lifted_gpu - lifted_ref):.4f}, "
+          f"per-env agreement {agree:.4f}, {n} envs)")
+    assert 0.3 < lifted_ref < 0.97 and abs(lifted_gpu - lifted_ref) < STATS_TOL, (lifted_gpu, lifted_ref)
     env.close()
+
+
+@pytest.mark.parametrize("task", ["pick_and_place", "handover"])
+def test_dense_staged_reward_in_step(task):
+    """reward_type='dense' - the reference's training configuration (benchmark/train.py on XarmPDHandoverNoGoal-v1) and
+    PickAndPlace's staged reward [REF xarm_handover.py:185-199; xarm_pick_and_place.py:166-175].  The in-step reward of EVERY env
+    (gripper contacts included) must equal the oracle's staged-reward function - itself pinned on the reference's own
+    compute_reward (tests/test_oracle_golden.py::test_dense_staged_rewards_match_reference) - evaluated on the step's own
+    outputs: hand position and achieved / desired goal from the returned observation, grasp flags from the state record
+    (PickAndPlace: the live flag; Handover: the flag as _set_action stored it before the step).  Tolerance 1e-6 absolute:
+    tanhf (device: 2 ulp) against glibc's; the stage constants (0.5, 1.5 / 2.25 ...) are exact.  Scripted closing / lifting
+    makes every stage occur.  Envs whose gripper touched nothing are also compared with the oracle ENV's reward (2.5e-4 =
+    0.25 x the 1e-3 position tolerance)."""
+    import torch
+    from tests.parity_util import run_dense_staged
+
+    class Dev:
+        def __init__(self, n, cfg):
+            self.e = _mk(task, n, seed=31, auto_reset=False, config=cfg)
+        def reset(self): self.e.reset()
+        def set_state(self, st): self.e.set_state(st)
+        def get_state(self): return self.e.get_state()
+        def get_obs(self): return {k: v.cpu().numpy() for k, v in self.e.get_obs().items()}
+        def step(self, a):
+            obs, rew, _, _ = self.e.step(torch.from_numpy(a).cuda())
+            return {k: v.cpu().numpy() for k, v in obs.items()}, rew.cpu().numpy()
+        def close(self): self.e.close()
+    run_dense_staged(task, Dev, 256)
 
 
 def test_heavy_solver_impulse_form_matches_velocity_form():
@@ -341,25 +375,26 @@ def test_handover_ezpolicy_statistics():
     fraction of envs in which a gripper closed on it."""
     import torch
     from gym_xarm_b200.policies import ezpolicy
-    n = 192
+    n = STATS_ENVS
     env = _mk("handover", n, seed=29, auto_reset=False)
-    ref = [orc.OracleEnv("handover", env_index=i, seed=29, auto_reset=0, goal_shape="ground") for i in range(n)]
+    ref = orc.OracleBatch("handover", n, seed=29, auto_reset=0, goal_shape="ground")
     obs = env.reset()
-    robs = [r.reset() for r in ref]
+    robs = ref.reset()["observation"]
     o_gpu = obs["observation"]
     for t in range(40):
         a_gpu = ezpolicy(o_gpu).clamp(-1, 1).float()
         o_gpu = env.step(a_gpu)[0]["observation"]
-        a_ref = [np.clip(ezpolicy(ro["observation"]), -1, 1).astype(np.float32) for ro in robs]
-        robs = [r.step(a)[0] for r, a in zip(ref, a_ref)]
+        a_ref = np.clip(ezpolicy(robs), -1, 1).astype(np.float32)
+        robs = ref.step(a_ref)[0]["observation"]
         assert torch.isfinite(o_gpu).all()
     og = o_gpu.cpu().numpy()
-    orf = np.stack([ro["observation"] for ro in robs])
     near_gpu = float((np.linalg.norm(og[:, 0:3] - og[:, 13:16], axis=1) < 0.1).mean())
-    near_ref = float((np.linalg.norm(orf[:, 0:3] - orf[:, 13:16], axis=1) < 0.1).mean())
-    z_gpu, z_ref = float(np.median(og[:, 2])), float(np.median(orf[:, 2]))
-    print(f"ezpolicy after 40 steps: gripper-1 within 10 cm of the lego CUDA {near_gpu:.3f} vs oracle {near_ref:.3f}; median lego z {z_gpu:.4f} vs {z_ref:.4f}")
-    assert abs(near_gpu - near_ref) < 0.06 and abs(z_gpu - z_ref) < 0.01
+    near_ref = float((np.linalg.norm(robs[:, 0:3] - robs[:, 13:16], axis=1) < 0.1).mean())
+    lift_gpu, lift_ref = float((og[:, 2] > 0.05).mean()), float((robs[:, 2] > 0.05).mean())
+    z_gpu, z_ref = float(np.median(og[:, 2])), float(np.median(robs[:, 2]))
+    print(f"ezpolicy after 40 steps ({n} envs): gripper-1 within 10 cm of the lego CUDA {near_gpu:.4f} vs oracle {near_ref:.4f}; "
+          f"lego lifted above 5 cm {lift_gpu:.4f} vs {lift_ref:.4f}; median lego z {z_gpu:.4f} vs {z_ref:.4f}")
+    assert abs(near_gpu - near_ref) < STATS_TOL and abs(lift_gpu - lift_ref) < STATS_TOL and abs(z_gpu - z_ref) < 0.01
     env.close()
 
 
@@ -370,11 +405,11 @@ def test_two_arm_contact_statistics_scripted_push(task):
     amplify float32 rounding, so the outcome is compared as statistics over the envs: the fraction of envs whose cube was
     pushed more than 1 cm and the mean push distance (PushWithDoor: also the mean door travel)."""
     import torch
-    n, steps = 64, 30
+    n, steps = STATS_ENVS, 30
     env = _mk(task, n, seed=41, auto_reset=False)
-    ref = [orc.OracleEnv(task, env_index=i, seed=41, auto_reset=0) for i in range(n)]
+    ref = orc.OracleBatch(task, n, seed=41, auto_reset=0)
     obs = env.reset()["observation"].cpu().numpy()
-    robs = np.stack([r.reset()["observation"] for r in ref])
+    robs = ref.reset()["observation"]
     nobj = 3 if task == "stack_tower" else 1
     h1 = 13 * nobj                                # hand-1 position; hand-2 follows 8 (StackTower: pos, vel, finger) or 6 words later
     h2 = h1 + (8 if task == "stack_tower" else 6)
@@ -398,16 +433,20 @@ def test_two_arm_contact_statistics_scripted_push(task):
     p0_gpu, p0_ref = obs[:, :3 * nobj].copy(), robs[:, :3 * nobj].copy()
     for t in range(steps):
         obs = env.step(torch.from_numpy(policy(obs)).cuda())[0]["observation"].cpu().numpy()
-        ar = policy(robs)
-        robs = np.stack([r.step(ar[i])[0]["observation"] for i, r in enumerate(ref)])
+        robs = ref.step(policy(robs))[0]["observation"]
         assert np.isfinite(obs).all()
     push_gpu = np.linalg.norm((obs[:, :3 * nobj] - p0_gpu).reshape(n, nobj, 3)[:, :, :2], axis=2).max(1)
     push_ref = np.linalg.norm((robs[:, :3 * nobj] - p0_ref).reshape(n, nobj, 3)[:, :, :2], axis=2).max(1)
     f_gpu, f_ref = float((push_gpu > 0.01).mean()), float((push_ref > 0.01).mean())
     m_gpu, m_ref = float(push_gpu.mean()), float(push_ref.mean())
-    print(f"{task} scripted push: pushed > 1 cm CUDA {f_gpu:.3f} vs oracle {f_ref:.3f}; mean push {m_gpu:.4f} vs {m_ref:.4f} m")
+    print(f"{task} scripted push ({n} envs): pushed > 1 cm CUDA {f_gpu:.4f} vs oracle {f_ref:.4f}; mean push {m_gpu:.5f} vs {m_ref:.5f} m")
+    if task == "push_with_door":
+        dq = 13 + 2 * 3 * 9   # door travel: state word after the cube
+        d_gpu, d_ref = float(np.abs(env.get_state()[:, dq]).mean()), float(np.abs(ref.get_state()[:, dq]).mean())
+        print(f"push_with_door: mean |door travel| CUDA {d_gpu:.5f} vs oracle {d_ref:.5f} m")
+        assert abs(d_gpu - d_ref) < 0.05 * max(d_ref, 0.01)
     assert f_ref > 0.1, "the script must reach the cubes"
-    assert abs(f_gpu - f_ref) < 0.08 and abs(m_gpu - m_ref) < 0.25 * max(m_ref, 0.02)
+    assert abs(f_gpu - f_ref) < STATS_TOL and abs(m_gpu - m_ref) < 0.05 * max(m_ref, 0.02)
     env.close()
 
 
@@ -492,6 +531,7 @@ def test_multi_object_parity(task, num_obj):
         r.set_state(s_)
     clean[:] = True
     rng = np.random.default_rng(9)
+    worst = Worst()
     for t in range(25):
         a = _actions(rng, task, n, env.act_dim)
         obs, rew, done, _ = env.step(torch.from_numpy(a).cuda())
@@ -499,15 +539,13 @@ def test_multi_object_parity(task, num_obj):
         clean &= np.array([r.arm_contacts() == 0 for r in ref])
         st, rst = env.get_state(), np.stack([r.get_state() for r in ref])
         assert np.isfinite(st).all()
-        for arm in range(narm):
-            sl = slice(arm * 27, arm * 27 + 9)
-            np.testing.assert_allclose(st[clean][:, sl], rst[clean][:, sl], atol=TOL, err_msg=f"{task} N={num_obj} step {t} arm {arm}")
-        for o in range(num_obj):
-            sl = slice(nq + 13 * o, nq + 13 * o + 7)
-            np.testing.assert_allclose(st[clean][:, sl], rst[clean][:, sl], atol=TOL, err_msg=f"{task} N={num_obj} step {t} obj {o}")
+        gobs = {k: v.cpu().numpy() for k, v in obs.items()}
+        robs_t = {k: np.stack([r[0][k] for r in res]) for k in gobs}
+        compare_full(task, num_obj, st, rst, gobs, robs_t, clean, worst, msg=f"N={num_obj} step {t}")
         ag, dg = obs["achieved_goal"].cpu().numpy(), obs["desired_goal"].cpu().numpy()
         want = orc.compute_reward(task, "sparse", num_obj, ag, dg)
         assert np.array_equal(rew.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    print(f"{task} N={num_obj}: worst |CUDA - oracle| over 25 steps, {int(clean.sum())} contact-free envs: {worst}")
     assert clean.sum() >= (n // 4 if task == "pick_and_place" else 1), f"only {clean.sum()} contact-free envs"
     env.close()
 

@@ -9,6 +9,7 @@ import pytest
 
 from oracle import oracle as orc
 from tests.hostsim import hostsim as hs
+from tests.parity_util import Worst, compare_full, run_dense_staged
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_logic.npz"))
 TASKS = ["reach", "pick_and_place", "stack_tower", "push_with_door", "handover"]
@@ -55,6 +56,7 @@ def test_step_parity_contact_free(task):
         r.set_state(s)
         r.arm_contacts()
     clean = np.ones(n, bool)
+    worst = Worst()
     rng = np.random.default_rng(3)
     ndof = 13 if task == "reach" else 9
     narm = 1 if task in ("reach", "pick_and_place") else 2
@@ -72,18 +74,13 @@ def test_step_parity_contact_free(task):
         st, rst = v.get_state(), np.stack([e.get_state() for e in ref])
         assert np.isfinite(st).all()
         c = clean
-        for arm in range(narm):
-            sl = slice(arm * 3 * ndof, arm * 3 * ndof + (9 if ndof == 9 else 7))  # Reach: the 7 arm joints (see DESIGN.md on its gripper)
-            np.testing.assert_allclose(st[c][:, sl], rst[c][:, sl], atol=TOL, err_msg=f"{task} step {t}")
-        for ob in range(NOBJ[task]):
-            sl = slice(nq + 13 * ob, nq + 13 * ob + 7)
-            np.testing.assert_allclose(st[c][:, sl], rst[c][:, sl], atol=TOL, err_msg=f"{task} step {t} obj {ob}")
-        np.testing.assert_allclose(o["observation"][c][:, :3] if task in ("reach", "pick_and_place") else o["observation"][c][:, :3],
-                                   np.stack([x[0]["observation"] for x in res])[c][:, :3], atol=TOL)
+        robs_t = {k: np.stack([x[0][k] for x in res]) for k in o}
+        compare_full(task, NOBJ[task], st, rst, o, robs_t, c, worst, msg=f"step {t}")   # whole state record + whole observation dict
         assert np.array_equal(d[c], np.array([x[2] for x in res])[c])
         assert np.array_equal(s[c], np.array([x[3]["is_success"] for x in res], np.float32)[c])
         want = orc.compute_reward(task, "sparse", max(NOBJ[task], 1), o["achieved_goal"], o["desired_goal"])
         assert np.array_equal(r.view(np.uint32), want.view(np.uint32))
+    print(f"{task}: worst |host build - oracle|: {worst}")
     assert clean.sum() >= 2
 
 
@@ -160,3 +157,23 @@ def test_auto_reset_and_stats_semantics():
     assert not np.array_equal(o["desired_goal"], g0)          # already the next episode's goal
     assert np.array_equal(v.get_state()[:, -5], np.zeros(3))  # step counter back to 0
     assert np.array_equal(v.get_state()[:, -4], np.full(3, 2.0))  # second episode
+
+
+@pytest.mark.parametrize("task", ["pick_and_place", "handover"])
+def test_dense_staged_reward_host_build(task):
+    """The staged dense rewards of the kernel code (host build) in a scripted rollout - every stage - against the oracle's
+    staged-reward function, itself pinned on the reference's compute_reward (same body as the -m gpu test)."""
+    class Host:
+        def __init__(self, n, cfg):
+            pp = task == "pick_and_place"
+            self.v = hs.HostSimVec(orc.make_config(task, num_envs=n, seed=31, auto_reset=0, reward_type="dense", goal_shape="air" if pp else "ground",
+                                                   init_grasp_rate=cfg.get("init_grasp_rate", 0.0)))
+        def reset(self): self.v.reset()
+        def set_state(self, st): self.v.set_state(st)
+        def get_state(self): return self.v.get_state()
+        def get_obs(self): return self.v.get_obs()
+        def step(self, a):
+            o, r, d, s, tr = self.v.step(a)
+            return o, r
+        def close(self): pass
+    run_dense_staged(task, Host, 48)
