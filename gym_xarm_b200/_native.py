@@ -11,7 +11,7 @@ class XarmConfig(C.Structure):
         ("task", C.c_int32), ("reward_type", C.c_int32), ("num_obj", C.c_int32), ("goal_shape", C.c_int32),
         ("init_grasp_rate", C.c_float), ("goal_ground_rate", C.c_float), ("same_side_rate", C.c_float),
         ("use_stand", C.c_int32), ("max_episode_steps", C.c_int32), ("auto_reset", C.c_int32),
-        ("device", C.c_int32), ("reserved", C.c_int32),
+        ("device", C.c_int32), ("stagger_phases", C.c_int32),
         ("num_envs", C.c_int64), ("env_index_base", C.c_int64), ("seed", C.c_uint64),
     ]
 
@@ -41,13 +41,16 @@ class XarmHerConfig(C.Structure):
     ]
 
 
+ABI_VERSION = 2   # XARM_ABI_VERSION of include/xarm_abi.h
+
 # every symbol include/xarm_abi.h declares
 ABI_SYMBOLS = [
     "xarm_task_dims", "xarm_create", "xarm_destroy", "xarm_bind", "xarm_reset", "xarm_step", "xarm_step_host",
     "xarm_reset_host", "xarm_compute_reward", "xarm_get_state", "xarm_set_state", "xarm_get_obs", "xarm_graph_capture",
     "xarm_episode_stats", "xarm_launch_count", "xarm_last_error", "xarm_abi_version", "xarm_set_profiling", "xarm_kernel_times",
+    "xarm_measure_fp32_peak",
     "xarm_vecnorm_create", "xarm_vecnorm_destroy", "xarm_vecnorm_reset", "xarm_vecnorm_step", "xarm_vecnorm_set_training",
-    "xarm_vecnorm_get_stats", "xarm_vecnorm_set_stats",
+    "xarm_vecnorm_get_stats", "xarm_vecnorm_set_stats", "xarm_vecnorm_normalize_obs", "xarm_vecnorm_normalize_reward",
     "xarm_her_create", "xarm_her_destroy", "xarm_her_begin", "xarm_her_add", "xarm_her_sample", "xarm_her_stats",
 ]
 
@@ -82,7 +85,7 @@ def load():
     L.xarm_bind.argtypes = [vp, C.POINTER(XarmBuffers)]
     L.xarm_reset.argtypes = [vp, vp, vp]
     L.xarm_step.argtypes = [vp, vp]
-    L.xarm_step_host.argtypes = [vp] + [vp] * 8 + [vp]
+    L.xarm_step_host.argtypes = [vp] + [vp] * 9 + [vp]
     L.xarm_reset_host.argtypes = [vp, vp, vp, vp, vp]
     L.xarm_compute_reward.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_int64, vp, vp]
     L.xarm_get_state.argtypes = [vp, vp]
@@ -92,12 +95,15 @@ def load():
     L.xarm_episode_stats.argtypes = [vp, C.POINTER(C.c_double), vp]
     L.xarm_set_profiling.argtypes = [vp, C.c_int32]
     L.xarm_kernel_times.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.xarm_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     dp = C.POINTER(C.c_double)
     L.xarm_vecnorm_create.argtypes = [C.POINTER(XarmVecNormConfig), C.POINTER(vp)]
     L.xarm_vecnorm_destroy.argtypes = [vp]
     L.xarm_vecnorm_reset.argtypes = [vp, vp, vp, vp]
     L.xarm_vecnorm_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.xarm_vecnorm_set_training.argtypes = [vp, C.c_int32]
+    L.xarm_vecnorm_normalize_obs.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int32, vp]
+    L.xarm_vecnorm_normalize_reward.argtypes = [vp, vp, C.c_int64, vp, vp]
     L.xarm_vecnorm_get_stats.argtypes = [vp, dp, dp, dp, dp]
     L.xarm_vecnorm_set_stats.argtypes = [vp, dp, dp, C.c_double, dp]
     L.xarm_her_create.argtypes = [C.POINTER(XarmHerConfig), C.POINTER(vp)]
@@ -108,6 +114,8 @@ def load():
     L.xarm_her_stats.argtypes = [vp, C.POINTER(C.c_int64)]
     L.xarm_launch_count.restype = C.c_int64
     L.xarm_last_error.restype = C.c_char_p
+    if L.xarm_abi_version() != ABI_VERSION:
+        raise XarmError(f"libxarm_b200.so has ABI version {L.xarm_abi_version()}, this package needs {ABI_VERSION}: rebuild (python -m gym_xarm_b200.build --force)")
     _lib = L
     return L
 

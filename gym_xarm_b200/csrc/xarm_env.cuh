@@ -207,7 +207,16 @@ struct ResetCfg {
   int64_t env_index_base;
   int32_t reward_type, goal_shape, max_episode_steps;
   float init_grasp_rate, goal_ground_rate, same_side_rate;
+  int32_t stagger;   // XarmConfig.stagger_phases
 };
+// step counter an env starts from at construction / after an explicit reset: 0, or (global index mod episode length) with
+// stagger_phases - time-limit endings then spread evenly over the steps
+template <class T>
+XD int initial_step_count(const ResetCfg& cfg, int64_t genv) {
+  if (!cfg.stagger) return 0;
+  const int limit = cfg.max_episode_steps > 0 ? cfg.max_episode_steps : T::MAX_STEPS;
+  return (int)(genv % limit);
+}
 
 template <class T>
 XD void set_joint_init(Env<T>& e, int a, float finger) {
@@ -302,7 +311,7 @@ template <class T>
 XD void env_construct(Env<T>& e, const ResetCfg& cfg, int64_t genv) {
   using MD = typename T::MD;
   Rng rng = {cfg.seed, (uint64_t)genv, 0u, 0u};
-  e.episode = 0; e.step_count = 0; e.d_old = 0.f; e.grasp[0] = 0; e.grasp[1] = 0; e.grasp_cmd[0] = 0; e.grasp_cmd[1] = 0; e.door_q = 0.f; e.door_qd = 0.f;
+  e.episode = 0; e.step_count = initial_step_count<T>(cfg, genv); e.d_old = 0.f; e.grasp[0] = 0; e.grasp[1] = 0; e.grasp_cmd[0] = 0; e.grasp_cmd[1] = 0; e.door_q = 0.f; e.door_qd = 0.f;
 #pragma unroll
   for (int a = 0; a < T::NARM; a++) {
     if (T::TASK == XARM_TASK_PICK_AND_PLACE) {  // its ctor never calls resetJointState [REF xarm_pick_and_place.py:76-79]

@@ -24,8 +24,9 @@ struct KArgs {
   const int* list;       // optional: thread t works on env list[t] (auto-reset tail); NULL = identity
   const int* list_count;
   // development timeline (XARM_TIMELINE=1): first block start / last block end of every pipeline launch, %globaltimer ns
-  unsigned long long* tl;  // [2 * XARM_TL_SLOTS] or NULL
+  unsigned long long* tl;  // [5 * XARM_TL_SLOTS + 8] or NULL
   int tl_slot;
+  int tl_branch;           // 0 main, 1 early, 2 late tail: env-substep counters at tl[5 * XARM_TL_SLOTS + {branch: heavy, 3 + branch: all}]
   // SM partition of a split step (xarm_lib.cu): launches of the main branch carry a work counter (blocks claim their
   // chunks dynamically) and leave at once when they land on an SM of sm_mask - those SMs belong to the early branch
   int light_dual;                  // list launches of the light kernel come in two register budgets (xarm_lib.cu)
@@ -133,6 +134,7 @@ XD void body_reset(const KArgs& a, int64_t i, bool clear_return) {
   Obs<T> o;
   get_obs<T>(e, o);
   e.d_old = np_dist(o.ag, o.dg, T::G);  // [REF xarm_reach.py:100]
+  if (clear_return) e.step_count = initial_step_count<T>(a.rc, a.rc.env_index_base + i);
   write_obs<T>(a, i, o);
   env_store<T>(e, a.state, a.n, i);
   a.need_reset[i] = 0;

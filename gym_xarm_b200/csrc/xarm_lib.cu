@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(128) k_pipe_action(KArgs a) {
 #endif
 template <class T>
 __global__ void __launch_bounds__(128, XARM_SETUP_MINB) k_pipe_setup(KArgs a, int sub, int* heavy_count) {
+  if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + 3 + a.tl_branch, (unsigned long long)(a.list ? *a.list_count : a.n));
   PIPE_LEAVE_RESERVED(a)
   tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) {
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* 
 template <class T>
 __global__ void __launch_bounds__(64) k_heavy_rows(KArgs a, int sub, const int* heavy_count, float* hrec) {
   if constexpr (task_has_heavy_rows<T>()) {
+    if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + a.tl_branch, (unsigned long long)*heavy_count);
     PIPE_LEAVE_RESERVED(a)
     const int count = *heavy_count;
     if (a.tl && a.tl_slot >= 0 && threadIdx.x == 0) a.tl[2 * XARM_TL_SLOTS + a.tl_slot] = (unsigned long long)count;
@@ -221,9 +223,11 @@ __global__ void __launch_bounds__(16 * XARM_HEAVY2_ENVS_PER_BLOCK) k_heavy_solve
 // tasks without a light form (two arms / door): every env takes the generic substep (rows in thread-local memory)
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_heavy_all(KArgs a, int sub) {
+  tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) {
     if (i >= 0) { Contacts<T> C; pipe_heavy<T>(a, i, sub, C); }
   }
+  tl_mark(a, 1);
 }
 template <class T>
 __global__ void __launch_bounds__(128) k_pipe_finish(KArgs a) {
@@ -311,6 +315,29 @@ __global__ void k_compute_reward(int task, int reward_type, int num_obj, int G, 
   out[i] = reward_stateless(task, reward_type, num_obj, task_threshold(task), a, d, G);
 }
 
+// numpy-facing path: rows of the terminal slab whose env finished in this step -> compact rows + env ids (only those cross PCIe)
+__global__ void __launch_bounds__(256) k_gather_terminal(const uint8_t* __restrict__ done, const float* __restrict__ term, int64_t n, int W,
+                                                         float* __restrict__ rows, int* __restrict__ ids, int* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = base + lane;
+    const bool on = i < n && done[i];
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (!m) continue;
+    int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(count, __popc(m));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (on) ids[slot0 + __popc(m & ((1u << lane) - 1u))] = (int)i;
+    // the warp copies its finished rows together: lanes over the words of a row
+    for (unsigned mm = m; mm; mm &= mm - 1) {
+      const int src_lane = __ffs(mm) - 1;
+      const int slot = slot0 + __popc(m & ((1u << src_lane) - 1u));
+      const float* src = term + (base + src_lane) * W;
+      for (int w = lane; w < W; w += 32) rows[(int64_t)slot * W + w] = src[w];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
@@ -360,6 +387,7 @@ struct PipeCtx {
   KArgs tl(const KArgs& a) {
     KArgs b = a;
     b.tl = timeline ? tl_dev : nullptr; b.tl_slot = cur_slot;
+    b.tl_branch = cur_branch == 'M' ? 0 : (cur_branch == 'E' ? 1 : 2);
     b.work = nullptr;
     if (dyn && reserve_sms > 0 && next_work < n_work) {
       b.work = work_base + next_work++;
@@ -464,7 +492,9 @@ struct OpsT {
     const unsigned solve_grid = fork_heavy || part ? c.heavy_grid * 3 : (unsigned)(c.max_blocks * 3 / 4);
     for (int sub = 0; sub < T::NSUB; sub++) {
       if constexpr (!HAS_LIGHT) {
-        k_pipe_heavy_all<T><<<g, 128, 0, s>>>(a, sub); g_launches++;
+        c.begin("heavy_all", s);
+        k_pipe_heavy_all<T><<<g, 128, 0, s>>>(c.tl(a), sub); g_launches++;
+        c.end(s);
       } else {
         int* hc = a.heavy_count + pass * XARM_MAX_SUBSTEPS + sub;
         c.begin("setup", s);
@@ -644,10 +674,15 @@ struct XarmHandle {
   cudaStream_t graph_stream = nullptr;
   int64_t graph_launches = 0;
   // device + pinned staging for the *_host entry points
-  float* d_io = nullptr;   // actions | obs | ag | dg | reward | success
+  float* d_io = nullptr;   // actions | obs | ag | dg | reward | success | terminal slab | gathered terminal rows
   uint8_t* d_flags = nullptr;  // done | truncated
+  int* d_term = nullptr;   // [1 + N]: number of finished envs of the step | their env ids
   float* h_io = nullptr;
   uint8_t* h_flags = nullptr;
+  int* h_term = nullptr;
+  cudaGraphExec_t graph_host = nullptr;   // the step on the host-path buffers (captured at the first xarm_step_host)
+  cudaStream_t graph_host_stream = nullptr, host_stream = nullptr;
+  int64_t graph_host_launches = 0;
   XarmBuffers host_bufs;
   XarmBuffers user_bufs;
   bool user_bound = false;
@@ -669,6 +704,7 @@ int xarm_task_dims(int32_t task, int32_t num_obj, int32_t* act_dim, int32_t* obs
   return XARM_OK;
 }
 
+int xarm_destroy(XarmHandle* h);
 int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   if (!cfg || !out) return fail(XARM_E_INVALID, "xarm_create: null argument");
   if (cfg->num_envs <= 0) return fail(XARM_E_INVALID, "xarm_create: num_envs must be positive");
@@ -694,7 +730,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   const int64_t n = c.num_envs;
   h->k.n = n; h->k.auto_reset = c.auto_reset;
   h->k.rc.seed = c.seed; h->k.rc.env_index_base = c.env_index_base; h->k.rc.reward_type = c.reward_type;
-  h->k.rc.goal_shape = c.goal_shape; h->k.rc.max_episode_steps = c.max_episode_steps;
+  h->k.rc.goal_shape = c.goal_shape; h->k.rc.max_episode_steps = c.max_episode_steps; h->k.rc.stagger = c.stagger_phases != 0;
   h->k.rc.init_grasp_rate = c.init_grasp_rate; h->k.rc.goal_ground_rate = c.goal_ground_rate; h->k.rc.same_side_rate = c.same_side_rate;
   // int scratch: reset list | heavy list | form | rng draw | early list | main list | early reset list | counters
   const int n_work = 128;  // work counters of the partitioned main branch (one per launch: 2 + 4 per substep)
@@ -711,24 +747,21 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   cudaError_t e7 = cudaStreamCreateWithFlags(&h->pipe.side, cudaStreamNonBlocking);
   if (e7 == cudaSuccess) e7 = cudaStreamCreateWithPriority(&h->pipe.e_main, cudaStreamNonBlocking, prio_hi);
   if (e7 == cudaSuccess) e7 = cudaStreamCreateWithPriority(&h->pipe.e_side, cudaStreamNonBlocking, prio_hi);
-  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) {
-    cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.reset_list); cudaFree(h->k.scratch);
-    if (h->pipe.side) cudaStreamDestroy(h->pipe.side);
-    if (h->pipe.e_main) cudaStreamDestroy(h->pipe.e_main);
-    if (h->pipe.e_side) cudaStreamDestroy(h->pipe.e_side);
-    delete h; cudaGetLastError();
-    return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc failed");
-  }
+  // every failure from here on leaves through ONE cleanup (xarm_destroy frees whatever was allocated so far)
+#define CREATE_FAIL(code, msg) do { std::string m_ = (msg); xarm_destroy(h); cudaGetLastError(); return fail((code), m_); } while (0)
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess)
+    CREATE_FAIL(XARM_E_NOMEM, "xarm_create: cudaMalloc failed");
   {
     int sms = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device));
+    cudaError_t ea = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+    if (ea != cudaSuccess) CREATE_FAIL(XARM_E_CUDA, std::string("cudaDeviceGetAttribute: ") + cudaGetErrorString(ea));
     h->pipe.heavy_grid = (unsigned)(sms > 0 ? sms : 148);
     h->pipe.max_blocks = (int64_t)h->pipe.heavy_grid * 4 - (getenv("XARM_RESERVE_BLOCKS") ? atoi(getenv("XARM_RESERVE_BLOCKS")) : 32);
     cudaError_t ep = (cudaError_t)ops.prepare();
-    if (ep != cudaSuccess) return fail(XARM_E_CUDA, std::string("cudaFuncSetAttribute(k_pipe_heavy): ") + cudaGetErrorString(ep));
+    if (ep != cudaSuccess) CREATE_FAIL(XARM_E_CUDA, std::string("cudaFuncSetAttribute(k_pipe_heavy): ") + cudaGetErrorString(ep));
   }
   if (ops.hrec_words() > 0) {
-    if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) { cudaGetLastError(); return fail(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed"); }
+    if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) CREATE_FAIL(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed");
   }
   {  // SMs reserved for the early branch of a split step
     const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 32;  // of 148: main branch (116 SMs) and early branch then take about equally long
@@ -755,8 +788,8 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   h->pipe.light_main_lat = !(getenv("XARM_LIGHT_MAIN_LAT") && atoi(getenv("XARM_LIGHT_MAIN_LAT")) == 0);
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
   h->pipe.timeline = getenv("XARM_TIMELINE") != nullptr;
-  if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }
-  if (h->pipe.timeline) cudaMemset(h->pipe.tl_dev, 0, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS);
+  if (h->pipe.timeline && cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * (5 * XARM_TL_SLOTS + 8)) != cudaSuccess) { cudaGetLastError(); h->pipe.timeline = false; }
+  if (h->pipe.timeline) cudaMemset(h->pipe.tl_dev, 0, sizeof(unsigned long long) * (5 * XARM_TL_SLOTS + 8));
   h->pipe.split = getenv("XARM_NO_SPLIT") == nullptr;
   h->pipe.dela = !(getenv("XARM_HEAVY_SOLVER") && strcmp(getenv("XARM_HEAVY_SOLVER"), "coop") == 0);
   h->k.heavy_list = h->k.reset_list + n; h->k.form = h->k.reset_list + 2 * n; h->k.rng_draw = h->k.reset_list + 3 * n;
@@ -766,11 +799,12 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   h->pipe.work_base = h->pipe.counters + XARM_PIPE_COUNTERS; h->pipe.n_work = n_work;
   h->pipe.reset_count_e = h->k.reset_count + 1; h->pipe.count_e = h->k.reset_count + 2; h->pipe.count_m = h->k.reset_count + 3;
   h->k.heavy_dir = 1;
-  CUDA_TRY(cudaMemset(h->k.reset_list, 0, sizeof(int) * n_int));
-  CUDA_TRY(cudaMemset(h->k.stats, 0, sizeof(double) * 5));
-  ops.init(h->k, 0);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(0));
+  cudaError_t ez = cudaMemset(h->k.reset_list, 0, sizeof(int) * n_int);
+  if (ez == cudaSuccess) ez = cudaMemset(h->k.stats, 0, sizeof(double) * 5);
+  if (ez == cudaSuccess) { ops.init(h->k, 0); ez = cudaGetLastError(); }
+  if (ez == cudaSuccess) ez = cudaStreamSynchronize(0);
+  if (ez != cudaSuccess) CREATE_FAIL(XARM_E_CUDA, std::string("xarm_create: ") + cudaGetErrorString(ez));
+#undef CREATE_FAIL
   *out = h;
   return XARM_OK;
 }
@@ -779,6 +813,10 @@ int xarm_destroy(XarmHandle* h) {
   if (!h) return XARM_OK;
   cudaSetDevice(h->cfg.device);
   if (h->graph) cudaGraphExecDestroy(h->graph);
+  if (h->graph_host) cudaGraphExecDestroy(h->graph_host);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  cudaFree(h->d_term);
+  if (h->h_term) cudaFreeHost(h->h_term);
   cudaFree(h->k.state); cudaFree(h->k.ep_return); cudaFree(h->k.need_reset); cudaFree(h->k.stats); cudaFree(h->k.reset_list); cudaFree(h->k.scratch);
   cudaFree(h->pipe.hrec); cudaFree(h->pipe.tl_dev);
   for (cudaEvent_t e : h->pipe.ev) cudaEventDestroy(e);
@@ -801,6 +839,9 @@ int xarm_bind(XarmHandle* h, const XarmBuffers* b) {
   if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }  // addresses changed: recapture
   return XARM_OK;
 }
+
+// capture launch_step_with(h, k, s) into *exec (shared by the device-buffer and the host-buffer paths)
+static int capture_step(XarmHandle* h, const KArgs& k, cudaStream_t s, bool with_gather, cudaGraphExec_t* exec, int64_t* n_launches);
 
 // one env step = the kernel pipeline of xarm_pipeline.cuh (action -> NSUB x {setup -> light || heavy} -> finish -> auto-reset tail)
 static int launch_step_with(XarmHandle* h, const KArgs& k, cudaStream_t s) {
@@ -834,24 +875,32 @@ int xarm_step(XarmHandle* h, void* stream) {
   return XARM_OK;
 }
 
+static void launch_gather_terminal(XarmHandle* h, cudaStream_t s);
+static int capture_step(XarmHandle* h, const KArgs& k, cudaStream_t s, bool with_gather, cudaGraphExec_t* exec, int64_t* n_launches) {
+  if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
+  cudaGraph_t g = nullptr;
+  int64_t before = g_launches.load();
+  CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  launch_step_with(h, k, s);
+  if (with_gather) launch_gather_terminal(h, s);
+  cudaError_t e = cudaStreamEndCapture(s, &g);
+  *n_launches = g_launches.load() - before;
+  g_launches = before;  // captured launches did not run
+  if (e != cudaSuccess) return fail(XARM_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+  e = cudaGraphInstantiate(exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { *exec = nullptr; return fail(XARM_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+  return XARM_OK;
+}
+
 int xarm_graph_capture(XarmHandle* h, void* stream) {
   if (!h) return fail(XARM_E_INVALID, "xarm_graph_capture: null handle");
   if (!h->bound) return fail(XARM_E_STATE, "xarm_graph_capture: call xarm_bind first");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   if (s == nullptr) return fail(XARM_E_INVALID, "xarm_graph_capture: needs a non-default stream");
-  if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
-  cudaGraph_t g = nullptr;
-  int64_t before = g_launches.load();
-  CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-  launch_step(h, s);
-  cudaError_t e = cudaStreamEndCapture(s, &g);
-  h->graph_launches = g_launches.load() - before;
-  g_launches = before;  // captured launches did not run
-  if (e != cudaSuccess) return fail(XARM_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-  e = cudaGraphInstantiate(&h->graph, g, 0);
-  cudaGraphDestroy(g);
-  if (e != cudaSuccess) { h->graph = nullptr; return fail(XARM_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+  int rc = capture_step(h, h->k, s, false, &h->graph, &h->graph_launches);
+  if (rc) return rc;
   h->graph_stream = s;
   return XARM_OK;
 }
@@ -860,11 +909,15 @@ static int ensure_host_io(XarmHandle* h) {
   if (h->d_io) return XARM_OK;
   const int64_t n = h->cfg.num_envs;
   const Ops& o = h->ops;
-  const size_t fl = (size_t)n * (o.A + o.O + 2 * o.G + 2);
-  CUDA_TRY(cudaMalloc(&h->d_io, fl * sizeof(float)));
+  const int W = o.O + 2 * o.G;
+  const size_t fl = (size_t)n * (o.A + W + 2), fl_dev = fl + (size_t)2 * n * W;   // + terminal slab + gathered rows
+  CUDA_TRY(cudaMalloc(&h->d_io, fl_dev * sizeof(float)));
   CUDA_TRY(cudaMalloc(&h->d_flags, 2 * n));
-  CUDA_TRY(cudaMallocHost(&h->h_io, fl * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&h->d_term, sizeof(int) * (1 + n)));
+  CUDA_TRY(cudaMallocHost(&h->h_io, (fl + (size_t)n * W) * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&h->h_flags, 2 * n));
+  CUDA_TRY(cudaMallocHost(&h->h_term, sizeof(int) * (1 + n)));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
   XarmBuffers& b = h->host_bufs;
   float* p = h->d_io;
   b.actions = p; p += n * o.A;
@@ -873,33 +926,57 @@ static int ensure_host_io(XarmHandle* h) {
   b.desired_goal = p; p += n * o.G;
   b.reward = p; p += n;
   b.success = p; p += n;
+  b.terminal_observation = p;   // [N, W]; the gathered rows follow at p + n * W
   b.done = h->d_flags; b.truncated = h->d_flags + n;
-  b.terminal_observation = nullptr;
   return XARM_OK;
+}
+static void launch_gather_terminal(XarmHandle* h, cudaStream_t s) {
+  const int64_t n = h->cfg.num_envs;
+  const int W = h->ops.O + 2 * h->ops.G;
+  cudaMemsetAsync(h->d_term, 0, sizeof(int), s);
+  const unsigned grid = (unsigned)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+  k_gather_terminal<<<grid, 256, 0, s>>>(h->host_bufs.done, h->host_bufs.terminal_observation, n, W, h->host_bufs.terminal_observation + n * W, h->d_term + 1, h->d_term);
+  g_launches++;
 }
 
 // The numpy-facing path: host buffers in, host buffers out.  Uses the library's own device staging; pinned host
-// staging keeps the copies asynchronous with respect to the step kernels.
+// staging keeps the copies asynchronous with respect to the step kernels.  The step itself is a replay of a CUDA graph
+// captured at the first call (XARM_HOST_GRAPH=0: plain launches).
 int xarm_step_host(XarmHandle* h, const float* actions, float* observation, float* achieved_goal, float* desired_goal,
-                   float* reward, uint8_t* done, float* success, uint8_t* truncated, void* stream) {
+                   float* reward, uint8_t* done, float* success, uint8_t* truncated, float* terminal_observation, void* stream) {
   if (!h || !actions) return fail(XARM_E_INVALID, "xarm_step_host: null argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   int rc = ensure_host_io(h);
   if (rc) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->host_stream;
   const int64_t n = h->cfg.num_envs;
   const Ops& o = h->ops;
+  const int W = o.O + 2 * o.G;
   KArgs k = h->k;
   k.b = h->host_bufs;
   float* hp = h->h_io;
   memcpy(hp, actions, sizeof(float) * n * o.A);
   CUDA_TRY(cudaMemcpyAsync((void*)k.b.actions, hp, sizeof(float) * n * o.A, cudaMemcpyHostToDevice, s));
-  launch_step_with(h, k, s);
-  CUDA_TRY(cudaGetLastError());
-  // one D2H copy of the contiguous float outputs, one of the flags
-  const size_t out_fl = (size_t)n * (o.O + 2 * o.G + 2);
+  static const bool use_graph = !(getenv("XARM_HOST_GRAPH") && atoi(getenv("XARM_HOST_GRAPH")) == 0);
+  if (use_graph && !h->pipe.trace) {
+    if (!h->graph_host || h->graph_host_stream != s) {
+      CUDA_TRY(cudaStreamSynchronize(s));
+      rc = capture_step(h, k, s, true, &h->graph_host, &h->graph_host_launches);
+      if (rc) return rc;
+      h->graph_host_stream = s;
+    }
+    CUDA_TRY(cudaGraphLaunch(h->graph_host, s));
+    g_launches += h->graph_host_launches;
+  } else {
+    launch_step_with(h, k, s);
+    launch_gather_terminal(h, s);
+    CUDA_TRY(cudaGetLastError());
+  }
+  // one D2H copy of the contiguous float outputs, one of the flags, one of the finished-env count
+  const size_t out_fl = (size_t)n * (W + 2);
   CUDA_TRY(cudaMemcpyAsync(hp + n * o.A, k.b.observation, out_fl * sizeof(float), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(h->h_flags, h->d_flags, 2 * n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->h_term, h->d_term, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   const float* q = hp + n * o.A;
   if (observation) memcpy(observation, q, sizeof(float) * n * o.O);
@@ -913,6 +990,14 @@ int xarm_step_host(XarmHandle* h, const float* actions, float* observation, floa
   if (success) memcpy(success, q, sizeof(float) * n);
   if (done) memcpy(done, h->h_flags, n);
   if (truncated) memcpy(truncated, h->h_flags + n, n);
+  const int n_term = h->h_term[0];
+  if (terminal_observation && n_term > 0) {   // second, small transfer: the rows of the envs that finished + their ids
+    float* hrows = hp + (size_t)n * (o.A + W + 2);
+    CUDA_TRY(cudaMemcpyAsync(hrows, k.b.terminal_observation + n * W, sizeof(float) * (size_t)n_term * W, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->h_term + 1, h->d_term + 1, sizeof(int) * n_term, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    for (int r = 0; r < n_term; r++) memcpy(terminal_observation + (size_t)h->h_term[1 + r] * W, hrows + (size_t)r * W, sizeof(float) * W);
+  }
   return XARM_OK;
 }
 
@@ -921,7 +1006,7 @@ int xarm_reset_host(XarmHandle* h, float* observation, float* achieved_goal, flo
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   int rc = ensure_host_io(h);
   if (rc) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->host_stream;
   const int64_t n = h->cfg.num_envs;
   const Ops& o = h->ops;
   KArgs k = h->k;
@@ -995,12 +1080,15 @@ int xarm_get_obs(XarmHandle* h, void* stream) {
 int xarm_set_profiling(XarmHandle* h, int32_t on) {
   if (!h) return fail(XARM_E_INVALID, "xarm_set_profiling: null handle");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
-  if (on && !h->pipe.tl_dev) CUDA_TRY(cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS));
-  if (h->pipe.tl_dev) CUDA_TRY(cudaMemset(h->pipe.tl_dev, 0, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS));
+  if (on && !h->pipe.tl_dev) CUDA_TRY(cudaMalloc(&h->pipe.tl_dev, sizeof(unsigned long long) * (5 * XARM_TL_SLOTS + 8)));
+  if (h->pipe.tl_dev) CUDA_TRY(cudaMemset(h->pipe.tl_dev, 0, sizeof(unsigned long long) * (5 * XARM_TL_SLOTS + 8)));
   CUDA_TRY(cudaDeviceSynchronize());
   const bool was = h->pipe.timeline;
   h->pipe.timeline = on != 0;   // (calling it again while on just clears the accumulators)
-  if (was != h->pipe.timeline && h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }  // the launches carry the buffer: recapture
+  if (was != h->pipe.timeline) {   // the launches carry the buffer: recapture
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    if (h->graph_host) { cudaGraphExecDestroy(h->graph_host); h->graph_host = nullptr; }
+  }
   return XARM_OK;
 }
 
@@ -1012,8 +1100,8 @@ int xarm_kernel_times(XarmHandle* h, char* out, int64_t cap) {
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   CUDA_TRY(cudaDeviceSynchronize());
   const size_t nslot = h->pipe.tl_names.size();
-  std::vector<unsigned long long> t(5 * XARM_TL_SLOTS);
-  CUDA_TRY(cudaMemcpy(t.data(), h->pipe.tl_dev, sizeof(unsigned long long) * 5 * XARM_TL_SLOTS, cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> t(5 * XARM_TL_SLOTS + 8);
+  CUDA_TRY(cudaMemcpy(t.data(), h->pipe.tl_dev, sizeof(unsigned long long) * (5 * XARM_TL_SLOTS + 8), cudaMemcpyDeviceToHost));
   std::vector<std::pair<std::string, std::pair<unsigned long long, unsigned long long>>> acc;
   for (size_t k = 0; k < nslot; k++) {
     unsigned long long ns = t[3 * XARM_TL_SLOTS + k], cnt = t[4 * XARM_TL_SLOTS + k];
@@ -1027,6 +1115,11 @@ int xarm_kernel_times(XarmHandle* h, char* out, int64_t cap) {
   char line[160];
   for (auto& kv : acc) {
     snprintf(line, sizeof(line), "%s %llu %.1f\n", kv.first.c_str(), kv.second.first, kv.second.second * 1e-3);
+    txt += line;
+  }
+  // env-substep counters per branch: "#heavy_envs" = envs that took the cooperative contact path, "#setup_envs" = all
+  for (int b = 0; b < 3; b++) {
+    snprintf(line, sizeof(line), "%c #heavy_envs %llu 0\n%c #setup_envs %llu 0\n", "MEL"[b], t[5 * XARM_TL_SLOTS + b], "MEL"[b], t[5 * XARM_TL_SLOTS + 3 + b]);
     txt += line;
   }
   if ((int64_t)txt.size() + 1 > cap) txt.resize(cap - 1);
@@ -1073,6 +1166,52 @@ int xarm_episode_stats(XarmHandle* h, double out[5], void* stream) {
   CUDA_TRY(cudaMemcpyAsync(out, h->k.stats, sizeof(double) * 5, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemsetAsync(h->k.stats, 0, sizeof(double) * 5, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  return XARM_OK;
+}
+
+// FP32 SIMT peak of the device, measured: 8 independent FMA chains per thread, full occupancy
+__global__ void __launch_bounds__(256) k_fma_chain(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true: keeps the chains alive
+}
+int xarm_measure_fp32_peak(int32_t device, double* tflops) {
+  if (!tflops) return fail(XARM_E_INVALID, "xarm_measure_fp32_peak: null argument");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(XARM_E_INVALID, "xarm_measure_fp32_peak: bad device ordinal");
+  CUDA_TRY(cudaSetDevice(device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  float* out = nullptr;
+  const unsigned grid = (unsigned)sms * 8;   // 8 x 256 threads per SM: all 64 warp slots
+  CUDA_TRY(cudaMalloc(&out, sizeof(float) * grid * 256));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 4096;   // x 64 FMAs per thread and iteration
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0, 0);
+    k_fma_chain<<<grid, 256>>>(out, iters, 0.999f, 0.001f);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 64.0 * iters * (double)grid * 256.0 / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  g_launches += 6;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  CUDA_TRY(cudaGetLastError());
+  *tflops = best;
   return XARM_OK;
 }
 
@@ -1158,6 +1297,32 @@ int xarm_vecnorm_step(XarmVecNorm* v, const float* obs, const float* reward, con
   k_vn_finalize<<<1, XARM_VN_MAX_OBS, 0, s>>>(v->st, c.num_envs, c.obs_dim, c.epsilon, tr && c.norm_obs, tr);
   k_vn_apply<<<v->grid, 256, 0, s>>>(v->st, obs, obs_out, c.num_envs, c.obs_dim, reward, reward_out, done, v->ret, c.clip_obs, c.clip_reward, c.norm_obs, c.norm_reward);
   g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_vecnorm_normalize_obs(XarmVecNorm* v, const float* obs, int64_t n, int64_t row_stride, float* out, int64_t out_stride, int32_t inverse, void* stream) {
+  if (!v || !obs || !out) return fail(XARM_E_INVALID, "xarm_vecnorm_normalize_obs: null argument");
+  const XarmVecNormConfig& c = v->cfg;
+  if (n < 0 || row_stride < c.obs_dim || out_stride < c.obs_dim) return fail(XARM_E_INVALID, "xarm_vecnorm_normalize_obs: n >= 0 and strides >= obs_dim required");
+  if (n == 0) return XARM_OK;
+  CUDA_TRY(cudaSetDevice(c.device));
+  const int64_t blocks = (n * c.obs_dim + 255) / 256;
+  k_vn_rows<<<(unsigned)(blocks < 4736 ? blocks : 4736), 256, 0, (cudaStream_t)stream>>>(v->st, obs, n, c.obs_dim, row_stride, out, out_stride, c.clip_obs, c.epsilon, c.norm_obs, inverse);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return XARM_OK;
+}
+
+int xarm_vecnorm_normalize_reward(XarmVecNorm* v, const float* reward, int64_t n, float* out, void* stream) {
+  if (!v || !reward || !out) return fail(XARM_E_INVALID, "xarm_vecnorm_normalize_reward: null argument");
+  if (n < 0) return fail(XARM_E_INVALID, "xarm_vecnorm_normalize_reward: n >= 0 required");
+  if (n == 0) return XARM_OK;
+  const XarmVecNormConfig& c = v->cfg;
+  CUDA_TRY(cudaSetDevice(c.device));
+  const int64_t blocks = (n + 255) / 256;
+  k_vn_reward_rows<<<(unsigned)(blocks < 4736 ? blocks : 4736), 256, 0, (cudaStream_t)stream>>>(v->st, reward, n, out, c.clip_reward, c.norm_reward);
+  g_launches++;
   CUDA_TRY(cudaGetLastError());
   return XARM_OK;
 }

@@ -360,6 +360,7 @@ XD void pipe_reset_stage(const KArgs& a, int64_t i, int stage, bool clear_return
   Obs<T> o;
   get_obs<T>(e, o);
   e.d_old = np_dist(o.ag, o.dg, T::G);  // [REF xarm_reach.py:100]
+  if (clear_return) e.step_count = initial_step_count<T>(a.rc, genv);   // explicit reset (xarm_reset): staggered phases, if configured
   write_obs<T>(a, i, o);
   env_store<T>(e, a.state, a.n, i);
   a.need_reset[i] = 0;

@@ -169,3 +169,27 @@ __global__ void __launch_bounds__(256) k_vn_apply(const VnStats* __restrict__ st
     }
   }
 }
+
+
+// VecNormalize.normalize_obs / unnormalize_obs on any batch of rows (apply only; rows may be strided)
+__global__ void __launch_bounds__(256) k_vn_rows(const VnStats* __restrict__ st, const float* __restrict__ src, int64_t n, int O, int64_t src_stride,
+                                                 float* __restrict__ dst, int64_t dst_stride, float clip_obs, float eps, int norm_obs, int inverse) {
+  const int64_t total = n * O;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / O;
+    const int c = (int)(e - r * O);
+    const float x = src[r * src_stride + c];
+    float y = x;
+    if (norm_obs) {
+      if (!inverse) y = fminf(fmaxf((x - st->fmean[c]) * st->finv[c], -clip_obs), clip_obs);
+      else y = (float)((double)x * sqrt(st->var[c] + (double)eps) + st->mean[c]);
+    }
+    dst[r * dst_stride + c] = y;
+  }
+}
+__global__ void __launch_bounds__(256) k_vn_reward_rows(const VnStats* __restrict__ st, const float* __restrict__ src, int64_t n, float* __restrict__ dst,
+                                                        float clip_reward, int norm_reward) {
+  const float rinv = st->rinv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = norm_reward ? fminf(fmaxf(src[i] * rinv, -clip_reward), clip_reward) : src[i];
+}

@@ -23,9 +23,18 @@ class InfoList:
     """Lazy `infos`: SB3 indexes a list of dicts; building 10^5 dicts per step on the host would dominate the step.
     Dicts are materialised on access from the step's host/device arrays."""
 
-    def __init__(self, env, success, truncated, done, terminal_obs=None):
+    def __init__(self, env, success, truncated, done, terminal_obs=None, key=None, terminal_key_obs=None):
+        """terminal_obs: [N, O + 2 G] slab (rows of finished envs valid).  key: the observation is obs[key] (VecExtractDictObs) -
+        terminal_observation is then the flat array.  terminal_key_obs: [N, O] replacement for the slab's observation part
+        (VecNormalize: the normalised terminal observation)."""
         self._env, self._success, self._truncated, self._done, self._term = env, success, truncated, done, terminal_obs
+        self._key, self._term_key = key, terminal_key_obs
         self._host = None
+
+    def view(self, key=None, terminal_key_obs=None):
+        """the same infos as seen through a wrapper (VecExtractDictObs / VecNormalize)"""
+        return InfoList(self._env, self._success, self._truncated, self._done, self._term, key if key is not None else self._key,
+                        terminal_key_obs if terminal_key_obs is not None else self._term_key)
 
     def __len__(self):
         return self._env.num_envs
@@ -34,19 +43,21 @@ class InfoList:
         if self._host is None:
             def h(x):
                 return x.cpu().numpy() if isinstance(x, torch.Tensor) else (None if x is None else np.asarray(x))
-            self._host = (h(self._success), h(self._truncated), h(self._done), h(self._term))
+            self._host = (h(self._success), h(self._truncated), h(self._done), h(self._term), h(self._term_key))
         return self._host
 
     def __getitem__(self, i):
         if isinstance(i, slice):
             return [self[j] for j in range(*i.indices(len(self)))]
-        s, t, d, term = self._fetch()
+        s, t, d, term, term_key = self._fetch()
         info = {"is_success": float(s[i]), "TimeLimit.truncated": bool(t[i])}
         if d[i] and term is not None:
             O, G = self._env.obs_dim, self._env.goal_dim
             row = term[i]
-            info["terminal_observation"] = {"observation": row[:O].copy(), "achieved_goal": row[O:O + G].copy(),
-                                            "desired_goal": row[O + G:].copy()}
+            full = {"observation": row[:O].copy(), "achieved_goal": row[O:O + G].copy(), "desired_goal": row[O + G:].copy()}
+            if term_key is not None:
+                full[self._key or "observation"] = term_key[i].copy()
+            info["terminal_observation"] = full[self._key] if self._key else full
         return info
 
     def __iter__(self):
@@ -62,12 +73,15 @@ class XarmVecEnv:
     output: 'torch' (device tensors, zero copies) or 'numpy' (host arrays through xarm_step_host - what SB3 consumes)
     env_index_base: global index of env 0 (RNG streams are keyed by the global env index, so a job sharded over
             several GPUs produces the same episodes as a single slab)
+    stagger_phases: env i starts (construction, explicit reset) at step counter (global index mod episode length): the
+            time-limit endings - and the auto-reset work they cause - then spread evenly over the steps instead of arriving
+            as one wave every episode length.  Off by default (and in every parity test).
     """
 
     metadata = {"render.modes": []}
 
     def __init__(self, task, num_envs=1, config=None, device="cuda:0", seed=0, env_index_base=0, auto_reset=True,
-                 output="torch", use_graph=True, max_episode_steps=None):
+                 output="torch", use_graph=True, max_episode_steps=None, stagger_phases=False):
         if task not in SPECS:
             raise ValueError(f"unknown task {task!r}")
         if not torch.cuda.is_available():
@@ -90,7 +104,7 @@ class XarmVecEnv:
             self.spec_task.task, REWARD_IDS[self.reward_type], self.num_obj, GOAL_IDS[self.config.get("goal_shape", "air")],
             float(self.config.get("init_grasp_rate", 0.0)), float(self.config.get("goal_ground_rate", 0.0)),
             float(self.config.get("same_side_rate", 0.5)), int(bool(self.config.get("use_stand", False))),
-            int(max_episode_steps or 0), int(bool(auto_reset)), dev_index, 0, self.num_envs, int(env_index_base), int(seed))
+            int(max_episode_steps or 0), int(bool(auto_reset)), dev_index, int(bool(stagger_phases)), self.num_envs, int(env_index_base), int(seed))
         self._h = C.c_void_p()
         _native.check(self._lib.xarm_create(C.byref(self._cfg), C.byref(self._h)), "xarm_create")
         sw = C.c_int32()
@@ -181,8 +195,7 @@ class XarmVecEnv:
         if self.output == "numpy" and mask is None:
             N, O, G = self.num_envs, self.obs_dim, self.goal_dim
             o, a, d = np.empty((N, O), np.float32), np.empty((N, G), np.float32), np.empty((N, G), np.float32)
-            _native.check(self._lib.xarm_reset_host(self._h, o.ctypes.data, a.ctypes.data, d.ctypes.data, self._cur_stream()),
-                          "xarm_reset_host")
+            _native.check(self._lib.xarm_reset_host(self._h, o.ctypes.data, a.ctypes.data, d.ctypes.data, None), "xarm_reset_host")
             return {"observation": o, "achieved_goal": a, "desired_goal": d}
         mp = None
         if mask is not None:
@@ -208,11 +221,12 @@ class XarmVecEnv:
             o, ag, dg = np.empty((N, O), np.float32), np.empty((N, G), np.float32), np.empty((N, G), np.float32)
             r, s = np.empty(N, np.float32), np.empty(N, np.float32)
             d, t = np.empty(N, np.uint8), np.empty(N, np.uint8)
+            term = np.zeros((N, O + 2 * G), np.float32)   # rows of the envs that finished are filled in (terminal_observation)
             _native.check(self._lib.xarm_step_host(self._h, actions.ctypes.data, o.ctypes.data, ag.ctypes.data, dg.ctypes.data,
-                                                  r.ctypes.data, d.ctypes.data, s.ctypes.data, t.ctypes.data, self._cur_stream()),
+                                                  r.ctypes.data, d.ctypes.data, s.ctypes.data, t.ctypes.data, term.ctypes.data, None),
                           "xarm_step_host")
             obs = {"observation": o, "achieved_goal": ag, "desired_goal": dg}
-            return obs, r, d.astype(bool), InfoList(self, s, t, d)
+            return obs, r, d.astype(bool), InfoList(self, s, t, d, term)
         actions = torch.as_tensor(actions, device=self.device, dtype=torch.float32)
         assert tuple(actions.shape) == (N, A), "action shape error"
         if actions.data_ptr() != self.actions.data_ptr():

@@ -34,18 +34,25 @@ class XarmVecExtractDictObs:
 
     def step_wait(self):
         obs, reward, done, info = self.venv.step_wait()
-        return obs[self.key], reward, done, info
+        return obs[self.key], reward, done, self._infos(info)
 
     def step(self, actions):
         obs, reward, done, info = self.venv.step(actions)
-        return obs[self.key], reward, done, info
+        return obs[self.key], reward, done, self._infos(info)
+
+    def _infos(self, info):
+        # the env this wrapper stands for ('...NoGoal') has a flat observation: so is its terminal_observation
+        return info.view(key=self.key) if hasattr(info, "view") else info
 
 
 class XarmVecNormalize:
     def __init__(self, venv, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0, clip_reward=10.0, gamma=0.99,
                  epsilon=1e-8, key="observation"):
-        if isinstance(venv, XarmVecExtractDictObs):   # make_vec('XarmPDHandoverNoGoal-v1'): normalise the key it extracts
+        self._flat = isinstance(venv, XarmVecExtractDictObs)
+        if self._flat:   # make_vec('XarmPDHandoverNoGoal-v1'): normalise the key it extracts
             venv, key = venv.venv, venv.key
+        if getattr(venv, "output", "torch") != "torch":
+            raise ValueError("XarmVecNormalize works on device tensors: construct the env with output='torch'")
         self.venv, self.key = venv, key
         self.num_envs, self.device = venv.num_envs, venv.device
         self.obs_dim = int(venv.obs_buf[key].shape[1])
@@ -55,11 +62,12 @@ class XarmVecNormalize:
         self._lib = _native.load()
         cfg = _native.XarmVecNormConfig(num_envs=self.num_envs, obs_dim=self.obs_dim, device=self.device.index or 0, gamma=gamma,
                                         clip_obs=clip_obs, clip_reward=clip_reward, epsilon=epsilon, norm_obs=int(norm_obs),
-                                        norm_reward=int(norm_reward), training=int(training), reserved=0)
+                                        norm_reward=int(norm_reward), training=int(training), reserved=0)  # noqa: E501
         self._h = C.c_void_p()
         _native.check(self._lib.xarm_vecnorm_create(C.byref(cfg), C.byref(self._h)), "xarm_vecnorm_create")
         self.obs_out = torch.empty(self.num_envs, self.obs_dim, device=self.device)
         self.reward_out = torch.empty(self.num_envs, device=self.device)
+        self.terminal_out = torch.zeros(self.num_envs, self.obs_dim, device=self.device)   # normalised terminal observations
         self.old_obs = self.old_reward = None
 
     # VecEnvWrapper surface
@@ -88,15 +96,43 @@ class XarmVecNormalize:
         d8 = done.view(torch.uint8) if done.dtype == torch.bool else done
         _native.check(self._lib.xarm_vecnorm_step(self._h, C.c_void_p(o.data_ptr()), C.c_void_p(rew.data_ptr()), C.c_void_p(d8.data_ptr()),
                                                  C.c_void_p(self.obs_out.data_ptr()), C.c_void_p(self.reward_out.data_ptr()), self._stream()), "xarm_vecnorm_step")
+        # SB3's VecNormalize.step_wait also normalises infos[i]['terminal_observation'] (with the statistics just updated)
+        if self.key == "observation" and hasattr(infos, "view"):
+            term = self.venv.terminal_buf
+            _native.check(self._lib.xarm_vecnorm_normalize_obs(self._h, C.c_void_p(term.data_ptr()), self.num_envs, term.shape[1],
+                                                              C.c_void_p(self.terminal_out.data_ptr()), self.obs_dim, 0, self._stream()), "xarm_vecnorm_normalize_obs")
+            infos = infos.view(key=self.key if self._flat else None, terminal_key_obs=self.terminal_out)
         return self.obs_out, self.reward_out, done, infos
 
-    def normalize(self, obs, reward, done):
-        """The kernels on arbitrary device batches [N, obs_dim], [N], [N] (tests, replay data)."""
-        d8 = done.view(torch.uint8) if done.dtype == torch.bool else done
-        oo, ro = torch.empty_like(obs), torch.empty_like(reward)
-        _native.check(self._lib.xarm_vecnorm_step(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(reward.data_ptr()), C.c_void_p(d8.data_ptr()),
-                                                 C.c_void_p(oo.data_ptr()), C.c_void_p(ro.data_ptr()), self._stream()), "xarm_vecnorm_step")
-        return oo, ro
+    def normalize_obs(self, obs):
+        """VecNormalize.normalize_obs on any device batch [n, obs_dim]: apply only (statistics and returns untouched)."""
+        return self._apply_obs(obs, 0)
+
+    def unnormalize_obs(self, obs):
+        return self._apply_obs(obs, 1)
+
+    def _apply_obs(self, obs, inverse):
+        obs = torch.as_tensor(obs, device=self.device, dtype=torch.float32)
+        single = obs.dim() == 1
+        o2 = obs.reshape(-1, obs.shape[-1]).contiguous()
+        if o2.shape[1] != self.obs_dim:
+            raise ValueError(f"expected [n, {self.obs_dim}] observations, got {tuple(obs.shape)}")
+        out = torch.empty_like(o2)
+        _native.check(self._lib.xarm_vecnorm_normalize_obs(self._h, C.c_void_p(o2.data_ptr()), o2.shape[0], self.obs_dim, C.c_void_p(out.data_ptr()),
+                                                          self.obs_dim, inverse, self._stream()), "xarm_vecnorm_normalize_obs")
+        return out[0] if single else out.reshape(obs.shape)
+
+    def normalize_reward(self, reward):
+        """VecNormalize.normalize_reward on any device batch [n]: apply only."""
+        r = torch.as_tensor(reward, device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(r)
+        _native.check(self._lib.xarm_vecnorm_normalize_reward(self._h, C.c_void_p(r.data_ptr()), r.numel(), C.c_void_p(out.data_ptr()), self._stream()),
+                      "xarm_vecnorm_normalize_reward")
+        return out
+
+    def normalize(self, obs, reward, done=None):
+        """normalize_obs + normalize_reward of a device batch of any size (replay data, evaluation): apply only."""
+        return self.normalize_obs(obs), self.normalize_reward(reward)
 
     def get_original_obs(self):
         return self.old_obs

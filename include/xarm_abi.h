@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define XARM_ABI_VERSION 1
+#define XARM_ABI_VERSION 2
 
 /* tasks: the five env classes of the hot path */
 enum {
@@ -62,7 +62,10 @@ typedef struct XarmConfig {
   int32_t max_episode_steps;  /* 0 = the registered TimeLimit (25/50/50/50/100) [REF gym_xarm/__init__.py:6-22] */
   int32_t auto_reset;         /* 1: VecEnv semantics - a finished env is reset inside xarm_step */
   int32_t device;             /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t stagger_phases;     /* 1: xarm_create / an explicit xarm_reset start env i at step counter (global index mod episode
+                                 length), so that time-limit endings - and with them the auto-reset work - spread evenly over the
+                                 steps instead of arriving as one wave every episode length (no reference counterpart: SubprocVecEnv
+                                 workers drift apart by themselves; off in every parity test) */
   int64_t num_envs;           /* envs in this slab */
   int64_t env_index_base;     /* global index of env 0 of the slab: RNG streams are keyed by the global index */
   uint64_t seed;
@@ -105,10 +108,13 @@ int xarm_reset(XarmHandle* h, const uint8_t* mask, void* stream);
  * when xarm_graph_capture() succeeded for this stream. */
 int xarm_step(XarmHandle* h, void* stream);
 
-/* Same step with HOST buffers (the path SB3's numpy VecEnv uses): copies actions H2D, steps, copies
- * observation|achieved|desired|reward|done|success|truncated D2H, synchronises.  NULL outputs are skipped. */
+/* Same step with HOST buffers (the path SB3's numpy VecEnv uses): copies actions H2D, steps (replaying a CUDA graph of its
+ * own, captured at the first call), copies observation|achieved|desired|reward|done|success|truncated D2H, synchronises.
+ * NULL outputs are skipped.  terminal_observation [N, O + 2 G] (may be NULL): rows of the envs that finished in this step
+ * receive observation|achieved|desired of the step BEFORE the auto-reset (SB3's infos[i]['terminal_observation']); other
+ * rows are left untouched.  Only the finished rows cross PCIe (gathered on the device).  stream NULL = the handle's own. */
 int xarm_step_host(XarmHandle* h, const float* actions, float* observation, float* achieved_goal, float* desired_goal,
-                   float* reward, uint8_t* done, float* success, uint8_t* truncated, void* stream);
+                   float* reward, uint8_t* done, float* success, uint8_t* truncated, float* terminal_observation, void* stream);
 int xarm_reset_host(XarmHandle* h, float* observation, float* achieved_goal, float* desired_goal, void* stream);
 
 /* Env.compute_reward(achieved_goal, desired_goal, info) for HER relabelling: batch form, device pointers
@@ -137,6 +143,10 @@ int xarm_episode_stats(XarmHandle* h, double out[5], void* stream);
  * out[cap] and returns the number of lines.  [no reference counterpart: PyBullet has no per-stage timers] */
 int xarm_set_profiling(XarmHandle* h, int32_t on);
 int xarm_kernel_times(XarmHandle* h, char* out, int64_t cap);
+/* Measured FP32 SIMT peak of `device` in TFLOP/s (the roofline this path is bound by is FP32 issue, and
+ * MEASURED_PEAKS.json has no FP32 figure): 8 independent FMA chains per thread at full occupancy, best of 5 launches of
+ * ~10 ms, CUDA events.  Synchronises the device. */
+int xarm_measure_fp32_peak(int32_t device, double* tflops);
 /* ---- caller side of the path: SB3 VecExtractDictObs + VecNormalize on the device
  * [REF benchmark/train.py:44-62,74-75: make_vec_env -> VecNormalize(env, norm_obs=True, norm_reward=True, clip_obs=10.)].
  * Semantics of stable-baselines3 1.x VecNormalize, pinned by the reference's saved benchmark/saved_data/
@@ -164,6 +174,12 @@ int xarm_vecnorm_reset(XarmVecNorm* v, const float* obs, float* obs_out, void* s
 int xarm_vecnorm_step(XarmVecNorm* v, const float* obs, const float* reward, const uint8_t* done, float* obs_out,
                       float* reward_out, void* stream);
 int xarm_vecnorm_set_training(XarmVecNorm* v, int32_t training);
+/* VecNormalize.normalize_obs / unnormalize_obs (inverse = 1) and normalize_reward on ARBITRARY device batches of n rows: apply
+ * only - neither the running statistics nor the discounted returns change.  Rows may be strided (row_stride / out_stride floats
+ * between rows, >= obs_dim): the observation part of a terminal-observation slab [N, O + 2 G] normalises without a copy. */
+int xarm_vecnorm_normalize_obs(XarmVecNorm* v, const float* obs, int64_t n, int64_t row_stride, float* out, int64_t out_stride,
+                               int32_t inverse, void* stream);
+int xarm_vecnorm_normalize_reward(XarmVecNorm* v, const float* reward, int64_t n, float* out, void* stream);
 /* obs_rms / ret_rms (HOST float64: mean[obs_dim], var[obs_dim], count; mean, var, count) - VecNormalize.save / load */
 int xarm_vecnorm_get_stats(XarmVecNorm* v, double* obs_mean, double* obs_var, double* obs_count, double* ret_stats3);
 int xarm_vecnorm_set_stats(XarmVecNorm* v, const double* obs_mean, const double* obs_var, double obs_count, const double* ret_stats3);

@@ -22,7 +22,7 @@ class XarmConfig(C.Structure):
         ("task", C.c_int32), ("reward_type", C.c_int32), ("num_obj", C.c_int32), ("goal_shape", C.c_int32),
         ("init_grasp_rate", C.c_float), ("goal_ground_rate", C.c_float), ("same_side_rate", C.c_float),
         ("use_stand", C.c_int32), ("max_episode_steps", C.c_int32), ("auto_reset", C.c_int32),
-        ("device", C.c_int32), ("reserved", C.c_int32),
+        ("device", C.c_int32), ("stagger_phases", C.c_int32),
         ("num_envs", C.c_int64), ("env_index_base", C.c_int64), ("seed", C.c_uint64),
     ]
 

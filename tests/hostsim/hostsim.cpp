@@ -134,6 +134,7 @@ HS* hs_create(int task, int reward_type, int num_obj, int goal_shape, double ini
   k.rc.seed = cfg->seed; k.rc.env_index_base = cfg->env_index_base; k.rc.reward_type = cfg->reward_type;
   k.rc.goal_shape = cfg->goal_shape; k.rc.max_episode_steps = cfg->max_episode_steps;
   k.rc.init_grasp_rate = cfg->init_grasp_rate; k.rc.goal_ground_rate = cfg->goal_ground_rate; k.rc.same_side_rate = cfg->same_side_rate;
+  k.rc.stagger = cfg->stagger_phases != 0;
   float* p = h->io.data();
   k.b.actions = p; p += n * o.A; k.b.observation = p; p += n * o.O; k.b.achieved_goal = p; p += n * o.G;
   k.b.desired_goal = p; p += n * o.G; k.b.reward = p; p += n; k.b.success = p; p += n;

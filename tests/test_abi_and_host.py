@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _header_functions():
     src = open(os.path.join(ROOT, "include", "xarm_abi.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(xarm_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(xarm_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(names) == sorted(_native.ABI_SYMBOLS)
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/xarm_abi.h but not exported"
-    assert L.xarm_abi_version() == 1
+    assert L.xarm_abi_version() == _native.ABI_VERSION == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _native.lib_path()], capture_output=True, text=True).stdout
     for n in names:
         assert re.search(rf"\bT {n}\b", out), n

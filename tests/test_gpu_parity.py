@@ -693,3 +693,93 @@ def test_nogoal_flat_obs_id_with_vecnormalize():
     assert float(on.abs().max()) <= 10.0 and vn.obs_rms.count == 64 + 1e-4
     vn.close()
     env.close()
+
+
+def test_numpy_path_infos_carry_terminal_observation():
+    """SB3 contract of the numpy-facing path (xarm_step_host): with auto-reset, infos[i]['terminal_observation'] of a finished
+    env is the observation dict of the step BEFORE the reset - equal, bit for bit, to the torch path's terminal slab; the
+    returned observation is already the next episode's.  (Off-policy SB3 algorithms and HerReplayBuffer store it as next_obs.)"""
+    import torch
+    from gym_xarm_b200 import XarmVecEnv
+    n = 512
+    et = XarmVecEnv("pick_and_place", n, device="cuda:0", seed=4, max_episode_steps=7)
+    en = XarmVecEnv("pick_and_place", n, device="cuda:0", seed=4, max_episode_steps=7, output="numpy")
+    et.reset()
+    en.reset()
+    rng = np.random.default_rng(8)
+    seen = 0
+    for t in range(16):
+        a = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        ot, rt, dt, it = et.step(torch.from_numpy(a).cuda())
+        on, rn, dn, inf = en.step(a)
+        assert np.array_equal(dt.cpu().numpy(), dn) and np.array_equal(ot["observation"].cpu().numpy(), on["observation"])
+        term = et.terminal_buf.cpu().numpy()
+        O, G = et.obs_dim, et.goal_dim
+        for i in np.flatnonzero(dn):
+            to = inf[int(i)]["terminal_observation"]
+            assert np.array_equal(to["observation"], term[i, :O]) and np.array_equal(to["achieved_goal"], term[i, O:O + G])
+            assert np.array_equal(to["desired_goal"], term[i, O + G:])
+            assert not np.array_equal(to["observation"], on["observation"][i])      # the returned obs is the reset one
+            ti = it[int(i)]["terminal_observation"]
+            assert np.array_equal(ti["observation"], to["observation"])
+            seen += 1
+        for i in np.flatnonzero(~dn)[:4]:
+            assert "terminal_observation" not in inf[int(i)]
+    assert seen >= 2 * n
+    et.close()
+    en.close()
+
+
+def test_vecnormalize_terminal_observation_and_apply_only():
+    """SB3 VecNormalize semantics beyond step(): (1) infos[i]['terminal_observation'] is normalised with the statistics of the
+    step (and is the flat array under the NoGoal id); (2) normalize_obs / unnormalize_obs / normalize_reward on batches of ANY
+    size are apply-only: running statistics and discounted returns do not move."""
+    import torch
+    import gym_xarm_b200 as gx
+    n = 256
+    env = gx.make_vec("XarmPDHandoverNoGoal-v1", n, device="cuda:0", seed=2, max_episode_steps=5)
+    vn = gx.XarmVecNormalize(env)
+    vn.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(5):
+        a = torch.rand(n, 8, generator=g, device="cuda") * 2 - 1
+        o, r, d, infos = vn.step(a)
+    assert bool(d.all())
+    om = vn.obs_rms
+    raw_term = env.venv.terminal_buf[:, :29].cpu().numpy().astype(np.float64)
+    want = np.clip((raw_term - om.mean) / np.sqrt(om.var + 1e-8), -10, 10)
+    for i in (0, 17, n - 1):
+        to = infos[i]["terminal_observation"]
+        assert to.shape == (29,)
+        np.testing.assert_allclose(to, want[i], atol=2e-4)
+    before = (vn.obs_rms, vn.ret_rms)
+    x = torch.randn(1000, 29, device="cuda") * 3
+    y = vn.normalize_obs(x)
+    np.testing.assert_allclose(y.cpu().numpy(), np.clip((x.cpu().numpy().astype(np.float64) - om.mean) / np.sqrt(om.var + 1e-8), -10, 10), atol=2e-4)
+    small = torch.randn(7, 29, device="cuda") * 0.5 + torch.from_numpy(om.mean).float().cuda()
+    back = vn.unnormalize_obs(vn.normalize_obs(small))
+    np.testing.assert_allclose(back.cpu().numpy(), small.cpu().numpy(), atol=1e-4, rtol=1e-4)
+    rr = vn.normalize_reward(torch.linspace(-3, 3, 33, device="cuda"))
+    np.testing.assert_allclose(rr.cpu().numpy(), np.clip(np.linspace(-3, 3, 33) / np.sqrt(vn.ret_rms.var + 1e-8), -10, 10), atol=1e-5)
+    after = (vn.obs_rms, vn.ret_rms)
+    assert np.array_equal(before[0].mean, after[0].mean) and before[0].count == after[0].count and before[1] == after[1]
+    vn.close()
+    env.close()
+
+
+def test_stagger_phases_spreads_the_time_limit_endings():
+    """stagger_phases (bench.py's default workload): env i starts at step counter (global index mod episode length), so every
+    step ends ~N / episode-length episodes by time limit instead of all N at once; without it the same envs end together."""
+    import torch
+    from gym_xarm_b200 import XarmVecEnv
+    n, L = 4000, 25
+    env = XarmVecEnv("reach", n, device="cuda:0", seed=3, stagger_phases=True, env_index_base=7)
+    env.reset()
+    assert np.array_equal(env.get_state()[:, -5], (np.arange(n) + 7) % L)
+    a = torch.zeros(n, 4, device="cuda")
+    counts = []
+    for t in range(2 * L):
+        _, _, d, infos = env.step(a)
+        counts.append(int(d.sum()))
+    assert min(counts) == max(counts) == n // L
+    env.close()
