@@ -427,8 +427,12 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
       _Pragma("unroll") for (int i = N - 1; i >= 0; i--) DELA_UNIT(i)
       if (lim_any) { _Pragma("unroll") for (int i = N - 1; i >= 0; i--) DELA_LIMIT(i) }
     }
-    // ---- normal rows
+    // ---- normal rows.  The Delassus column of row c is loaded BEFORE the row's update chain (it does not depend on the
+    // solve): a lane past this env's contacts (the other env of the warp has more) broadcasts an exact zero, so it may read
+    // any finite column - column 0, always built - and the loads need no branch (shared-memory latency off the critical path).
     for (int c = 0; c < nc_max; c++) {
+      const float* c_ = A + (c < nc ? D::NU + 3 * c : 0) * 64 + l;
+      const float a0 = c_[0], a1 = c_[16], a2 = c_[32], a3 = c_[48];
       const float x_ = fmaf(-s0, dinv0, cn);
       const float xn_ = fminf(fmaxf(x_, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
       const float d0 = xn_ - appn;
@@ -436,11 +440,13 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
       const bool own_ = l == c;
       appn = own_ ? xn_ : appn; cn = fmaf(-appn, cfmr0, appn + rhs0);
       bad = bad || (own_ && fabsf(d0) > sthr * dinv_t);
-      if (c < nc) DELA_APPLY(D::NU + 3 * c, d_)  // (columns past this env's rows were never built)
+      s0 = fmaf(a0, d_, s0); s1 = fmaf(a1, d_, s1); s2 = fmaf(a2, d_, s2); s3 = fmaf(a3, d_, s3);
     }
     // ---- friction pairs (implicit cone)
     const float lim = mu * appn, lim2 = lim * lim;
     for (int c = 0; c < nc_max; c++) {
+      const float* c_ = A + (c < nc ? D::NU + 3 * c + 1 : 0) * 64 + l;
+      const float p0 = c_[0], p1 = c_[16], p2 = c_[32], p3 = c_[48], q0 = c_[64], q1 = c_[80], q2 = c_[96], q3 = c_[112];
       float xa = fmaf(-s1, di1, ca), xb = fmaf(-s2, di2, cb);
       const float l2 = xa * xa + xb * xb;
       const float sc = l2 > lim2 ? lim * rsqrtf(l2) : 1.f;
@@ -450,11 +456,8 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
       const bool own_ = l == c;
       app1 = own_ ? xa : app1; app2 = own_ ? xb : app2; ca = app1 + rhs1; cb = app2 + rhs2;
       bad = bad || (own_ && (fabsf(da) > sthr * di1_t || fabsf(db) > sthr * di2_t));
-      if (c < nc) {
-        const float* c_ = A + (D::NU + 3 * c + 1) * 64 + l;
-        s0 += c_[0] * da_ + c_[64] * db_; s1 += c_[16] * da_ + c_[80] * db_;
-        s2 += c_[32] * da_ + c_[96] * db_; s3 += c_[48] * da_ + c_[112] * db_;
-      }
+      s0 += p0 * da_ + q0 * db_; s1 += p1 * da_ + q1 * db_;
+      s2 += p2 * da_ + q2 * db_; s3 += p3 * da_ + q3 * db_;
     }
     const uint32_t bb = __ballot_sync(FULL, bad);
     if (!done && ((bb >> (threadIdx.x & 16)) & 0xffffu) == 0u) {  // this env is finished: switch its rows off

@@ -97,30 +97,43 @@ __global__ void __launch_bounds__(128) k_pipe_action(KArgs a) {
 #ifndef XARM_LIGHT_MINB
 #define XARM_LIGHT_MINB 4
 #endif
-template <class T>
-__global__ void __launch_bounds__(128, XARM_SETUP_MINB) k_pipe_setup(KArgs a, int sub, int* heavy_count) {
+// (A 255-register form of this kernel with the link passes unrolled - every array in registers - was measured for the short
+// lists of the auto-reset tail: 70 us per launch against 71 us.  ncu on tail-sized launches: no_instruction is 8 of 12.5 stall
+// cycles per issue - a lone warp per SM is bound by instruction fetch and branch bubbles of ~130 KB of once-executed code, not
+// by the thread-local arrays.  profiles/r2c_*.)
+#define XARM_LAT_MAX 4096
+template <class T, bool LAT>
+__device__ __forceinline__ void setup_body(const KArgs& a, int sub, int* heavy_count) {
+  if (a.list && a.light_dual && LAT != (*a.list_count <= XARM_LAT_MAX)) return;
   if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + 3 + a.tl_branch, (unsigned long long)(a.list ? *a.list_count : a.n));
   PIPE_LEAVE_RESERVED(a)
   tl_mark(a, 0);
   PIPE_FOR_EACH(a, t, i) {
-    const bool heavy = i >= 0 && pipe_setup<T>(a, i, sub);
+    const bool heavy = i >= 0 && pipe_setup<T, LAT>(a, i, sub);
     list_append(heavy, i, a.heavy_list, heavy_count, a.heavy_dir);
   }
   tl_mark(a, 1);
 }
+template <class T>
+__global__ void __launch_bounds__(128, XARM_SETUP_MINB) k_pipe_setup(KArgs a, int sub, int* heavy_count) { setup_body<T, false>(a, sub, heavy_count); }
+
 // Two register budgets of the same light kernel.  LAT = false: 128 registers (some spills), 4 blocks per SM - the
 // throughput form (main branch, reset waves).  LAT = true: 160 registers (no hot spills: 86 instead of 121 us per warp) -
 // the latency form for SHORT lists (the auto-reset tail of an ordinary step).  A list launch carries both; each looks at
 // the list size and one of them leaves at once (the register budget is fixed per launch, the list size is not known on
 // the host).
-#define XARM_LIGHT_LAT_MAX 4096
-template <class T, bool LAT>
+#define XARM_LIGHT_LAT_MAX XARM_LAT_MAX
+template <class T, bool LAT, bool REGROWS = false>
 __device__ __forceinline__ void light_body(const KArgs& a) {
   extern __shared__ float light_mrows[];  // [XARM_MROW_WORDS][128]: the manifold rows of this block's envs
   PIPE_LEAVE_RESERVED(a)
   if (a.list && a.light_dual && LAT != (*a.list_count <= XARM_LIGHT_LAT_MAX)) return;
   tl_mark(a, 0);
-  PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_light<T>(a, i, light_mrows + threadIdx.x, 128); }
+  if constexpr (REGROWS) {   // tail form: the manifold rows in registers too (static indices after unrolling)
+    PIPE_FOR_EACH(a, t, i) { if (i >= 0) { float mr[XARM_MROW_WORDS]; pipe_light<T>(a, i, mr, 1); } }
+  } else {
+    PIPE_FOR_EACH(a, t, i) { if (i >= 0) pipe_light<T>(a, i, light_mrows + threadIdx.x, 128); }
+  }
   tl_mark(a, 1);
 }
 template <class T>
@@ -130,6 +143,9 @@ __global__ void __launch_bounds__(128, 4) k_pipe_light(KArgs a) { light_body<T, 
 #endif
 template <class T>
 __global__ void __maxnreg__(XARM_LIGHT_LAT_REGS) k_pipe_light_lat(KArgs a) { light_body<T, true>(a); }
+// tail form: 255 registers, no shared memory - for the short lists of the early branch (one warp per SM)
+template <class T>
+__global__ void __maxnreg__(255) k_pipe_light_tail(KArgs a) { light_body<T, true, true>(a); }
 // Heavy envs of this substep.  One warp per block, a few blocks per SM at most: the contact rows of the generic solver
 // (Contacts<T>, ~6 KB per env) live in SHARED memory, one record per lane at an odd word stride (bank-conflict free).
 // In thread-local memory the 50 sweeps stream every row from L2 again (160 KB per warp per sweep) and one heavy warp
@@ -379,6 +395,8 @@ struct PipeCtx {
   // gets a work counter and the mask of the SMs it must leave to the early branch
   bool dyn = false;
   bool light_dual = true;   // XARM_LIGHT_DUAL=0: one light kernel form everywhere
+  bool main_fork = true;    // XARM_MAIN_FORK=0: the main branch of a split step keeps one stream (heavy kernels, then light)
+  bool tail_lat = true;     // XARM_TAIL_LAT=0: the early branch keeps the round-1 kernels (128-register setup, 160-register light with shared-memory rows)
   bool light_main_lat = true;    // XARM_LIGHT_MAIN_LAT=0: the partitioned main branch keeps the 128-register form (A/B)
   int setup_bps = 4;   // resident blocks per SM of the partitioned main branch's setup kernel (XARM_SETUP_BPS)
   int reserve_sms = 0, n_work = 0, next_work = 0;
@@ -524,7 +542,8 @@ struct OpsT {
         if (c.cur_branch == 'E' && c.light_dual) {   // short list -> latency form, long list -> throughput form
           KArgs al = c.tl(a);
           al.light_dual = 1;
-          k_pipe_light_lat<T><<<XARM_LIGHT_LAT_MAX / 128, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(al);
+          if (c.tail_lat) k_pipe_light_tail<T><<<XARM_LIGHT_LAT_MAX / 128, 128, 0, s>>>(al);
+          else k_pipe_light_lat<T><<<XARM_LIGHT_LAT_MAX / 128, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(al);
           k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(al);
           g_launches++;
         } else if (part && c.light_main_lat) {   // partitioned main branch: nothing runs next to it on its SMs - 3 blocks of the 160-register form
@@ -601,7 +620,8 @@ struct OpsT {
     m.list = c.list_m; m.list_count = c.count_m;
     c.cur_branch = 'M';
     c.dyn = true; c.next_work = 0;
-    step_branch(c, m, 0, false, s, s);
+    // the main branch's heavy kernels (few envs: latency bound) run on a side stream next to its light kernel
+    step_branch(c, m, 0, false, s, c.main_fork ? c.side : s);
     c.dyn = false;
     cudaStreamWaitEvent(s, join, 0);
     // late tail: envs of the main branch that finished although the predictor said no (normally none)
@@ -764,7 +784,10 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) CREATE_FAIL(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed");
   }
   {  // SMs reserved for the early branch of a split step
-    const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 32;  // of 148: main branch (116 SMs) and early branch then take about equally long
+    // Round 2 (staggered phases: ~2.7 k finishers in EVERY step): the early branch is a latency chain of 105 substeps whatever the
+    // number of SMs it owns (36.7 ms with 32 reserved SMs, 38.5 ms with none), while the main branch loses the SMs it leaves
+    // (21 ms on 116 SMs, 15 ms on 148): reservation is off by default now.
+    const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 0;
     if (want > 0 && ops.hrec_words() > 0) {
       unsigned* d_seen = nullptr;
       unsigned seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -785,6 +808,8 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   }
   if (getenv("XARM_SETUP_BPS")) h->pipe.setup_bps = atoi(getenv("XARM_SETUP_BPS"));
   h->pipe.light_dual = !(getenv("XARM_LIGHT_DUAL") && atoi(getenv("XARM_LIGHT_DUAL")) == 0);
+  h->pipe.main_fork = !(getenv("XARM_MAIN_FORK") && atoi(getenv("XARM_MAIN_FORK")) == 0);
+  h->pipe.tail_lat = !(getenv("XARM_TAIL_LAT") && atoi(getenv("XARM_TAIL_LAT")) == 0);
   h->pipe.light_main_lat = !(getenv("XARM_LIGHT_MAIN_LAT") && atoi(getenv("XARM_LIGHT_MAIN_LAT")) == 0);
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
   h->pipe.timeline = getenv("XARM_TIMELINE") != nullptr;

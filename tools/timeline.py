@@ -8,7 +8,7 @@ from gym_xarm_b200 import XarmVecEnv, _native
 import bench
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
-env = XarmVecEnv("pick_and_place", n, config=bench.bench_config("pick_and_place"), device="cuda:0", seed=0, auto_reset=True)
+env = XarmVecEnv("pick_and_place", n, config=bench.bench_config("pick_and_place"), device="cuda:0", seed=0, auto_reset=True, stagger_phases=bool(os.environ.get("STAGGER")))
 env.reset()
 if not os.environ.get("NO_GRAPH"):
     env.capture_graph()
