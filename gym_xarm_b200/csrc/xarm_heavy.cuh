@@ -291,13 +291,19 @@ struct DelaLayout {
 #define RL(p) (*(p))
 #define RL4(p) (*(p))
 #endif
-template <class T>
-__device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec, float* sm, int l, bool valid) {
+// COMPACT (the fused kernel, record in shared memory): a row is [M^-1 J^T (15) pad | rhs dinv cfmr mu] = 20 words and the lane's
+// own J rows arrive in registers (Jr[3][16]: the lane that built them keeps them) - 4.2 KB instead of 7.2 KB of rows per env.
+template <class T, bool COMPACT = false>
+__device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec, float* sm, int l, bool valid, const float (*Jr)[16] = nullptr) {
   using R = HeavyRec<T>;
   using D = DelaLayout<T>;
+  constexpr int RS = COMPACT ? 20 : R::ROW, VO = COMPACT ? 0 : 16, CO = COMPACT ? 16 : 32;
   using MD = typename T::MD;
   constexpr int N = R::N;
   constexpr unsigned FULL = 0xffffffffu;
+#ifdef XARM_FUSED_PROF
+  const long long dp0_ = clock64();
+#endif
   float* A = sm;
   float* Vu = sm + D::VU;
   float* lam = sm + D::LAM;
@@ -316,18 +322,23 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
   float Jn[16], Ja[16], Jb[16];
   float rhs0 = 0.f, dinv0 = 1.f, cfmr0 = 0.f, rhs1 = 0.f, di1 = 1.f, rhs2 = 0.f, di2 = 1.f, mu = 0.f;
   {
-    const float4* r4 = reinterpret_cast<const float4*>(rec + R::HDR + (own_c ? l * 3 : 0) * R::ROW);
+    const float4* r4 = reinterpret_cast<const float4*>(rec + R::HDR + (own_c ? l * 3 : 0) * RS);
+    if constexpr (COMPACT) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const float4 a = own_c ? RL4(r4 + u) : make_float4(0, 0, 0, 0);
-      const float4 b = own_c ? RL4(r4 + R::ROW / 4 + u) : make_float4(0, 0, 0, 0);
-      const float4 c = own_c ? RL4(r4 + 2 * (R::ROW / 4) + u) : make_float4(0, 0, 0, 0);
-      Jn[4 * u] = a.x; Jn[4 * u + 1] = a.y; Jn[4 * u + 2] = a.z; Jn[4 * u + 3] = a.w;
-      Ja[4 * u] = b.x; Ja[4 * u + 1] = b.y; Ja[4 * u + 2] = b.z; Ja[4 * u + 3] = b.w;
-      Jb[4 * u] = c.x; Jb[4 * u + 1] = c.y; Jb[4 * u + 2] = c.z; Jb[4 * u + 3] = c.w;
+      for (int q = 0; q < 16; q++) { Jn[q] = own_c ? Jr[0][q] : 0.f; Ja[q] = own_c ? Jr[1][q] : 0.f; Jb[q] = own_c ? Jr[2][q] : 0.f; }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const float4 a = own_c ? RL4(r4 + u) : make_float4(0, 0, 0, 0);
+        const float4 b = own_c ? RL4(r4 + RS / 4 + u) : make_float4(0, 0, 0, 0);
+        const float4 c = own_c ? RL4(r4 + 2 * (RS / 4) + u) : make_float4(0, 0, 0, 0);
+        Jn[4 * u] = a.x; Jn[4 * u + 1] = a.y; Jn[4 * u + 2] = a.z; Jn[4 * u + 3] = a.w;
+        Ja[4 * u] = b.x; Ja[4 * u + 1] = b.y; Ja[4 * u + 2] = b.z; Ja[4 * u + 3] = b.w;
+        Jb[4 * u] = c.x; Jb[4 * u + 1] = c.y; Jb[4 * u + 2] = c.z; Jb[4 * u + 3] = c.w;
+      }
     }
     if (own_c) {
-      const float4 k0 = RL4(r4 + 8), k1 = RL4(r4 + R::ROW / 4 + 8), k2 = RL4(r4 + 2 * (R::ROW / 4) + 8);
+      const float4 k0 = RL4(r4 + CO / 4), k1 = RL4(r4 + RS / 4 + CO / 4), k2 = RL4(r4 + 2 * (RS / 4) + CO / 4);
       rhs0 = k0.x; dinv0 = k0.y; cfmr0 = k0.z; mu = k0.w;
       rhs1 = k1.x; di1 = k1.y; rhs2 = k2.x; di2 = k2.y;
     }
@@ -364,7 +375,7 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
   }
 #pragma unroll 4
   for (int k = D::NU; k < Rn; k++) {
-    const float* row = rec + R::HDR + (k - D::NU) * R::ROW + 16;
+    const float* row = rec + R::HDR + (k - D::NU) * RS + VO;
     const float4* v4 = reinterpret_cast<const float4*>(row);
     const float4 V0 = RL4(v4), V1 = RL4(v4 + 1), V2 = RL4(v4 + 2), V3 = RL4(v4 + 3);
     const float vl = l < N ? RL(row + l) : (l == N ? RL(row + MD::F1) + gr * RL(row + MD::F2) : 0.f);
@@ -379,6 +390,10 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
   // Limit rows carry the SIGNED impulse q = sign * app in sign * [0, hi]: x = q + sign * rhs - s3 * den, and the
   // broadcast delta is already the joint-space one.  A finished env (exit test) has its rows switched off: dinv = 0,
   // c = app, so every delta is exactly zero.
+#ifdef XARM_FUSED_PROF
+  const long long dp1_ = clock64();
+  int its_ = 0;
+#endif
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   float appn = 0.f, app1 = 0.f, app2 = 0.f, mapp = 0.f, q = 0.f;
   const int nc_max = max(nc, __shfl_xor_sync(FULL, nc, 16));
@@ -466,8 +481,14 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
       dinv0 = 0.f; cfmr0 = 0.f; rhs0 = 0.f; cn = appn;
       di1 = 0.f; di2 = 0.f; rhs1 = 0.f; rhs2 = 0.f; ca = app1; cb = app2; mu = 1e30f;   // (cone never bites: impulses stay)
     }
+#ifdef XARM_FUSED_PROF
+    its_++;
+#endif
     if (__all_sync(FULL, done)) break;
   }
+#ifdef XARM_FUSED_PROF
+  if (blockIdx.x == 0 && threadIdx.x == 0) printf("[dela prof] nc %d nc_max %d | build %lld | %d sweeps %lld cycles\n", nc, nc_max, dp1_ - dp0_, its_, clock64() - dp1_);
+#endif
 #undef DELA_APPLY
 #undef DELA_UNIT
 #undef DELA_LIMIT
@@ -479,8 +500,8 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
 #pragma unroll
   for (int k = 0; k < D::NU; k++) u0 += Vu[k * 16 + l] * lam[k];
   for (int k = D::NU; k < Rn; k += 2) {
-    u0 += RL(rec + R::HDR + (k - D::NU) * R::ROW + 16 + l) * lam[k];
-    if (k + 1 < Rn) u1 += RL(rec + R::HDR + (k + 1 - D::NU) * R::ROW + 16 + l) * lam[k + 1];
+    u0 += RL(rec + R::HDR + (k - D::NU) * RS + VO + l) * lam[k];
+    if (k + 1 < Rn) u1 += RL(rec + R::HDR + (k + 1 - D::NU) * RS + VO + l) * lam[k + 1];
   }
   __syncwarp();
   return u0 + u1;
@@ -632,6 +653,239 @@ __device__ __forceinline__ void heavy_integrate_coop(const KArgs& a, int t, bool
       st[(int64_t)(w0 + 10) * n + i] = b.w.x; st[(int64_t)(w0 + 11) * n + i] = b.w.y; st[(int64_t)(w0 + 12) * n + i] = b.w.z;
     }
   }
+}
+
+// ---- Fused heavy substep: collision, rows and the impulse-space joint loop in ONE launch, 16 lanes per env.
+// Round 1 ran k_heavy_rows (one THREAD per env: generic collision + rows through a 5.8 KB thread-local Contacts record into
+// a 7.2 KB global record) and then k_heavy_solve2.  In the auto-reset tail of a step that is two dependent launches per
+// substep, each at the latency floor of a lone warp (~60 + ~115 us), 105 substeps in sequence.  Here the 16 lanes of the env
+// share that work: lane p < 4 collides pair p (lego-table, finger1-lego, finger2-lego, hand-lego: the fixed pair order of
+// sub_setup; with MAXC = 16 = 4 pairs x 4 points and XARM_MAXAC = 12 = 3 gripper pairs x 4 no cap can bite, so the pairs are
+// independent), lane c < nc builds the three rows of contact c with the arithmetic of sub_setup's row loop
+// (setupMultiBodyContactConstraint), lanes 0..9 build the arm's motor / limit / gear rows (arm_rows), and the
+// record stays in shared memory, in the HeavyRec layout heavy_solve_dela reads.  Same results as k_heavy_rows + k_heavy_solve2
+// bit for bit (tests/test_gpu_parity.py::test_fused_heavy_kernel_equals_rows_then_solve).
+template <class T>
+struct FusedLayout {
+  using R = HeavyRec<T>;
+  static constexpr int CROW = 20;                     // compact row: M^-1 J^T (15) pad | rhs dinv cfmr mu (J stays in the owner lane's registers)
+  static constexpr int REC = 0;                       // the record: header + compact rows
+  static constexpr int DELA = (R::HDR + T::MAXC * 3 * CROW + 31) / 32 * 32;   // DelaLayout slot (bank-aligned: a multiple of 32 words)
+  // scratch that lives where the Delassus matrix is built later: dynamics pass of the setup kernel, env state, contact points
+  static constexpr int DYN = DELA;                    // 126 words (dyn_store order)
+  static constexpr int ST = DYN + 128;                // state words 0..39 (q, qd, qt, object) | 40, 41: the two grasp words
+  static constexpr int PTS = ST + 48;                 // [4 pairs][4 points][pa 3 | pb 3 | n 3 | depth]
+  static constexpr int CNT = PTS + 160;               // points per pair [4]
+  static constexpr int SLOT = DELA + DelaLayout<T>::SLOT;   // = 16 mod 32: the two envs of a warp use different banks
+  static_assert(DELA % 32 == 0 && SLOT % 32 == 16 && CNT + 4 <= DELA + DelaLayout<T>::A_WORDS, "fused heavy kernel: shared-memory layout");
+  static_assert(T::NARM == 1 && T::NOBJ == 1 && T::NTABLE == 1 && !T::HAS_GROUND && !T::FINGER_TABLE && T::MAXC >= 16 && XARM_MAXAC >= 12,
+                "fused heavy kernel: one arm, one object, one table; the contact caps never bite");
+};
+
+template <class T>
+__device__ __forceinline__ void heavy_fused_body(const KArgs& a, int t, bool valid, int sub, float* sm, int l) {
+  using R = HeavyRec<T>;
+  using F = FusedLayout<T>;
+  using MD = typename T::MD;
+  constexpr int N = R::N;
+  constexpr unsigned FULL = 0xffffffffu;
+  const float h = (float)T::H;
+  const int64_t n = a.n;
+  const int64_t i = valid ? (int64_t)a.heavy_list[a.heavy_dir * t] : 0;
+#ifdef XARM_FUSED_PROF
+  long long pc_[8]; int pn_ = 0;
+#define FPROF() pc_[pn_++] = clock64();
+#else
+#define FPROF()
+#endif
+  FPROF()
+  float* rec = sm + F::REC;
+  float* dyn = sm + F::DYN;
+  float* st = sm + F::ST;
+  float* pts = sm + F::PTS;
+  float* cnt = sm + F::CNT;
+  // ---- the dynamics pass the setup kernel left in the scratch slab, and the env state
+  if (valid) {
+    for (int w = l; w < pipe_dyn_words<T>(); w += 16) dyn[w] = a.scratch[(int64_t)w * n + i];
+    for (int w = l; w < 40; w += 16) st[w] = a.state[(int64_t)w * n + i];
+    if (l < 2) st[40 + l] = a.state[(int64_t)(state_words<T>() - 2 + l) * n + i];
+  }
+  __syncwarp();
+  const float* Minv = dyn + 6 * N;
+  const float* qdu = Minv + R::NT;
+  const float* Rh = qdu + N;
+  const V3 opos = v3(st[27], st[28], st[29]);
+  Q4 oq; oq.x = st[30]; oq.y = st[31]; oq.z = st[32]; oq.w = st[33];
+  const M3 oR = quat_to_m3(oq);
+  const int grasp_cmd0 = ((int)st[40] >> 1) & 1;
+  FPROF()
+  // ---- 1. collision: lane p collides pair p
+  if (valid && l < 4) {
+    Box ob; ob.c = opos; ob.R = oR; ob.h = v3(T::OBJ_HX, T::OBJ_HY, T::OBJ_HZ);
+    Box A, B;
+    if (l == 0) {
+      A = ob;
+      B.c = v3(T::table_x(0), 0.f, -(float)XARM_TABLE_HALF_Z); B.R = m3_identity();
+      B.h = v3((float)XARM_TABLE_HALF_X, (float)XARM_TABLE_HALF_Y, (float)XARM_TABLE_HALF_Z);
+    } else {
+      ArmDyn<MD> D;
+#pragma unroll
+      for (int k = 0; k < 9; k++) D.Rh.m[k] = Rh[k];
+      D.ph = v3(Rh[9], Rh[10], Rh[11]); D.pf1 = v3(Rh[12], Rh[13], Rh[14]); D.pf2 = v3(Rh[15], Rh[16], Rh[17]);
+      A = arm_box<T>(D, l == 3 ? 0 : l);   // pair 1: finger 1, pair 2: finger 2, pair 3: hand
+      B = ob;
+    }
+    int k = 0;
+    CPoint cp[4];
+    const V3 d = A.c - B.c;
+    const float rr = norm(A.h) + norm(B.h) + (float)XARM_CONTACT_MARGIN;
+    if (!(dot(d, d) > rr * rr)) k = box_box(A, B, cp, 4);
+    cnt[l] = (float)k;
+    for (int j = 0; j < k; j++) {
+      float* o = pts + (l * 4 + j) * 10;
+      o[0] = cp[j].pa.x; o[1] = cp[j].pa.y; o[2] = cp[j].pa.z; o[3] = cp[j].pb.x; o[4] = cp[j].pb.y; o[5] = cp[j].pb.z;
+      o[6] = cp[j].n.x; o[7] = cp[j].n.y; o[8] = cp[j].n.z; o[9] = cp[j].depth;
+    }
+  }
+  __syncwarp();
+  FPROF()
+  const int c0 = valid ? (int)cnt[0] : 0, c1 = valid ? (int)cnt[1] : 0, c2 = valid ? (int)cnt[2] : 0, c3 = valid ? (int)cnt[3] : 0;
+  const int nc = c0 + c1 + c2 + c3;
+  // ---- 2. unconstrained velocity of the object, its world inverse inertia (every lane: a few dozen flops)
+  const V3 bv = v3(st[34], st[35], st[36]), bw = v3(st[37], st[38], st[39]);
+  const float kl = (float)XARM_MB_LINEAR_DAMPING * (1.f + norm(bv)), ka = (float)XARM_MB_ANGULAR_DAMPING * (1.f + norm(bw));
+  V3 vu = bv + h * ((-kl) * bv); vu.z -= h * (float)XARM_GRAVITY;
+  const V3 wu = bw + h * ((-ka) * bw);
+  const float lx = 2 * T::OBJ_HX, ly = 2 * T::OBJ_HY, lz = 2 * T::OBJ_HZ, m12 = T::OBJ_MASS / 12.f;
+  const S3 Il = {1.f / (m12 * (ly * ly + lz * lz)), 0, 0, 1.f / (m12 * (lx * lx + lz * lz)), 0, 1.f / (m12 * (lx * lx + ly * ly))};
+  const S3 Iinv = rotate_sym(oR, Il);
+  // ---- 3. the header: inverse joint inertia, motor / limit / gear rows (arm_rows), unconstrained velocities, nc
+  {
+    for (int w = l; w < R::HDR; w += 16) rec[w] = w < R::NT ? Minv[w] : 0.f;
+    __syncwarp();
+    uint32_t lo = 0u, hi = 0u;
+    if (l < N) {
+      const float den = Minv[tri(l, l)], qu = qdu[l], q = st[l], qt = st[2 * N + l];
+      const float pen_lo = q - MD::lo(l), pen_hi = MD::hi(l) - q;
+      float lr = 0.f;
+      if (pen_lo <= 0.f) { lo = 1u; lr = (-pen_lo * (float)XARM_ERP / h - qu) / den; }
+      else if (pen_hi <= 0.f) { hi = 1u; lr = (-pen_hi * (float)XARM_ERP / h + qu) / den; }
+      const float target = (float)(XARM_MOTOR_KP * XARM_MOTOR_ERP) * (qt - q) / h;
+      rec[R::LRHS + l] = lr;
+      rec[R::MRHS + l] = (target - qu) / den;
+      rec[R::QDU + l] = qu;
+    }
+    const uint32_t blo = (__ballot_sync(FULL, lo != 0u) >> (threadIdx.x & 16)) & 0x1ffu;
+    const uint32_t bhi = (__ballot_sync(FULL, hi != 0u) >> (threadIdx.x & 16)) & 0x1ffu;
+    if (l == N) {
+      const float gr = (float)XARM_GEAR_RATIO;
+      const int f1 = MD::F1, f2 = MD::F2 < 0 ? 0 : MD::F2;
+      const float den = Minv[tri(f1, f1)] + 2.f * gr * Minv[tri(f1, f2)] + gr * gr * Minv[tri(f2, f2)];
+      const float rel = qdu[f1] + gr * qdu[f2];
+      const float pos_err = (float)XARM_GEAR_ERP * (st[f1] + gr * st[f2]);
+      rec[R::GEAR] = (-pos_err * (float)XARM_ERP / h - rel) / den; rec[R::GEAR + 1] = 1.f / den; rec[R::GEAR + 2] = den;
+      rec[R::LIM] = (float)blo; rec[R::LIM + 1] = (float)bhi;
+      rec[R::VU] = vu.x; rec[R::VU + 1] = vu.y; rec[R::VU + 2] = vu.z;
+      rec[R::WU] = wu.x; rec[R::WU + 1] = wu.y; rec[R::WU + 2] = wu.z;
+      rec[R::NC] = (float)nc;
+    }
+  }
+  FPROF()
+  // ---- 4. rows of contact l (normal + two friction directions), as sub_setup's row loop
+  float Jr[3][16];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+#pragma unroll
+    for (int q = 0; q < 16; q++) Jr[k][q] = 0.f;
+  if (l < nc) {
+    const int p = l < c0 ? 0 : (l < c0 + c1 ? 1 : (l < c0 + c1 + c2 ? 2 : 3));
+    const int j = l - (p == 0 ? 0 : (p == 1 ? c0 : (p == 2 ? c0 + c1 : c0 + c1 + c2)));
+    const float* o = pts + (p * 4 + j) * 10;
+    const V3 pa = v3(o[0], o[1], o[2]), pb = v3(o[3], o[4], o[5]), nrm = v3(o[6], o[7], o[8]);
+    const float depth = o[9];
+    const bool arm = p > 0;            // pairs 1..3: side A is a gripper link, side B the object; pair 0: side A the object
+    const bool soft = p == 1 || p == 2;
+    const float fo = (float)XARM_DEFAULT_FRICTION;
+    const float ff = (T::FRICTION_SWITCH && grasp_cmd0) ? (float)XARM_FINGER_FRICTION_GRASP : (float)XARM_FINGER_FRICTION_FREE;
+    const float mu = fminf(p == 0 ? fo * (float)XARM_TABLE_FRICTION : (soft ? ff * fo : fo * fo), (float)XARM_MAX_FRICTION);
+    float erp = (float)XARM_ERP2, cfm0 = 0.f;
+    if (soft) {
+      const float ks = (float)XARM_FINGER_STIFFNESS, kd = (float)XARM_FINGER_DAMPING;
+      cfm0 = 1.f / (h * ks + kd); erp = h * ks / (h * ks + kd); cfm0 /= h;
+    }
+    V3 dir[3];
+    dir[0] = nrm;
+    plane_space(nrm, dir[1], dir[2]);
+    const float s1 = arm ? -1.f : 1.f;
+    const float inv_m = 1.f / T::OBJ_MASS;
+    const int which = p == 3 ? 0 : p;
+    float cfmr = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const V3 d = dir[k];
+      float den = 0.f, rel = 0.f;
+      const V3 r = (s1 > 0.f ? pa : pb) - opos;
+      const V3 rxd = cross(r, d), ir = Iinv * rxd;
+      const V3 Jo = s1 * rxd, Vo = s1 * ir;
+      den += 1.f / T::OBJ_MASS + dot(rxd, ir);
+      rel += s1 * (dot(d, vu) + dot(rxd, wu));
+      float J[N], V[N];
+#pragma unroll
+      for (int q = 0; q < N; q++) { J[q] = 0.f; V[q] = 0.f; }
+      if (arm) {
+        const V3 pxd = cross(pa, d);
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+          const bool on = q < 7 || (which == 1 && q == MD::F1) || (which == 2 && q == MD::F2);
+          const float* S = dyn + 6 * q;
+          J[q] = on ? 1.f * (dot(v3(S[0], S[1], S[2]), pxd) + dot(v3(S[3], S[4], S[5]), d)) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int q2 = 0; q2 < N; q2++) sacc += Minv[tri(q, q2)] * J[q2];
+          V[q] = sacc;
+          den += J[q] * sacc;
+          rel += J[q] * qdu[q];
+        }
+      }
+      float rhs, dinv;
+      if (k == 0) {
+        dinv = 1.f / (den + cfm0);
+        const float pen = -depth + (float)XARM_LINEAR_SLOP;
+        float pos_err = 0.f, vel_err = -rel;
+        if (pen > 0.f) vel_err -= pen / h; else pos_err = -pen * erp / h;
+        rhs = (pos_err + vel_err) * dinv;
+        cfmr = cfm0 * dinv;
+      } else {
+        dinv = 1.f / den;
+        rhs = -rel * dinv;
+      }
+      float* ro = rec + R::HDR + (l * 3 + k) * F::CROW;
+#pragma unroll
+      for (int q = 0; q < N; q++) { Jr[k][q] = J[q]; ro[q] = V[q]; }
+      Jr[k][9] = s1 * d.x; Jr[k][10] = s1 * d.y; Jr[k][11] = s1 * d.z; Jr[k][12] = Jo.x; Jr[k][13] = Jo.y; Jr[k][14] = Jo.z; Jr[k][15] = 0.f;
+      ro[9] = s1 * inv_m * d.x; ro[10] = s1 * inv_m * d.y; ro[11] = s1 * inv_m * d.z; ro[12] = Vo.x; ro[13] = Vo.y; ro[14] = Vo.z; ro[15] = 0.f;
+      ro[16] = rhs; ro[17] = dinv; ro[18] = cfmr; ro[19] = mu;
+    }
+  }
+  const int grasp_now = (c1 > 0 && c2 > 0) ? 1 : 0;   // both fingers hold manifold points with the lego in this collision pass
+  __syncwarp();
+  FPROF()
+  // ---- 5. the joint loop (it builds the Delassus matrix over the scratch above), stepPositionsMultiDof
+  const float u = heavy_solve_dela<T, true>(rec, sm + F::DELA, l, valid, Jr);
+  FPROF()
+  heavy_integrate_coop<T>(a, t, valid, rec, u, l);
+  FPROF()
+#ifdef XARM_FUSED_PROF
+  if (blockIdx.x == 0 && threadIdx.x == 0 && sub == 3)
+    printf("[fused prof] nc %d | load %lld | collide %lld | header %lld | rows %lld | solve %lld | integrate %lld cycles\n", nc,
+           pc_[1] - pc_[0], pc_[2] - pc_[1], pc_[3] - pc_[2], pc_[4] - pc_[3], pc_[5] - pc_[4], pc_[6] - pc_[5]);
+#endif
+  if (valid && sub == T::NSUB - 1 && l == 0 && MD::HAS_BOXES)
+    a.state[(int64_t)(state_words<T>() - 2) * n + i] = grasp_word(grasp_now, grasp_cmd0);
+  __syncwarp();
 }
 
 // 16 lanes of the solve kernel: record -> shared memory, joint loop, stepPositionsMultiDof, state

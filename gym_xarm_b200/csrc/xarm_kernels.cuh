@@ -29,7 +29,9 @@ struct KArgs {
   int tl_branch;           // 0 main, 1 early, 2 late tail: env-substep counters at tl[5 * XARM_TL_SLOTS + {branch: heavy, 3 + branch: all}]
   // SM partition of a split step (xarm_lib.cu): launches of the main branch carry a work counter (blocks claim their
   // chunks dynamically) and leave at once when they land on an SM of sm_mask - those SMs belong to the early branch
+  int spread4_max;                 // setup kernel: lists up to this size run 4 lanes per env (xarm_lib.cu: pipe_spread_setup)
   int light_dual;                  // list launches of the light kernel come in two register budgets (xarm_lib.cu)
+  int heavy_dual;                  // heavy kernels come in two forms: 1 = this launch works only on lists <= XARM_FUSED_MAX (fused), 2 = only on longer ones
   int* work;                       // NULL: static block-stride loop, every SM
   unsigned long long sm_mask[4];   // bit smid set: reserved for the early branch
 };

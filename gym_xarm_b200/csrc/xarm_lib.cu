@@ -39,7 +39,15 @@ __device__ __forceinline__ bool on_reserved_sm(const KArgs& a) {
   asm("mov.u32 %0, %%smid;" : "=r"(smid));
   return (a.sm_mask[(smid >> 6) & 3u] >> (smid & 63u)) & 1ull;
 }
-#define PIPE_LEAVE_RESERVED(a) if ((a).work && on_reserved_sm(a)) return;
+// Guard: if EVERY block of a launch landed on reserved SMs (other streams or processes may fill the rest), nobody would be left
+// to do the work.  Every block counts its arrival in a.work[1]; the last one to arrive stays and works wherever it runs.
+__device__ __forceinline__ bool pipe_is_last_arrival(const KArgs& a) {
+  __shared__ int last_;
+  if (threadIdx.x == 0) last_ = atomicAdd(a.work + 1, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  return last_ != 0;
+}
+#define PIPE_LEAVE_RESERVED(a) if ((a).work) { const bool res_ = on_reserved_sm(a); if (!pipe_is_last_arrival(a) && res_) return; }
 // next chunk (of `chunk` work items) of this block: static stride or claimed from a.work; uniform over the block
 __device__ __forceinline__ int64_t pipe_next(const KArgs& a, int64_t prev, int chunk) {
   if (!a.work) return prev < 0 ? (int64_t)blockIdx.x * chunk : prev + (int64_t)gridDim.x * chunk;
@@ -57,8 +65,16 @@ __device__ __forceinline__ int pipe_spread(const KArgs& a) {
   const int c = *a.list_count;
   return c <= 64 ? 32 : (c <= 256 ? 8 : 1);
 }
-#define PIPE_FOR_EACH(a, t, i)                                                                                   \
-  for (int64_t sp_ = pipe_spread(a), bound_ = ((a).list ? (int64_t)*(a).list_count : (a).n) * sp_,              \
+// the setup kernel (collision code: many data-dependent paths) also spreads mid-sized lists - the ~3 k finishers a staggered
+// step resets - 4 lanes per env: a warp then serialises the paths of 8 envs instead of 32
+__device__ __forceinline__ int pipe_spread_setup(const KArgs& a) {
+  if (!a.list) return 1;
+  const int c = *a.list_count;
+  return c <= 64 ? 32 : (c <= 640 ? 8 : (c <= a.spread4_max ? 4 : 1));
+}
+#define PIPE_FOR_EACH(a, t, i) PIPE_FOR_EACH_SP(a, t, i, pipe_spread(a))
+#define PIPE_FOR_EACH_SP(a, t, i, spread_)                                                                       \
+  for (int64_t sp_ = (spread_), bound_ = ((a).list ? (int64_t)*(a).list_count : (a).n) * sp_,              \
                base_ = pipe_next(a, -1, blockDim.x);                                                            \
        base_ < bound_; base_ = pipe_next(a, base_, blockDim.x))                                                  \
     if (const int64_t tv_ = base_ + threadIdx.x; true)                                                           \
@@ -101,14 +117,14 @@ __global__ void __launch_bounds__(128) k_pipe_action(KArgs a) {
 // lists of the auto-reset tail: 70 us per launch against 71 us.  ncu on tail-sized launches: no_instruction is 8 of 12.5 stall
 // cycles per issue - a lone warp per SM is bound by instruction fetch and branch bubbles of ~130 KB of once-executed code, not
 // by the thread-local arrays.  profiles/r2c_*.)
-#define XARM_LAT_MAX 4096
+#define XARM_LAT_MAX 16384   // (the ~7 k candidates of a staggered step take the latency forms too: one block of 128 per SM)
 template <class T, bool LAT>
 __device__ __forceinline__ void setup_body(const KArgs& a, int sub, int* heavy_count) {
   if (a.list && a.light_dual && LAT != (*a.list_count <= XARM_LAT_MAX)) return;
   if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + 3 + a.tl_branch, (unsigned long long)(a.list ? *a.list_count : a.n));
   PIPE_LEAVE_RESERVED(a)
   tl_mark(a, 0);
-  PIPE_FOR_EACH(a, t, i) {
+  PIPE_FOR_EACH_SP(a, t, i, pipe_spread_setup(a)) {
     const bool heavy = i >= 0 && pipe_setup<T, LAT>(a, i, sub);
     list_append(heavy, i, a.heavy_list, heavy_count, a.heavy_dir);
   }
@@ -181,9 +197,14 @@ __global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* 
 // record in global memory.  k_heavy_solve: 16 lanes per env, 8 envs per 128-thread block, records staged in shared
 // memory (3 blocks = 24 envs = 12 warps per SM instead of the single warp of the thread-per-env form).
 #define XARM_HEAVY_ENVS_PER_BLOCK 8
+// Lists of heavy envs up to this size take the fused kernel (latency form: 5 warps per SM), longer ones - the reset wave of a batch
+// whose episodes run in phase, the steps after it - k_heavy_rows + k_heavy_solve2 (throughput forms).  Both are launched; the
+// list size, known on the device only, decides which one works.
+#define XARM_FUSED_MAX 4096
 template <class T>
 __global__ void __launch_bounds__(64) k_heavy_rows(KArgs a, int sub, const int* heavy_count, float* hrec) {
   if constexpr (task_has_heavy_rows<T>()) {
+    if (a.heavy_dual == 2 && *heavy_count <= XARM_FUSED_MAX) return;
     if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + a.tl_branch, (unsigned long long)*heavy_count);
     PIPE_LEAVE_RESERVED(a)
     const int count = *heavy_count;
@@ -226,12 +247,34 @@ __global__ void __launch_bounds__(16 * XARM_HEAVY2_ENVS_PER_BLOCK) k_heavy_solve
     extern __shared__ float4 heavy_smem4[];
     const int g = threadIdx.x >> 4, l = threadIdx.x & 15;
     float* sm = reinterpret_cast<float*>(heavy_smem4) + (size_t)g * DelaLayout<T>::SLOT;
+    if (a.heavy_dual == 2 && *heavy_count <= XARM_FUSED_MAX) return;
     PIPE_LEAVE_RESERVED(a)
     const int count = *heavy_count;
     bool any = false;
     for (int64_t base = pipe_next(a, -1, XARM_HEAVY2_ENVS_PER_BLOCK); base < count; base = pipe_next(a, base, XARM_HEAVY2_ENVS_PER_BLOCK)) {
       if (!any) { tl_mark(a, 0); any = true; }
       heavy_solve2_body<T>(a, (int)base + g, base + g < count, hrec, sm, l);
+    }
+    if (any) tl_mark(a, 1);
+  }
+}
+// Fused form (heavy_fused_body): collision + rows + joint loop in one launch, the record never leaves shared memory.
+#define XARM_FUSED_BLOCKS_PER_SM 5
+template <class T>
+__global__ void __launch_bounds__(32) k_heavy_fused(KArgs a, int sub, const int* heavy_count) {
+  if constexpr (task_has_heavy_rows<T>()) {
+    extern __shared__ float4 heavy_smem4[];
+    const int g = threadIdx.x >> 4, l = threadIdx.x & 15;
+    float* sm = reinterpret_cast<float*>(heavy_smem4) + (size_t)g * FusedLayout<T>::SLOT;
+    if (a.heavy_dual == 1 && *heavy_count > XARM_FUSED_MAX) return;
+    if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + a.tl_branch, (unsigned long long)*heavy_count);
+    PIPE_LEAVE_RESERVED(a)
+    const int count = *heavy_count;
+    if (a.tl && a.tl_slot >= 0 && threadIdx.x == 0) a.tl[2 * XARM_TL_SLOTS + a.tl_slot] = (unsigned long long)count;
+    bool any = false;
+    for (int64_t base = pipe_next(a, -1, 2); base < count; base = pipe_next(a, base, 2)) {
+      if (!any) { tl_mark(a, 0); any = true; }
+      heavy_fused_body<T>(a, (int)base + g, base + g < count, sub, sm, l);
     }
     if (any) tl_mark(a, 1);
   }
@@ -364,7 +407,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 // fork/join plumbing of the pipeline: a side stream for the heavy kernels and a pool of dependency events
 struct PipeCtx {
   cudaStream_t side = nullptr;          // heavy kernels of the main branch
-  cudaStream_t e_main = nullptr, e_side = nullptr;  // the early branch (high priority): envs that may finish this step
+  cudaStream_t e_main = nullptr, e_side = nullptr, e_side2 = nullptr;  // the early branch (high priority): envs that may finish this step
   int *list_e = nullptr, *list_m = nullptr, *reset_list_e = nullptr;   // [N] each
   int *count_e = nullptr, *count_m = nullptr, *reset_count_e = nullptr, *counters = nullptr;
   int n_counters = 0;
@@ -395,6 +438,8 @@ struct PipeCtx {
   // gets a work counter and the mask of the SMs it must leave to the early branch
   bool dyn = false;
   bool light_dual = true;   // XARM_LIGHT_DUAL=0: one light kernel form everywhere
+  bool main_wait = true;    // XARM_MAIN_WAIT=0: the main branch starts together with the early branch
+  bool fused = true;        // XARM_HEAVY_FUSED=0: k_heavy_rows + k_heavy_solve2 (round 1) instead of k_heavy_fused
   bool main_fork = true;    // XARM_MAIN_FORK=0: the main branch of a split step keeps one stream (heavy kernels, then light)
   bool tail_lat = true;     // XARM_TAIL_LAT=0: the early branch keeps the round-1 kernels (128-register setup, 160-register light with shared-memory rows)
   bool light_main_lat = true;    // XARM_LIGHT_MAIN_LAT=0: the partitioned main branch keeps the 128-register form (A/B)
@@ -408,7 +453,7 @@ struct PipeCtx {
     b.tl_branch = cur_branch == 'M' ? 0 : (cur_branch == 'E' ? 1 : 2);
     b.work = nullptr;
     if (dyn && reserve_sms > 0 && next_work < n_work) {
-      b.work = work_base + next_work++;
+      b.work = work_base + next_work; next_work += 2;   // [0] chunk claims, [1] block arrivals
       for (int k = 0; k < 4; k++) b.sm_mask[k] = sm_mask[k];
     }
     return b;
@@ -477,6 +522,10 @@ struct OpsT {
   static size_t hrec_words() {  // per env: record of the cooperative heavy solver (0: task has none)
     if constexpr (task_has_heavy_rows<T>()) return HeavyRec<T>::WORDS; else return 0;
   }
+  static size_t fused_smem_bytes() {
+    if constexpr (task_has_heavy_rows<T>()) return (size_t)2 * FusedLayout<T>::SLOT * sizeof(float);
+    else return 0;
+  }
   static size_t dela_smem_bytes() {
     if constexpr (task_has_heavy_rows<T>()) return (size_t)XARM_HEAVY2_ENVS_PER_BLOCK * DelaLayout<T>::SLOT * sizeof(float);
     else return 0;
@@ -491,7 +540,9 @@ struct OpsT {
     if constexpr (task_has_heavy_rows<T>()) {
       int rc = (int)cudaFuncSetAttribute(k_heavy_solve<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_smem_bytes());
       if (rc) return rc;
-      return (int)cudaFuncSetAttribute(k_heavy_solve2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dela_smem_bytes());
+      rc = (int)cudaFuncSetAttribute(k_heavy_solve2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dela_smem_bytes());
+      if (rc) return rc;
+      return (int)cudaFuncSetAttribute(k_heavy_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes());
     }
     else if constexpr (HAS_LIGHT) return (int)cudaFuncSetAttribute(k_pipe_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem_bytes());
     return 0;
@@ -502,7 +553,8 @@ struct OpsT {
   // sh != s: the heavy kernels run on sh next to k_pipe_light (fork / join); sh == s: one stream, heavy kernels first.
   // The main branch of a split step uses one stream: its kernels fill the GPU anyway, and with a single kernel in
   // flight at a time the block slots that pgrid() leaves free really stay free for the early branch.
-  static void simulate(PipeCtx& c, const KArgs& a, int pass, cudaStream_t s, cudaStream_t sh) {
+  static void simulate(PipeCtx& c, const KArgs& a, int pass, cudaStream_t s, cudaStream_t sh, cudaStream_t sh2 = nullptr) {
+    cudaEvent_t join2_pending = nullptr;
     const bool part = c.dyn && c.reserve_sms > 0;   // partitioned main branch: full grids, dynamic chunks
     const dim3 g = part ? dim3(c.heavy_grid * 4) : pgrid(c, a.n);
     const bool fork_heavy = sh != s;
@@ -526,14 +578,34 @@ struct OpsT {
           cudaStreamWaitEvent(sh, fork, 0);
         }
         if constexpr (task_has_heavy_rows<T>()) {
-          c.begin("heavy_rows", sh);
-          k_heavy_rows<T><<<rows_grid, 64, 0, sh>>>(c.tl(a), sub, hc, c.hrec);
-          c.end(sh);
-          c.begin("heavy_solve", sh);
-          if (c.dela) k_heavy_solve2<T><<<solve_grid / 3 * XARM_HEAVY2_BLOCKS_PER_SM, 16 * XARM_HEAVY2_ENVS_PER_BLOCK, dela_smem_bytes(), sh>>>(c.tl(a), hc, c.hrec);
-          else k_heavy_solve<T><<<solve_grid, 128, coop_smem_bytes(), sh>>>(c.tl(a), hc, c.hrec);
-          c.end(sh);
-          g_launches++;
+          cudaEvent_t join2 = nullptr;
+          if (c.fused && c.dela) {
+            c.begin("heavy_fused", sh);
+            KArgs af = c.tl(a); af.heavy_dual = 1;
+            k_heavy_fused<T><<<solve_grid / 3 * XARM_FUSED_BLOCKS_PER_SM, 32, fused_smem_bytes(), sh>>>(af, sub, hc);
+            c.end(sh);
+          }
+          {
+            // the throughput pair: after the fused kernel on the same stream, or - early branch, where every launch on the chain
+            // counts - next to it on a third stream
+            cudaStream_t sr = sh;
+            if (c.fused && c.dela && sh2 && fork_heavy) {
+              cudaEvent_t fork2 = c.next(); join2 = c.next();
+              cudaEventRecord(fork2, s); cudaStreamWaitEvent(sh2, fork2, 0);
+              sr = sh2;
+            }
+            c.begin("heavy_rows", sr);
+            KArgs ar = c.tl(a); ar.heavy_dual = (c.fused && c.dela) ? 2 : 0;
+            k_heavy_rows<T><<<rows_grid, 64, 0, sr>>>(ar, sub, hc, c.hrec);
+            c.end(sr);
+            c.begin("heavy_solve", sr);
+            KArgs as = c.tl(a); as.heavy_dual = ar.heavy_dual;
+            if (c.dela) k_heavy_solve2<T><<<solve_grid / 3 * XARM_HEAVY2_BLOCKS_PER_SM, 16 * XARM_HEAVY2_ENVS_PER_BLOCK, dela_smem_bytes(), sr>>>(as, hc, c.hrec);
+            else k_heavy_solve<T><<<solve_grid, 128, coop_smem_bytes(), sr>>>(as, hc, c.hrec);
+            c.end(sr);
+            g_launches += 2;
+            if (join2) { cudaEventRecord(join2, sh2); join2_pending = join2; }
+          }
         } else {
           k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), sh>>>(a, sub, hc);
         }
@@ -553,42 +625,44 @@ struct OpsT {
         }
         c.end(s);
         if (fork_heavy) cudaStreamWaitEvent(s, join, 0);
+        if (join2_pending) { cudaStreamWaitEvent(s, join2_pending, 0); join2_pending = nullptr; }
         g_launches += 3;
       }
     }
   }
   // Env.reset() of the envs in r.list (all envs when r.list is NULL)
-  static void reset_passes(PipeCtx& c, const KArgs& r, int pass, int clear_return, cudaStream_t s, cudaStream_t sh) {
+  static void reset_passes(PipeCtx& c, const KArgs& r, int pass, int clear_return, cudaStream_t s, cudaStream_t sh, cudaStream_t sh2 = nullptr) {
     const dim3 g = pgrid(c, r.n);
     if (reset_has_servo<T>())
       for (int rep = 0; rep < 5; rep++) {
         c.begin("reset_stage", s);
         k_pipe_reset_stage<T><<<g, 128, 0, s>>>(c.tl(r), rep, 0); g_launches++;
         c.end(s);
-        simulate(c, r, pass++, s, sh);
+        simulate(c, r, pass++, s, sh, sh2);
       }
     k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, XARM_RESET_PLACE, 0); g_launches++;
-    simulate(c, r, pass++, s, sh);
+    simulate(c, r, pass++, s, sh, sh2);
     k_pipe_reset_stage<T><<<g, 128, 0, s>>>(r, XARM_RESET_FINISH, clear_return); g_launches++;
   }
   // one branch of a step: _set_action, stepSimulation, outputs for the envs of a.list (all envs when NULL), then
   // Env.reset() of the envs that finished (VecEnv auto-reset) through the same pipeline
-  static void step_branch(PipeCtx& c, const KArgs& a, int pass, bool tail, cudaStream_t s, cudaStream_t sh) {
+  static void step_branch(PipeCtx& c, const KArgs& a, int pass, bool tail, cudaStream_t s, cudaStream_t sh, cudaEvent_t stepped = nullptr, cudaStream_t sh2 = nullptr) {
     const dim3 g = c.dyn && c.reserve_sms > 0 ? dim3(c.heavy_grid * 4) : pgrid(c, a.n);
     c.cur_tail = tail ? 1 : 0;
     c.begin("action", s);
     k_pipe_action<T><<<g, 128, 0, s>>>(c.tl(a));
     c.end(s);
-    simulate(c, a, pass, s, sh);
+    simulate(c, a, pass, s, sh, sh2);
     c.begin("finish", s);
     k_pipe_finish<T><<<g, 128, 0, s>>>(c.tl(a));
     c.end(s);
+    if (stepped) cudaEventRecord(stepped, s);   // the envs of this branch have made their step (their auto-reset passes follow)
     g_launches += 2;
     if (a.auto_reset && tail) {
       c.cur_tail = 1;
       KArgs r = a;
       r.list = a.reset_list; r.list_count = a.reset_count;
-      reset_passes(c, r, pass + 1, 0, s, sh);
+      reset_passes(c, r, pass + 1, 0, s, sh, sh2);
     }
   }
   static void step(PipeCtx& c, const KArgs& a0, cudaStream_t s) {
@@ -614,8 +688,13 @@ struct OpsT {
     e.heavy_list = a.heavy_list + (a.n - 1); e.heavy_dir = -1;
     e.reset_list = c.reset_list_e; e.reset_count = c.reset_count_e;
     c.cur_branch = 'E';
-    step_branch(c, e, XARM_PIPE_PASSES / 2, true, c.e_main, c.e_side);
+    // The early branch is the critical path of the step: 15 + 90 substeps in sequence.  Its first pass (the step of the ~5 k envs
+    // that may finish, ~2 k of them in gripper contact) is throughput work, and next to the main branch it takes 12-13 ms
+    // instead of ~5: the main branch (which has 20 ms of slack) starts when that pass is over.
+    cudaEvent_t e_stepped = c.main_wait ? c.next() : nullptr;
+    step_branch(c, e, XARM_PIPE_PASSES / 2, true, c.e_main, c.e_side, e_stepped, c.e_side2);
     cudaEventRecord(join, c.e_main);
+    if (e_stepped) cudaStreamWaitEvent(s, e_stepped, 0);
     KArgs m = a;
     m.list = c.list_m; m.list_count = c.count_m;
     c.cur_branch = 'M';
@@ -753,7 +832,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   h->k.rc.goal_shape = c.goal_shape; h->k.rc.max_episode_steps = c.max_episode_steps; h->k.rc.stagger = c.stagger_phases != 0;
   h->k.rc.init_grasp_rate = c.init_grasp_rate; h->k.rc.goal_ground_rate = c.goal_ground_rate; h->k.rc.same_side_rate = c.same_side_rate;
   // int scratch: reset list | heavy list | form | rng draw | early list | main list | early reset list | counters
-  const int n_work = 128;  // work counters of the partitioned main branch (one per launch: 2 + 4 per substep)
+  const int n_work = 256;  // work counters of the partitioned main branch (a pair per launch: 2 + 4 launches per substep)
   const int n_counters = XARM_PIPE_COUNTERS + n_work + 4;
   const size_t n_int = (size_t)7 * n + n_counters;
   int prio_lo = 0, prio_hi = 0;
@@ -767,6 +846,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   cudaError_t e7 = cudaStreamCreateWithFlags(&h->pipe.side, cudaStreamNonBlocking);
   if (e7 == cudaSuccess) e7 = cudaStreamCreateWithPriority(&h->pipe.e_main, cudaStreamNonBlocking, prio_hi);
   if (e7 == cudaSuccess) e7 = cudaStreamCreateWithPriority(&h->pipe.e_side, cudaStreamNonBlocking, prio_hi);
+  if (e7 == cudaSuccess) e7 = cudaStreamCreateWithPriority(&h->pipe.e_side2, cudaStreamNonBlocking, prio_hi);
   // every failure from here on leaves through ONE cleanup (xarm_destroy frees whatever was allocated so far)
 #define CREATE_FAIL(code, msg) do { std::string m_ = (msg); xarm_destroy(h); cudaGetLastError(); return fail((code), m_); } while (0)
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess)
@@ -784,10 +864,11 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     if (cudaMalloc(&h->pipe.hrec, sizeof(float) * ops.hrec_words() * n) != cudaSuccess) CREATE_FAIL(XARM_E_NOMEM, "xarm_create: cudaMalloc (heavy records) failed");
   }
   {  // SMs reserved for the early branch of a split step
-    // Round 2 (staggered phases: ~2.7 k finishers in EVERY step): the early branch is a latency chain of 105 substeps whatever the
-    // number of SMs it owns (36.7 ms with 32 reserved SMs, 38.5 ms with none), while the main branch loses the SMs it leaves
-    // (21 ms on 116 SMs, 15 ms on 148): reservation is off by default now.
-    const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 0;
+    // Round 2 (staggered phases: ~2.7 k finishers in EVERY step): the early branch is a latency chain of 105 substeps, ~200 us each
+    // when it runs alone (one warp per scheduler, bound by instruction fetch and dependent issue) and ~260 us when its warps share
+    // schedulers with the main branch's.  36 reserved SMs: the chain's passes take 3.85 ms instead of 5.5-5.7 next to the main
+    // branch (3.0 alone); the main branch, which has ~10 ms of slack, takes 15.6 ms on the other 112 SMs instead of 10.4.
+    const int want = getenv("XARM_RESERVE_SMS") ? atoi(getenv("XARM_RESERVE_SMS")) : 36;
     if (want > 0 && ops.hrec_words() > 0) {
       unsigned* d_seen = nullptr;
       unsigned seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -808,7 +889,12 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   }
   if (getenv("XARM_SETUP_BPS")) h->pipe.setup_bps = atoi(getenv("XARM_SETUP_BPS"));
   h->pipe.light_dual = !(getenv("XARM_LIGHT_DUAL") && atoi(getenv("XARM_LIGHT_DUAL")) == 0);
-  h->pipe.main_fork = !(getenv("XARM_MAIN_FORK") && atoi(getenv("XARM_MAIN_FORK")) == 0);
+  h->pipe.main_wait = !(getenv("XARM_MAIN_WAIT") && atoi(getenv("XARM_MAIN_WAIT")) == 0);
+  h->pipe.fused = !(getenv("XARM_HEAVY_FUSED") && atoi(getenv("XARM_HEAVY_FUSED")) == 0);
+  // With the SM partition on, the main branch's heavy kernel must NOT run next to its light kernel: its resident blocks (47 KB of
+  // shared memory each) fill the unreserved SMs, the light kernel's blocks then only find room on the reserved SMs - where they
+  // leave at once - and the launch's last block does all the work alone (measured: 77 ms per launch).
+  h->pipe.main_fork = getenv("XARM_MAIN_FORK") ? atoi(getenv("XARM_MAIN_FORK")) != 0 : h->pipe.reserve_sms == 0;
   h->pipe.tail_lat = !(getenv("XARM_TAIL_LAT") && atoi(getenv("XARM_TAIL_LAT")) == 0);
   h->pipe.light_main_lat = !(getenv("XARM_LIGHT_MAIN_LAT") && atoi(getenv("XARM_LIGHT_MAIN_LAT")) == 0);
   h->pipe.trace = getenv("XARM_TRACE_STAGES") != nullptr;
@@ -824,6 +910,8 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
   h->pipe.work_base = h->pipe.counters + XARM_PIPE_COUNTERS; h->pipe.n_work = n_work;
   h->pipe.reset_count_e = h->k.reset_count + 1; h->pipe.count_e = h->k.reset_count + 2; h->pipe.count_m = h->k.reset_count + 3;
   h->k.heavy_dir = 1;
+  h->k.heavy_dual = 0;
+  h->k.spread4_max = getenv("XARM_SETUP_SPREAD4") ? atoi(getenv("XARM_SETUP_SPREAD4")) : 0;   // measured neutral at 3.4 k envs (56 vs 62 us in quiet passes, slower next to the main branch): off
   cudaError_t ez = cudaMemset(h->k.reset_list, 0, sizeof(int) * n_int);
   if (ez == cudaSuccess) ez = cudaMemset(h->k.stats, 0, sizeof(double) * 5);
   if (ez == cudaSuccess) { ops.init(h->k, 0); ez = cudaGetLastError(); }
@@ -848,6 +936,7 @@ int xarm_destroy(XarmHandle* h) {
   if (h->pipe.side) cudaStreamDestroy(h->pipe.side);
   if (h->pipe.e_main) cudaStreamDestroy(h->pipe.e_main);
   if (h->pipe.e_side) cudaStreamDestroy(h->pipe.e_side);
+  if (h->pipe.e_side2) cudaStreamDestroy(h->pipe.e_side2);
   cudaFree(h->d_io); cudaFree(h->d_flags);
   if (h->h_io) cudaFreeHost(h->h_io);
   if (h->h_flags) cudaFreeHost(h->h_flags);

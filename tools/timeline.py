@@ -33,12 +33,12 @@ for t in range(steps):
                 acc[r[1]][0] += 1; acc[r[1]][1] += r[3] - r[2]
             print(f" branch {br}: {t0/1e3:.2f} .. {t1/1e3:.2f} ms | " + " | ".join(f"{k}: {v[0]} x {v[1]/v[0]:.0f} us = {v[1]/1e3:.2f} ms" for k, v in acc.items()))
         if os.environ.get("PASSES"):
-            for name in ("setup", "heavy_rows", "heavy_solve", "heavy_solve16", "light"):
+            for name in ("setup", "heavy_rows", "heavy_solve", "heavy_fused", "light"):
                 rb = sorted([r for r in rows if r[0] == "E" and r[1] == name], key=lambda r: r[2])
                 per = [rb[k:k + 15] for k in range(0, len(rb), 15)]
                 print(f"  E {name:12s} per pass avg us: " + " ".join(f"{sum(r[3]-r[2] for r in p_)/len(p_):.0f}" for p_ in per) + "   max: " + " ".join(f"{max(r[3]-r[2] for r in p_):.0f}" for p_ in per))
             for br in "EM":
-                rb = sorted([r for r in rows if r[0] == br and r[1] == "heavy_rows"], key=lambda r: r[2])
+                rb = sorted([r for r in rows if r[0] == br and r[1] in ("heavy_rows", "heavy_fused")], key=lambda r: r[2])
                 per = [rb[k:k + 15] for k in range(0, len(rb), 15)]
                 print(f"  {br} heavy env count per pass (avg): " + " ".join(f"{sum(r[4] for r in p_)/len(p_):.0f}" for p_ in per))
             rb = sorted([r for r in rows if r[0] == "E"], key=lambda r: r[2])
