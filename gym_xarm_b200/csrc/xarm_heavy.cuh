@@ -431,6 +431,9 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
     bad = bad || (own_ && fabsf(delta) > sthr * uden_t);                                                          \
     DELA_APPLY((o_), d_)                                                                                          \
   }
+#ifndef XARM_DELA_UNROLL_STR
+#define XARM_DELA_UNROLL_STR "unroll 1"   /* contact loops of the sweep (a lone warp pays the loop branch on its critical path) */
+#endif
   for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
     bool bad = false;
     if (it & 1) {
@@ -445,6 +448,7 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
     // ---- normal rows.  The Delassus column of row c is loaded BEFORE the row's update chain (it does not depend on the
     // solve): a lane past this env's contacts (the other env of the warp has more) broadcasts an exact zero, so it may read
     // any finite column - column 0, always built - and the loads need no branch (shared-memory latency off the critical path).
+    _Pragma(XARM_DELA_UNROLL_STR)
     for (int c = 0; c < nc_max; c++) {
       const float* c_ = A + (c < nc ? D::NU + 3 * c : 0) * 64 + l;
       const float a0 = c_[0], a1 = c_[16], a2 = c_[32], a3 = c_[48];
@@ -459,6 +463,7 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
     }
     // ---- friction pairs (implicit cone)
     const float lim = mu * appn, lim2 = lim * lim;
+    _Pragma(XARM_DELA_UNROLL_STR)
     for (int c = 0; c < nc_max; c++) {
       const float* c_ = A + (c < nc ? D::NU + 3 * c + 1 : 0) * 64 + l;
       const float p0 = c_[0], p1 = c_[16], p2 = c_[32], p3 = c_[48], q0 = c_[64], q1 = c_[80], q2 = c_[96], q3 = c_[112];

@@ -193,6 +193,23 @@ __global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* 
     }
   }
 }
+// Tasks whose generic contact record does not fit shared memory 32 lanes wide (two arms, several objects, the door: ~9 KB per
+// env): the heavy envs of the substep - the minority there - keep the record in thread-local memory, one thread per env.
+template <class T>
+constexpr bool heavy_record_fits_smem() { return heavy_smem_bytes_of<T>() <= 160 * 1024; }
+template <class T>
+__global__ void __launch_bounds__(64) k_pipe_heavy_local(KArgs a, int sub, const int* heavy_count) {
+  if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + a.tl_branch, (unsigned long long)*heavy_count);
+  PIPE_LEAVE_RESERVED(a)
+  const int count = *heavy_count;
+  bool any = false;
+  for (int64_t base = pipe_next(a, -1, blockDim.x); base < count; base = pipe_next(a, base, blockDim.x)) {
+    if (!any) { tl_mark(a, 0); any = true; }
+    const int64_t t = base + threadIdx.x;
+    if (t < count) { Contacts<T> C; pipe_heavy<T>(a, a.heavy_list[a.heavy_dir * t], sub, C); }
+  }
+  if (any) tl_mark(a, 1);
+}
 // Cooperative heavy path (tasks with HeavyRec: PickAndPlace).  k_heavy_rows: one thread per heavy env, generic setup ->
 // record in global memory.  k_heavy_solve: 16 lanes per env, 8 envs per 128-thread block, records staged in shared
 // memory (3 blocks = 24 envs = 12 warps per SM instead of the single warp of the thread-per-env form).
@@ -437,6 +454,7 @@ struct PipeCtx {
   // SM partition (XARM_RESERVE_SMS, default 32; 0 = off): while `dyn` is set (main branch of a split step) every launch
   // gets a work counter and the mask of the SMs it must leave to the early branch
   bool dyn = false;
+  bool light_multi = true;  // XARM_LIGHT_MULTI=0: tasks with several islands (two arms, door, several objects) take the generic substep for every env (round 1)
   bool light_dual = true;   // XARM_LIGHT_DUAL=0: one light kernel form everywhere
   bool main_wait = true;    // XARM_MAIN_WAIT=0: the main branch starts together with the early branch
   bool fused = true;        // XARM_HEAVY_FUSED=0: k_heavy_rows + k_heavy_solve2 (round 1) instead of k_heavy_fused
@@ -544,7 +562,7 @@ struct OpsT {
       if (rc) return rc;
       return (int)cudaFuncSetAttribute(k_heavy_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes());
     }
-    else if constexpr (HAS_LIGHT) return (int)cudaFuncSetAttribute(k_pipe_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem_bytes());
+    else if constexpr (heavy_record_fits_smem<T>()) return (int)cudaFuncSetAttribute(k_pipe_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem_bytes());
     return 0;
   }
   static void init(const KArgs& a, cudaStream_t s) { k_init<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
@@ -561,7 +579,7 @@ struct OpsT {
     const unsigned rows_grid = fork_heavy || part ? c.heavy_grid * 4 : (unsigned)c.max_blocks;
     const unsigned solve_grid = fork_heavy || part ? c.heavy_grid * 3 : (unsigned)(c.max_blocks * 3 / 4);
     for (int sub = 0; sub < T::NSUB; sub++) {
-      if constexpr (!HAS_LIGHT) {
+      if (!task_single_island_pair<T>() && !c.light_multi) {   // XARM_LIGHT_MULTI=0 (A/B): every env through the generic substep
         c.begin("heavy_all", s);
         k_pipe_heavy_all<T><<<g, 128, 0, s>>>(c.tl(a), sub); g_launches++;
         c.end(s);
@@ -606,8 +624,12 @@ struct OpsT {
             g_launches += 2;
             if (join2) { cudaEventRecord(join2, sh2); join2_pending = join2; }
           }
-        } else {
+        } else if constexpr (heavy_record_fits_smem<T>()) {
           k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), sh>>>(a, sub, hc);
+        } else {
+          c.begin("heavy_local", sh);
+          k_pipe_heavy_local<T><<<rows_grid, 64, 0, sh>>>(c.tl(a), sub, hc);
+          c.end(sh);
         }
         if (fork_heavy) cudaEventRecord(join, sh);
         c.begin("light", s);
@@ -888,6 +910,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     }
   }
   if (getenv("XARM_SETUP_BPS")) h->pipe.setup_bps = atoi(getenv("XARM_SETUP_BPS"));
+  h->pipe.light_multi = !(getenv("XARM_LIGHT_MULTI") && atoi(getenv("XARM_LIGHT_MULTI")) == 0);
   h->pipe.light_dual = !(getenv("XARM_LIGHT_DUAL") && atoi(getenv("XARM_LIGHT_DUAL")) == 0);
   h->pipe.main_wait = !(getenv("XARM_MAIN_WAIT") && atoi(getenv("XARM_MAIN_WAIT")) == 0);
   h->pipe.fused = !(getenv("XARM_HEAVY_FUSED") && atoi(getenv("XARM_HEAVY_FUSED")) == 0);

@@ -21,55 +21,19 @@
 #define XARM_FORM_HEAVY 1
 
 template <class T>
-XHD int pipe_ar_words() { return T::NARM * (T::MD::N * (T::MD::N + 1) / 2 + 2 * T::MD::N + 5) + 4; }
+XHD int pipe_ar_words() { return ar_words<T>(); }
 template <class T>
 XHD int pipe_sb_words() { return T::NARM * T::MD::N + 6 * (T::NOBJ > 0 ? T::NOBJ : 1) + 1; }
-XHD int pipe_mi_words() { return 3 + 1 + 12 + 12 + 6; }
+XHD int pipe_mi_words() { return mi_words(); }
 template <class T>
 XHD int pipe_dyn_words() { return T::MD::N * 6 + T::MD::N * (T::MD::N + 1) / 2 + T::MD::N + 9 + 9; }  // ArmDyn of a heavy env
 template <class T>
 XHD int pipe_scratch_words() {
-  const int light = pipe_ar_words<T>() + pipe_sb_words<T>() + pipe_mi_words(), heavy = pipe_dyn_words<T>();
+  const int light = pipe_ar_words<T>() + pipe_sb_words<T>() + pipe_mi_words() * (T::NOBJ > 0 ? T::NOBJ : 1), heavy = pipe_dyn_words<T>();
   return light > heavy ? light : heavy;
 }
 
-// ---- scratch records: word w of env i at base[w * n + i]
-template <class T>
-XD void ar_store(const ArmRows<T>& AR, float* __restrict__ s, int64_t n, int64_t i) {
-  constexpr int N = T::MD::N, NT = N * (N + 1) / 2;
-  int w = 0;
-#pragma unroll
-  for (int a = 0; a < T::NARM; a++) {
-#pragma unroll
-    for (int k = 0; k < NT; k++) s[(w++) * n + i] = AR.Mi[a][k];
-#pragma unroll
-    for (int k = 0; k < N; k++) s[(w++) * n + i] = AR.mrhs[a][k];
-#pragma unroll
-    for (int k = 0; k < N; k++) s[(w++) * n + i] = AR.lrhs[a][k];
-    s[(w++) * n + i] = (float)AR.lim_lo[a]; s[(w++) * n + i] = (float)AR.lim_hi[a];  // bit masks < 2^13: exact
-    s[(w++) * n + i] = AR.grhs[a]; s[(w++) * n + i] = AR.gdinv[a]; s[(w++) * n + i] = AR.gden[a];
-  }
-  s[(w++) * n + i] = AR.dl_rhs; s[(w++) * n + i] = AR.dl_sign; s[(w++) * n + i] = AR.dm_rhs;
-  s[(w++) * n + i] = (float)AR.door_lim;
-}
-template <class T>
-XD void ar_load(ArmRows<T>& AR, const float* __restrict__ s, int64_t n, int64_t i) {
-  constexpr int N = T::MD::N, NT = N * (N + 1) / 2;
-  int w = 0;
-#pragma unroll
-  for (int a = 0; a < T::NARM; a++) {
-#pragma unroll
-    for (int k = 0; k < NT; k++) AR.Mi[a][k] = s[(w++) * n + i];
-#pragma unroll
-    for (int k = 0; k < N; k++) AR.mrhs[a][k] = s[(w++) * n + i];
-#pragma unroll
-    for (int k = 0; k < N; k++) AR.lrhs[a][k] = s[(w++) * n + i];
-    AR.lim_lo[a] = (uint32_t)s[(w++) * n + i]; AR.lim_hi[a] = (uint32_t)s[(w++) * n + i];
-    AR.grhs[a] = s[(w++) * n + i]; AR.gdinv[a] = s[(w++) * n + i]; AR.gden[a] = s[(w++) * n + i];
-  }
-  AR.dl_rhs = s[(w++) * n + i]; AR.dl_sign = s[(w++) * n + i]; AR.dm_rhs = s[(w++) * n + i];
-  AR.door_lim = (int)s[(w++) * n + i];
-}
+// ---- scratch records: word w of env i at base[w * n + i] (ar_store / ar_load / mi_store / mi_load: xarm_sim.cuh)
 template <class T>
 XD void sb_store(const SubBase<T>& B, float* __restrict__ s, int64_t n, int64_t i) {
   int w = 0;
@@ -98,31 +62,6 @@ XD void sb_load(SubBase<T>& B, const float* __restrict__ s, int64_t n, int64_t i
   }
   B.door_qdu = s[(w++) * n + i];
 }
-XD void mi_store(const ManifoldIn& M, float* __restrict__ s, int64_t n, int64_t i) {
-  int w = 0;
-  s[(w++) * n + i] = M.n.x; s[(w++) * n + i] = M.n.y; s[(w++) * n + i] = M.n.z; s[(w++) * n + i] = M.mu;
-#pragma unroll
-  for (int c = 0; c < 4; c++) { s[(w++) * n + i] = M.r[c].x; s[(w++) * n + i] = M.r[c].y; s[(w++) * n + i] = M.r[c].z; }
-#pragma unroll
-  for (int c = 0; c < 4; c++)
-#pragma unroll
-    for (int k = 0; k < 3; k++) s[(w++) * n + i] = M.rhs[c][k];
-  s[(w++) * n + i] = M.Iinv.xx; s[(w++) * n + i] = M.Iinv.xy; s[(w++) * n + i] = M.Iinv.xz;
-  s[(w++) * n + i] = M.Iinv.yy; s[(w++) * n + i] = M.Iinv.yz; s[(w++) * n + i] = M.Iinv.zz;
-}
-XD void mi_load(ManifoldIn& M, const float* __restrict__ s, int64_t n, int64_t i) {
-  int w = 0;
-  M.n.x = s[(w++) * n + i]; M.n.y = s[(w++) * n + i]; M.n.z = s[(w++) * n + i]; M.mu = s[(w++) * n + i];
-#pragma unroll
-  for (int c = 0; c < 4; c++) { M.r[c].x = s[(w++) * n + i]; M.r[c].y = s[(w++) * n + i]; M.r[c].z = s[(w++) * n + i]; }
-#pragma unroll
-  for (int c = 0; c < 4; c++)
-#pragma unroll
-    for (int k = 0; k < 3; k++) M.rhs[c][k] = s[(w++) * n + i];
-  M.Iinv.xx = s[(w++) * n + i]; M.Iinv.xy = s[(w++) * n + i]; M.Iinv.xz = s[(w++) * n + i];
-  M.Iinv.yy = s[(w++) * n + i]; M.Iinv.yz = s[(w++) * n + i]; M.Iinv.zz = s[(w++) * n + i];
-}
-
 // the dynamics pass of a heavy env (joint subspaces, inverse inertia, unconstrained velocities, gripper frames): the
 // heavy path reuses it instead of running arm_dynamics again
 template <class T>
@@ -185,24 +124,53 @@ XD bool pipe_setup(const KArgs& a, int64_t i, int sub) {
   env_load<T>(e, a.state, a.n, i);
   ArmRows<T> AR;
   SubBase<T> B;
-  ManifoldIn MI;
   const bool last = sub == T::NSUB - 1;
-  const int g0 = e.grasp[0];
-  int nc = 0;
-  ArmDyn<typename T::MD> D[1];
-  // heavy: a gripper link touches the object - or (rare) an arm joint sits on a limit: the light solver keeps no rows for those
-  if (!sub_setup_lean<T, FLAT>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc, D) || ((AR.lim_lo[0] | AR.lim_hi[0]) & 0x7fu) != 0u) {
-    a.form[i] = XARM_FORM_HEAVY;
-    dyn_store<T>(D[0], a.scratch, a.n, i);  // the heavy path continues from this dynamics pass
-    return true;
+  if constexpr (task_single_island_pair<T>()) {
+    ManifoldIn MI;
+    const int g0 = e.grasp[0];
+    int nc = 0;
+    ArmDyn<typename T::MD> D[1];
+    // heavy: a gripper link touches the object - or (rare) an arm joint sits on a limit: the light solver keeps no rows for those
+    if (!sub_setup_lean<T, FLAT>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc, D) || arm_joint_on_limit<T>(AR)) {
+      a.form[i] = XARM_FORM_HEAVY;
+      dyn_store<T>(D[0], a.scratch, a.n, i);  // the heavy path continues from this dynamics pass
+      return true;
+    }
+    float* s = a.scratch;
+    ar_store<T>(AR, s, a.n, i); s += (int64_t)pipe_ar_words<T>() * a.n;
+    sb_store<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
+    if (nc > 0) mi_store(MI, s, a.n, i);
+    a.form[i] = XARM_FORM_LIGHT | (nc << 8);
+    if (last && e.grasp[0] != g0) a.state[(int64_t)(state_words<T>() - 2) * a.n + i] = grasp_word(e.grasp[0], e.grasp_cmd[0]);  // grasp flag of the last collision pass
+    return false;
+  } else {
+    // several islands (two arms, several objects, the door): heavy = any contact outside "object on one static box"
+    constexpr int NO = T::NOBJ > 0 ? T::NOBJ : 1;
+    ManifoldIn MI[NO];
+    int nc[NO];
+    ArmDyn<typename T::MD> D[T::NARM];
+    int g0[2] = {e.grasp[0], e.grasp[1]};
+    if (!sub_setup_lean_multi<T, FLAT>(e, T::DAMP_EACH || sub == 0, last, AR, B, MI, nc, D) || arm_joint_on_limit<T>(AR)) {
+      a.form[i] = XARM_FORM_HEAVY;   // (the generic heavy path makes its own dynamics pass)
+      return true;
+    }
+    float* s = a.scratch;
+    ar_store<T>(AR, s, a.n, i); s += (int64_t)pipe_ar_words<T>() * a.n;
+    sb_store<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
+    int packed = 0;
+#pragma unroll
+    for (int o = 0; o < T::NOBJ; o++) {
+      if (nc[o] > 0) mi_store(MI[o], s + (int64_t)(o * pipe_mi_words()) * a.n, a.n, i);
+      packed |= nc[o] << (3 * o);
+    }
+    a.form[i] = XARM_FORM_LIGHT | (packed << 8);
+    if (last) {
+#pragma unroll
+      for (int arm = 0; arm < T::NARM; arm++)
+        if (e.grasp[arm] != g0[arm]) a.state[(int64_t)(state_words<T>() - 2 + arm) * a.n + i] = grasp_word(e.grasp[arm], e.grasp_cmd[arm]);
+    }
+    return false;
   }
-  float* s = a.scratch;
-  ar_store<T>(AR, s, a.n, i); s += (int64_t)pipe_ar_words<T>() * a.n;
-  sb_store<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
-  if (nc > 0) mi_store(MI, s, a.n, i);
-  a.form[i] = XARM_FORM_LIGHT | (nc << 8);
-  if (last && e.grasp[0] != g0) a.state[(int64_t)(state_words<T>() - 2) * a.n + i] = grasp_word(e.grasp[0], e.grasp_cmd[0]);  // grasp flag of the last collision pass
-  return false;
 }
 
 // ---- substep, part 2 (light envs): PGS over the arm rows and the object's manifold, then stepPositionsMultiDof.
@@ -211,16 +179,27 @@ template <class T>
 XD void pipe_light(const KArgs& a, int64_t i, float* mrows, int stride) {
   const int f = a.form[i];
   if ((f & 0xff) != XARM_FORM_LIGHT) return;
-  const int nc = f >> 8;
-  ArmRows<T> AR;
   SubBase<T> B;
-  ManifoldIn MI;
-  const float* s = a.scratch;
-  ar_load<T>(AR, s, a.n, i); s += (int64_t)pipe_ar_words<T>() * a.n;
-  sb_load<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
-  if (nc > 0) mi_load(MI, s, a.n, i);
   SubSol<T> S;
-  sub_solve_light<T>(AR, nc, MI, mrows, stride, S);
+  const float* s = a.scratch;
+  if constexpr (task_single_island_pair<T>()) {
+    const int nc = f >> 8;
+    ArmRows<T> AR;
+    ManifoldIn MI;
+    ar_load<T>(AR, s, a.n, i); s += (int64_t)pipe_ar_words<T>() * a.n;
+    sb_load<T>(B, s, a.n, i); s += (int64_t)pipe_sb_words<T>() * a.n;
+    if (nc > 0) mi_load(MI, s, a.n, i);
+    sub_solve_light<T>(AR, nc, MI, mrows, stride, S);
+  } else {
+    constexpr int NO = T::NOBJ > 0 ? T::NOBJ : 1;
+    int nc[NO];
+#pragma unroll
+    for (int o = 0; o < NO; o++) nc[o] = (f >> (8 + 3 * o)) & 7;
+    const float* s_sb = s + (int64_t)pipe_ar_words<T>() * a.n;
+    const float* s_mi = s_sb + (int64_t)pipe_sb_words<T>() * a.n;
+    sub_solve_light_multi<T>(s, s_mi, a.n, i, nc, mrows, stride, S);
+    sb_load<T>(B, s_sb, a.n, i);
+  }
   Env<T> e;
   env_load_dyn<T>(e, a.state, a.n, i);
   sub_integrate<T>(e, B, S);

@@ -1194,6 +1194,181 @@ XD bool sub_setup_lean(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR,
   return true;
 }
 
+// Lean setup for every other task shape (two arms, several objects, the door): the light form there is "no gripper link
+// touches anything, no object touches another object or a door bar, and every object rests on (or falls towards) at most
+// one static box".  Then every arm, the door and every object is an island of its own (section 5.4 of DESIGN.md): their rows
+// never read each other's velocities.  Same pair set, culls and row arithmetic as sub_setup; any point on a pair outside
+// "object x static box" sends the env through the generic path (return false; D[] stays valid).
+template <class T, bool FLAT = false>
+XD bool sub_setup_lean_multi(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, SubBase<T>& B, ManifoldIn* MI, int* nc_out,
+                             ArmDyn<typename T::MD>* D) {  // MI[NO], nc_out[NO], D[NARM]
+  using MD = typename T::MD;
+  constexpr int NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1;
+  const float h = (float)T::H;
+#pragma unroll 1
+  for (int a = 0; a < NA; a++) arm_dynamics<T, FLAT>(a, e.arm[a], apply_damping, D[a]);
+#pragma unroll
+  for (int o = 0; o < NO; o++) nc_out[o] = 0;
+  float door_qdu = 0.f;
+  if (T::HAS_DOOR) {
+    const float v = e.door_qd;
+    const float f = (apply_damping ? -(float)XARM_DOOR_DAMPING * v : 0.f) - (float)XARM_DOOR_MASS * v * (float)XARM_MB_LINEAR_DAMPING * (1.f + fabsf(v));
+    door_qdu = v + h * f / (float)XARM_DOOR_MASS;
+  }
+  if (NOBJ > 0) {
+    Box ob[NO];
+#pragma unroll 1
+    for (int o = 0; o < NOBJ; o++) { ob[o].c = e.obj[o].pos; ob[o].R = quat_to_m3(e.obj[o].quat); ob[o].h = v3(T::OBJ_HX, T::OBJ_HY, T::OBJ_HZ); }
+    const float r_ob = norm(ob[0].h);
+    CPoint one[1];
+    // ---- pairs whose points make the env heavy: object - object, gripper - object, anything - door bars, finger - table
+#pragma unroll 1
+    for (int o = 0; o < NOBJ; o++)
+#pragma unroll 1
+      for (int p2 = o + 1; p2 < NOBJ; p2++) {
+        const V3 d = ob[o].c - ob[p2].c;
+        const float rr = r_ob + r_ob + (float)XARM_CONTACT_MARGIN;
+        if (dot(d, d) > rr * rr) continue;
+        if (box_box(ob[o], ob[p2], one, 1) > 0) return false;
+      }
+    Box bar[3];
+    if (T::HAS_DOOR) {
+      const float b1[3] = XARM_DOOR_FIXED_BAR1, b2[3] = XARM_DOOR_FIXED_BAR2, org[3] = XARM_DOOR_ORIGIN, bh[3] = XARM_DOOR_BAR_HALF;
+      for (int b = 0; b < 3; b++) { bar[b].R = m3_identity(); bar[b].h = v3(bh[0], bh[1], bh[2]); }
+      bar[0].c = v3(b1[0], b1[1], b1[2]); bar[1].c = v3(b2[0], b2[1], b2[2]);
+      bar[2].c = v3(org[0], org[1], org[2]) + e.door_q * door_axis();
+      const float r_bar = norm(bar[0].h);
+#pragma unroll 1
+      for (int o = 0; o < NOBJ; o++)
+#pragma unroll 1
+        for (int b = 0; b < 3; b++) {
+          const V3 d = ob[o].c - bar[b].c;
+          const float rr = r_ob + r_bar + (float)XARM_CONTACT_MARGIN;
+          if (dot(d, d) > rr * rr) continue;
+          if (box_box(ob[o], bar[b], one, 1) > 0) return false;
+        }
+    }
+    if (MD::HAS_BOXES) {
+#pragma unroll 1
+      for (int a = 0; a < NA; a++)
+#pragma unroll 1
+        for (int which = 1; which <= 3; which++) {
+          const Box g = arm_box<T>(D[a], which == 3 ? 0 : which);
+          const float r_g = norm(g.h);
+#pragma unroll 1
+          for (int o = 0; o < NOBJ; o++) {
+            const V3 d = g.c - ob[o].c;
+            const float rr = r_g + r_ob + (float)XARM_CONTACT_MARGIN;
+            if (dot(d, d) > rr * rr) continue;
+            if (box_box(g, ob[o], one, 1) > 0) return false;
+          }
+          if (T::HAS_DOOR) {
+            const float r_bar = norm(bar[0].h);
+#pragma unroll 1
+            for (int b = 0; b < 3; b++) {
+              const V3 d = g.c - bar[b].c;
+              const float rr = r_g + r_bar + (float)XARM_CONTACT_MARGIN;
+              if (dot(d, d) > rr * rr) continue;
+              if (box_box(g, bar[b], one, 1) > 0) return false;
+            }
+          }
+          if (T::FINGER_TABLE && which != 3) {
+#pragma unroll 1
+            for (int k = 0; k < T::NTABLE; k++) {
+              Box tb;
+              tb.R = m3_identity();
+              tb.c = v3(T::table_x(k), 0.f, -(float)XARM_TABLE_HALF_Z);
+              tb.h = v3((float)XARM_TABLE_HALF_X, (float)XARM_TABLE_HALF_Y, (float)XARM_TABLE_HALF_Z);
+              const V3 d = g.c - tb.c;
+              const float rr = r_g + norm(tb.h) + (float)XARM_CONTACT_MARGIN;
+              if (dot(d, d) > rr * rr) continue;
+              if (box_box(g, tb, one, 1) > 0) return false;
+            }
+          }
+        }
+    }
+    // ---- every object against the static boxes (tables, ground): at most one of them may produce points
+#pragma unroll 1
+    for (int o = 0; o < NOBJ; o++) {
+      CPoint pts[4];
+      int npts = 0, npair = 0;
+      float mu = 0.f;
+#pragma unroll 1
+      for (int k = 0; k < T::NTABLE + (T::HAS_GROUND ? 1 : 0); k++) {
+        Box tb;
+        tb.R = m3_identity();
+        if (k < T::NTABLE) {
+          tb.c = v3(T::table_x(k), 0.f, -(float)XARM_TABLE_HALF_Z);
+          tb.h = v3((float)XARM_TABLE_HALF_X, (float)XARM_TABLE_HALF_Y, (float)XARM_TABLE_HALF_Z);
+        } else {
+          tb.c = v3(0.f, 0.f, (float)XARM_GROUND_Z - 5.f); tb.h = v3(100.f, 100.f, 5.f);
+        }
+        const V3 d = ob[o].c - tb.c;
+        const float rr = r_ob + norm(tb.h) + (float)XARM_CONTACT_MARGIN;
+        if (dot(d, d) > rr * rr) continue;
+        CPoint p4[4];
+        const int kk = box_box(ob[o], tb, p4, 4);
+        if (kk > 0) {
+          if (++npair > 1) return false;
+          npts = kk;
+          mu = fminf((float)XARM_DEFAULT_FRICTION * (k < T::NTABLE ? (float)XARM_TABLE_FRICTION : 1.0f), (float)XARM_MAX_FRICTION);
+#pragma unroll
+          for (int c = 0; c < 4; c++) pts[c] = p4[c];
+        }
+      }
+      const ObjState& b = e.obj[o];
+      const float kl = (float)XARM_MB_LINEAR_DAMPING * (1.f + norm(b.v)), ka = (float)XARM_MB_ANGULAR_DAMPING * (1.f + norm(b.w));
+      V3 vu = b.v + h * ((-kl) * b.v); vu.z -= h * (float)XARM_GRAVITY;
+      const V3 wu = b.w + h * ((-ka) * b.w);
+      B.vu[o] = vu; B.wu[o] = wu;
+      if (npts > 0) {
+        ManifoldIn& M = MI[o];
+        M.mu = mu;
+        const float lx = 2 * T::OBJ_HX, ly = 2 * T::OBJ_HY, lz = 2 * T::OBJ_HZ, m12 = T::OBJ_MASS / 12.f;
+        const S3 Il = {1.f / (m12 * (ly * ly + lz * lz)), 0, 0, 1.f / (m12 * (lx * lx + lz * lz)), 0, 1.f / (m12 * (lx * lx + ly * ly))};
+        const S3 Iinv = rotate_sym(ob[o].R, Il);
+        M.Iinv = Iinv;
+        M.n = pts[0].n;
+        V3 t1, t2;
+        plane_space(M.n, t1, t2);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const bool on = c < npts;
+          const V3 r = on ? pts[c].pa - b.pos : v3(0, 0, 0);
+          M.r[c] = r;
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const V3 d = k == 0 ? M.n : (k == 1 ? t1 : t2);
+            const V3 rxd = cross(r, d), ir = Iinv * rxd;
+            float den = 0.f, rel = 0.f;
+            den += 1.f / T::OBJ_MASS + dot(rxd, ir);
+            rel += 1.f * (dot(d, vu) + dot(rxd, wu));
+            float rhs;
+            if (k == 0) {
+              const float dinv = 1.f / (den + 0.f);
+              const float pen = -pts[c].depth + (float)XARM_LINEAR_SLOP;
+              float pos_err = 0.f, vel_err = -rel;
+              if (pen > 0.f) vel_err -= pen / h; else pos_err = -pen * (float)XARM_ERP2 / h;
+              rhs = (pos_err + vel_err) * dinv;
+            } else {
+              rhs = -rel * (1.f / den);
+            }
+            M.rhs[c][k] = on ? rhs : 0.f;
+          }
+        }
+      }
+      nc_out[o] = npts;
+    }
+    if (last && MD::HAS_BOXES)
+#pragma unroll
+      for (int a = 0; a < NA; a++) e.grasp[a] = 0;  // no gripper contact in this (the last) collision pass
+  } else {
+    B.vu[0] = v3(0, 0, 0); B.wu[0] = v3(0, 0, 0);
+  }
+  arm_rows<T>(e, D, door_qdu, AR, B);
+  return true;
+}
+
 // ---- row updates shared by the solver forms (they act on the local register arrays Mi, iden, dqd, ... of the caller)
 // one unit row (J = sign * e_i) of arm a: motors and joint limits
 #define UNIT_ROW(a, i, sign, rhs_, lo_, hi_, app_)                                   \
@@ -1413,6 +1588,223 @@ XD void sub_solve_light(const ArmRows<T>& AR, int nc, const ManifoldIn& MI, floa
   S.dv[0] = v; S.dw[0] = w; S.ddoor = 0.f;
 }
 
+// ---- Light form of the tasks with several islands (two arms, several objects, the door): sub_setup_lean_multi guarantees
+// that every arm, the door and every object with a manifold is an island - no row of one reads a velocity of another.  The
+// joint loop of Bullet interleaves their rows, but a Gauss-Seidel sweep over independent islands gives every island the
+// impulses it would get alone, so the islands are swept ONE AFTER THE OTHER (only one island's rows in registers at a time).
+// What the islands share is the loop's exit test (max over ALL rows): every island returns a bit per sweep ("some row of
+// mine moved more than the threshold"); the joint loop leaves after the first sweep whose bit is clear in every island, and
+// if that happens before the last sweep the islands are swept again up to there (rare: arms and objects at rest).
+// Rows of one arm in the scratch-slab order of ar_store: Mi[NT] | mrhs[N] | lrhs[N] | lim_lo lim_hi | grhs gdinv gden.
+template <class T>
+XHD int ar_arm_words() { return T::MD::N * (T::MD::N + 1) / 2 + 2 * T::MD::N + 5; }
+template <class T>
+XD uint64_t light_island_arm(const float* __restrict__ s, int64_t n, int64_t i, int sweeps, float* dqd_out) {
+  using MD = typename T::MD;
+  constexpr int N = MD::N, NT = N * (N + 1) / 2;
+  float Mi[1][NT], iden[1][N], dqd[1][N], mrhs[1][N], mapp[1][N], lrhs[1][N], lapp[1][N];
+  uint32_t lim_lo[1], lim_hi[1];
+  float grhs[1], gapp[1], gdinv[1];
+  const float hi_arm = (float)(T::ARM_FORCE * T::TIME_STEP), hi_fin = (float)(T::FINGER_FORCE * T::TIME_STEP);
+  const float hi_gear = (float)(XARM_GEAR_MAX_FORCE * T::TIME_STEP), hi_lim = (float)XARM_LIMIT_MAX_IMPULSE;
+  const float gr = (float)XARM_GEAR_RATIO;
+  const float sthr_ = sqrtf((float)XARM_RESIDUAL_THRESHOLD);
+  (void)hi_gear; (void)gr; (void)hi_lim;
+  int w = 0;
+#pragma unroll
+  for (int k = 0; k < NT; k++) Mi[0][k] = s[(w++) * n + i];
+#pragma unroll
+  for (int k = 0; k < N; k++) { mrhs[0][k] = s[(w++) * n + i]; mapp[0][k] = 0.f; lapp[0][k] = 0.f; dqd[0][k] = 0.f; iden[0][k] = 1.f / Mi[0][tri(k, k)]; }
+#pragma unroll
+  for (int k = 0; k < N; k++) lrhs[0][k] = s[(w++) * n + i];
+  lim_lo[0] = (uint32_t)s[(w++) * n + i]; lim_hi[0] = (uint32_t)s[(w++) * n + i];
+  grhs[0] = s[(w++) * n + i]; gdinv[0] = s[(w++) * n + i]; gapp[0] = 0.f;
+  uint64_t bad = 0;
+  for (int it = 0; it < sweeps; it++) {
+    bool resid_bad = false;
+    if (it & 1) {
+      ARM_LIMITS_FWD_GRIPPER(0) ARM_MOTORS_FWD(0) GEAR_ROW(0)
+    } else {
+      GEAR_ROW(0) ARM_MOTORS_BWD(0) ARM_LIMITS_BWD_GRIPPER(0)
+    }
+    bad |= (uint64_t)(resid_bad ? 1u : 0u) << it;
+  }
+#pragma unroll
+  for (int k = 0; k < N; k++) dqd_out[k] = dqd[0][k];
+  return bad;
+}
+// the door's two rows (default velocity motor, violated limit); words dl_rhs dl_sign dm_rhs door_lim at s
+XD uint64_t light_island_door(const float* __restrict__ s, int64_t n, int64_t i, int sweeps, float& ddoor_out) {
+  const float dl_rhs = s[0 * n + i], dl_sign = s[1 * n + i], dm_rhs = s[2 * n + i];
+  const bool door_lim = (int)s[3 * n + i] != 0;
+  const float door_den = 1.f / (float)XARM_DOOR_MASS, hi_lim = (float)XARM_LIMIT_MAX_IMPULSE;
+  const float sthr_ = sqrtf((float)XARM_RESIDUAL_THRESHOLD);
+  float ddoor = 0.f, dl_app = 0.f, dm_app = 0.f;
+  uint64_t bad = 0;
+  for (int it = 0; it < sweeps; it++) {
+    bool resid_bad = false;
+    if (it & 1) { DOOR_LIMIT_ROW() DOOR_MOTOR_ROW() } else { DOOR_MOTOR_ROW() DOOR_LIMIT_ROW() }
+    bad |= (uint64_t)(resid_bad ? 1u : 0u) << it;
+  }
+  ddoor_out = ddoor;
+  return bad;
+}
+// one object's manifold against a static box (the manifold part of sub_solve_light)
+template <class T>
+XD uint64_t light_island_manifold(const ManifoldIn& MI, int nc, float* mrows, int stride, int sweeps, V3& v_out, V3& w_out) {
+  const float inv_obj_mass = 1.f / T::OBJ_MASS;
+  const float sthr_ = sqrtf((float)XARM_RESIDUAL_THRESHOLD);
+  manifold_rows_store<T>(MI, nc, mrows, stride);
+  const V3 n = MI.n;
+  const float mu = MI.mu;
+  V3 t1, t2;
+  plane_space(n, t1, t2);
+  const V3 nm = inv_obj_mass * n, t1m = inv_obj_mass * t1, t2m = inv_obj_mass * t2;
+  float an[4], a1[4], a2[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) { an[c] = 0.f; a1[c] = 0.f; a2[c] = 0.f; }
+  V3 v = v3(0, 0, 0), w = v3(0, 0, 0);
+  uint64_t bad = 0;
+#define MR(c, k) mrows[(size_t)(24 * (c) + (k)) * stride]
+#define MRV(c, k) v3(MR(c, k), MR(c, (k) + 1), MR(c, (k) + 2))
+  for (int it = 0; it < sweeps; it++) {
+    bool resid_bad = false;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {  // normal rows
+      const float dn = MR(c, 19);
+      float delta = MR(c, 18) - (dot(n, v) + dot(MRV(c, 0), w)) * dn;
+      const float sum = an[c] + delta;
+      const float sumc = fminf(fmaxf(sum, 0.f), (float)XARM_CONTACT_MAX_IMPULSE);
+      delta = (sumc == sum) ? delta : sumc - an[c];
+      an[c] = sumc;
+      v += delta * nm; w += delta * MRV(c, 3);
+      resid_bad = resid_bad || fabsf(delta) > sthr_ * dn;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {  // friction pairs, implicit cone
+      const float lim = mu * an[c];
+      const float d1 = MR(c, 21), d2 = MR(c, 23);
+      float da = MR(c, 20) - (dot(t1, v) + dot(MRV(c, 6), w)) * d1, db = MR(c, 22) - (dot(t2, v) + dot(MRV(c, 12), w)) * d2;
+      float sa = a1[c] + da, sb = a2[c] + db;
+      const float l2 = sa * sa + sb * sb;
+      if (l2 > lim * lim) {
+        const float len = sqrtf(l2);
+        if (len > lim) { const float sc = lim / len; sa *= sc; sb *= sc; da = sa - a1[c]; db = sb - a2[c]; }
+      }
+      a1[c] = sa; a2[c] = sb;
+      v += da * t1m; w += da * MRV(c, 9);
+      v += db * t2m; w += db * MRV(c, 15);
+      resid_bad = resid_bad || fabsf(da) > sthr_ * d1 || fabsf(db) > sthr_ * d2;
+    }
+    bad |= (uint64_t)(resid_bad ? 1u : 0u) << it;
+  }
+#undef MR
+#undef MRV
+  v_out = v; w_out = w;
+  return bad;
+}
+
+// ---- scratch records of the rows (the pipeline's setup kernel writes them, its light kernel reads them; word w of env i at
+// base[w * n + i]).  The fused per-env substep() uses the same records with n = 1.
+template <class T>
+XD void ar_store(const ArmRows<T>& AR, float* __restrict__ s, int64_t n, int64_t i) {
+  constexpr int N = T::MD::N, NT = N * (N + 1) / 2;
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++) {
+#pragma unroll
+    for (int k = 0; k < NT; k++) s[(w++) * n + i] = AR.Mi[a][k];
+#pragma unroll
+    for (int k = 0; k < N; k++) s[(w++) * n + i] = AR.mrhs[a][k];
+#pragma unroll
+    for (int k = 0; k < N; k++) s[(w++) * n + i] = AR.lrhs[a][k];
+    s[(w++) * n + i] = (float)AR.lim_lo[a]; s[(w++) * n + i] = (float)AR.lim_hi[a];  // bit masks < 2^13: exact
+    s[(w++) * n + i] = AR.grhs[a]; s[(w++) * n + i] = AR.gdinv[a]; s[(w++) * n + i] = AR.gden[a];
+  }
+  s[(w++) * n + i] = AR.dl_rhs; s[(w++) * n + i] = AR.dl_sign; s[(w++) * n + i] = AR.dm_rhs;
+  s[(w++) * n + i] = (float)AR.door_lim;
+}
+template <class T>
+XD void ar_load(ArmRows<T>& AR, const float* __restrict__ s, int64_t n, int64_t i) {
+  constexpr int N = T::MD::N, NT = N * (N + 1) / 2;
+  int w = 0;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++) {
+#pragma unroll
+    for (int k = 0; k < NT; k++) AR.Mi[a][k] = s[(w++) * n + i];
+#pragma unroll
+    for (int k = 0; k < N; k++) AR.mrhs[a][k] = s[(w++) * n + i];
+#pragma unroll
+    for (int k = 0; k < N; k++) AR.lrhs[a][k] = s[(w++) * n + i];
+    AR.lim_lo[a] = (uint32_t)s[(w++) * n + i]; AR.lim_hi[a] = (uint32_t)s[(w++) * n + i];
+    AR.grhs[a] = s[(w++) * n + i]; AR.gdinv[a] = s[(w++) * n + i]; AR.gden[a] = s[(w++) * n + i];
+  }
+  AR.dl_rhs = s[(w++) * n + i]; AR.dl_sign = s[(w++) * n + i]; AR.dm_rhs = s[(w++) * n + i];
+  AR.door_lim = (int)s[(w++) * n + i];
+}
+XD void mi_store(const ManifoldIn& M, float* __restrict__ s, int64_t n, int64_t i) {
+  int w = 0;
+  s[(w++) * n + i] = M.n.x; s[(w++) * n + i] = M.n.y; s[(w++) * n + i] = M.n.z; s[(w++) * n + i] = M.mu;
+#pragma unroll
+  for (int c = 0; c < 4; c++) { s[(w++) * n + i] = M.r[c].x; s[(w++) * n + i] = M.r[c].y; s[(w++) * n + i] = M.r[c].z; }
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) s[(w++) * n + i] = M.rhs[c][k];
+  s[(w++) * n + i] = M.Iinv.xx; s[(w++) * n + i] = M.Iinv.xy; s[(w++) * n + i] = M.Iinv.xz;
+  s[(w++) * n + i] = M.Iinv.yy; s[(w++) * n + i] = M.Iinv.yz; s[(w++) * n + i] = M.Iinv.zz;
+}
+XD void mi_load(ManifoldIn& M, const float* __restrict__ s, int64_t n, int64_t i) {
+  int w = 0;
+  M.n.x = s[(w++) * n + i]; M.n.y = s[(w++) * n + i]; M.n.z = s[(w++) * n + i]; M.mu = s[(w++) * n + i];
+#pragma unroll
+  for (int c = 0; c < 4; c++) { M.r[c].x = s[(w++) * n + i]; M.r[c].y = s[(w++) * n + i]; M.r[c].z = s[(w++) * n + i]; }
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) M.rhs[c][k] = s[(w++) * n + i];
+  M.Iinv.xx = s[(w++) * n + i]; M.Iinv.xy = s[(w++) * n + i]; M.Iinv.xz = s[(w++) * n + i];
+  M.Iinv.yy = s[(w++) * n + i]; M.Iinv.yz = s[(w++) * n + i]; M.Iinv.zz = s[(w++) * n + i];
+}
+
+XHD int mi_words() { return 3 + 1 + 12 + 12 + 6; }
+template <class T>
+constexpr bool task_single_island_pair() { return T::NARM == 1 && !T::HAS_DOOR && T::NOBJ <= 1; }   // Reach, PickAndPlace with one lego: sub_setup_lean + sub_solve_light
+
+// the multi-island light solve: rows from the scratch records (ar | door words at the end of ar | mi[o] at s_mi + o * mi_words),
+// nc[o] manifold points of object o.  mrows: room for ONE manifold's rows (reused object after object).
+template <class T>
+XD void sub_solve_light_multi(const float* __restrict__ s_ar, const float* __restrict__ s_mi, int64_t n, int64_t i, const int* nc,
+                              float* mrows, int stride, SubSol<T>& S) {
+  constexpr int NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1;
+  static_assert(XARM_SOLVER_ITERATIONS <= 63, "one bit per sweep");
+  int sweeps = XARM_SOLVER_ITERATIONS;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    uint64_t bad = 0;
+#pragma unroll 1
+    for (int a = 0; a < NA; a++) bad |= light_island_arm<T>(s_ar + (int64_t)(a * ar_arm_words<T>()) * n, n, i, sweeps, S.dqd[a]);
+    S.ddoor = 0.f;
+    if (T::HAS_DOOR) bad |= light_island_door(s_ar + (int64_t)(NA * ar_arm_words<T>()) * n, n, i, sweeps, S.ddoor);
+#pragma unroll 1
+    for (int o = 0; o < NO; o++) {
+      S.dv[o] = v3(0, 0, 0); S.dw[o] = v3(0, 0, 0);
+      if (o < NOBJ && nc[o] > 0) {
+        ManifoldIn MI;
+        mi_load(MI, s_mi + (int64_t)(o * mi_words()) * n, n, i);
+        bad |= light_island_manifold<T>(MI, nc[o], mrows, stride, sweeps, S.dv[o], S.dw[o]);
+      }
+    }
+    // the joint loop leaves after the first sweep in which no row of any island moved more than the threshold
+    const uint64_t good = ~bad & ((1ull << sweeps) - 1ull);
+    if (good == 0ull) break;
+    int first = 0;
+    while (!((good >> first) & 1ull)) first++;
+    if (first + 1 >= sweeps) break;
+    sweeps = first + 1;
+  }
+}
+
 // Generic form: the joint loop of btMultiBodyConstraintSolver::solveSingleIteration over ALL rows of the env -
 // non-contact rows of every arm and the door (forward on odd sweeps, backward on even ones), the normal rows of every
 // contact, then its friction pairs (implicit cone) - until no row moved more than the residual threshold.  Contact rows
@@ -1582,22 +1974,49 @@ XD void sub_integrate(Env<T>& e, const SubBase<T>& B, const SubSol<T>& S) {
 
 // One internal substep, fused: collide -> unconstrained velocities -> rows -> PGS -> integrate.
 template <class T>
-constexpr bool task_has_light() { return T::NARM == 1 && !T::HAS_DOOR && T::NOBJ <= 1; }
+constexpr bool task_has_light() { return true; }   // every task has a light solver form (single island pair or multi-island)
+template <class T>
+XHD int ar_words() { return T::NARM * ar_arm_words<T>() + 4; }   // ar_store record: per arm, then dl_rhs dl_sign dm_rhs door_lim
+template <class T>
+XD bool arm_joint_on_limit(const ArmRows<T>& AR) {   // the light forms keep limit rows for the gripper dofs only
+  uint32_t m = 0u;
+#pragma unroll
+  for (int a = 0; a < T::NARM; a++) m |= AR.lim_lo[a] | AR.lim_hi[a];
+  return (m & 0x7fu) != 0u;
+}
 template <class T>
 NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
   ArmRows<T> AR;
   SubBase<T> B;
   SubSol<T> S;
   ManifoldIn MI;
-  if constexpr (task_has_light<T>()) {
+  if constexpr (task_single_island_pair<T>()) {
     int nc = 0;
     ArmDyn<typename T::MD> D[1];
-    if (sub_setup_lean<T>(e, apply_damping, last, AR, B, MI, nc, D) && ((AR.lim_lo[0] | AR.lim_hi[0]) & 0x7fu) == 0u) {  // (arm-joint limits: generic form)
+    if (sub_setup_lean<T>(e, apply_damping, last, AR, B, MI, nc, D) && !arm_joint_on_limit<T>(AR)) {  // (arm-joint limits: generic form)
       float mrows[XARM_MROW_WORDS];
       sub_solve_light<T>(AR, nc, MI, mrows, 1, S);
       sub_integrate<T>(e, B, S);
       return;
     }
+  } else {
+    constexpr int NO = T::NOBJ > 0 ? T::NOBJ : 1;
+    ManifoldIn MIs[NO];
+    int nc[NO];
+    ArmDyn<typename T::MD> D[T::NARM];
+    int g0[T::NARM];
+    for (int a = 0; a < T::NARM; a++) g0[a] = e.grasp[a];
+    if (sub_setup_lean_multi<T>(e, apply_damping, last, AR, B, MIs, nc, D) && !arm_joint_on_limit<T>(AR)) {
+      float rec_ar[T::NARM * (T::MD::N * (T::MD::N + 1) / 2 + 2 * T::MD::N + 5) + 4], rec_mi[NO * 34];
+      static_assert(sizeof(rec_mi) / sizeof(float) / NO == 34, "ManifoldIn record");
+      ar_store<T>(AR, rec_ar, 1, 0);
+      for (int o = 0; o < T::NOBJ; o++) if (nc[o] > 0) mi_store(MIs[o], rec_mi + o * mi_words(), 1, 0);
+      float mrows[XARM_MROW_WORDS];
+      sub_solve_light_multi<T>(rec_ar, rec_mi, 1, 0, nc, mrows, 1, S);
+      sub_integrate<T>(e, B, S);
+      return;
+    }
+    for (int a = 0; a < T::NARM; a++) e.grasp[a] = g0[a];   // (the lean setup may have cleared the flags before it found a contact)
   }
   Contacts<T> C;
   const int form = sub_setup<T>(e, apply_damping, last, AR, C, B, MI);
