@@ -34,7 +34,7 @@ ENV_ID = {"reach": "XarmReach-v0", "pick_and_place": "XarmPDPickAndPlace-v0", "s
 FP32_NOMINAL_TFLOPS = 74.4  # 148 SM x 128 lanes x 2 x 1.965 GHz; the measured figure comes from xarm_measure_fp32_peak
 KERNEL_NAMES = {"setup": "k_pipe_setup", "light": "k_pipe_light", "heavy_rows": "k_heavy_rows", "heavy_solve": "k_heavy_solve2",
                 "action": "k_pipe_action", "finish": "k_pipe_finish", "reset_stage": "k_pipe_reset_stage", "heavy_all": "k_pipe_heavy_all",
-                "heavy_fused": "k_heavy_fused", "heavy_local": "k_pipe_heavy_local"}
+                "heavy_fused": "k_heavy_fused", "heavy_local": "k_pipe_heavy_local", "heavy_rec": "k_pipe_heavy_rec"}
 
 
 def bench_config(task):

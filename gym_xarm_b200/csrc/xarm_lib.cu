@@ -197,13 +197,43 @@ __global__ void __launch_bounds__(32) k_pipe_heavy(KArgs a, int sub, const int* 
 // env): the heavy envs of the substep - the minority there - keep the record in thread-local memory, one thread per env.
 template <class T>
 constexpr bool heavy_record_fits_smem() { return heavy_smem_bytes_of<T>() <= 160 * 1024; }
+// Two forms, both launched, the list size decides on the device (as for the other heavy kernels):
+//  RECORD IN SHARED MEMORY (lists <= XARM_HEAVY_REC_MAX): 8 envs per block, one lane each, the env's record packed in shared
+//    memory (3 blocks = 24 envs per SM).  Thread-local memory is interleaved over the 32 lanes of a warp, so a warp's records
+//    occupy 32 x 9 KB of cache whatever the number of active lanes: the 50 sweeps then stream every row from L2 (2-3 ms per
+//    substep measured for ANY list size, one env per thread as well as one env per 8 lanes).
+//  DENSE, thread-local (longer lists: the reset wave of a batch whose episodes run in phase): one env per thread.
+#define XARM_HEAVY_REC_MAX 12288
+#define XARM_HEAVY_REC_LANES 8
+template <class T>
+constexpr size_t heavy_rec_smem_bytes() { return (size_t)heavy_stride_words<T>() * XARM_HEAVY_REC_LANES * sizeof(float); }
+template <class T>
+__global__ void __launch_bounds__(XARM_HEAVY_REC_LANES) k_pipe_heavy_rec(KArgs a, int sub, const int* heavy_count) {
+  extern __shared__ float4 heavy_smem4[];
+  float* heavy_smem = reinterpret_cast<float*>(heavy_smem4);
+  const int count = *heavy_count;
+  if (count > XARM_HEAVY_REC_MAX) return;
+  if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + a.tl_branch, (unsigned long long)count);
+  PIPE_LEAVE_RESERVED(a)
+  bool any = false;
+  for (int64_t base = pipe_next(a, -1, XARM_HEAVY_REC_LANES); base < count; base = pipe_next(a, base, XARM_HEAVY_REC_LANES)) {
+    if (!any) { tl_mark(a, 0); any = true; }
+    const int64_t t = base + threadIdx.x;
+    if (t < count) {
+      Contacts<T>& C = *reinterpret_cast<Contacts<T>*>(heavy_smem + (size_t)threadIdx.x * heavy_stride_words<T>());
+      pipe_heavy<T>(a, a.heavy_list[a.heavy_dir * t], sub, C);
+    }
+  }
+  if (any) tl_mark(a, 1);
+}
 template <class T>
 __global__ void __launch_bounds__(64) k_pipe_heavy_local(KArgs a, int sub, const int* heavy_count) {
-  if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + a.tl_branch, (unsigned long long)*heavy_count);
-  PIPE_LEAVE_RESERVED(a)
   const int count = *heavy_count;
+  if (count <= XARM_HEAVY_REC_MAX) return;
+  if (a.tl && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.tl + 5 * XARM_TL_SLOTS + a.tl_branch, (unsigned long long)count);
+  PIPE_LEAVE_RESERVED(a)
   bool any = false;
-  for (int64_t base = pipe_next(a, -1, blockDim.x); base < count; base = pipe_next(a, base, blockDim.x)) {
+  for (int64_t base = pipe_next(a, -1, 64); base < count; base = pipe_next(a, base, 64)) {
     if (!any) { tl_mark(a, 0); any = true; }
     const int64_t t = base + threadIdx.x;
     if (t < count) { Contacts<T> C; pipe_heavy<T>(a, a.heavy_list[a.heavy_dir * t], sub, C); }
@@ -563,7 +593,7 @@ struct OpsT {
       return (int)cudaFuncSetAttribute(k_heavy_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes());
     }
     else if constexpr (heavy_record_fits_smem<T>()) return (int)cudaFuncSetAttribute(k_pipe_heavy<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem_bytes());
-    return 0;
+    else return (int)cudaFuncSetAttribute(k_pipe_heavy_rec<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_rec_smem_bytes<T>());
   }
   static void init(const KArgs& a, cudaStream_t s) { k_init<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
   static void obs(const KArgs& a, cudaStream_t s) { k_obs<T><<<grid(a.n), 128, 0, s>>>(a); g_launches++; }
@@ -627,9 +657,13 @@ struct OpsT {
         } else if constexpr (heavy_record_fits_smem<T>()) {
           k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), sh>>>(a, sub, hc);
         } else {
+          c.begin("heavy_rec", sh);
+          k_pipe_heavy_rec<T><<<c.heavy_grid * 3, XARM_HEAVY_REC_LANES, heavy_rec_smem_bytes<T>(), sh>>>(c.tl(a), sub, hc);
+          c.end(sh);
           c.begin("heavy_local", sh);
           k_pipe_heavy_local<T><<<rows_grid, 64, 0, sh>>>(c.tl(a), sub, hc);
           c.end(sh);
+          g_launches++;
         }
         if (fork_heavy) cudaEventRecord(join, sh);
         c.begin("light", s);
@@ -901,7 +935,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
         cudaFree(d_seen);
         int total = 0, taken = 0;
         for (int id = 0; id < 256; id++) total += (seen[id >> 5] >> (id & 31)) & 1u;
-        if (total >= 4 * want)
+        if (total >= 2 * want)
           for (int id = 0; id < 256 && taken < want; id++)
             if ((seen[id >> 5] >> (id & 31)) & 1u) { h->pipe.sm_mask[id >> 6] |= 1ull << (id & 63); taken++; }
         h->pipe.reserve_sms = taken;
