@@ -130,8 +130,22 @@ __device__ __forceinline__ void setup_body(const KArgs& a, int sub, int* heavy_c
   }
   tl_mark(a, 1);
 }
+// Register budget of the setup kernel.  Single-island-pair tasks (Reach, PickAndPlace with one lego): the FLAT form - link passes
+// unrolled, f[] / I[] / S[] / M[] in registers, 255 registers, 2 blocks per SM.  The rolled 128-register form (4 blocks per SM) keeps a
+// 2.1 KB thread-local stack frame per thread: 165 MB over the resident threads of a full-size launch, more than the L2 holds - 270 MB
+// read + 330 MB written per launch (profiles/r2o_traffic_summary.txt), and that stream evicts the early branch's working set from the
+// L2: with the FLAT form the main branch's launch takes the same 277 us at half the warps and the early branch's kernels run 8-13 %
+// faster next to it (setup 71 -> 62 us, fused heavy 171 -> 159 us; 4.93 -> 5.07 M env-steps/s).  XARM_SETUP_FLAT=0/1 overrides (A/B).
 template <class T>
-__global__ void __launch_bounds__(128, XARM_SETUP_MINB) k_pipe_setup(KArgs a, int sub, int* heavy_count) { setup_body<T, false>(a, sub, heavy_count); }
+constexpr bool setup_flat() {
+#ifdef XARM_SETUP_FLAT
+  return XARM_SETUP_FLAT != 0;
+#else
+  return task_single_island_pair<T>();
+#endif
+}
+template <class T>
+__global__ void __launch_bounds__(128, setup_flat<T>() ? 2 : XARM_SETUP_MINB) k_pipe_setup(KArgs a, int sub, int* heavy_count) { setup_body<T, setup_flat<T>()>(a, sub, heavy_count); }
 
 // Two register budgets of the same light kernel.  LAT = false: 128 registers (some spills), 4 blocks per SM - the
 // throughput form (main branch, reset waves).  LAT = true: 160 registers (no hot spills: 86 instead of 121 us per warp) -
@@ -484,6 +498,7 @@ struct PipeCtx {
   // SM partition (XARM_RESERVE_SMS, default 32; 0 = off): while `dyn` is set (main branch of a split step) every launch
   // gets a work counter and the mask of the SMs it must leave to the early branch
   bool dyn = false;
+  bool e_swap = true;       // XARM_E_SWAP=0: the early branch's heavy kernels on the side stream, its light kernel on the chain's stream (round 2 start)
   bool light_multi = true;  // XARM_LIGHT_MULTI=0: tasks with several islands (two arms, door, several objects) take the generic substep for every env (round 1)
   bool light_dual = true;   // XARM_LIGHT_DUAL=0: one light kernel form everywhere
   bool main_wait = true;    // XARM_MAIN_WAIT=0: the main branch starts together with the early branch
@@ -491,7 +506,7 @@ struct PipeCtx {
   bool main_fork = true;    // XARM_MAIN_FORK=0: the main branch of a split step keeps one stream (heavy kernels, then light)
   bool tail_lat = true;     // XARM_TAIL_LAT=0: the early branch keeps the round-1 kernels (128-register setup, 160-register light with shared-memory rows)
   bool light_main_lat = true;    // XARM_LIGHT_MAIN_LAT=0: the partitioned main branch keeps the 128-register form (A/B)
-  int setup_bps = 4;   // resident blocks per SM of the partitioned main branch's setup kernel (XARM_SETUP_BPS)
+  int setup_bps = 0;   // resident blocks per SM of the partitioned main branch's setup kernel (XARM_SETUP_BPS; 0 = what the kernel's register budget allows)
   int reserve_sms = 0, n_work = 0, next_work = 0;
   int* work_base = nullptr;
   unsigned long long sm_mask[4] = {0, 0, 0, 0};
@@ -616,11 +631,15 @@ struct OpsT {
       } else {
         int* hc = a.heavy_count + pass * XARM_MAX_SUBSTEPS + sub;
         c.begin("setup", s);
-        k_pipe_setup<T><<<part ? dim3(c.heavy_grid * c.setup_bps) : g, 128, 0, s>>>(c.tl(a), sub, hc);
+        k_pipe_setup<T><<<part ? dim3(c.heavy_grid * (c.setup_bps > 0 ? c.setup_bps : (setup_flat<T>() ? 2 : 4))) : g, 128, 0, s>>>(c.tl(a), sub, hc);
         c.end(s);
-        cudaEvent_t join = nullptr;
+        // Early branch (XARM_E_SWAP, default on): the fused heavy kernel - the critical path of every substep there - stays on the
+        // chain's own stream right behind the setup kernel, and the light kernel takes the side stream.
+        const bool swap = c.e_swap && c.cur_branch == 'E' && fork_heavy && task_has_heavy_rows<T>() && c.fused && c.dela;
+        const cudaStream_t hs = swap ? s : sh, ls = swap ? sh : s;
+        cudaEvent_t join = nullptr, fork = nullptr;
         if (fork_heavy) {
-          cudaEvent_t fork = c.next();
+          fork = c.next();
           join = c.next();
           cudaEventRecord(fork, s);
           cudaStreamWaitEvent(sh, fork, 0);
@@ -628,18 +647,18 @@ struct OpsT {
         if constexpr (task_has_heavy_rows<T>()) {
           cudaEvent_t join2 = nullptr;
           if (c.fused && c.dela) {
-            c.begin("heavy_fused", sh);
+            c.begin("heavy_fused", hs);
             KArgs af = c.tl(a); af.heavy_dual = 1;
-            k_heavy_fused<T><<<solve_grid / 3 * XARM_FUSED_BLOCKS_PER_SM, 32, fused_smem_bytes(), sh>>>(af, sub, hc);
-            c.end(sh);
+            k_heavy_fused<T><<<solve_grid / 3 * XARM_FUSED_BLOCKS_PER_SM, 32, fused_smem_bytes(), hs>>>(af, sub, hc);
+            c.end(hs);
           }
           {
             // the throughput pair: after the fused kernel on the same stream, or - early branch, where every launch on the chain
             // counts - next to it on a third stream
-            cudaStream_t sr = sh;
+            cudaStream_t sr = hs;
             if (c.fused && c.dela && sh2 && fork_heavy) {
-              cudaEvent_t fork2 = c.next(); join2 = c.next();
-              cudaEventRecord(fork2, s); cudaStreamWaitEvent(sh2, fork2, 0);
+              join2 = c.next();
+              cudaStreamWaitEvent(sh2, fork, 0);
               sr = sh2;
             }
             c.begin("heavy_rows", sr);
@@ -665,22 +684,21 @@ struct OpsT {
           c.end(sh);
           g_launches++;
         }
-        if (fork_heavy) cudaEventRecord(join, sh);
-        c.begin("light", s);
+        c.begin("light", ls);
         if (c.cur_branch == 'E' && c.light_dual) {   // short list -> latency form, long list -> throughput form
           KArgs al = c.tl(a);
           al.light_dual = 1;
-          if (c.tail_lat) k_pipe_light_tail<T><<<XARM_LIGHT_LAT_MAX / 128, 128, 0, s>>>(al);
-          else k_pipe_light_lat<T><<<XARM_LIGHT_LAT_MAX / 128, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(al);
-          k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(al);
+          if (c.tail_lat) k_pipe_light_tail<T><<<XARM_LIGHT_LAT_MAX / 128, 128, 0, ls>>>(al);
+          else k_pipe_light_lat<T><<<XARM_LIGHT_LAT_MAX / 128, 128, XARM_MROW_WORDS * 128 * sizeof(float), ls>>>(al);
+          k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), ls>>>(al);
           g_launches++;
         } else if (part && c.light_main_lat) {   // partitioned main branch: nothing runs next to it on its SMs - 3 blocks of the 160-register form
-          k_pipe_light_lat<T><<<c.heavy_grid * 3, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(c.tl(a));
+          k_pipe_light_lat<T><<<c.heavy_grid * 3, 128, XARM_MROW_WORDS * 128 * sizeof(float), ls>>>(c.tl(a));
         } else {
-          k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), s>>>(c.tl(a));
+          k_pipe_light<T><<<g, 128, XARM_MROW_WORDS * 128 * sizeof(float), ls>>>(c.tl(a));
         }
-        c.end(s);
-        if (fork_heavy) cudaStreamWaitEvent(s, join, 0);
+        c.end(ls);
+        if (fork_heavy) { cudaEventRecord(join, sh); cudaStreamWaitEvent(s, join, 0); }
         if (join2_pending) { cudaStreamWaitEvent(s, join2_pending, 0); join2_pending = nullptr; }
         g_launches += 3;
       }
@@ -872,6 +890,9 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
                    (c.task == XARM_TASK_PICK_AND_PLACE && c.reward_type == XARM_REWARD_DENSE_O2G) ||
                    (c.task == XARM_TASK_REACH && c.reward_type == XARM_REWARD_DENSE_DIFF);
   if (!ok_reward) return fail(XARM_E_INVALID, "xarm_create: reward_type not implemented for this task");
+  // config['use_stand'] [REF xarm_handover.py:391-392]: a 0.07 x 0.06 x 0.01 static box under every goal.  The collider is not
+  // built: refuse the config instead of simulating a different world silently.
+  if (c.use_stand) return fail(XARM_E_INVALID, "xarm_create: use_stand=True is not implemented (the stand collider under the goal is not simulated)");
   int ndev = 0;
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (c.device < 0 || c.device >= ndev) return fail(XARM_E_INVALID, "xarm_create: bad device ordinal");
@@ -944,6 +965,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     }
   }
   if (getenv("XARM_SETUP_BPS")) h->pipe.setup_bps = atoi(getenv("XARM_SETUP_BPS"));
+  h->pipe.e_swap = !(getenv("XARM_E_SWAP") && atoi(getenv("XARM_E_SWAP")) == 0);
   h->pipe.light_multi = !(getenv("XARM_LIGHT_MULTI") && atoi(getenv("XARM_LIGHT_MULTI")) == 0);
   h->pipe.light_dual = !(getenv("XARM_LIGHT_DUAL") && atoi(getenv("XARM_LIGHT_DUAL")) == 0);
   h->pipe.main_wait = !(getenv("XARM_MAIN_WAIT") && atoi(getenv("XARM_MAIN_WAIT")) == 0);

@@ -735,6 +735,7 @@ struct Contacts {
   static constexpr int N = T::MD::N, MAXC = T::MAXC, MAXAC = XARM_MAXAC;
   int nc, nac, npair;                    // contact points, points on gripper links, pairs that produced points
   uint8_t ba[MAXC], bb[MAXC];            // body codes of side A / side B (normal points from B to A)
+  uint8_t pair[MAXC];                    // which collision pair produced the point (the points of one pair share the normal)
   int8_t slot[MAXC];                     // row-pool slot of the arm side (-1: none)
   int8_t o1[MAXC], o2[MAXC];             // object index of the first / second object side (-1: none); o2 only for object-object
   float s1[MAXC];                        // sign of the first object side (+1 side A, -1 side B); the second is always -1
@@ -780,7 +781,7 @@ XD int add_pair(Contacts<T>& C, const Box& A, const Box& B, int ca, int cb, floa
   }
   for (int i = 0; i < k; i++) {
     int c = C.nc++;
-    C.ba[c] = (uint8_t)ca; C.bb[c] = (uint8_t)cb;
+    C.ba[c] = (uint8_t)ca; C.bb[c] = (uint8_t)cb; C.pair[c] = (uint8_t)C.npair;
     C.pa[c] = pts[i].pa; C.pb[c] = pts[i].pb; C.dir[c][0] = pts[i].n; C.depth[c] = pts[i].depth;
     C.mu[c] = mu; C.erp[c] = erp; C.cfm0[c] = cfm;
     C.slot[c] = with_arm ? (int8_t)(C.nac++) : (int8_t)-1;
@@ -875,7 +876,7 @@ XD void arm_rows(const Env<T>& e, const ArmDyn<typename T::MD>* D, float door_qd
 // collide -> unconstrained velocities -> rows.  Returns which solver form applies.
 template <class T>
 XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Contacts<T>& C, SubBase<T>& B, ManifoldIn& MI,
-                 const ArmDyn<typename T::MD>* Dpre = nullptr) {
+                 const ArmDyn<typename T::MD>* Dpre = nullptr, S3* Iinv_out = nullptr) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1, NT = N * (N + 1) / 2;
   const float h = (float)T::H;
@@ -899,6 +900,7 @@ XD int sub_setup(Env<T>& e, bool apply_damping, bool last, ArmRows<T>& AR, Conta
       const float lx = 2 * T::OBJ_HX, ly = 2 * T::OBJ_HY, lz = 2 * T::OBJ_HZ, m12 = T::OBJ_MASS / 12.f;
       S3 Il = {1.f / (m12 * (ly * ly + lz * lz)), 0, 0, 1.f / (m12 * (lx * lx + lz * lz)), 0, 1.f / (m12 * (lx * lx + ly * ly))};
       Iinv[o] = rotate_sym(ob[o].R, Il);
+      if (Iinv_out) Iinv_out[o] = Iinv[o];
     }
     Box tb[T::NTABLE];
     for (int k = 0; k < T::NTABLE; k++) {
@@ -2031,8 +2033,18 @@ XD void substep_generic(Env<T>& e, bool apply_damping, bool last, Contacts<T>& C
   SubBase<T> B;
   SubSol<T> S;
   ManifoldIn MI;
+#if defined(XARM_REC_PROF) && defined(__CUDA_ARCH__)
+  const long long t0_ = clock64();
+#endif
   const int form = sub_setup<T>(e, apply_damping, last, AR, C, B, MI);
+#if defined(XARM_REC_PROF) && defined(__CUDA_ARCH__)
+  const long long t1_ = clock64();
+#endif
   sub_solve_generic<T>(AR, C, S, form == SOLVE_GENERIC_JOINT ? SOLVE_GENERIC_JOINT : SOLVE_GENERIC_DECOUPLED);
+#if defined(XARM_REC_PROF) && defined(__CUDA_ARCH__)
+  const long long t2_ = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) printf("[rec prof] nc %d nac %d | setup %lld | solve %lld cycles\n", C.nc, C.nac, t1_ - t0_, t2_ - t1_);
+#endif
   sub_integrate<T>(e, B, S);
 }
 

@@ -58,7 +58,7 @@ typedef struct XarmConfig {
   float init_grasp_rate;      /* config['init_grasp_rate'] */
   float goal_ground_rate;     /* config['goal_ground_rate'] */
   float same_side_rate;       /* config['same_side_rate'] */
-  int32_t use_stand;          /* config['use_stand'] (accepted; the stand is not simulated) */
+  int32_t use_stand;          /* config['use_stand']: must be 0 - xarm_create refuses 1 (the stand collider is not built) */
   int32_t max_episode_steps;  /* 0 = the registered TimeLimit (25/50/50/50/100) [REF gym_xarm/__init__.py:6-22] */
   int32_t auto_reset;         /* 1: VecEnv semantics - a finished env is reset inside xarm_step */
   int32_t device;             /* CUDA device ordinal */
