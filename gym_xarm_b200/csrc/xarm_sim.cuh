@@ -1823,32 +1823,49 @@ XD float arm_dot(const float* J, const float* dqd) {  // three partial sums: sho
   }
   return (s0 + s1) + s2;
 }
+// An island description restricts the loop to a subset of the env's rows (substep_generic_islands below): the arms in
+// `arm_mask`, the door when `door_on`, the contacts idx[0..n_idx) (ascending: the joint loop's order); it then runs exactly
+// `sweeps` sweeps and returns a bit per sweep ("a row moved more than the threshold") instead of leaving by itself, and
+// writes only the velocity changes of the bodies it swept.
+struct GenericIsland {
+  uint32_t arm_mask;
+  bool door_on;
+  const uint8_t* idx;
+  int n_idx;
+  int sweeps;
+  uint32_t obj_mask;
+};
 template <class T>
-XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, int /*form*/) {
+XD uint64_t sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, int /*form*/, const GenericIsland* isl = nullptr) {
   using MD = typename T::MD;
   constexpr int N = MD::N, NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1, NT = N * (N + 1) / 2;
   SOLVER_LOCALS_FROM(AR)
   V3 dv[NO], dw[NO];
 #pragma unroll
   for (int o = 0; o < NO; o++) { dv[o] = v3(0, 0, 0); dw[o] = v3(0, 0, 0); }
-  const int nc = C.nc;
-  for (int it = 0; it < XARM_SOLVER_ITERATIONS; it++) {
+  const int nc = isl ? isl->n_idx : C.nc;
+  const uint32_t arm_mask = isl ? isl->arm_mask : 0xffffffffu;
+  const bool door_on = isl ? isl->door_on : true;
+  const int max_sweeps = isl ? isl->sweeps : XARM_SOLVER_ITERATIONS;
+  uint64_t bad_bits = 0;
+  for (int it = 0; it < max_sweeps; it++) {
     bool resid_bad = false;
     if (it & 1) {
 #pragma unroll
       for (int a = 0; a < NA; a++) {
-        ARM_LIMITS_FWD(a) ARM_MOTORS_FWD(a) GEAR_ROW(a)
+        if (arm_mask >> a & 1u) { ARM_LIMITS_FWD(a) ARM_MOTORS_FWD(a) GEAR_ROW(a) }
       }
-      if (T::HAS_DOOR) { DOOR_LIMIT_ROW() DOOR_MOTOR_ROW() }
+      if (T::HAS_DOOR && door_on) { DOOR_LIMIT_ROW() DOOR_MOTOR_ROW() }
     } else {
-      if (T::HAS_DOOR) { DOOR_MOTOR_ROW() DOOR_LIMIT_ROW() }
+      if (T::HAS_DOOR && door_on) { DOOR_MOTOR_ROW() DOOR_LIMIT_ROW() }
 #pragma unroll
       for (int a = NA - 1; a >= 0; a--) {
-        GEAR_ROW(a) ARM_MOTORS_BWD(a) ARM_LIMITS_BWD(a)
+        if (arm_mask >> a & 1u) { GEAR_ROW(a) ARM_MOTORS_BWD(a) ARM_LIMITS_BWD(a) }
       }
     }
     // ---- normal rows
-    for (int c = 0; c < nc; c++) {
+    for (int ci = 0; ci < nc; ci++) {
+      const int c = isl ? (int)isl->idx[ci] : ci;
       const int o1 = NOBJ <= 1 ? (C.o1[c] >= 0 ? 0 : -1) : C.o1[c];
       const int o2 = NOBJ > 1 ? C.o2[c] : -1;
       const int sl = C.slot[c];
@@ -1879,7 +1896,8 @@ XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, in
       if (T::HAS_DOOR) ddoor += C.jdoor[T::HAS_DOOR ? c : 0][0] * d0 / (float)XARM_DOOR_MASS;
     }
     // ---- friction pairs (implicit cone: the pair is scaled back onto mu * normal impulse)
-    for (int c = 0; c < nc; c++) {
+    for (int ci = 0; ci < nc; ci++) {
+      const int c = isl ? (int)isl->idx[ci] : ci;
       const int o1 = NOBJ <= 1 ? (C.o1[c] >= 0 ? 0 : -1) : C.o1[c];
       const int o2 = NOBJ > 1 ? C.o2[c] : -1;
       const int sl = C.slot[c];
@@ -1924,15 +1942,111 @@ XD void sub_solve_generic(const ArmRows<T>& AR, Contacts<T>& C, SubSol<T>& S, in
       }
       if (T::HAS_DOOR) ddoor += (C.jdoor[T::HAS_DOOR ? c : 0][1] * da + C.jdoor[T::HAS_DOOR ? c : 0][2] * db) / (float)XARM_DOOR_MASS;
     }
-    if (!resid_bad) break;
+    if (isl) bad_bits |= (uint64_t)(resid_bad ? 1u : 0u) << it;
+    else if (!resid_bad) break;
   }
 #pragma unroll
   for (int a = 0; a < NA; a++)
+    if (arm_mask >> a & 1u) {
 #pragma unroll
-    for (int i = 0; i < N; i++) S.dqd[a][i] = dqd[a][i];
+      for (int i = 0; i < N; i++) S.dqd[a][i] = dqd[a][i];
+    }
 #pragma unroll
-  for (int o = 0; o < NO; o++) { S.dv[o] = dv[o]; S.dw[o] = dw[o]; }
-  S.ddoor = ddoor;
+  for (int o = 0; o < NO; o++)
+    if (!isl || (isl->obj_mask >> o & 1u)) { S.dv[o] = dv[o]; S.dw[o] = dw[o]; }
+  if (door_on) S.ddoor = ddoor;
+  return bad_bits;
+}
+
+// ---- Generic substep of the multi-island tasks with the simple islands taken out of the joint loop.  In a heavy env of those
+// tasks most rows still belong to islands the light forms can sweep: an arm that touches nothing (registers, light_island_arm),
+// an object whose only points come from ONE pair with a static box (light_island_manifold), the door when nothing touches it.
+// The generic loop - ~750 cycles per row for a lone thread: dynamic body indices, rows streamed from the record - keeps only
+// the rows of the coupled remainder.  Islands are independent, so every row gets the impulses of the joint loop (the manifold
+// form rounds differently from the generic contact row: heavy envs are compared statistically); the loop's exit test is
+// rebuilt from the islands' per-sweep bits as in sub_solve_light_multi.
+template <class T>
+XD void solve_generic_islands(const Env<T>& e, const ArmRows<T>& AR, Contacts<T>& C, const S3* Iinv, SubSol<T>& S) {
+  using MD = typename T::MD;
+  constexpr int NA = T::NARM, NOBJ = T::NOBJ, NO = NOBJ > 0 ? NOBJ : 1;
+#ifdef XARM_HOST_SIM
+  if (getenv("XARM_NO_ISLANDS")) { sub_solve_generic<T>(AR, C, S, SOLVE_GENERIC_JOINT); return; }   // test hook: the plain joint loop
+#endif
+  // ---- which bodies the coupled remainder holds
+  uint32_t arm_in = 0u, obj_gen = 0u;
+  bool door_in = false;
+  int first[NO], cnt[NO];
+  bool one_pair[NO];
+#pragma unroll
+  for (int o = 0; o < NO; o++) { first[o] = -1; cnt[o] = 0; one_pair[o] = true; }
+  for (int c = 0; c < C.nc; c++) {
+    const int ca = C.ba[c], cb = C.bb[c];
+    if (C.slot[c] >= 0) arm_in |= 1u << (NA == 1 ? 0 : bc_arm(bc_is_arm(ca) ? ca : cb));
+    if (T::HAS_DOOR && (ca == BC_DOOR || cb == BC_DOOR)) door_in = true;
+    const int o1 = C.o1[c], o2 = NOBJ > 1 ? C.o2[c] : -1;
+    const bool simple = bc_is_obj(ca) && cb == BC_STATIC && C.cfm0[c] == 0.f;   // object (side A) on a static box
+    if (!simple) {
+      if (o1 >= 0) obj_gen |= 1u << o1;
+      if (o2 >= 0) obj_gen |= 1u << o2;
+    } else {
+      const int o = o1 < 0 ? 0 : o1;
+      if (first[o] < 0) first[o] = c; else if (C.pair[c] != C.pair[first[o]]) one_pair[o] = false;
+      cnt[o]++;
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < NO; o++) if (!one_pair[o] || cnt[o] > 4) obj_gen |= 1u << o;
+  for (int a = 0; a < NA; a++) if (((AR.lim_lo[a] | AR.lim_hi[a]) & 0x7fu) != 0u) arm_in |= 1u << a;   // arm-joint limit rows: generic form only
+  uint8_t idx[T::MAXC];
+  int n_idx = 0;
+  for (int c = 0; c < C.nc; c++) {
+    const int o1 = C.o1[c], o2 = NOBJ > 1 ? C.o2[c] : -1;
+    const bool in_gen = C.slot[c] >= 0 || (o1 >= 0 && (obj_gen >> o1 & 1u)) || (o2 >= 0 && (obj_gen >> o2 & 1u)) || (o1 < 0 && o2 < 0);
+    if (in_gen) idx[n_idx++] = (uint8_t)c;
+  }
+  float rec_ar[T::NARM * (T::MD::N * (T::MD::N + 1) / 2 + 2 * T::MD::N + 5) + 4];
+  ar_store<T>(AR, rec_ar, 1, 0);
+  int sweeps = XARM_SOLVER_ITERATIONS;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    uint64_t bad = 0;
+#pragma unroll 1
+    for (int a = 0; a < NA; a++)
+      if (!(arm_in >> a & 1u)) bad |= light_island_arm<T>(rec_ar + a * ar_arm_words<T>(), 1, 0, sweeps, S.dqd[a]);
+    S.ddoor = 0.f;
+    if (T::HAS_DOOR && !door_in) bad |= light_island_door(rec_ar + NA * ar_arm_words<T>(), 1, 0, sweeps, S.ddoor);
+#pragma unroll 1
+    for (int o = 0; o < NO; o++) {
+      if (obj_gen >> o & 1u) continue;
+      S.dv[o] = v3(0, 0, 0); S.dw[o] = v3(0, 0, 0);
+      if (o < NOBJ && cnt[o] > 0) {
+        ManifoldIn MI;
+        const int c0 = first[o];
+        MI.n = C.dir[c0][0]; MI.mu = C.mu[c0]; MI.Iinv = Iinv[o];
+        int k = 0;
+        for (int c = c0; c < C.nc && k < 4; c++) {
+          if (C.o1[c] != (NOBJ <= 1 ? C.o1[c0] : o) || C.pair[c] != C.pair[c0]) continue;
+          MI.r[k] = C.pa[c] - e.obj[o].pos;
+          MI.rhs[k][0] = C.rhs[c][0]; MI.rhs[k][1] = C.rhs[c][1]; MI.rhs[k][2] = C.rhs[c][2];
+          k++;
+        }
+        for (; k < 4; k++) { MI.r[k] = v3(0, 0, 0); MI.rhs[k][0] = 0.f; MI.rhs[k][1] = 0.f; MI.rhs[k][2] = 0.f; }
+        float mrows[XARM_MROW_WORDS];
+        bad |= light_island_manifold<T>(MI, cnt[o], mrows, 1, sweeps, S.dv[o], S.dw[o]);
+      }
+    }
+    if (n_idx > 0 || arm_in != 0u || (T::HAS_DOOR && door_in)) {
+      for (int k = 0; k < n_idx; k++) { const int c = idx[k]; C.app[c][0] = 0.f; C.app[c][1] = 0.f; C.app[c][2] = 0.f; }
+      GenericIsland isl = {arm_in, T::HAS_DOOR && door_in, idx, n_idx, sweeps, obj_gen};
+      bad |= sub_solve_generic<T>(AR, C, S, SOLVE_GENERIC_JOINT, &isl);
+    }
+    const uint64_t good = ~bad & ((1ull << sweeps) - 1ull);
+    if (good == 0ull) break;
+    int firstg = 0;
+    while (!((good >> firstg) & 1ull)) firstg++;
+    if (firstg + 1 >= sweeps) break;
+    sweeps = firstg + 1;
+  }
 }
 
 // stepPositionsMultiDof: add the solved velocity changes, integrate joints and boxes
@@ -2021,8 +2135,14 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
     for (int a = 0; a < T::NARM; a++) e.grasp[a] = g0[a];   // (the lean setup may have cleared the flags before it found a contact)
   }
   Contacts<T> C;
-  const int form = sub_setup<T>(e, apply_damping, last, AR, C, B, MI);
-  sub_solve_generic<T>(AR, C, S, form == SOLVE_GENERIC_JOINT ? SOLVE_GENERIC_JOINT : SOLVE_GENERIC_DECOUPLED);
+  if constexpr (task_single_island_pair<T>()) {
+    const int form = sub_setup<T>(e, apply_damping, last, AR, C, B, MI);
+    sub_solve_generic<T>(AR, C, S, form == SOLVE_GENERIC_JOINT ? SOLVE_GENERIC_JOINT : SOLVE_GENERIC_DECOUPLED);
+  } else {
+    S3 Iinv[T::NOBJ > 0 ? T::NOBJ : 1];
+    sub_setup<T>(e, apply_damping, last, AR, C, B, MI, nullptr, Iinv);
+    solve_generic_islands<T>(e, AR, C, Iinv, S);
+  }
   sub_integrate<T>(e, B, S);
 }
 // the same substep without the light solver (pipeline: envs the setup kernel classified as not light).  The contact
@@ -2036,11 +2156,13 @@ XD void substep_generic(Env<T>& e, bool apply_damping, bool last, Contacts<T>& C
 #if defined(XARM_REC_PROF) && defined(__CUDA_ARCH__)
   const long long t0_ = clock64();
 #endif
-  const int form = sub_setup<T>(e, apply_damping, last, AR, C, B, MI);
+  S3 Iinv_[T::NOBJ > 0 ? T::NOBJ : 1];
+  const int form = sub_setup<T>(e, apply_damping, last, AR, C, B, MI, nullptr, Iinv_);
 #if defined(XARM_REC_PROF) && defined(__CUDA_ARCH__)
   const long long t1_ = clock64();
 #endif
-  sub_solve_generic<T>(AR, C, S, form == SOLVE_GENERIC_JOINT ? SOLVE_GENERIC_JOINT : SOLVE_GENERIC_DECOUPLED);
+  if constexpr (task_single_island_pair<T>()) sub_solve_generic<T>(AR, C, S, form == SOLVE_GENERIC_JOINT ? SOLVE_GENERIC_JOINT : SOLVE_GENERIC_DECOUPLED);
+  else solve_generic_islands<T>(e, AR, C, Iinv_, S);
 #if defined(XARM_REC_PROF) && defined(__CUDA_ARCH__)
   const long long t2_ = clock64();
   if (blockIdx.x == 0 && threadIdx.x == 0) printf("[rec prof] nc %d nac %d | setup %lld | solve %lld cycles\n", C.nc, C.nac, t1_ - t0_, t2_ - t1_);

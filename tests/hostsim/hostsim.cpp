@@ -170,6 +170,8 @@ void hs_get_state(HS* h, float* out) {
   const int64_t n = h->cfg.num_envs; const int S = h->ops.S;
   for (int64_t i = 0; i < n; i++) for (int w = 0; w < S; w++) out[i * S + w] = h->state[(size_t)w * n + i];
 }
+// light / heavy classification the setup pass of the LAST substep left (pipeline mode): 1 = heavy
+void hs_get_forms(HS* h, int* out) { for (int64_t i = 0; i < h->cfg.num_envs; i++) out[i] = h->k.form[i] & 0xff; }
 void hs_set_state(HS* h, const float* in) {
   const int64_t n = h->cfg.num_envs; const int S = h->ops.S;
   for (int64_t i = 0; i < n; i++) for (int w = 0; w < S; w++) h->state[(size_t)w * n + i] = in[i * S + w];

@@ -48,6 +48,7 @@ def lib():
         L.hs_get_obs.argtypes = [C.c_void_p, fp, fp, fp]
         L.hs_step.argtypes = [C.c_void_p, fp, fp, fp, fp, fp, u8p, fp, u8p]
         L.hs_get_state.argtypes = [C.c_void_p, fp]
+        L.hs_get_forms.argtypes = [C.c_void_p, ip]
         L.hs_set_state.argtypes = [C.c_void_p, fp]
         L.hs_compute_reward.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, C.c_int64, fp]
         L.hs_box_box.argtypes = [fp, fp, fp]
@@ -114,6 +115,12 @@ class HostSimVec:
         s = np.zeros((self.n, self.S), FT)
         self.L.hs_get_state(self.h, _f(s))
         return s
+
+    def get_forms(self):
+        """1 where the setup pass of the last substep classified the env as heavy (pipeline mode)"""
+        f = np.zeros(self.n, np.int32)
+        self.L.hs_get_forms(self.h, f.ctypes.data_as(C.POINTER(C.c_int)))
+        return f
 
     def set_state(self, s):
         s = np.ascontiguousarray(s, FT)
