@@ -475,15 +475,20 @@ __device__ __forceinline__ float heavy_solve_dela(const float* __restrict__ rec,
       const float p0 = c_[0], p1 = c_[16], p2 = c_[32], p3 = c_[48], q0 = c_[64], q1 = c_[80], q2 = c_[96], q3 = c_[112];
       float xa = fmaf(-s1, di1, ca), xb = fmaf(-s2, di2, cb);
       const float l2 = xa * xa + xb * xb;
-      const float sc = l2 > lim2 ? lim * rsqrtf(l2) : 1.f;
+      // rsqrtf() wraps MUFU.RSQ in a denormal fix-up (two compares, two multiplies) that sits on the row's dependency chain;
+      // rsqrt.approx.ftz on max(l2, 1e-30) is the same MUFU result for every l2 >= 1e-30 and stays finite below (a pair of
+      // impulses < 1e-15 against a cone radius that is smaller still): friction step 166 -> 131 cycles (tools/micro/unit_micro.cu)
+      float rs_;
+      asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs_) : "f"(fmaxf(l2, 1e-30f)));
+      const float sc = l2 > lim2 ? lim * rs_ : 1.f;
       xa *= sc; xb *= sc;
       const float da = xa - app1, db = xb - app2;
       const float da_ = __shfl_sync(FULL, da, c, 16), db_ = __shfl_sync(FULL, db, c, 16);
       const bool own_ = l == c;
       app1 = own_ ? xa : app1; app2 = own_ ? xb : app2; ca = app1 + rhs1; cb = app2 + rhs2;
       bad = bad || (own_ && (fabsf(da) > sthr * di1_t || fabsf(db) > sthr * di2_t));
-      s0 += p0 * da_ + q0 * db_; s1 += p1 * da_ + q1 * db_;
-      s2 += p2 * da_ + q2 * db_; s3 += p3 * da_ + q3 * db_;
+      s0 = fmaf(q0, db_, fmaf(p0, da_, s0)); s1 = fmaf(q1, db_, fmaf(p1, da_, s1));
+      s2 = fmaf(q2, db_, fmaf(p2, da_, s2)); s3 = fmaf(q3, db_, fmaf(p3, da_, s3));
     }
     const uint32_t bb = __ballot_sync(FULL, bad);
     if (!done && ((bb >> (threadIdx.x & 16)) & 0xffffu) == 0u) {  // this env is finished: switch its rows off

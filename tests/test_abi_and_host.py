@@ -61,6 +61,21 @@ def test_her_create_rejects_bad_configs_without_gpu():
         XarmHerReplayBuffer(num_envs=8, obs_dim=24, goal_dim=3, action_dim=4, task=1, max_episode_length=50, goal_selection_strategy="final")
 
 
+def test_use_stand_is_refused_not_ignored():
+    """config['use_stand']=True [REF xarm_handover.py:391-392] puts a static box under every goal; the collider is not built, so
+    xarm_create must refuse the config (before any CUDA call) instead of simulating a different world silently."""
+    import pytest
+    from gym_xarm_b200 import _native
+    L = _native.load()
+    cfg = _native.XarmConfig(task=4, reward_type=1, num_obj=1, goal_shape=1, init_grasp_rate=0.0, goal_ground_rate=0.0, same_side_rate=0.5,
+                             use_stand=1, max_episode_steps=0, auto_reset=1, device=0, stagger_phases=0, num_envs=4, env_index_base=0, seed=0)
+    h = C.c_void_p()
+    rc = L.xarm_create(C.byref(cfg), C.byref(h))
+    assert rc == -1 and b"use_stand" in L.xarm_last_error()
+    with pytest.raises(NotImplementedError):
+        _native.check(rc, "xarm_create")
+
+
 def test_task_dims_without_gpu():
     from gym_xarm_b200 import _native, SPECS
     L = _native.load()
