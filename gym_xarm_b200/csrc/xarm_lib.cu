@@ -498,6 +498,7 @@ struct PipeCtx {
   // SM partition (XARM_RESERVE_SMS, default 32; 0 = off): while `dyn` is set (main branch of a split step) every launch
   // gets a work counter and the mask of the SMs it must leave to the early branch
   bool dyn = false;
+  int rec_bps = 3;          // XARM_REC_BPS: resident blocks per SM of k_pipe_heavy_rec (8 envs each; their thread-local frames compete with the records for the L1 / shared-memory array)
   bool e_swap = true;       // XARM_E_SWAP=0: the early branch's heavy kernels on the side stream, its light kernel on the chain's stream (round 2 start)
   bool light_multi = true;  // XARM_LIGHT_MULTI=0: tasks with several islands (two arms, door, several objects) take the generic substep for every env (round 1)
   bool light_dual = true;   // XARM_LIGHT_DUAL=0: one light kernel form everywhere
@@ -677,7 +678,7 @@ struct OpsT {
           k_pipe_heavy<T><<<c.heavy_grid, 32, heavy_smem_bytes(), sh>>>(a, sub, hc);
         } else {
           c.begin("heavy_rec", sh);
-          k_pipe_heavy_rec<T><<<c.heavy_grid * 3, XARM_HEAVY_REC_LANES, heavy_rec_smem_bytes<T>(), sh>>>(c.tl(a), sub, hc);
+          k_pipe_heavy_rec<T><<<c.heavy_grid * c.rec_bps, XARM_HEAVY_REC_LANES, heavy_rec_smem_bytes<T>(), sh>>>(c.tl(a), sub, hc);
           c.end(sh);
           c.begin("heavy_local", sh);
           k_pipe_heavy_local<T><<<rows_grid, 64, 0, sh>>>(c.tl(a), sub, hc);
@@ -965,6 +966,7 @@ int xarm_create(const XarmConfig* cfg, XarmHandle** out) {
     }
   }
   if (getenv("XARM_SETUP_BPS")) h->pipe.setup_bps = atoi(getenv("XARM_SETUP_BPS"));
+  if (getenv("XARM_REC_BPS")) h->pipe.rec_bps = atoi(getenv("XARM_REC_BPS")) > 0 ? atoi(getenv("XARM_REC_BPS")) : 3;
   h->pipe.e_swap = !(getenv("XARM_E_SWAP") && atoi(getenv("XARM_E_SWAP")) == 0);
   h->pipe.light_multi = !(getenv("XARM_LIGHT_MULTI") && atoi(getenv("XARM_LIGHT_MULTI")) == 0);
   h->pipe.light_dual = !(getenv("XARM_LIGHT_DUAL") && atoi(getenv("XARM_LIGHT_DUAL")) == 0);

@@ -298,9 +298,15 @@ XD bool pipe_may_finish(const KArgs& a, int64_t i) {
         const float* ob = a.b.observation + i * T::O + 8 + 16 * o + 13;
         const float hd2 = ob[0] * ob[0] + ob[1] * ob[1] + ob[2] * ob[2];
         const float R = 0.11f, H1 = 0.13f, H2 = 0.24f;
-        const float mid = fminf(free_travel, R), far = fminf(1.5f * sqrtf(v2) * dt_step + (float)XARM_GRAVITY * dt_step * dt_step + 0.003f, R);
+        // between H1 and H2 the hand can still reach the lego within the step and push it for the rest of its travel: at most
+        // ~(H2 - hd).  Round 2 end (tools/late_tail_diag.py, 200 staggered steps): the ~15 finishers the predictor missed were (a)
+        // legos just outside H1 at rest (d 0.075-0.079 against a free-travel reach of 0.073-0.076) and (b) legos INSIDE H1 that no
+        // gripper link touched yet - their reach had stayed the free-travel bound because it was min()-ed with the untouched-lego bound
+        // above; a lego inside H1 may be carried R whether or not it is touched now.
+        const float hd = sqrtf(hd2);
+        const float mid = fminf(fmaxf(free_travel, H2 - hd + 0.01f), R), far = fminf(1.5f * sqrtf(v2) * dt_step + (float)XARM_GRAVITY * dt_step * dt_step + 0.003f, R);
         const float tight = hd2 < H1 * H1 ? R : (hd2 > H2 * H2 ? far : mid);   // (NaN: mid)
-        reach = fminf(reach, T::THRESHOLD + tight);
+        reach = hd2 < H1 * H1 ? T::THRESHOLD + R : fminf(reach, T::THRESHOLD + tight);
       }
       all_near = all_near && d2 < reach * reach;
     }

@@ -5,17 +5,19 @@
 #include <cstdio>
 #define FULL 0xffffffffu
 // MODE bits: 1 = Delassus column from shared memory (else registers), 2 = residual ("bad") bookkeeping, 4 = contact rows too,
-// 8 = no normal rows, 16 = no friction rows, 32 = friction apply as an FMA chain, 64 = rsqrt.approx.ftz on max(l2, tiny)
+// 8 = no normal rows, 16 = no friction rows, 32 = friction apply as an FMA chain, 64 = rsqrt.approx.ftz on max(l2, tiny),
+// 128 = friction: broadcast the un-scaled (sticking) deltas first, a corrective exchange only when an owner lane's pair leaves the cone
 template <int MODE>
-__global__ void k(float* out, long long* cyc, int sweeps, float uden, float uhi, float sthr, int nc) {
+__global__ void k(float* out, long long* cyc, int sweeps, float uden, float uhi, float sthr, int nc, float mu_in) {
   __shared__ float A[2][64 * 64];
   const int l = threadIdx.x & 15, g = threadIdx.x >> 4;
   float* Ag = A[g];
   for (int i = threadIdx.x & 15; i < 64 * 64; i += 16) Ag[i] = 1e-3f * ((i * 7) % 13) - 5e-3f;
   __syncwarp();
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.01f * l, mapp = 0.f, urhs = 0.1f + 0.01f * l, cu = urhs;
-  float appn = 0.f, app1 = 0.f, app2 = 0.f, cn = 0.2f, ca = 0.01f, cb = -0.02f, dinv0 = 0.7f, di1 = 0.6f, di2 = 0.5f, cfmr0 = 0.f, rhs0 = 0.2f, rhs1 = 0.01f, rhs2 = -0.02f, mu = 0.5f;
+  float appn = 0.f, app1 = 0.f, app2 = 0.f, cn = 0.2f, ca = 0.01f, cb = -0.02f, dinv0 = 0.7f, di1 = 0.6f, di2 = 0.5f, cfmr0 = 0.f, rhs0 = 0.2f, rhs1 = 0.01f, rhs2 = -0.02f, mu = mu_in;
   const float uden_t = uden;
+  if (MODE & 8) appn = 1.f;   // friction rows alone: a normal impulse for the cone to refer to
   float rc[10][4];
 #pragma unroll
   for (int k2 = 0; k2 < 10; k2++) { rc[k2][0] = Ag[k2 * 64 + l]; rc[k2][1] = Ag[k2 * 64 + l + 16]; rc[k2][2] = Ag[k2 * 64 + l + 32]; rc[k2][3] = Ag[k2 * 64 + l + 48]; }
@@ -57,6 +59,27 @@ if (!(MODE & 16))
         const float* c_ = Ag + (10 + 3 * c + 1) * 64 + l;
         const float p0 = c_[0], p1 = c_[16], p2 = c_[32], p3 = c_[48], q0 = c_[64], q1 = c_[80], q2 = c_[96], q3 = c_[112];
         float xa = fmaf(-s1, di1, ca), xb = fmaf(-s2, di2, cb);
+        if (MODE & 128) {
+          const float l2s = xa * xa + xb * xb;
+          const bool own_ = l == c;
+          const bool slide = own_ && l2s > lim2;
+          const float da = xa - app1, db = xb - app2;
+          const float da_ = __shfl_sync(FULL, da, c, 16), db_ = __shfl_sync(FULL, db, c, 16);
+          float na = own_ ? xa : app1, nb = own_ ? xb : app2;
+          s0 = fmaf(q0, db_, fmaf(p0, da_, s0)); s1 = fmaf(q1, db_, fmaf(p1, da_, s1)); s2 = fmaf(q2, db_, fmaf(p2, da_, s2)); s3 = fmaf(q3, db_, fmaf(p3, da_, s3));
+          if (__any_sync(FULL, slide)) {
+            float r_; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r_) : "f"(fmaxf(l2s, 1e-30f)));
+            const float sc = lim * r_;
+            const float xs = slide ? xa * sc : xa, ys = slide ? xb * sc : xb;
+            const float ea = slide ? xs - xa : 0.f, eb = slide ? ys - xb : 0.f;
+            const float ea_ = __shfl_sync(FULL, ea, c, 16), eb_ = __shfl_sync(FULL, eb, c, 16);
+            if (own_) { na = xs; nb = ys; }
+            s0 = fmaf(q0, eb_, fmaf(p0, ea_, s0)); s1 = fmaf(q1, eb_, fmaf(p1, ea_, s1)); s2 = fmaf(q2, eb_, fmaf(p2, ea_, s2)); s3 = fmaf(q3, eb_, fmaf(p3, ea_, s3));
+          }
+          bad = bad || (own_ && (fabsf(na - app1) > sthr * di1 || fabsf(nb - app2) > sthr * di2));
+          app1 = na; app2 = nb; ca = app1 + rhs1; cb = app2 + rhs2;
+          continue;
+        }
         const float l2 = xa * xa + xb * xb;
         float sc;
         if (MODE & 64) { float r_; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r_) : "f"(fmaxf(l2, 1e-30f))); sc = l2 > lim2 ? lim * r_ : 1.f; }
@@ -78,9 +101,9 @@ if (!(MODE & 16))
   if (threadIdx.x == 0) cyc[0] = t1 - t0;
 }
 template <int MODE>
-static double run(float* out, long long* cyc, int sweeps, int nc) {
+static double run(float* out, long long* cyc, int sweeps, int nc, float mu = 0.5f) {
   long long h = 0;
-  for (int rep = 0; rep < 2; rep++) { k<MODE><<<1, 32>>>(out, cyc, sweeps, 0.5f, 1e3f, 3e-4f, nc); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); }
+  for (int rep = 0; rep < 2; rep++) { k<MODE><<<1, 32>>>(out, cyc, sweeps, 0.5f, 1e3f, 3e-4f, nc, mu); cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost); }
   return (double)h / sweeps;
 }
 int main() {
@@ -96,6 +119,10 @@ int main() {
   printf("friction only: FMA-chain apply %.0f | approx rsqrt %.0f | both %.0f\n", (run<7 + 8 + 32>(out, cyc, sweeps, nc) - b) / nc,
          (run<7 + 8 + 64>(out, cyc, sweeps, nc) - b) / nc, (run<7 + 8 + 32 + 64>(out, cyc, sweeps, nc) - b) / nc);
   printf("normal + friction, both friction changes: %.0f per contact\n", (run<7 + 32 + 64>(out, cyc, sweeps, nc) - b) / nc);
+  printf("friction only, stick-first exchange: cone never bites (mu 1e6) %.0f | cone always bites (mu 1e-6) %.0f   [reference form: %.0f | %.0f]\n",
+         (run<7 + 8 + 128>(out, cyc, sweeps, nc, 1e6f) - b) / nc, (run<7 + 8 + 128>(out, cyc, sweeps, nc, 1e-6f) - b) / nc,
+         (run<7 + 8 + 32 + 64>(out, cyc, sweeps, nc, 1e6f) - b) / nc, (run<7 + 8 + 32 + 64>(out, cyc, sweeps, nc, 1e-6f) - b) / nc);
+
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
   return 0;
