@@ -1986,8 +1986,8 @@ XD void solve_generic_islands(const Env<T>& e, const ArmRows<T>& AR, Contacts<T>
     const int o1 = C.o1[c], o2 = NOBJ > 1 ? C.o2[c] : -1;
     const bool simple = bc_is_obj(ca) && cb == BC_STATIC && C.cfm0[c] == 0.f;   // object (side A) on a static box
     if (!simple) {
-      if (o1 >= 0) obj_gen |= 1u << o1;
-      if (o2 >= 0) obj_gen |= 1u << o2;
+      if (o1 >= 0) obj_gen |= 1u << (o1 & 3);
+      if (NOBJ > 1 && o2 >= 0) obj_gen |= 1u << (o2 & 3);
     } else {
       const int o = o1 < 0 ? 0 : o1;
       if (first[o] < 0) first[o] = c; else if (C.pair[c] != C.pair[first[o]]) one_pair[o] = false;
@@ -2001,7 +2001,7 @@ XD void solve_generic_islands(const Env<T>& e, const ArmRows<T>& AR, Contacts<T>
   int n_idx = 0;
   for (int c = 0; c < C.nc; c++) {
     const int o1 = C.o1[c], o2 = NOBJ > 1 ? C.o2[c] : -1;
-    const bool in_gen = C.slot[c] >= 0 || (o1 >= 0 && (obj_gen >> o1 & 1u)) || (o2 >= 0 && (obj_gen >> o2 & 1u)) || (o1 < 0 && o2 < 0);
+    const bool in_gen = C.slot[c] >= 0 || (o1 >= 0 && (obj_gen >> (o1 & 3) & 1u)) || (NOBJ > 1 && o2 >= 0 && (obj_gen >> (o2 & 3) & 1u)) || (o1 < 0 && o2 < 0);
     if (in_gen) idx[n_idx++] = (uint8_t)c;
   }
   float rec_ar[T::NARM * (T::MD::N * (T::MD::N + 1) / 2 + 2 * T::MD::N + 5) + 4];
