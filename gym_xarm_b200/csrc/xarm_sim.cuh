@@ -2122,7 +2122,12 @@ NOINL void substep(Env<T>& e, bool apply_damping, bool last) {
     ArmDyn<typename T::MD> D[T::NARM];
     int g0[T::NARM];
     for (int a = 0; a < T::NARM; a++) g0[a] = e.grasp[a];
-    if (sub_setup_lean_multi<T>(e, apply_damping, last, AR, B, MIs, nc, D) && !arm_joint_on_limit<T>(AR)) {
+#ifdef XARM_HOST_SIM
+    const bool no_lean_ = getenv("XARM_NO_LEAN") != nullptr;   // test hook: every env through the generic setup + solve
+#else
+    const bool no_lean_ = false;
+#endif
+    if (!no_lean_ && sub_setup_lean_multi<T>(e, apply_damping, last, AR, B, MIs, nc, D) && !arm_joint_on_limit<T>(AR)) {
       float rec_ar[T::NARM * (T::MD::N * (T::MD::N + 1) / 2 + 2 * T::MD::N + 5) + 4], rec_mi[NO * 34];
       static_assert(sizeof(rec_mi) / sizeof(float) / NO == 34, "ManifoldIn record");
       ar_store<T>(AR, rec_ar, 1, 0);

@@ -123,3 +123,37 @@ def test_island_split_of_the_generic_solve_matches_the_joint_loop(task):
         assert moved > 0
     print(f"{task}: island split vs joint loop, worst |state difference| after one step {worst:.2e}; env-steps that ended in the heavy form: {heavy_steps}")
     assert heavy_steps > 0, "the scenario never reached a heavy env: nothing was compared"
+
+
+@pytest.mark.parametrize("task", ["stack_tower", "push_with_door", "handover"])
+def test_lean_multi_island_setup_classifies_like_the_generic_setup(task):
+    """The lean setup of the multi-island tasks calls an env light when NO pair outside "object x one static box" has a point; the
+    generic setup (full collision record) is the reference for that decision.  Fused per-env form with the lean path (default)
+    against the same form with XARM_NO_LEAN=1 (generic setup + island-split solve for every env), per step from re-synchronised
+    states, full-range random actions (Handover: fingers reach the tables): a pair the lean setup overlooked would show as a
+    missing contact, i.e. a difference far above rounding.  Same compilation on both sides (no FMA contraction on the host), so
+    what remains is the order of operations of the manifold rows."""
+    import os
+    n = 96
+    cfg = orc.make_config(task, num_envs=n, seed=9, auto_reset=0, goal_shape="ground")
+    a, b = hs.HostSimVec(cfg, pipeline=False), hs.HostSimVec(cfg, pipeline=False)
+    a.reset()
+    b.reset()
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for t in range(25):
+        act = rng.uniform(-1, 1, (n, a.A)).astype(np.float32)
+        if t % 3 == 0:
+            act[:, 2] = -1.0          # arm 0 all the way down every third step: gripper - table / object contacts for sure
+            act[:, a.A // 2 + 2] = -1.0
+        b.set_state(a.get_state())
+        a.step(act)
+        os.environ["XARM_NO_LEAN"] = "1"
+        try:
+            b.step(act)
+        finally:
+            del os.environ["XARM_NO_LEAN"]
+        d = np.abs(a.get_state().astype(np.float64) - b.get_state())
+        worst = max(worst, float(d.max()))
+        assert d.max() < 1e-4, (t, float(d.max()), np.unravel_index(d.argmax(), d.shape))
+    print(f"{task}: lean multi-island path vs generic setup for every env, worst |state difference| after one step {worst:.2e}")
