@@ -374,7 +374,7 @@ def main():
                                 "synchronised: all envs start their episodes together",
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
                        "timing": "CUDA events on the launching stream around every step, summed; max over ranks",
-                       "cuda_graph": not args.no_graph, "mapping": "one thread per env (16 lanes per env in the coupled contact solver); step = kernel pipeline action -> 15 x {setup -> light | heavy_rows -> heavy_solve} -> finish -> auto-reset passes; envs that may finish run as an early branch on reserved SMs"},
+                       "cuda_graph": not args.no_graph, "mapping": "one thread per env (16 lanes per env in the coupled contact solver); step = kernel pipeline action -> 15 x {setup -> light | fused heavy (collision + rows + joint loop)} -> finish -> auto-reset passes; envs that may finish run as an early branch on reserved SMs"},
             "clocks": R["clocks"], "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                            "steps": Ke, "path": "XarmVecEnv(output='numpy').step -> xarm_step_host (pinned staging, CUDA-graph replay, "
                                                                  "terminal observations of the finished envs gathered on the device); same phase and step count as value"},
