@@ -189,3 +189,26 @@ def test_bench_reference_arm_runs_on_cpu():
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "env-steps/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_committed_traffic_capture_matches_its_launch_list():
+    """profiles/traffic_pick_and_place.json (what bench.py quotes as roofline.traffic) must be what tools/ncu_traffic.py computes
+    from the committed ncu launch list of the same capture, and it must carry the hash of the kernel sources in this tree."""
+    import glob
+    import importlib.util
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "profiles", "traffic_pick_and_place.json")))
+    lists = sorted(glob.glob(os.path.join(root, "profiles", "r2z_launches_one_step.csv.gz")))
+    assert lists, "the launch list of the capture is not committed"
+    spec = importlib.util.spec_from_file_location("ncu_traffic", os.path.join(root, "tools", "ncu_traffic.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    out = m.parse(lists[-1], "pick_and_place", 131072, write=False)
+    assert abs(out["dram_bytes_per_step"] - d["dram_bytes_per_step"]) <= 1e-6 * d["dram_bytes_per_step"]
+    assert {k["kernel"] for k in out["kernels"]} == {k["kernel"] for k in d["kernels"]}
+    import bench
+    import pytest
+    if d["kernel_source_hash"] != bench.kernel_source_hash():   # bench.py then prints traffic = null with a note; not a test failure
+        pytest.skip("the committed capture is from other kernel sources than this tree: re-run tools/ncu_traffic.py on a GPU box")

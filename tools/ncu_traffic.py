@@ -41,10 +41,11 @@ def run(task, n):
     print("profiled one step of", n, task, "envs after", pre, "pre-roll steps;", env.episode_stats())
 
 
-def parse(path, task, n):
+def parse(path, task, n, write=True):
     import bench
+    import gzip
     rows = []
-    with open(path, newline="") as f:
+    with (gzip.open(path, "rt", newline="") if path.endswith(".gz") else open(path, newline="")) as f:
         lines = [l for l in f if not l.startswith("==")]
     rd = csv.DictReader(lines)
     for r in rd:
@@ -77,6 +78,8 @@ def parse(path, task, n):
            "note": "ncu dram__bytes_read.sum + dram__bytes_write.sum over every kernel launch of one staggered, pre-rolled step "
                    "(plain launches, --clock-control none; per-launch times under ncu are serialised and cold-cache: shares only)"}
     dst = os.path.join(ROOT, "profiles", f"traffic_{task}.json")
+    if not write:
+        return out
     json.dump(out, open(dst, "w"), indent=1)
     print(f"{dst}: {total / 1e9:.3f} GB of DRAM traffic per step of {n} envs ({total / (bench.ALGO_BYTES[task] * n):.1f} x the algorithmic {bench.ALGO_BYTES[task] * n / 1e6:.1f} MB)")
     for k in kernels[:10]:
